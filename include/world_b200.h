@@ -1,0 +1,114 @@
+/* world_b200.h -- batched C ABI of the B200-native WORLD analysis engine.
+ *
+ * The reference (mmorise/World) has no plugin registry; its boundary is the public C API of
+ * src/world/*.h.  That API is kept source-compatible in include/world/*.h
+ * (single utterance, host pointers).  This header is the thin extern "C" layer underneath it:
+ * the same stages, N utterances per call, plain pointers and sizes, no C++/torch types.
+ *
+ * Conventions
+ *   - Batches are padded row-major arrays:  x[n_utts][x_stride] (doubles in [-1,1]),
+ *     time_axis / f0 [n_utts][f0_stride], spectrogram / aperiodicity
+ *     [n_utts][f0_stride][fft_size/2+1].  Per-utterance valid lengths are HOST int arrays
+ *     (x_lengths[n_utts], f0_lengths[n_utts]); NULL means "every row is full"
+ *     (x_stride samples / f0_stride frames).  Padding is never read; padded frames are never
+ *     written.
+ *   - The *_batch functions take DEVICE pointers for the big arrays and enqueue their work on
+ *     the context's stream (world_b200_set_stream); they do not synchronise.  The *_host
+ *     functions take host pointers, stage through device memory and return when the results are
+ *     in the caller's buffers.
+ *   - Every function returns 0 on success or a WORLD_B200_E* code; world_b200_last_error()
+ *     describes the failure.  (The reference returns void and has undefined behaviour on bad
+ *     input; the legacy wrappers in include/world/ keep `void` and print the message.)
+ *   - Frame counts follow the reference exactly: world_b200_frames() ==
+ *     GetSamplesForDIO()/GetSamplesForHarvest() (dio.cpp:639-641, harvest.cpp:1219-1221).
+ */
+#ifndef WORLD_B200_H_
+#define WORLD_B200_H_
+
+#include "world/dio.h"
+#include "world/harvest.h"
+#include "world/cheaptrick.h"
+#include "world/d4c.h"
+#include "world/stonemask.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WORLD_B200_OK 0
+#define WORLD_B200_ECUDA 1     /* a CUDA runtime call or kernel failed                        */
+#define WORLD_B200_ENOMEM 2    /* device scratch could not be allocated                       */
+#define WORLD_B200_EINVAL 3    /* argument outside what the on-chip kernels support           */
+#define WORLD_B200_EDOMAIN 4   /* a frame hit a case that is undefined in the reference
+                                  (e.g. f0 below the floor implied by fft_size); see message  */
+
+typedef struct WorldB200 WorldB200;
+
+/* Creates a context on CUDA device `device` (tables, scratch arena, status word).  Fails with
+ * WORLD_B200_ECUDA when no usable device exists: there is no CPU fallback. */
+int world_b200_create(int device, WorldB200 **ctx);
+void world_b200_destroy(WorldB200 *ctx);
+/* cuda_stream is a cudaStream_t; NULL selects the default stream. */
+int world_b200_set_stream(WorldB200 *ctx, void *cuda_stream);
+/* Upper bound (bytes) of internal scratch one stage call may hold; batches are processed in
+ * utterance chunks that fit it.  Default 12 GiB. */
+int world_b200_set_scratch_budget(WorldB200 *ctx, unsigned long long bytes);
+int world_b200_synchronize(WorldB200 *ctx);
+const char *world_b200_last_error(const WorldB200 *ctx);
+/* Number of kernels this context has launched so far (bench.py reports it). */
+unsigned long long world_b200_launch_count(const WorldB200 *ctx);
+
+/* int(1000.0 * x_length / fs / frame_period) + 1 */
+int world_b200_frames(int fs, int x_length, double frame_period);
+
+/* ---- batched stages, device pointers -------------------------------------------------- */
+/* Dio() over a batch (dio.h:38).  Writes time_axis and f0 rows of world_b200_frames() entries. */
+int world_b200_dio_batch(WorldB200 *ctx, const double *x, int n_utts, int x_stride,
+                         const int *x_lengths, int fs, const DioOption *option,
+                         double *time_axis, double *f0, int f0_stride);
+/* Harvest() over a batch (harvest.h:35). */
+int world_b200_harvest_batch(WorldB200 *ctx, const double *x, int n_utts, int x_stride,
+                             const int *x_lengths, int fs, const HarvestOption *option,
+                             double *time_axis, double *f0, int f0_stride);
+/* StoneMask() over a batch (stonemask.h:27). refined_f0 may alias f0. */
+int world_b200_stonemask_batch(WorldB200 *ctx, const double *x, int n_utts, int x_stride,
+                               const int *x_lengths, int fs, const double *time_axis,
+                               const double *f0, const int *f0_lengths, int f0_stride,
+                               double *refined_f0);
+/* CheapTrick() over a batch (cheaptrick.h:38); option->fft_size selects the row width. */
+int world_b200_cheaptrick_batch(WorldB200 *ctx, const double *x, int n_utts, int x_stride,
+                                const int *x_lengths, int fs, const double *time_axis,
+                                const double *f0, const int *f0_lengths, int f0_stride,
+                                const CheapTrickOption *option, double *spectrogram);
+/* D4C() over a batch (d4c.h:35); fft_size is CheapTrick's. */
+int world_b200_d4c_batch(WorldB200 *ctx, const double *x, int n_utts, int x_stride,
+                         const int *x_lengths, int fs, const double *time_axis,
+                         const double *f0, const int *f0_lengths, int f0_stride, int fft_size,
+                         const D4COption *option, double *aperiodicity);
+
+/* ---- whole analysis chain, host pointers ---------------------------------------------- */
+#define WORLD_B200_F0_DIO_STONEMASK 0
+#define WORLD_B200_F0_HARVEST 1
+
+typedef struct {
+  int f0_method;                 /* WORLD_B200_F0_*                                  */
+  DioOption dio;                 /* used when f0_method == DIO_STONEMASK             */
+  HarvestOption harvest;         /* used when f0_method == HARVEST                   */
+  CheapTrickOption cheaptrick;
+  D4COption d4c;
+} WorldB200AnalysisOption;
+
+void world_b200_default_analysis_option(int fs, int f0_method, WorldB200AnalysisOption *option);
+
+/* {Dio+StoneMask | Harvest} -> CheapTrick -> D4C for n_utts host waveforms; outputs are host
+ * arrays laid out as described above.  Input upload, compute and result download are pipelined
+ * over utterance chunks.  Any output pointer may be NULL to skip its download. */
+int world_b200_analyze_host(WorldB200 *ctx, const double *x, int n_utts, int x_stride,
+                            const int *x_lengths, int fs, const WorldB200AnalysisOption *option,
+                            double *time_axis, double *f0, int f0_stride, double *spectrogram,
+                            double *aperiodicity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WORLD_B200_H_ */

@@ -1,0 +1,120 @@
+"""ctypes access to the checkers (test infrastructure only):
+  * oracle/_ref/libworld_ref.so  -- the unmodified reference compiled from /root/reference
+  * oracle/libworld_oracle.so    -- our CPU restatement (oracle/world_oracle.cpp)
+Both export the reference's C API, so one wrapper class serves both."""
+import ctypes as C
+import os
+import wave
+
+import numpy as np
+
+from world_b200.api import DioOption, HarvestOption, CheapTrickOption, D4COption
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libworld_ref.so")
+ORACLE_LIB = os.path.join(ROOT, "oracle", "libworld_oracle.so")
+_P = C.c_void_p
+
+
+def read_wav(path):
+    """mono PCM -> float64 in [-1, 1) exactly like tools/audioio.cpp:236-249 (int / 2^(nbit-1))."""
+    with wave.open(path, "rb") as w:
+        assert w.getnchannels() == 1 and w.getsampwidth() == 2
+        fs = w.getframerate()
+        pcm = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+    return pcm.astype(np.float64) / 32768.0, fs
+
+
+class RefWorld:
+    def __init__(self, path=REF_LIB):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        # RTLD_LOCAL: these symbols have the same names as the product's legacy API
+        self.lib = C.CDLL(path, mode=os.RTLD_LOCAL | os.RTLD_NOW)
+        L = self.lib
+        L.GetSamplesForDIO.restype = C.c_int
+        L.GetSamplesForDIO.argtypes = [C.c_int, C.c_int, C.c_double]
+        L.GetSamplesForHarvest.restype = C.c_int
+        L.GetSamplesForHarvest.argtypes = [C.c_int, C.c_int, C.c_double]
+        L.GetFFTSizeForCheapTrick.restype = C.c_int
+        L.GetF0FloorForCheapTrick.restype = C.c_double
+        L.GetF0FloorForCheapTrick.argtypes = [C.c_int, C.c_int]
+        L.Dio.argtypes = [_P, C.c_int, C.c_int, C.POINTER(DioOption), _P, _P]
+        L.Harvest.argtypes = [_P, C.c_int, C.c_int, C.POINTER(HarvestOption), _P, _P]
+        L.StoneMask.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]
+        L.CheapTrick.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.POINTER(CheapTrickOption), _P]
+        L.D4C.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.POINTER(D4COption), _P]
+        for f in (L.Dio, L.Harvest, L.StoneMask, L.CheapTrick, L.D4C):
+            f.restype = None
+
+    # options
+    def dio_option(self):
+        o = DioOption(); self.lib.InitializeDioOption(C.byref(o)); return o
+
+    def harvest_option(self):
+        o = HarvestOption(); self.lib.InitializeHarvestOption(C.byref(o)); return o
+
+    def cheaptrick_option(self, fs):
+        o = CheapTrickOption(); self.lib.InitializeCheapTrickOption(C.c_int(fs), C.byref(o)); return o
+
+    def d4c_option(self):
+        o = D4COption(); self.lib.InitializeD4COption(C.byref(o)); return o
+
+    def frames(self, fs, n, frame_period=5.0):
+        return self.lib.GetSamplesForDIO(fs, n, frame_period)
+
+    @staticmethod
+    def _rows(a):
+        ptrs = (C.c_void_p * a.shape[0])(*[a[i].ctypes.data for i in range(a.shape[0])])
+        return ptrs
+
+    def dio(self, x, fs, opt=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        opt = opt or self.dio_option()
+        L = self.lib.GetSamplesForDIO(fs, len(x), opt.frame_period)
+        t = np.zeros(L); f0 = np.zeros(L)
+        self.lib.Dio(x.ctypes.data, len(x), fs, C.byref(opt), t.ctypes.data, f0.ctypes.data)
+        return t, f0
+
+    def harvest(self, x, fs, opt=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        opt = opt or self.harvest_option()
+        L = self.lib.GetSamplesForHarvest(fs, len(x), opt.frame_period)
+        t = np.zeros(L); f0 = np.zeros(L)
+        self.lib.Harvest(x.ctypes.data, len(x), fs, C.byref(opt), t.ctypes.data, f0.ctypes.data)
+        return t, f0
+
+    def stonemask(self, x, fs, t, f0):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        t = np.ascontiguousarray(t); f0 = np.ascontiguousarray(f0)
+        out = np.zeros_like(f0)
+        self.lib.StoneMask(x.ctypes.data, len(x), fs, t.ctypes.data, f0.ctypes.data, len(f0), out.ctypes.data)
+        return out
+
+    def cheaptrick(self, x, fs, t, f0, opt=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        t = np.ascontiguousarray(t); f0 = np.ascontiguousarray(f0)
+        opt = opt or self.cheaptrick_option(fs)
+        sp = np.zeros((len(f0), opt.fft_size // 2 + 1))
+        rows = self._rows(sp)
+        self.lib.CheapTrick(x.ctypes.data, len(x), fs, t.ctypes.data, f0.ctypes.data, len(f0), C.byref(opt), rows)
+        return sp
+
+    def d4c(self, x, fs, t, f0, fft_size, opt=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        t = np.ascontiguousarray(t); f0 = np.ascontiguousarray(f0)
+        opt = opt or self.d4c_option()
+        ap = np.zeros((len(f0), fft_size // 2 + 1))
+        rows = self._rows(ap)
+        self.lib.D4C(x.ctypes.data, len(x), fs, t.ctypes.data, f0.ctypes.data, len(f0), fft_size, C.byref(opt), rows)
+        return ap
+
+
+def rel_err(got, want, floor=0.0):
+    """max |got-want| / max(|want|, floor); exact zeros in `want` must be matched exactly unless floor>0."""
+    got = np.asarray(got, dtype=np.float64); want = np.asarray(want, dtype=np.float64)
+    den = np.maximum(np.abs(want), floor)
+    diff = np.abs(got - want)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r = np.where(den > 0, diff / den, np.where(diff == 0, 0.0, np.inf))
+    return r

@@ -1,0 +1,302 @@
+"""ctypes mirror of the batched C ABI (include/world_b200.h) and of the reference's operator
+names (Dio / Harvest / StoneMask / CheapTrick / D4C, src/world/*.h).
+
+This module is plumbing: it loads ``world_b200/lib/libworld_b200.so`` (hand-written sm_100a CUDA
+behind an extern "C" ABI), hands it raw pointers and returns arrays.  There is no Python or CPU
+implementation of any stage behind it -- if the library or a CUDA device is missing, loading
+or ``World()`` raises.
+
+Arrays: every batched call takes ``x`` as a 2-D float64 array ``[n_utts, x_stride]``.
+``torch`` CUDA tensors are passed by device pointer (zero copy, work is enqueued on torch's
+current stream); outputs are allocated with torch on the same device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "lib", "libworld_b200.so")
+
+
+class DioOption(C.Structure):  # dio.h:16-23
+    _fields_ = [("f0_floor", C.c_double), ("f0_ceil", C.c_double), ("channels_in_octave", C.c_double),
+                ("frame_period", C.c_double), ("speed", C.c_int), ("allowed_range", C.c_double)]
+
+
+class HarvestOption(C.Structure):  # harvest.h:16-20
+    _fields_ = [("f0_floor", C.c_double), ("f0_ceil", C.c_double), ("frame_period", C.c_double)]
+
+
+class CheapTrickOption(C.Structure):  # cheaptrick.h:16-20
+    _fields_ = [("q1", C.c_double), ("f0_floor", C.c_double), ("fft_size", C.c_int)]
+
+
+class D4COption(C.Structure):  # d4c.h:16-18
+    _fields_ = [("threshold", C.c_double)]
+
+
+class AnalysisOption(C.Structure):
+    _fields_ = [("f0_method", C.c_int), ("dio", DioOption), ("harvest", HarvestOption),
+                ("cheaptrick", CheapTrickOption), ("d4c", D4COption)]
+
+
+F0_DIO_STONEMASK = 0
+F0_HARVEST = 1
+
+_P = C.c_void_p
+_IP = C.POINTER(C.c_int)
+
+# every symbol include/world_b200.h and include/world/*.h declare: (restype, argtypes)
+ABI = {
+    "world_b200_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "world_b200_destroy": (None, [_P]),
+    "world_b200_set_stream": (C.c_int, [_P, _P]),
+    "world_b200_set_scratch_budget": (C.c_int, [_P, C.c_ulonglong]),
+    "world_b200_synchronize": (C.c_int, [_P]),
+    "world_b200_last_error": (C.c_char_p, [_P]),
+    "world_b200_launch_count": (C.c_ulonglong, [_P]),
+    "world_b200_frames": (C.c_int, [C.c_int, C.c_int, C.c_double]),
+    "world_b200_dio_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, C.POINTER(DioOption), _P, _P, C.c_int]),
+    "world_b200_harvest_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, C.POINTER(HarvestOption), _P, _P, C.c_int]),
+    "world_b200_stonemask_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, _P, _P, _IP, C.c_int, _P]),
+    "world_b200_cheaptrick_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, _P, _P, _IP, C.c_int,
+                                              C.POINTER(CheapTrickOption), _P]),
+    "world_b200_d4c_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, _P, _P, _IP, C.c_int, C.c_int,
+                                       C.POINTER(D4COption), _P]),
+    "world_b200_default_analysis_option": (None, [C.c_int, C.c_int, C.POINTER(AnalysisOption)]),
+    "world_b200_analyze_host": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, C.POINTER(AnalysisOption),
+                                          _P, _P, C.c_int, _P, _P]),
+    # legacy single-utterance API (host pointers)
+    "Dio": (None, [_P, C.c_int, C.c_int, C.POINTER(DioOption), _P, _P]),
+    "Harvest": (None, [_P, C.c_int, C.c_int, C.POINTER(HarvestOption), _P, _P]),
+    "StoneMask": (None, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
+    "CheapTrick": (None, [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.POINTER(CheapTrickOption), _P]),
+    "D4C": (None, [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.POINTER(D4COption), _P]),
+    "InitializeDioOption": (None, [C.POINTER(DioOption)]),
+    "InitializeHarvestOption": (None, [C.POINTER(HarvestOption)]),
+    "InitializeCheapTrickOption": (None, [C.c_int, C.POINTER(CheapTrickOption)]),
+    "InitializeD4COption": (None, [C.POINTER(D4COption)]),
+    "GetSamplesForDIO": (C.c_int, [C.c_int, C.c_int, C.c_double]),
+    "GetSamplesForHarvest": (C.c_int, [C.c_int, C.c_int, C.c_double]),
+    "GetFFTSizeForCheapTrick": (C.c_int, [C.c_int, C.POINTER(CheapTrickOption)]),
+    "GetF0FloorForCheapTrick": (C.c_double, [C.c_int, C.c_int]),
+}
+
+
+class WorldError(RuntimeError):
+    pass
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    path = path or os.environ.get("WORLD_B200_LIB") or DEFAULT_LIB
+    if not os.path.exists(path):
+        raise WorldError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in ABI.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+def _int_array(v, n):
+    if v is None:
+        return None, None
+    arr = (C.c_int * n)(*[int(t) for t in v])
+    return arr, arr
+
+
+class World:
+    """One analysis context on one GPU.  Method names and argument meaning follow the
+    reference's C API; every method takes a batch."""
+
+    def __init__(self, device: int = 0, lib_path: str | None = None, array_module: str = "torch"):
+        self.lib = load_library(lib_path)
+        self._h = _P()
+        rc = self.lib.world_b200_create(device, C.byref(self._h))
+        if rc != 0:
+            raise WorldError(f"world_b200_create(device={device}) failed with code {rc}: "
+                             "a CUDA device is required (no CPU path)")
+        self.device = device
+        self.xp = array_module
+        if array_module == "torch":
+            import torch
+            self.torch = torch
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            self.lib.world_b200_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise WorldError(f"world_b200 error {rc}: {self.lib.world_b200_last_error(self._h).decode()}")
+
+    def _use_current_stream(self):
+        if self.xp == "torch":
+            s = self.torch.cuda.current_stream(self.device).cuda_stream
+            self._check(self.lib.world_b200_set_stream(self._h, _P(s)))
+
+    def _empty(self, like, shape):
+        if self.xp == "torch":
+            return self.torch.empty(shape, dtype=self.torch.float64, device=like.device)
+        import numpy as np
+        return np.empty(shape, dtype=np.float64)
+
+    def _zeros(self, like, shape):
+        out = self._empty(like, shape)
+        if self.xp == "torch":
+            out.zero_()
+        else:
+            out[...] = 0.0
+        return out
+
+    def synchronize(self):
+        self._check(self.lib.world_b200_synchronize(self._h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.world_b200_launch_count(self._h))
+
+    def set_scratch_budget(self, nbytes: int):
+        self._check(self.lib.world_b200_set_scratch_budget(self._h, nbytes))
+
+    def frames(self, fs, x_length, frame_period=5.0) -> int:
+        return int(self.lib.world_b200_frames(fs, x_length, frame_period))
+
+    # -- options -----------------------------------------------------------------------------
+    def dio_option(self) -> DioOption:
+        o = DioOption()
+        self.lib.InitializeDioOption(C.byref(o))
+        return o
+
+    def harvest_option(self) -> HarvestOption:
+        o = HarvestOption()
+        self.lib.InitializeHarvestOption(C.byref(o))
+        return o
+
+    def cheaptrick_option(self, fs) -> CheapTrickOption:
+        o = CheapTrickOption()
+        self.lib.InitializeCheapTrickOption(fs, C.byref(o))
+        return o
+
+    def d4c_option(self) -> D4COption:
+        o = D4COption()
+        self.lib.InitializeD4COption(C.byref(o))
+        return o
+
+    # -- stages ------------------------------------------------------------------------------
+    def _f0_stride(self, fs, x, x_lengths, frame_period):
+        n, stride = x.shape
+        lens = [stride] * n if x_lengths is None else [int(v) for v in x_lengths]
+        fl = [self.frames(fs, v, frame_period) for v in lens]
+        return max(fl), fl
+
+    def dio(self, x, fs, option: DioOption | None = None, x_lengths=None):
+        option = option or self.dio_option()
+        n, stride = x.shape
+        f_stride, fl = self._f0_stride(fs, x, x_lengths, option.frame_period)
+        t = self._zeros(x, (n, f_stride))
+        f0 = self._zeros(x, (n, f_stride))
+        xl, keep = _int_array(x_lengths, n)
+        self._use_current_stream()
+        self._check(self.lib.world_b200_dio_batch(self._h, _ptr(x), n, stride, xl, fs, C.byref(option),
+                                                  _ptr(t), _ptr(f0), f_stride))
+        return t, f0, fl
+
+    def harvest(self, x, fs, option: HarvestOption | None = None, x_lengths=None):
+        option = option or self.harvest_option()
+        n, stride = x.shape
+        f_stride, fl = self._f0_stride(fs, x, x_lengths, option.frame_period)
+        t = self._zeros(x, (n, f_stride))
+        f0 = self._zeros(x, (n, f_stride))
+        xl, keep = _int_array(x_lengths, n)
+        self._use_current_stream()
+        self._check(self.lib.world_b200_harvest_batch(self._h, _ptr(x), n, stride, xl, fs, C.byref(option),
+                                                      _ptr(t), _ptr(f0), f_stride))
+        return t, f0, fl
+
+    def stonemask(self, x, fs, time_axis, f0, x_lengths=None, f0_lengths=None):
+        n, stride = x.shape
+        out = self._zeros(x, tuple(f0.shape))
+        xl, k1 = _int_array(x_lengths, n)
+        fl, k2 = _int_array(f0_lengths, n)
+        self._use_current_stream()
+        self._check(self.lib.world_b200_stonemask_batch(self._h, _ptr(x), n, stride, xl, fs, _ptr(time_axis),
+                                                        _ptr(f0), fl, f0.shape[1], _ptr(out)))
+        return out
+
+    def cheaptrick(self, x, fs, time_axis, f0, option: CheapTrickOption | None = None, x_lengths=None,
+                   f0_lengths=None, out=None):
+        option = option or self.cheaptrick_option(fs)
+        n, stride = x.shape
+        bins = option.fft_size // 2 + 1
+        if out is None:
+            out = self._zeros(x, (n, f0.shape[1], bins))
+        xl, k1 = _int_array(x_lengths, n)
+        fl, k2 = _int_array(f0_lengths, n)
+        self._use_current_stream()
+        self._check(self.lib.world_b200_cheaptrick_batch(self._h, _ptr(x), n, stride, xl, fs, _ptr(time_axis),
+                                                         _ptr(f0), fl, f0.shape[1], C.byref(option), _ptr(out)))
+        return out
+
+    def d4c(self, x, fs, time_axis, f0, fft_size, option: D4COption | None = None, x_lengths=None,
+            f0_lengths=None, out=None):
+        option = option or self.d4c_option()
+        n, stride = x.shape
+        bins = fft_size // 2 + 1
+        if out is None:
+            out = self._zeros(x, (n, f0.shape[1], bins))
+        xl, k1 = _int_array(x_lengths, n)
+        fl, k2 = _int_array(f0_lengths, n)
+        self._use_current_stream()
+        self._check(self.lib.world_b200_d4c_batch(self._h, _ptr(x), n, stride, xl, fs, _ptr(time_axis), _ptr(f0),
+                                                  fl, f0.shape[1], fft_size, C.byref(option), _ptr(out)))
+        return out
+
+    def analysis_option(self, fs, f0_method=F0_HARVEST) -> AnalysisOption:
+        o = AnalysisOption()
+        self.lib.world_b200_default_analysis_option(fs, f0_method, C.byref(o))
+        return o
+
+    def analyze_host(self, x_host, fs, option: AnalysisOption, x_lengths=None, time_axis=None, f0=None,
+                     spectrogram=None, aperiodicity=None, f0_stride=None):
+        """Whole chain on HOST arrays (numpy or pinned torch CPU tensors); outputs are written
+        into the given host arrays (allocated with numpy when None)."""
+        import numpy as np
+        n, stride = x_host.shape
+        frame_period = option.dio.frame_period if option.f0_method == F0_DIO_STONEMASK else option.harvest.frame_period
+        lens = [stride] * n if x_lengths is None else [int(v) for v in x_lengths]
+        fl = [self.frames(fs, v, frame_period) for v in lens]
+        f0_stride = f0_stride or max(fl)
+        bins = option.cheaptrick.fft_size // 2 + 1
+        if time_axis is None:
+            time_axis = np.zeros((n, f0_stride))
+        if f0 is None:
+            f0 = np.zeros((n, f0_stride))
+        if spectrogram is None:
+            spectrogram = np.zeros((n, f0_stride, bins))
+        if aperiodicity is None:
+            aperiodicity = np.zeros((n, f0_stride, bins))
+        xl, keep = _int_array(x_lengths, n)
+        self._check(self.lib.world_b200_analyze_host(self._h, _ptr(x_host), n, stride, xl, fs, C.byref(option),
+                                                     _ptr(time_axis), _ptr(f0), f0_stride, _ptr(spectrogram),
+                                                     _ptr(aperiodicity)))
+        return time_axis, f0, spectrogram, aperiodicity, fl

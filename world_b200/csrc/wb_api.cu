@@ -1,0 +1,374 @@
+// wb_api.cu -- context, scratch arena and the extern "C" ABI declared in include/world_b200.h,
+// plus the legacy single-utterance entry points of include/world/*.h implemented as n_utts = 1
+// batches (reference boundary: src/world/{dio,harvest,stonemask,cheaptrick,d4c}.h).
+#include "wb_internal.h"
+#include "../../include/world_b200.h"
+#include <stdio.h>
+#include <vector>
+
+struct WorldB200 {
+  wb::Ctx c;
+  int *lens_dev = nullptr;
+  size_t lens_cap = 0;
+};
+
+namespace wb {
+
+unsigned long long g_launches = 0;
+
+#ifndef WB_EMU
+static int cuda_fail(Ctx *ctx, cudaError_t e, const char *what) {
+  ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return WORLD_B200_ECUDA;
+}
+#define WB_CUDA(ctx, call, what)                                \
+  do {                                                          \
+    cudaError_t e_ = (call);                                    \
+    if (e_ != cudaSuccess) return cuda_fail((ctx), e_, (what)); \
+  } while (0)
+#endif
+
+int dev_check(Ctx *ctx, const char *what) {
+#ifndef WB_EMU
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(ctx, e, what);
+#else
+  (void)ctx; (void)what;
+#endif
+  return 0;
+}
+
+int dev_sync(Ctx *ctx) {
+#ifndef WB_EMU
+  WB_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "stream synchronize");
+#else
+  (void)ctx;
+#endif
+  return 0;
+}
+
+int dev_memcpy_h2d(Ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return 0;
+#ifndef WB_EMU
+  WB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream), "memcpy h2d");
+#else
+  (void)ctx; memcpy(dst, src, bytes);
+#endif
+  return 0;
+}
+
+int dev_memcpy_d2h(Ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes == 0) return 0;
+#ifndef WB_EMU
+  WB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream), "memcpy d2h");
+#else
+  (void)ctx; memcpy(dst, src, bytes);
+#endif
+  return 0;
+}
+
+int dev_memset(Ctx *ctx, void *dst, int value, size_t bytes) {
+  if (bytes == 0) return 0;
+#ifndef WB_EMU
+  WB_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream), "memset");
+#else
+  (void)ctx; memset(dst, value, bytes);
+#endif
+  return 0;
+}
+
+void *dev_malloc(Ctx *ctx, size_t bytes) {
+  void *p = nullptr;
+#ifndef WB_EMU
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    cuda_fail(ctx, e, "cudaMalloc");
+    cudaGetLastError();
+    return nullptr;
+  }
+#else
+  (void)ctx;
+  p = malloc(bytes);
+#endif
+  return p;
+}
+
+void dev_free(void *p) {
+  if (!p) return;
+#ifndef WB_EMU
+  cudaFree(p);
+#else
+  free(p);
+#endif
+}
+
+// One block of `bytes` device scratch, valid until the next arena_block() call on this
+// context.  Stage drivers lay out their scratch with ArenaPlan and ask for the total; the block
+// only grows (sync + free + cudaMalloc), so steady-state calls allocate nothing.
+unsigned char *arena_block(Ctx *ctx, size_t bytes) {
+  Arena &a = ctx->arena;
+  if (bytes > a.capacity) {
+    dev_sync(ctx);
+    dev_free(a.base);
+    a.base = nullptr;
+    a.capacity = 0;
+    const size_t want = bytes + (bytes >> 4) + (1 << 20);
+    a.base = (unsigned char *)dev_malloc(ctx, want);
+    if (!a.base) return nullptr;
+    a.capacity = want;
+  }
+  a.used = bytes;
+  return a.base;
+}
+
+int ctx_init_tables(Ctx *ctx) {
+  // twiddles in long double so that every entry is correctly rounded
+  std::vector<double2> tw(WB_TW_N / 2);
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (int k = 0; k < WB_TW_N / 2; ++k) {
+    const long double a = two_pi * (long double)k / (long double)WB_TW_N;
+    tw[k].x = (double)cosl(a);
+    tw[k].y = (double)(-sinl(a));
+  }
+  ctx->twiddle = (double2 *)dev_malloc(ctx, tw.size() * sizeof(double2));
+  if (!ctx->twiddle) return WORLD_B200_ENOMEM;
+  std::vector<uint32_t> jump((size_t)WB_RNG_NJ * 32 * 16 * 4);
+  rng_build_jump_tables(jump.data());
+  ctx->rng_jump = (uint32_t *)dev_malloc(ctx, jump.size() * 4);
+  ctx->status_dev = (int *)dev_malloc(ctx, sizeof(int));
+  if (!ctx->rng_jump || !ctx->status_dev) return WORLD_B200_ENOMEM;
+  int rc = dev_memcpy_h2d(ctx, ctx->twiddle, tw.data(), tw.size() * sizeof(double2));
+  if (!rc) rc = dev_memcpy_h2d(ctx, ctx->rng_jump, jump.data(), jump.size() * 4);
+  if (!rc) rc = dev_memset(ctx, ctx->status_dev, 0, sizeof(int));
+  if (!rc) rc = dev_sync(ctx);
+  return rc;
+}
+
+}  // namespace wb
+
+using namespace wb;
+
+// ------------------------------------------------------------------------------------------
+static int upload_lengths(WorldB200 *h, int n, int x_stride, const int *x_lengths, int f_stride,
+                          const int *f_lengths, Batch *b) {
+  Ctx *ctx = &h->c;
+  if ((size_t)2 * n > h->lens_cap) {
+    dev_sync(ctx);
+    dev_free(h->lens_dev);
+    h->lens_cap = (size_t)2 * n + 64;
+    h->lens_dev = (int *)dev_malloc(ctx, h->lens_cap * sizeof(int));
+    if (!h->lens_dev) { h->lens_cap = 0; return WORLD_B200_ENOMEM; }
+  }
+  std::vector<int> tmp((size_t)2 * n);
+  int mx = 0, mf = 0;
+  for (int i = 0; i < n; ++i) {
+    const int xl = x_lengths ? x_lengths[i] : x_stride;
+    const int fl = f_lengths ? f_lengths[i] : f_stride;
+    if (xl < 1 || xl > x_stride || fl < 0 || fl > f_stride) {
+      ctx->last_error = "utterance length outside its padded row";
+      return WORLD_B200_EINVAL;
+    }
+    tmp[i] = xl; tmp[n + i] = fl;
+    if (xl > mx) mx = xl;
+    if (fl > mf) mf = fl;
+  }
+  // the previous call's kernels may still read lens_dev: same stream, so ordering is preserved
+  int rc = dev_memcpy_h2d(ctx, h->lens_dev, tmp.data(), tmp.size() * sizeof(int));
+  if (rc) return rc;
+#ifndef WB_EMU
+  // tmp is pageable: cudaMemcpyAsync has staged it before returning
+#endif
+  b->x_len = h->lens_dev; b->f_len = h->lens_dev + n;
+  b->max_x_len = mx; b->max_f_len = mf;
+  return 0;
+}
+
+static int frames_for(int fs, int x_length, double frame_period) {
+  return static_cast<int>(1000.0 * x_length / fs / frame_period) + 1;
+}
+
+extern "C" {
+
+int world_b200_frames(int fs, int x_length, double frame_period) {
+  return frames_for(fs, x_length, frame_period);
+}
+
+int world_b200_create(int device, WorldB200 **out) {
+  if (!out) return WORLD_B200_EINVAL;
+  *out = nullptr;
+  WorldB200 *h = new WorldB200;
+  h->c.device = device;
+#ifndef WB_EMU
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    fprintf(stderr, "world_b200: no usable CUDA device (%s); this library has no CPU path\n",
+            e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+    delete h;
+    return WORLD_B200_ECUDA;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return WORLD_B200_ECUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->c.sm_count = prop.multiProcessorCount;
+#endif
+  int rc = ctx_init_tables(&h->c);
+  if (rc) {
+    fprintf(stderr, "world_b200: context creation failed: %s\n", h->c.last_error.c_str());
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+void world_b200_destroy(WorldB200 *h) {
+  if (!h) return;
+  dev_sync(&h->c);
+  dev_free(h->c.twiddle);
+  dev_free(h->c.rng_jump);
+  dev_free(h->c.status_dev);
+  dev_free(h->c.arena.base);
+  dev_free(h->lens_dev);
+  delete h;
+}
+
+int world_b200_set_stream(WorldB200 *h, void *stream) {
+  if (!h) return WORLD_B200_EINVAL;
+  h->c.stream = (wb_stream_t)stream;
+  return 0;
+}
+
+int world_b200_set_scratch_budget(WorldB200 *h, unsigned long long bytes) {
+  if (!h || bytes < ((unsigned long long)64 << 20)) return WORLD_B200_EINVAL;
+  h->c.scratch_budget = (size_t)bytes;
+  return 0;
+}
+
+int world_b200_synchronize(WorldB200 *h) {
+  if (!h) return WORLD_B200_EINVAL;
+  int rc = dev_sync(&h->c);
+  if (rc) return rc;
+  int status = 0;
+  rc = dev_memcpy_d2h(&h->c, &status, h->c.status_dev, sizeof(int));
+  if (!rc) rc = dev_sync(&h->c);
+  if (rc) return rc;
+  if (status) {
+    char msg[160];
+    snprintf(msg, sizeof msg,
+             "device status 0x%x: %s%s%s", status,
+             (status & 1) ? "[analysis window longer than fft_size: f0 below the fft_size floor] " : "",
+             (status & 2) ? "[smoothing width exceeds the spectrum] " : "",
+             (status & 4) ? "[scratch overflow] " : "");
+    h->c.last_error = msg;
+    dev_memset(&h->c, h->c.status_dev, 0, sizeof(int));
+    return WORLD_B200_EDOMAIN;
+  }
+  return 0;
+}
+
+const char *world_b200_last_error(const WorldB200 *h) { return h ? h->c.last_error.c_str() : "null context"; }
+
+unsigned long long world_b200_launch_count(const WorldB200 *) { return wb::g_launches; }
+
+int world_b200_cheaptrick_batch(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths,
+                                int fs, const double *time_axis, const double *f0, const int *f0_lengths,
+                                int f0_stride, const CheapTrickOption *opt, double *spectrogram) {
+  if (!h || !x || !time_axis || !f0 || !opt || !spectrogram || n < 0 || fs <= 0) return WORLD_B200_EINVAL;
+  Batch b;
+  b.x = x; b.n = n; b.x_stride = x_stride; b.fs = fs; b.time_axis = time_axis; b.f0 = f0; b.f_stride = f0_stride;
+  int rc = upload_lengths(h, n, x_stride, x_lengths, f0_stride, f0_lengths, &b);
+  if (rc) return rc;
+  return cheaptrick_run(&h->c, b, opt->q1, opt->fft_size, spectrogram);
+}
+
+int world_b200_d4c_batch(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths, int fs,
+                         const double *time_axis, const double *f0, const int *f0_lengths, int f0_stride,
+                         int fft_size, const D4COption *opt, double *aperiodicity) {
+  if (!h || !x || !time_axis || !f0 || !opt || !aperiodicity || n < 0 || fs <= 0) return WORLD_B200_EINVAL;
+  Batch b;
+  b.x = x; b.n = n; b.x_stride = x_stride; b.fs = fs; b.time_axis = time_axis; b.f0 = f0; b.f_stride = f0_stride;
+  int rc = upload_lengths(h, n, x_stride, x_lengths, f0_stride, f0_lengths, &b);
+  if (rc) return rc;
+  return d4c_run(&h->c, b, fft_size, opt->threshold, aperiodicity);
+}
+
+int world_b200_stonemask_batch(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths,
+                               int fs, const double *time_axis, const double *f0, const int *f0_lengths,
+                               int f0_stride, double *refined_f0) {
+  if (!h || !x || !time_axis || !f0 || !refined_f0 || n < 0 || fs <= 0) return WORLD_B200_EINVAL;
+  Batch b;
+  b.x = x; b.n = n; b.x_stride = x_stride; b.fs = fs; b.time_axis = time_axis; b.f0 = f0; b.f_stride = f0_stride;
+  int rc = upload_lengths(h, n, x_stride, x_lengths, f0_stride, f0_lengths, &b);
+  if (rc) return rc;
+  return stonemask_run(&h->c, b, refined_f0);
+}
+
+static int f0_lengths_from_x(int n, int x_stride, const int *x_lengths, int fs, double frame_period,
+                             int f0_stride, std::vector<int> *out, std::string *err) {
+  out->resize(n);
+  for (int i = 0; i < n; ++i) {
+    const int xl = x_lengths ? x_lengths[i] : x_stride;
+    (*out)[i] = frames_for(fs, xl, frame_period);
+    if ((*out)[i] > f0_stride) {
+      *err = "f0_stride smaller than the frame count of an utterance";
+      return WORLD_B200_EINVAL;
+    }
+  }
+  return 0;
+}
+
+int world_b200_dio_batch(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths, int fs,
+                         const DioOption *opt, double *time_axis, double *f0, int f0_stride) {
+  if (!h || !x || !time_axis || !f0 || !opt || n < 0 || fs <= 0) return WORLD_B200_EINVAL;
+  std::vector<int> fl;
+  int rc = f0_lengths_from_x(n, x_stride, x_lengths, fs, opt->frame_period, f0_stride, &fl, &h->c.last_error);
+  if (rc) return rc;
+  Batch b;
+  b.x = x; b.n = n; b.x_stride = x_stride; b.fs = fs; b.time_axis = time_axis; b.f0 = f0; b.f_stride = f0_stride;
+  rc = upload_lengths(h, n, x_stride, x_lengths, f0_stride, fl.data(), &b);
+  if (rc) return rc;
+  DioParams p = {opt->f0_floor, opt->f0_ceil, opt->channels_in_octave, opt->frame_period,
+                 opt->allowed_range, opt->speed};
+  return dio_run(&h->c, b, p, time_axis, f0);
+}
+
+int world_b200_harvest_batch(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths,
+                             int fs, const HarvestOption *opt, double *time_axis, double *f0, int f0_stride) {
+  if (!h || !x || !time_axis || !f0 || !opt || n < 0 || fs <= 0) return WORLD_B200_EINVAL;
+  std::vector<int> fl;
+  int rc = f0_lengths_from_x(n, x_stride, x_lengths, fs, opt->frame_period, f0_stride, &fl, &h->c.last_error);
+  if (rc) return rc;
+  Batch b;
+  b.x = x; b.n = n; b.x_stride = x_stride; b.fs = fs; b.time_axis = time_axis; b.f0 = f0; b.f_stride = f0_stride;
+  rc = upload_lengths(h, n, x_stride, x_lengths, f0_stride, fl.data(), &b);
+  if (rc) return rc;
+  HarvestParams p = {opt->f0_floor, opt->f0_ceil, opt->frame_period};
+  return harvest_run(&h->c, b, p, time_axis, f0);
+}
+
+// ---- option helpers: pure host arithmetic, the reference's expressions verbatim in meaning
+void InitializeDioOption(DioOption *o) {
+  o->channels_in_octave = 2.0; o->f0_ceil = 800.0; o->f0_floor = 71.0; o->frame_period = 5;
+  o->speed = 1; o->allowed_range = 0.1;
+}
+void InitializeHarvestOption(HarvestOption *o) { o->f0_ceil = 800.0; o->f0_floor = 71.0; o->frame_period = 5; }
+void InitializeD4COption(D4COption *o) { o->threshold = 0.85; }
+int GetFFTSizeForCheapTrick(int fs, const CheapTrickOption *o) {
+  return static_cast<int>(pow(2.0, 1.0 + static_cast<int>(log(3.0 * fs / o->f0_floor + 1) / wb::kLog2)));
+}
+double GetF0FloorForCheapTrick(int fs, int fft_size) { return 3.0 * fs / (fft_size - 3.0); }
+void InitializeCheapTrickOption(int fs, CheapTrickOption *o) {
+  o->q1 = -0.15; o->f0_floor = 71.0; o->fft_size = GetFFTSizeForCheapTrick(fs, o);
+}
+int GetSamplesForDIO(int fs, int x_length, double frame_period) { return frames_for(fs, x_length, frame_period); }
+int GetSamplesForHarvest(int fs, int x_length, double frame_period) { return frames_for(fs, x_length, frame_period); }
+
+void world_b200_default_analysis_option(int fs, int f0_method, WorldB200AnalysisOption *o) {
+  o->f0_method = f0_method;
+  InitializeDioOption(&o->dio);
+  InitializeHarvestOption(&o->harvest);
+  InitializeCheapTrickOption(fs, &o->cheaptrick);
+  InitializeD4COption(&o->d4c);
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+// wb_cheaptrick.cu -- K-CT: spectral envelope, one CTA per (utterance, frame).
+//
+// Replaces the frame loop of CheapTrick() (cheaptrick.cpp:200-229) and its helpers
+// (GetWindowedWaveform :112-142, GetPowerSpectrum :64-82, AddInfinitesimalNoise :147-151,
+// SmoothingWithRecovery :22-57) plus common.cpp's DCCorrection/LinearSmoothing.  Algorithm card:
+// SURVEY.md A1.  Everything between the waveform read and the spectrogram row write stays in
+// shared memory: three real FFTs (window spectrum, cepstrum, liftered cepstrum back -- the
+// last two are transforms of real even sequences, so the reference's c2r is a forward r2c
+// here), the index-order running sum of LinearSmoothing on one thread, log/exp fused in.
+//
+// HBM traffic per frame (algorithmic): (2h+1)*8 B of waveform (L2 hits after the first frame of
+// a hop), 16 B of f0/time, (2h+1 + fft/2+1)*4 B of materialised draws, (fft/2+1)*8 B written.
+#include "wb_internal.h"
+#include "wb_spectral.cuh"
+
+namespace wb {
+
+struct CtParams {
+  const double *x; const int *x_len; int x_stride;
+  const double *time_axis; const double *f0; const int *f_len; int f_stride;
+  int fs, fft_size, lg_fft;
+  double q1, f0_floor;
+  const unsigned *draws; size_t draw_stride; const unsigned *draw_off;
+  double *out;            // [n][f_stride][fft/2+1]
+  const double2 *tw;
+  int *status;
+};
+
+WB_DEV double ct_effective_f0(double f0, double f0_floor) {
+  return f0 <= f0_floor ? 500.0 : f0;  // kDefaultF0, cheaptrick.cpp:218
+}
+
+// draws consumed by frame = window samples + spectrum bins
+WB_KERNEL_PLAIN ct_count_kernel(const double *__restrict__ f0, const int *__restrict__ f_len,
+                                int f_stride, int n_utts, int fs, int fft_size, double f0_floor,
+                                unsigned *__restrict__ counts) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)n_utts * f_stride) return;
+  const int u = (int)(g / f_stride), i = (int)(g % f_stride);
+  unsigned c = 0;
+  if (i < f_len[u]) {
+    const double f = ct_effective_f0(f0[g], f0_floor);
+    const int h = round_half_away(1.5 * fs / f);
+    c = (unsigned)(2 * h + 1) + (unsigned)(fft_size / 2 + 1);
+  }
+  counts[g] = c;
+}
+
+WB_KERNEL(128, 4) ct_frame_kernel(CtParams p) {
+  WB_DYN_SMEM(double, smem);
+  const int tid = WB_TID, nth = WB_NTH;
+  const int u = blockIdx.y, i = blockIdx.x;
+  if (i >= p.f_len[u]) return;
+  const int N = p.fft_size, half = N / 2;
+  double *buf = smem;                 // N + 2
+  double *ext = smem + (N + 2);       // N + 2
+  double *red = ext + (N + 2);        // WB_RED_DOUBLES
+
+  const size_t fidx = (size_t)u * p.f_stride + i;
+  const double f = ct_effective_f0(p.f0[fidx], p.f0_floor);
+  const double t = p.time_axis[fidx];
+  const int fs = p.fs;
+  const int x_len = p.x_len[u];
+  const double *x = p.x + (size_t)u * p.x_stride;
+  const unsigned *draw = p.draws + (size_t)u * p.draw_stride + p.draw_off[fidx];
+
+  const int h = round_half_away(1.5 * fs / f);
+  const int nwin = 2 * h + 1;
+  double *row = p.out + fidx * (size_t)(half + 1);
+  if (nwin > N) {  // f0 below the floor implied by fft_size: undefined in the reference
+    if (tid == 0) atomicOr_status(p.status, 1);
+    return;
+  }
+  const int origin = round_half_away(t * fs + 0.001);
+
+  // ---- F0-adaptive Hanning window, normalised to unit energy (cheaptrick.cpp:97-106)
+  double sq = 0.0;
+  for (int j = tid; j < nwin; j += nth) {
+    const double pos = (j - h) / 1.5 / fs;
+    const double w = 0.5 * cos(kPi * pos * f) + 0.5;
+    ext[j] = w;
+    sq += w * w;
+  }
+  const double norm = sqrt(block_sum(sq, red));
+  // ---- windowed waveform + 1e-12 * randn, weighted-mean removal (:126-137)
+  double s1 = 0.0, s2 = 0.0;
+  for (int j = tid; j < nwin; j += nth) {
+    const double w = ext[j] / norm;
+    ext[j] = w;
+    const int idx = imin(x_len - 1, imax(0, origin + j - h));
+    const double v = x[idx] * w + randn_value(draw[j]) * kTiny;
+    buf[j] = v;
+    s1 += v;
+    s2 += w;
+  }
+  block_sum2(s1, s2, red);
+  const double coef = s1 / s2;
+  for (int j = tid; j < N + 2; j += nth) buf[j] = (j < nwin) ? buf[j] - ext[j] * coef : 0.0;
+  WB_SYNC();
+
+  // ---- power spectrum (:71-78) into ext[0..half]
+  rfft_forward(buf, p.lg_fft, p.tw);
+  {
+    const double2 *z = reinterpret_cast<const double2 *>(buf);
+    for (int k = tid; k <= half; k += nth) { const double2 c = z[k]; ext[k] = c.x * c.x + c.y * c.y; }
+  }
+  WB_SYNC();
+  dc_correction(ext, f, fs, N, buf);
+  if (!linear_smoothing<true>(ext, f * 2.0 / 3.0, fs, N, ext, buf, red)) {
+    if (tid == 0) atomicOr_status(p.status, 2);
+    return;
+  }
+  // ---- + |randn| * eps (:147-151), log, mirror (:39-42)
+  for (int k = tid; k <= half; k += nth) {
+    const double v = ext[k] + fabs(randn_value(draw[nwin + k])) * kEps;
+    const double l = log(v);
+    buf[k] = l;
+    if (k > 0 && k < half) buf[N - k] = l;
+  }
+  WB_SYNC();
+  rfft_forward(buf, p.lg_fft, p.tw);
+  // ---- liftering in the cepstrum domain (:28-37, 45-49)
+  {
+    const double2 *z = reinterpret_cast<const double2 *>(buf);
+    for (int k = tid; k <= half; k += nth) {
+      double sl = 1.0, cl = (1.0 - 2.0 * p.q1) + 2.0 * p.q1;
+      if (k > 0) {
+        const double quef = static_cast<double>(k) / fs;
+        sl = sin(kPi * f * quef) / (kPi * f * quef);
+        cl = (1.0 - 2.0 * p.q1) + 2.0 * p.q1 * cos(2.0 * kPi * quef * f);
+      }
+      ext[k] = z[k].x * sl * cl / N;
+    }
+  }
+  WB_SYNC();
+  for (int k = tid; k <= half; k += nth) {
+    const double v = ext[k];
+    buf[k] = v;
+    if (k > 0 && k < half) buf[N - k] = v;
+  }
+  WB_SYNC();
+  rfft_forward(buf, p.lg_fft, p.tw);
+  {
+    const double2 *z = reinterpret_cast<const double2 *>(buf);
+    for (int k = tid; k <= half; k += nth) row[k] = exp(z[k].x);
+  }
+}
+
+int cheaptrick_run(Ctx *ctx, const Batch &b, double q1, int fft_size, double *spectrogram) {
+  if (b.n <= 0 || b.max_f_len <= 0) return 0;
+  int lg = 0;
+  while ((1 << lg) < fft_size) ++lg;
+  if ((1 << lg) != fft_size || fft_size < 16 || fft_size > WB_TW_N) {
+    ctx->last_error = "CheapTrick: fft_size must be a power of two in [16, 8192]";
+    return 3;
+  }
+  const double f0_floor = 3.0 * b.fs / (fft_size - 3.0);  // GetF0FloorForCheapTrick, :196-198
+  const int bins = fft_size / 2 + 1;
+  // a frame draws at most (fft_size - 2) + bins numbers (2h+1 <= fft_size - 2 above the floor)
+  const size_t max_per_frame = (size_t)fft_size + bins;
+  const size_t draw_stride_full = max_per_frame * (size_t)b.max_f_len;
+  // utterances per chunk so that the draw scratch fits the budget
+  const size_t per_utt_bytes = draw_stride_full * 4 + (size_t)b.f_stride * 8 + 64;
+  int chunk = (int)imin(b.n, (int)dmax(1.0, (double)ctx->scratch_budget / (double)per_utt_bytes));
+  const size_t smem = (size_t)(2 * (fft_size + 2) + WB_RED_DOUBLES) * sizeof(double);
+#ifndef WB_EMU
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaFuncSetAttribute(ct_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+#endif
+  for (int u0 = 0; u0 < b.n; u0 += chunk) {
+    const int n = imin(chunk, b.n - u0);
+    ArenaPlan plan;
+    const size_t o_counts = plan.add((size_t)n * b.f_stride * 4);
+    const size_t o_offs = plan.add((size_t)n * b.f_stride * 4);
+    const size_t o_totals = plan.add((size_t)n * 4);
+    const size_t o_draws = plan.add((size_t)n * draw_stride_full * 4);
+    unsigned char *blk = arena_block(ctx, plan.total);
+    if (!blk) return 2;
+    unsigned *counts = (unsigned *)(blk + o_counts), *offs = (unsigned *)(blk + o_offs);
+    unsigned *totals = (unsigned *)(blk + o_totals), *draws = (unsigned *)(blk + o_draws);
+    const double *f0 = b.f0 + (size_t)u0 * b.f_stride;
+    const int *f_len = b.f_len + u0;
+    const long long total_slots = (long long)n * b.f_stride;
+    WB_LAUNCH_FLAT(ct_count_kernel, dim3((unsigned)((total_slots + 255) / 256)), 256, 0, ctx->stream,
+                   f0, f_len, b.f_stride, n, b.fs, fft_size, f0_floor, counts);
+    scan_counts(ctx, counts, f_len, b.f_stride, nullptr, offs, totals, n);
+    rng_fill(ctx, totals, draws, draw_stride_full, draw_stride_full, n);
+    CtParams p;
+    p.x = b.x + (size_t)u0 * b.x_stride; p.x_len = b.x_len + u0; p.x_stride = b.x_stride;
+    p.time_axis = b.time_axis + (size_t)u0 * b.f_stride; p.f0 = f0; p.f_len = f_len;
+    p.f_stride = b.f_stride; p.fs = b.fs; p.fft_size = fft_size; p.lg_fft = lg;
+    p.q1 = q1; p.f0_floor = f0_floor;
+    p.draws = draws; p.draw_stride = draw_stride_full; p.draw_off = offs;
+    p.out = spectrogram + (size_t)u0 * b.f_stride * bins;
+    p.tw = ctx->twiddle; p.status = ctx->status_dev;
+    WB_LAUNCH_COOP(ct_frame_kernel, dim3((unsigned)b.max_f_len, (unsigned)n), 128, smem, ctx->stream, p);
+    int rc = dev_check(ctx, "cheaptrick");
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace wb

@@ -1,0 +1,394 @@
+// wb_d4c.cu -- K-LT + K-D4C: band aperiodicity, one CTA per (utterance, frame), two passes.
+//
+// Replaces D4C() (d4c.cpp:342-403): pass A = D4CLoveTrain (:260-285, :227-252), pass B =
+// D4CGeneralBody (:293-321) with GetStaticCentroid/GetCentroid (:90-140),
+// GetSmoothedPowerSpectrum (:149-166), GetStaticGroupDelay (:172-188), GetCoarseAperiodicity
+// (:194-225) and GetAperiodicity (:330-338).  Algorithm card: SURVEY.md A2.
+//
+// The reference's single randn stream runs through all of pass A and then all of pass B, so the
+// driver counts pass-A draws, runs K-LT, counts pass-B draws of the frames K-LT selected
+// (continuing after the pass-A total) and only then runs K-D4C.  std::sort + cumulative sum is
+// restated as an order-statistic selection (k-th largest by bisection on the IEEE bit pattern)
+// followed by a masked sum: the quantity needed is sum(smallest m)/sum(all).
+// Every output row is written exactly once: by K-LT (default 1-1e-12 rows for unvoiced or
+// rejected frames, d4c.cpp:323-328) or by K-D4C.
+#include "wb_internal.h"
+#include "wb_spectral.cuh"
+
+namespace wb {
+
+struct D4cParams {
+  const double *x; const int *x_len; int x_stride;
+  const double *time_axis; const double *f0; const int *f_len; int f_stride;
+  int fs;
+  int ct_fft_size;          // rows have ct_fft_size/2+1 bins
+  int lt_fft, lt_lg, b0, b1, b2;
+  int d_fft, d_lg, n_ap, win_len, bd;
+  double threshold;
+  const double *nuttall;    // [win_len]
+  const unsigned *draws; size_t draw_stride;
+  const unsigned *off_a; unsigned *count_b; const unsigned *off_b;
+  unsigned char *selected;  // [n][f_stride]
+  double *out;
+  const double2 *tw;
+  int *status;
+};
+
+WB_KERNEL_PLAIN d4c_count_a_kernel(const double *__restrict__ f0, const int *__restrict__ f_len,
+                                   int f_stride, int n_utts, int fs, unsigned *__restrict__ counts) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)n_utts * f_stride) return;
+  const int u = (int)(g / f_stride), i = (int)(g % f_stride);
+  unsigned c = 0;
+  if (i < f_len[u] && f0[g] != 0.0) {
+    const double f = dmax(f0[g], 40.0);
+    c = (unsigned)(2 * round_half_away(3.0 * fs / f / 2.0) + 1);
+  }
+  counts[g] = c;
+}
+
+// F0-adaptive window + noise + weighted mean removal (d4c.cpp:21-83).  v -> dst_v[0..nwin),
+// window -> dst_w[0..nwin) (strides let callers interleave).  window_type 1 = Hanning,
+// 2 = Blackman.  Ends with a barrier; every thread returns the same nwin.
+WB_DEV int d4c_windowed(const double *__restrict__ x, int x_len, int fs, double f, double pos,
+                        int window_type, double ratio, const unsigned *__restrict__ draw,
+                        double *dst_v, double *dst_w, int stride, double *red) {
+  const int tid = WB_TID, nth = WB_NTH;
+  const int h = round_half_away(ratio * fs / f / 2.0);
+  const int nwin = 2 * h + 1;
+  const int origin = round_half_away(pos * fs + 0.001);
+  double s1 = 0.0, s2 = 0.0;
+  for (int j = tid; j < nwin; j += nth) {
+    const double position = (2.0 * (j - h) / ratio) / fs;
+    double w;
+    if (window_type == 1)
+      w = 0.5 * cos(kPi * position * f) + 0.5;
+    else
+      w = 0.42 + 0.5 * cos(kPi * position * f) + 0.08 * cos(kPi * position * f * 2);
+    const int idx = imin(x_len - 1, imax(0, origin + j - h));
+    const double v = x[idx] * w + randn_value(draw[j]) * 0.000001;  // kSafeGuardD4C
+    dst_v[(size_t)j * stride] = v;
+    dst_w[(size_t)j * stride] = w;
+    s1 += v;
+    s2 += w;
+  }
+  block_sum2(s1, s2, red);
+  const double coef = s1 / s2;
+  for (int j = tid; j < nwin; j += nth)
+    dst_v[(size_t)j * stride] = dst_v[(size_t)j * stride] - dst_w[(size_t)j * stride] * coef;
+  WB_SYNC();
+  return nwin;
+}
+
+WB_DEV void d4c_fill_row(double *row, int bins) {
+  for (int k = WB_TID; k < bins; k += WB_NTH) row[k] = 1.0 - kTiny;
+}
+
+// ------------------------------------------------------------------ pass A: LoveTrain
+WB_KERNEL(128, 4) d4c_lovetrain_kernel(D4cParams p) {
+  WB_DYN_SMEM(double, smem);
+  const int tid = WB_TID, nth = WB_NTH;
+  const int u = blockIdx.y, i = blockIdx.x;
+  if (i >= p.f_len[u]) return;
+  const size_t fidx = (size_t)u * p.f_stride + i;
+  const int bins = p.ct_fft_size / 2 + 1;
+  double *row = p.out + fidx * (size_t)bins;
+  const double f0 = p.f0[fidx];
+  if (f0 == 0.0) {
+    d4c_fill_row(row, bins);
+    if (tid == 0) { p.selected[fidx] = 0; p.count_b[fidx] = 0; }
+    return;
+  }
+  const int N = p.lt_fft, half = N / 2;
+  double *buf = smem;            // N + 2
+  double *win = smem + (N + 2);  // N
+  double *red = win + N;
+  const double f = dmax(f0, 40.0);
+  const double *x = p.x + (size_t)u * p.x_stride;
+  const unsigned *draw = p.draws + (size_t)u * p.draw_stride + p.off_a[fidx];
+  const int nwin = d4c_windowed(x, p.x_len[u], p.fs, f, p.time_axis[fidx], 2, 3.0, draw, buf, win, 1, red);
+  for (int j = nwin + tid; j < N + 2; j += nth) buf[j] = 0.0;
+  WB_SYNC();
+  rfft_forward(buf, p.lt_lg, p.tw);
+  // cumulative power b0+1..b1 and b0+1..b2 (d4c.cpp:241-249)
+  const double2 *z = reinterpret_cast<const double2 *>(buf);
+  double s_lo = 0.0, s_hi = 0.0;
+  const int hi_end = imin(p.b2, half);
+  for (int k = p.b0 + 1 + tid; k <= hi_end; k += nth) {
+    const double2 c = z[k];
+    const double pw = c.x * c.x + c.y * c.y;
+    s_hi += pw;
+    if (k <= p.b1) s_lo += pw;
+  }
+  block_sum2(s_lo, s_hi, red);
+  const double ap0 = s_lo / s_hi;
+  const bool sel = ap0 > p.threshold;  // d4c.cpp:386
+  if (!sel) d4c_fill_row(row, bins);
+  if (tid == 0) {
+    p.selected[fidx] = sel ? 1 : 0;
+    unsigned c = 0;
+    if (sel) {
+      const double fb = dmax(47.0, f0);  // kFloorF0D4C
+      c = 3u * (unsigned)(2 * round_half_away(4.0 * p.fs / fb / 2.0) + 1);
+    }
+    p.count_b[fidx] = c;
+  }
+}
+
+// k-th largest (1-based) of the non-negative doubles a[0..n): bisection on the bit pattern.
+WB_DEV double select_kth_largest(const double *a, int n, int kth, double *red) {
+  const int tid = WB_TID, nth = WB_NTH;
+  unsigned long long pat = 0ull;
+  for (int bit = 62; bit >= 0; --bit) {
+    const unsigned long long cand = pat | (1ull << bit);
+    int c = 0;
+    for (int j = tid; j < n; j += nth) {
+      const double v = a[j];
+      unsigned long long bits;
+#ifdef WB_EMU
+      memcpy(&bits, &v, 8);
+#else
+      bits = (unsigned long long)__double_as_longlong(v);
+#endif
+      c += (bits >= cand) ? 1 : 0;
+    }
+    c = block_sum_int(c, red);
+    if (c >= kth) pat = cand;
+  }
+  double r;
+#ifdef WB_EMU
+  memcpy(&r, &pat, 8);
+#else
+  r = __longlong_as_double((long long)pat);
+#endif
+  return r;
+}
+
+// ------------------------------------------------------------------ pass B: general body
+WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
+  WB_DYN_SMEM(double, smem);
+  const int tid = WB_TID, nth = WB_NTH;
+  const int u = blockIdx.y, i = blockIdx.x;
+  if (i >= p.f_len[u]) return;
+  const size_t fidx = (size_t)u * p.f_stride + i;
+  if (!p.selected[fidx]) return;
+  const int N = p.d_fft, half = N / 2, fs = p.fs;
+  double *zb = smem;                       // 2N (+2): complex FFT buffer / smoothing scratch
+  double *cent = zb + 2 * N + 2;           // half + 1
+  double *pw = cent + (half + 1);          // half + 1
+  double *red = pw + (half + 1);           // WB_RED_DOUBLES
+  double *red_big = red + WB_RED_DOUBLES;  // nth + 1
+  double *coarse = red_big + (nth + 1);    // n_ap + 2
+  double2 *z = reinterpret_cast<double2 *>(zb);
+
+  const double f = dmax(47.0, p.f0[fidx]);
+  const double t = p.time_axis[fidx];
+  const double *x = p.x + (size_t)u * p.x_stride;
+  const int x_len = p.x_len[u];
+  const unsigned *draw = p.draws + (size_t)u * p.draw_stride + p.off_b[fidx];
+
+  // ---- static centroid = centroid(t - 1/4f) + centroid(t + 1/4f)   (d4c.cpp:90-140)
+  for (int pass = 0; pass < 2; ++pass) {
+    const double pos = pass == 0 ? t - 0.25 / f : t + 0.25 / f;
+    // re = windowed sample, im = window (scratch) while the mean is removed
+    const int nwin = d4c_windowed(x, x_len, fs, f, pos, 2, 4.0, draw, zb, zb + 1, 2, red);
+    draw += nwin;
+    double sq = 0.0;
+    for (int j = tid; j < nwin; j += nth) sq += z[j].x * z[j].x;
+    const double rt = sqrt(block_sum(sq, red));
+    for (int j = tid; j < N; j += nth) {
+      if (j < nwin) {
+        const double v = z[j].x / rt;
+        z[j] = make_double2(v, v * (j + 1.0));
+      } else {
+        z[j] = make_double2(0.0, 0.0);
+      }
+    }
+    WB_SYNC();
+    cfft_forward(z, p.d_lg, p.tw);
+    for (int k = tid; k <= half; k += nth) {
+      double2 A, B;
+      split_pair(z, N, k, A, B);
+      const double c = B.x * A.x + A.y * B.y;
+      cent[k] = pass == 0 ? c : cent[k] + c;
+    }
+    WB_SYNC();
+  }
+  dc_correction(cent, f, fs, N, zb);
+
+  // ---- smoothed power spectrum (d4c.cpp:149-166)
+  {
+    const int nwin = d4c_windowed(x, x_len, fs, f, t, 1, 4.0, draw, zb, zb + N + 2, 1, red);
+    for (int j = nwin + tid; j < N + 2; j += nth) zb[j] = 0.0;
+    WB_SYNC();
+    rfft_forward(zb, p.d_lg, p.tw);
+    for (int k = tid; k <= half; k += nth) { const double2 c = z[k]; pw[k] = c.x * c.x + c.y * c.y; }
+    WB_SYNC();
+    dc_correction(pw, f, fs, N, zb);
+    if (!linear_smoothing<false>(pw, f, fs, N, pw, zb, red_big)) {
+      if (tid == 0) atomicOr_status(p.status, 2);
+      return;
+    }
+  }
+  // ---- static group delay (d4c.cpp:172-188): g = cent / pw, two smoothers
+  for (int k = tid; k <= half; k += nth) pw[k] = cent[k] / pw[k];
+  WB_SYNC();
+  bool ok = linear_smoothing<false>(pw, f / 2.0, fs, N, pw, zb, red_big);
+  ok = ok && linear_smoothing<false>(pw, f, fs, N, cent, zb, red_big);
+  if (!ok) {
+    if (tid == 0) atomicOr_status(p.status, 2);
+    return;
+  }
+  for (int k = tid; k <= half; k += nth) pw[k] = pw[k] - cent[k];
+  WB_SYNC();
+
+  // ---- coarse aperiodicity per 3 kHz band (d4c.cpp:194-225)
+  const int half_w = p.win_len / 2;
+  for (int b = 0; b < p.n_ap; ++b) {
+    const int center = static_cast<int>(3000.0 * (b + 1) * N / fs);
+    for (int j = tid; j < N + 2; j += nth)
+      zb[j] = (j <= half_w * 2) ? pw[center - half_w + j] * __ldg(&p.nuttall[j]) : 0.0;
+    WB_SYNC();
+    rfft_forward(zb, p.d_lg, p.tw);
+    double tot = 0.0;
+    for (int k = tid; k <= half; k += nth) {
+      const double2 c = z[k];
+      const double v = c.x * c.x + c.y * c.y;
+      cent[k] = v;
+      tot += v;
+    }
+    tot = block_sum(tot, red);  // contains the barrier that publishes cent[]
+    const int n_small = half - p.bd;  // entries in the sorted prefix, index half-bd-1 inclusive
+    const double kth = select_kth_largest(cent, half + 1, p.bd + 1, red);
+    double below = 0.0;
+    int n_below = 0;
+    for (int k = tid; k <= half; k += nth)
+      if (cent[k] < kth) { below += cent[k]; ++n_below; }
+    below = block_sum(below, red);
+    n_below = block_sum_int(n_below, red);
+    const double small = below + (double)(n_small - n_below) * kth;
+    if (tid == 0) {
+      const double c = 10.0 * log10(small / tot);
+      coarse[b + 1] = dmin(0.0, c + (f - 100.0) / 50.0);  // d4c.cpp:314-316
+    }
+    WB_SYNC();
+  }
+  if (tid == 0) { coarse[0] = -60.0; coarse[p.n_ap + 1] = -kTiny; }
+  WB_SYNC();
+
+  // ---- interp1 onto the CheapTrick frequency grid, dB -> amplitude (d4c.cpp:330-338, 372-383)
+  const int bins = p.ct_fft_size / 2 + 1;
+  double *row = p.out + fidx * (size_t)bins;
+  const int nx = p.n_ap + 2;
+  for (int k = tid; k < bins; k += nth) {
+    const double xi = static_cast<double>(k) * fs / p.ct_fft_size;
+    int idx = 0;  // number of axis points <= xi
+    for (int j = 0; j < nx; ++j) {
+      const double xj = (j == nx - 1) ? fs / 2.0 : j * 3000.0;
+      idx += (xj <= xi) ? 1 : 0;
+    }
+    idx = imin(nx - 1, imax(1, idx));
+    const double x0 = (idx - 1) * 3000.0;
+    const double x1 = (idx == nx - 1) ? fs / 2.0 : idx * 3000.0;
+    const double s = (xi - x0) / (x1 - x0);
+    const double y = coarse[idx - 1] + s * (coarse[idx] - coarse[idx - 1]);
+    row[k] = pow(10.0, y / 20.0);
+  }
+}
+
+int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *aperiodicity) {
+  if (b.n <= 0 || b.max_f_len <= 0) return 0;
+  const int fs = b.fs;
+  D4cParams p;
+  memset(&p, 0, sizeof(p));
+  p.fs = fs;
+  p.ct_fft_size = fft_size;
+  p.threshold = threshold;
+  // sizes with the reference's expressions (host libm), d4c.cpp:350-365 and :262-272
+  p.d_fft = static_cast<int>(pow(2.0, 1.0 + static_cast<int>(log(4.0 * fs / 47.0 + 1) / kLog2)));
+  p.lt_fft = static_cast<int>(pow(2.0, 1.0 + static_cast<int>(log(3.0 * fs / 40.0 + 1) / kLog2)));
+  for (p.d_lg = 0; (1 << p.d_lg) < p.d_fft; ++p.d_lg) {}
+  for (p.lt_lg = 0; (1 << p.lt_lg) < p.lt_fft; ++p.lt_lg) {}
+  if (p.d_fft > WB_TW_N || p.lt_fft > WB_TW_N || fft_size < 4) {
+    ctx->last_error = "D4C: sampling rate too high for the on-chip FFT (fft > 8192)";
+    return 3;
+  }
+  p.n_ap = static_cast<int>(dmin(15000.0, fs / 2.0 - 3000.0) / 3000.0);
+  if (p.n_ap < 0) p.n_ap = 0;
+  p.win_len = static_cast<int>(3000.0 * p.d_fft / fs) * 2 + 1;
+  p.bd = round_half_away(p.d_fft * 8.0 / p.win_len);
+  p.b0 = static_cast<int>(ceil(100.0 * p.lt_fft / fs));
+  p.b1 = static_cast<int>(ceil(4000.0 * p.lt_fft / fs));
+  p.b2 = static_cast<int>(ceil(7900.0 * p.lt_fft / fs));
+  const int bins = fft_size / 2 + 1;
+
+  // Nuttall window of the band analysis (common.cpp:113-121), host libm like the reference
+  double *nuttall_host = new double[p.win_len];
+  for (int i = 0; i < p.win_len; ++i) {
+    const double tmp = i / (p.win_len - 1.0);
+    nuttall_host[i] = 0.355768 - 0.487396 * cos(2.0 * kPi * tmp) + 0.144232 * cos(4.0 * kPi * tmp) -
+                      0.012604 * cos(6.0 * kPi * tmp);
+  }
+
+  const size_t max_a = (size_t)(2 * round_half_away(3.0 * fs / 40.0 / 2.0) + 1);
+  const size_t max_b = 3 * (size_t)(2 * round_half_away(4.0 * fs / 47.0 / 2.0) + 1);
+  const size_t draw_stride_full = (max_a + max_b) * (size_t)b.max_f_len;
+  const size_t per_utt_bytes = draw_stride_full * 4 + (size_t)b.f_stride * 24 + 64;
+  int chunk = (int)imin(imin(b.n, 65535), (int)dmax(1.0, (double)ctx->scratch_budget / (double)per_utt_bytes));
+  const int body_threads = 256;
+  const size_t smem_lt = (size_t)((p.lt_fft + 2) + p.lt_fft + WB_RED_DOUBLES) * sizeof(double);
+  const size_t smem_body = (size_t)((2 * p.d_fft + 2) + 2 * (p.d_fft / 2 + 1) + WB_RED_DOUBLES +
+                                    (body_threads + 1) + (p.n_ap + 2) + 2) * sizeof(double);
+#ifndef WB_EMU
+  cudaFuncSetAttribute(d4c_lovetrain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lt);
+  cudaFuncSetAttribute(d4c_body_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_body);
+#endif
+  int rc = 0;
+  for (int u0 = 0; u0 < b.n && rc == 0; u0 += chunk) {
+    const int n = imin(chunk, b.n - u0);
+    const size_t slots = (size_t)n * b.f_stride;
+    ArenaPlan plan;
+    const size_t o_ca = plan.add(slots * 4), o_oa = plan.add(slots * 4);
+    const size_t o_cb = plan.add(slots * 4), o_ob = plan.add(slots * 4);
+    const size_t o_ta = plan.add((size_t)n * 4), o_tab = plan.add((size_t)n * 4);
+    const size_t o_sel = plan.add(slots), o_nut = plan.add((size_t)p.win_len * 8);
+    const size_t o_draws = plan.add((size_t)n * draw_stride_full * 4);
+    unsigned char *blk = arena_block(ctx, plan.total);
+    if (!blk) { rc = 2; break; }
+    unsigned *count_a = (unsigned *)(blk + o_ca), *off_a = (unsigned *)(blk + o_oa);
+    unsigned *count_b = (unsigned *)(blk + o_cb), *off_b = (unsigned *)(blk + o_ob);
+    unsigned *total_a = (unsigned *)(blk + o_ta), *total_ab = (unsigned *)(blk + o_tab);
+    unsigned char *selected = blk + o_sel;
+    double *nuttall = (double *)(blk + o_nut);
+    unsigned *draws = (unsigned *)(blk + o_draws);
+    dev_memcpy_h2d(ctx, nuttall, nuttall_host, (size_t)p.win_len * 8);
+    const double *f0 = b.f0 + (size_t)u0 * b.f_stride;
+    const int *f_len = b.f_len + u0;
+    p.x = b.x + (size_t)u0 * b.x_stride; p.x_len = b.x_len + u0; p.x_stride = b.x_stride;
+    p.time_axis = b.time_axis + (size_t)u0 * b.f_stride; p.f0 = f0; p.f_len = f_len;
+    p.f_stride = b.f_stride;
+    p.nuttall = nuttall; p.draws = draws; p.draw_stride = draw_stride_full;
+    p.off_a = off_a; p.count_b = count_b; p.off_b = off_b; p.selected = selected;
+    p.out = aperiodicity + (size_t)u0 * b.f_stride * bins;
+    p.tw = ctx->twiddle; p.status = ctx->status_dev;
+
+    WB_LAUNCH_FLAT(d4c_count_a_kernel, dim3((unsigned)((slots + 255) / 256)), 256, 0, ctx->stream, f0,
+                   f_len, b.f_stride, n, fs, count_a);
+    scan_counts(ctx, count_a, f_len, b.f_stride, nullptr, off_a, total_a, n);
+    rng_fill(ctx, total_a, draws, draw_stride_full, max_a * (size_t)b.max_f_len, n);
+    WB_LAUNCH_COOP(d4c_lovetrain_kernel, dim3((unsigned)b.max_f_len, (unsigned)n), 128, smem_lt,
+                   ctx->stream, p);
+    scan_counts(ctx, count_b, f_len, b.f_stride, total_a, off_b, total_ab, n);
+    // regenerates the pass-A prefix as well (identical values) -- simple, and pass A is ~20 % of the stream
+    rng_fill(ctx, total_ab, draws, draw_stride_full, draw_stride_full, n);
+    WB_LAUNCH_COOP(d4c_body_kernel, dim3((unsigned)b.max_f_len, (unsigned)n), body_threads, smem_body,
+                   ctx->stream, p);
+    rc = dev_check(ctx, "d4c");
+  }
+  // nuttall_host was copied with an async copy from pageable memory: the runtime stages it
+  // before returning, so it can be released here.
+  delete[] nuttall_host;
+  return rc;
+}
+
+}  // namespace wb

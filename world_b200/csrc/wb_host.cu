@@ -1,0 +1,260 @@
+// wb_host.cu -- host-pointer entry points built on the device-pointer ABI:
+//   * world_b200_analyze_host(): {Dio+StoneMask | Harvest} -> CheapTrick -> D4C for N host
+//     waveforms, upload / compute / download pipelined over utterance chunks on three streams;
+//   * the reference's own single-utterance functions (Dio, Harvest, StoneMask, CheapTrick, D4C;
+//     src/world/*.h) as n_utts = 1 batches on a lazily created process-wide context, so existing
+//     callers relink unchanged.  They keep the reference's `void` signature; failures are
+//     reported on stderr and leave the outputs zero-filled.
+#include "wb_internal.h"
+#include "../../include/world_b200.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#include <mutex>
+
+using namespace wb;
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+int ensure(Ctx *ctx, DevBuf *b, size_t bytes) {
+  if (bytes <= b->cap) return 0;
+  dev_free(b->p);
+  b->p = dev_malloc(ctx, bytes);
+  b->cap = b->p ? bytes : 0;
+  return b->p ? 0 : WORLD_B200_ENOMEM;
+}
+
+Ctx *ctx_of(WorldB200 *h) { return reinterpret_cast<Ctx *>(h); }  // Ctx is the first member
+
+}  // namespace
+
+extern "C" int world_b200_analyze_host(WorldB200 *h, const double *x, int n_utts, int x_stride,
+                                       const int *x_lengths, int fs, const WorldB200AnalysisOption *opt,
+                                       double *time_axis, double *f0, int f0_stride, double *spectrogram,
+                                       double *aperiodicity) {
+  if (!h || !x || !opt || n_utts < 0 || fs <= 0 || x_stride <= 0 || f0_stride <= 0) return WORLD_B200_EINVAL;
+  Ctx *ctx = ctx_of(h);
+  const int bins = opt->cheaptrick.fft_size / 2 + 1;
+  const double frame_period =
+      opt->f0_method == WORLD_B200_F0_HARVEST ? opt->harvest.frame_period : opt->dio.frame_period;
+  // chunk so that two sets of device buffers (double buffering) stay within ~1/3 of the budget
+  const size_t per_utt = (size_t)x_stride * 8 + (size_t)f0_stride * (16 + 2 * (size_t)bins * 8);
+  int chunk = (int)dmax(1.0, dmin((double)n_utts, (double)(ctx->scratch_budget / 3) / (double)(2 * per_utt)));
+  if (chunk > 256) chunk = 256;
+
+#ifndef WB_EMU
+  cudaStream_t s_compute = ctx->stream, s_in = nullptr, s_out = nullptr;
+  if (cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess) {
+    ctx->last_error = "cudaStreamCreate failed";
+    return WORLD_B200_ECUDA;
+  }
+  cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming);
+  }
+#endif
+  DevBuf dx[2], dt[2], df[2], dsp[2], dap[2];
+  int rc = 0;
+  for (int i = 0; i < 2 && !rc; ++i) {
+    rc = ensure(ctx, &dx[i], (size_t)chunk * x_stride * 8);
+    if (!rc) rc = ensure(ctx, &dt[i], (size_t)chunk * f0_stride * 8);
+    if (!rc) rc = ensure(ctx, &df[i], (size_t)chunk * f0_stride * 8);
+    if (!rc) rc = ensure(ctx, &dsp[i], (size_t)chunk * f0_stride * bins * 8);
+    if (!rc) rc = ensure(ctx, &dap[i], (size_t)chunk * f0_stride * bins * 8);
+  }
+  std::vector<int> flen(n_utts > 0 ? n_utts : 1);
+  for (int i = 0; i < n_utts && !rc; ++i) {
+    flen[i] = world_b200_frames(fs, x_lengths ? x_lengths[i] : x_stride, frame_period);
+    if (flen[i] > f0_stride) { ctx->last_error = "f0_stride too small"; rc = WORLD_B200_EINVAL; }
+  }
+  int it = 0;
+  for (int u0 = 0; u0 < n_utts && !rc; u0 += chunk, ++it) {
+    const int n = imin(chunk, n_utts - u0);
+    const int s = it & 1;
+    const int *xl = x_lengths ? x_lengths + u0 : nullptr;
+    const size_t fsz = (size_t)n * f0_stride;
+#ifndef WB_EMU
+    // buffers of slot s are free once the download issued two iterations ago has finished
+    if (it >= 2) cudaStreamWaitEvent(s_in, ev_out[s], 0);
+    cudaMemcpyAsync(dx[s].p, x + (size_t)u0 * x_stride, (size_t)n * x_stride * 8, cudaMemcpyHostToDevice, s_in);
+    cudaEventRecord(ev_in[s], s_in);
+    cudaStreamWaitEvent(s_compute, ev_in[s], 0);
+    if (it >= 2) cudaStreamWaitEvent(s_compute, ev_out[s], 0);
+#else
+    memcpy(dx[s].p, x + (size_t)u0 * x_stride, (size_t)n * x_stride * 8);
+#endif
+    dev_memset(ctx, dt[s].p, 0, fsz * 8);
+    dev_memset(ctx, df[s].p, 0, fsz * 8);
+    const double *xd = (const double *)dx[s].p;
+    double *td = (double *)dt[s].p, *fd = (double *)df[s].p;
+    if (opt->f0_method == WORLD_B200_F0_HARVEST) {
+      rc = world_b200_harvest_batch(h, xd, n, x_stride, xl, fs, &opt->harvest, td, fd, f0_stride);
+    } else {
+      rc = world_b200_dio_batch(h, xd, n, x_stride, xl, fs, &opt->dio, td, fd, f0_stride);
+      if (!rc) rc = world_b200_stonemask_batch(h, xd, n, x_stride, xl, fs, td, fd, flen.data() + u0, f0_stride, fd);
+    }
+    if (!rc && spectrogram)
+      rc = world_b200_cheaptrick_batch(h, xd, n, x_stride, xl, fs, td, fd, flen.data() + u0, f0_stride,
+                                       &opt->cheaptrick, (double *)dsp[s].p);
+    if (!rc && aperiodicity)
+      rc = world_b200_d4c_batch(h, xd, n, x_stride, xl, fs, td, fd, flen.data() + u0, f0_stride,
+                                opt->cheaptrick.fft_size, &opt->d4c, (double *)dap[s].p);
+    if (rc) break;
+#ifndef WB_EMU
+    cudaEventRecord(ev_done[s], s_compute);
+    cudaStreamWaitEvent(s_out, ev_done[s], 0);
+    if (time_axis) cudaMemcpyAsync(time_axis + (size_t)u0 * f0_stride, td, fsz * 8, cudaMemcpyDeviceToHost, s_out);
+    if (f0) cudaMemcpyAsync(f0 + (size_t)u0 * f0_stride, fd, fsz * 8, cudaMemcpyDeviceToHost, s_out);
+    if (spectrogram)
+      cudaMemcpyAsync(spectrogram + (size_t)u0 * f0_stride * bins, dsp[s].p, fsz * bins * 8, cudaMemcpyDeviceToHost, s_out);
+    if (aperiodicity)
+      cudaMemcpyAsync(aperiodicity + (size_t)u0 * f0_stride * bins, dap[s].p, fsz * bins * 8, cudaMemcpyDeviceToHost, s_out);
+    cudaEventRecord(ev_out[s], s_out);
+#else
+    if (time_axis) memcpy(time_axis + (size_t)u0 * f0_stride, td, fsz * 8);
+    if (f0) memcpy(f0 + (size_t)u0 * f0_stride, fd, fsz * 8);
+    if (spectrogram) memcpy(spectrogram + (size_t)u0 * f0_stride * bins, dsp[s].p, fsz * bins * 8);
+    if (aperiodicity) memcpy(aperiodicity + (size_t)u0 * f0_stride * bins, dap[s].p, fsz * bins * 8);
+#endif
+  }
+#ifndef WB_EMU
+  cudaStreamSynchronize(s_in);
+  cudaStreamSynchronize(s_compute);
+  cudaStreamSynchronize(s_out);
+  for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_done[i]); cudaEventDestroy(ev_out[i]); }
+  cudaStreamDestroy(s_in);
+  cudaStreamDestroy(s_out);
+  if (!rc) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); rc = WORLD_B200_ECUDA; }
+  }
+#endif
+  for (int i = 0; i < 2; ++i) { dev_free(dx[i].p); dev_free(dt[i].p); dev_free(df[i].p); dev_free(dsp[i].p); dev_free(dap[i].p); }
+  if (!rc) rc = world_b200_synchronize(h);
+  return rc;
+}
+
+// ------------------------------------------------------------------ legacy single-utterance API
+namespace {
+std::mutex g_legacy_mutex;
+WorldB200 *g_legacy = nullptr;
+
+WorldB200 *legacy_ctx() {
+  if (!g_legacy) {
+    int dev = 0;
+    if (const char *e = getenv("WORLD_B200_DEVICE")) dev = atoi(e);
+    if (world_b200_create(dev, &g_legacy) != 0) {
+      fprintf(stderr, "world_b200: cannot create a CUDA context for the legacy API (no CPU path)\n");
+      g_legacy = nullptr;
+    }
+  }
+  return g_legacy;
+}
+
+void report(WorldB200 *h, const char *fn, int rc) {
+  if (rc) fprintf(stderr, "world_b200: %s failed (%d): %s\n", fn, rc, world_b200_last_error(h));
+}
+
+// stage(x dev, t dev, f0 dev) helpers share the upload of x / time / f0
+struct Legacy1 {
+  WorldB200 *h; Ctx *ctx;
+  double *x = nullptr, *t = nullptr, *f = nullptr;
+  int rc = 0;
+  Legacy1(const double *xh, int x_length, const double *th, const double *fh, int f0_length) {
+    h = legacy_ctx();
+    ctx = h ? ctx_of(h) : nullptr;
+    if (!h) { rc = WORLD_B200_ECUDA; return; }
+    x = (double *)dev_malloc(ctx, (size_t)x_length * 8);
+    t = (double *)dev_malloc(ctx, (size_t)imax(1, f0_length) * 8);
+    f = (double *)dev_malloc(ctx, (size_t)imax(1, f0_length) * 8);
+    if (!x || !t || !f) { rc = WORLD_B200_ENOMEM; return; }
+    rc = dev_memcpy_h2d(ctx, x, xh, (size_t)x_length * 8);
+    if (!rc && th) rc = dev_memcpy_h2d(ctx, t, th, (size_t)f0_length * 8);
+    if (!rc && fh) rc = dev_memcpy_h2d(ctx, f, fh, (size_t)f0_length * 8);
+    if (!rc && !th) rc = dev_memset(ctx, t, 0, (size_t)imax(1, f0_length) * 8);
+    if (!rc && !fh) rc = dev_memset(ctx, f, 0, (size_t)imax(1, f0_length) * 8);
+  }
+  ~Legacy1() { dev_free(x); dev_free(t); dev_free(f); }
+};
+}  // namespace
+
+extern "C" {
+
+void Dio(const double *x, int x_length, int fs, const DioOption *option, double *temporal_positions, double *f0) {
+  std::lock_guard<std::mutex> lock(g_legacy_mutex);
+  const int L = GetSamplesForDIO(fs, x_length, option->frame_period);
+  Legacy1 d(x, x_length, nullptr, nullptr, L);
+  int rc = d.rc;
+  if (!rc) rc = world_b200_dio_batch(d.h, d.x, 1, x_length, nullptr, fs, option, d.t, d.f, L);
+  if (!rc) rc = dev_memcpy_d2h(d.ctx, temporal_positions, d.t, (size_t)L * 8);
+  if (!rc) rc = dev_memcpy_d2h(d.ctx, f0, d.f, (size_t)L * 8);
+  if (!rc) rc = world_b200_synchronize(d.h);
+  if (d.h) report(d.h, "Dio", rc);
+}
+
+void Harvest(const double *x, int x_length, int fs, const HarvestOption *option, double *temporal_positions,
+             double *f0) {
+  std::lock_guard<std::mutex> lock(g_legacy_mutex);
+  const int L = GetSamplesForHarvest(fs, x_length, option->frame_period);
+  Legacy1 d(x, x_length, nullptr, nullptr, L);
+  int rc = d.rc;
+  if (!rc) rc = world_b200_harvest_batch(d.h, d.x, 1, x_length, nullptr, fs, option, d.t, d.f, L);
+  if (!rc) rc = dev_memcpy_d2h(d.ctx, temporal_positions, d.t, (size_t)L * 8);
+  if (!rc) rc = dev_memcpy_d2h(d.ctx, f0, d.f, (size_t)L * 8);
+  if (!rc) rc = world_b200_synchronize(d.h);
+  if (d.h) report(d.h, "Harvest", rc);
+}
+
+void StoneMask(const double *x, int x_length, int fs, const double *temporal_positions, const double *f0,
+               int f0_length, double *refined_f0) {
+  std::lock_guard<std::mutex> lock(g_legacy_mutex);
+  Legacy1 d(x, x_length, temporal_positions, f0, f0_length);
+  int rc = d.rc;
+  if (!rc) rc = world_b200_stonemask_batch(d.h, d.x, 1, x_length, nullptr, fs, d.t, d.f, nullptr, f0_length, d.f);
+  if (!rc) rc = dev_memcpy_d2h(d.ctx, refined_f0, d.f, (size_t)f0_length * 8);
+  if (!rc) rc = world_b200_synchronize(d.h);
+  if (d.h) report(d.h, "StoneMask", rc);
+}
+
+static void rows_out(Legacy1 &d, const char *name, int rc, double *dev_rows, int f0_length, int bins, double **rows) {
+  std::vector<double> flat((size_t)f0_length * bins);
+  if (!rc) rc = dev_memcpy_d2h(d.ctx, flat.data(), dev_rows, flat.size() * 8);
+  if (!rc) rc = world_b200_synchronize(d.h);
+  if (!rc)
+    for (int i = 0; i < f0_length; ++i) memcpy(rows[i], flat.data() + (size_t)i * bins, (size_t)bins * 8);
+  if (d.h) report(d.h, name, rc);
+}
+
+void CheapTrick(const double *x, int x_length, int fs, const double *temporal_positions, const double *f0,
+                int f0_length, const CheapTrickOption *option, double **spectrogram) {
+  std::lock_guard<std::mutex> lock(g_legacy_mutex);
+  Legacy1 d(x, x_length, temporal_positions, f0, f0_length);
+  const int bins = option->fft_size / 2 + 1;
+  double *rows = d.rc ? nullptr : (double *)dev_malloc(d.ctx, (size_t)imax(1, f0_length) * bins * 8);
+  int rc = d.rc ? d.rc : (rows ? 0 : WORLD_B200_ENOMEM);
+  if (!rc) rc = world_b200_cheaptrick_batch(d.h, d.x, 1, x_length, nullptr, fs, d.t, d.f, nullptr, f0_length, option, rows);
+  rows_out(d, "CheapTrick", rc, rows, f0_length, bins, spectrogram);
+  dev_free(rows);
+}
+
+void D4C(const double *x, int x_length, int fs, const double *temporal_positions, const double *f0, int f0_length,
+         int fft_size, const D4COption *option, double **aperiodicity) {
+  std::lock_guard<std::mutex> lock(g_legacy_mutex);
+  Legacy1 d(x, x_length, temporal_positions, f0, f0_length);
+  const int bins = fft_size / 2 + 1;
+  double *rows = d.rc ? nullptr : (double *)dev_malloc(d.ctx, (size_t)imax(1, f0_length) * bins * 8);
+  int rc = d.rc ? d.rc : (rows ? 0 : WORLD_B200_ENOMEM);
+  if (!rc) rc = world_b200_d4c_batch(d.h, d.x, 1, x_length, nullptr, fs, d.t, d.f, nullptr, f0_length, fft_size, option, rows);
+  rows_out(d, "D4C", rc, rows, f0_length, bins, aperiodicity);
+  dev_free(rows);
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// wb_internal.h -- host-side context shared by the stage drivers (not part of the public ABI).
+#pragma once
+#include "wb_platform.cuh"
+#include "wb_block.cuh"
+#include "wb_fft.cuh"
+#include <string>
+
+#define WB_RNG_CHUNK 128   // draws produced by one rng_fill thread
+#define WB_RNG_NJ 24       // jump tables J_k = T^(12*128*2^k): reach 2^31 draws per utterance
+#define WB_RNG_WARPS 4
+
+namespace wb {
+
+// Bump allocator over one device allocation; stage drivers carve their scratch out of it and
+// reset it when they return.  Grows (cudaMalloc) only when a request does not fit.
+struct Arena {
+  unsigned char *base = nullptr;
+  size_t capacity = 0, used = 0;
+};
+
+struct Ctx {
+  int device = 0;
+  wb_stream_t stream = 0;
+  double2 *twiddle = nullptr;        // [WB_TW_N/2] exp(-j 2 pi k / WB_TW_N)
+  uint32_t *rng_jump = nullptr;      // [WB_RNG_NJ][32][16] uint4
+  Arena arena;
+  size_t scratch_budget = (size_t)12 << 30;  // bytes of scratch a stage may use per chunk
+  int sm_count = 148;
+  int *status_dev = nullptr;         // sticky device-side error word
+  std::string last_error;
+};
+
+// memory helpers (wb_api.cu / emu)
+int ctx_init_tables(Ctx *ctx);
+unsigned char *arena_block(Ctx *ctx, size_t bytes);  // nullptr + last_error on failure
+struct ArenaPlan {                                   // lay out 256-byte aligned sub-blocks
+  size_t total = 0;
+  size_t add(size_t bytes) { const size_t off = total; total += (bytes + 255) & ~(size_t)255; return off; }
+};
+
+void *dev_malloc(Ctx *ctx, size_t bytes);
+void dev_free(void *p);
+int dev_memcpy_h2d(Ctx *ctx, void *dst, const void *src, size_t bytes);
+int dev_memcpy_d2h(Ctx *ctx, void *dst, const void *src, size_t bytes);
+int dev_memset(Ctx *ctx, void *dst, int value, size_t bytes);
+int dev_sync(Ctx *ctx);
+int dev_check(Ctx *ctx, const char *what);      // cudaGetLastError -> last_error
+
+// wb_rng.cu
+void rng_build_jump_tables(uint32_t *tables);
+void rng_fill(const Ctx *ctx, const unsigned *totals_dev, unsigned *out, size_t utt_stride,
+              size_t max_draws_per_utt, int n_utts);
+void scan_counts(const Ctx *ctx, const unsigned *counts, const int *lens_dev, int stride,
+                 const unsigned *base, unsigned *offsets, unsigned *totals, int n_utts);
+
+// Device-resident batch: N utterances, padded rows.
+struct Batch {
+  const double *x;        // [n][x_stride]
+  const int *x_len;       // [n] device
+  int n, x_stride, fs;
+  const double *time_axis;  // [n][f_stride]
+  const double *f0;         // [n][f_stride]
+  const int *f_len;         // [n] device
+  int f_stride;
+  int max_x_len, max_f_len;  // host-known maxima
+};
+
+// stage drivers (each: enqueue on ctx->stream, return 0 / error code)
+int cheaptrick_run(Ctx *ctx, const Batch &b, double q1, int fft_size, double *spectrogram);
+int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *aperiodicity);
+int stonemask_run(Ctx *ctx, const Batch &b, double *refined_f0);
+struct DioParams { double f0_floor, f0_ceil, channels_in_octave, frame_period, allowed_range; int speed; };
+int dio_run(Ctx *ctx, const Batch &b, const DioParams &p, double *time_axis_out, double *f0_out);
+struct HarvestParams { double f0_floor, f0_ceil, frame_period; };
+int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &p, double *time_axis_out, double *f0_out);
+
+}  // namespace wb

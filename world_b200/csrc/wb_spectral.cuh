@@ -1,0 +1,86 @@
+// wb_spectral.cuh -- block-cooperative restatements of the reference's shared spectral
+// helpers: DCCorrection (common.cpp:56-75), LinearSmoothing (common.cpp:27-46,
+// 77-111), interp1Q (matlabfunctions.cpp:214-235), and the draw -> normal mapping of randn
+// (matlabfunctions.cpp:263).  All operate on shared-memory vectors of fft_size/2+1 doubles.
+#pragma once
+#include "wb_platform.cuh"
+#include "wb_block.cuh"
+
+namespace wb {
+
+// randn(): tmp / 268435456.0 - 6.0 with tmp the stored 32-bit sum
+WB_DEV double randn_value(unsigned tmp) { return (double)tmp / 268435456.0 - 6.0; }
+
+// One interp1Q sample: y[base] + (y[base+1]-y[base]) * frac with base = int((xi-x0)/dx).
+// The reference zeroes delta_y[ny-1]; `ny` reproduces that.
+WB_DEV double interp1q_at(double x0, double dx, const double *y, int ny, double xi) {
+  const double r = (xi - x0) / dx;
+  const int base = static_cast<int>(r);
+  const double frac = r - base;
+  const double dy = (base + 1 < ny) ? (y[base + 1] - y[base]) : 0.0;
+  return y[base] + dy * frac;
+}
+
+// DCCorrection(in -> in, in place).  `tmp` needs upper_limit doubles.  Ends with a barrier.
+WB_DEV void dc_correction(double *spec, double f0, int fs, int fft_size, double *tmp) {
+  const int tid = WB_TID, nth = WB_NTH;
+  const int upper_limit = 2 + static_cast<int>(f0 * fft_size / fs);
+  const int n_rep = upper_limit - 1;
+  const double dx = -static_cast<double>(fs) / fft_size;
+  for (int i = tid; i < n_rep; i += nth) {
+    const double xi = static_cast<double>(i) * fs / fft_size;
+    tmp[i] = interp1q_at(f0, dx, spec, upper_limit + 1, xi);
+  }
+  WB_SYNC();
+  for (int i = tid; i < n_rep; i += nth) spec[i] = spec[i] + tmp[i];
+  WB_SYNC();
+}
+
+// Capacity (in doubles) the `seg` scratch of linear_smoothing must have for a given half size.
+WB_HD inline int smoothing_capacity(int fft_size) { return fft_size + 2; }
+
+// LinearSmoothing(in -> out); in == out allowed.  `seg` is scratch of smoothing_capacity().
+// kSequential = true reproduces the reference's index-order running sum bit for bit
+// (mandatory for CheapTrick); false uses a blocked scan (D4C: measured
+// insensitive).  Returns false (all threads) if the smoothing width does not fit the scratch.
+template <bool kSequential>
+WB_DEV bool linear_smoothing(const double *in, double width, int fs, int fft_size, double *out,
+                             double *seg, double *red_big) {
+  const int tid = WB_TID, nth = WB_NTH;
+  const int half = fft_size / 2;
+  const int boundary = static_cast<int>(width * fft_size / fs) + 1;
+  const int n_ext = half + boundary * 2 + 1;
+  if (boundary > half || n_ext > smoothing_capacity(fft_size)) return false;
+
+  // mirror-extend and scale:  seg[i] = ext[i] * fs / fft_size   (common.cpp:30-41)
+  for (int i = tid; i < n_ext; i += nth) {
+    double v;
+    if (i < boundary) v = in[boundary - i];
+    else if (i < half + boundary) v = in[i - boundary];
+    else v = in[half - (i - (half + boundary))];
+    seg[i] = v * fs / fft_size;
+  }
+  WB_SYNC();
+  if (kSequential) {
+    if (tid == 0) {
+      double run = seg[0];
+      for (int i = 1; i < n_ext; ++i) { run = seg[i] + run; seg[i] = run; }
+    }
+    WB_SYNC();
+  } else {
+    block_inclusive_scan(seg, n_ext, red_big);
+  }
+  const double origin = -(boundary - 0.5) * fs / fft_size;
+  const double dx = static_cast<double>(fs) / fft_size;
+  for (int i = tid; i <= half; i += nth) {
+    const double lo_x = static_cast<double>(i) / fft_size * fs - width / 2.0;
+    const double hi_x = lo_x + width;
+    const double lo = interp1q_at(origin, dx, seg, n_ext, lo_x);
+    const double hi = interp1q_at(origin, dx, seg, n_ext, hi_x);
+    out[i] = (hi - lo) / width;
+  }
+  WB_SYNC();
+  return true;
+}
+
+}  // namespace wb
