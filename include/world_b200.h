@@ -1,7 +1,7 @@
 /* world_b200.h -- batched C ABI of the B200-native WORLD analysis engine.
  *
  * The reference (mmorise/World) has no plugin registry; its boundary is the public C API of
- * src/world/*.h.  That API is kept source-compatible in include/world/*.h
+ * the src/world headers.  That API is kept source-compatible in include/world/
  * (single utterance, host pointers).  This header is the thin extern "C" layer underneath it:
  * the same stages, N utterances per call, plain pointers and sizes, no C++/torch types.
  *
@@ -57,6 +57,10 @@ int world_b200_synchronize(WorldB200 *ctx);
 const char *world_b200_last_error(const WorldB200 *ctx);
 /* Number of kernels this context has launched so far (bench.py reports it). */
 unsigned long long world_b200_launch_count(const WorldB200 *ctx);
+
+/* Test hook: first n_draws values of the reference's randn() stream (matlabfunctions.cpp:237-264)
+ * as raw 32-bit sums (value = sum / 2^28 - 6) into a DEVICE buffer of n_draws uint32. */
+int world_b200_randn_stream(WorldB200 *ctx, unsigned n_draws, unsigned *out_dev);
 
 /* int(1000.0 * x_length / fs / frame_period) + 1 */
 int world_b200_frames(int fs, int x_length, double frame_period);

@@ -1,0 +1,65 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The unmodified reference compiled into oracle/_ref (prebuilt file travels to the GPU box)."""
+    from refworld import RefWorld, REF_LIB
+    if not os.path.exists(REF_LIB):
+        if os.path.isdir("/root/reference/src"):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+        else:
+            pytest.skip("oracle/_ref/libworld_ref.so missing and /root/reference absent")
+    return RefWorld(REF_LIB)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "vaiueo2d.npz"))
+
+
+@pytest.fixture(scope="session")
+def emu():
+    """Single-thread host emulation of the kernel sources (logic check without a GPU)."""
+    from world_b200.api import World
+    path = os.path.join(ROOT, "tests", "emu", "libworld_b200_emu.so")
+    subprocess.check_call([os.path.join(ROOT, "tests", "emu", "build.sh")], stdout=subprocess.DEVNULL)
+    return World(lib_path=path, array_module="numpy")
+
+
+@pytest.fixture(scope="session")
+def gpu_world():
+    import torch
+    from world_b200.api import World
+    torch.cuda.set_device(0)
+    return World(device=0)

@@ -1,0 +1,37 @@
+"""CPU-side logic checks: the kernel sources compiled as a single-thread host emulation
+(tests/emu) against the golden vectors and the compiled reference.  This is not the product
+path (that is tests/test_gpu_parity.py, -m gpu); it exists so that arithmetic mistakes are caught
+in the GPU-less build container."""
+import numpy as np
+import pytest
+
+import test_parity_common as pc
+
+
+def test_reference_reproduces_its_own_goldens(ref, golden):
+    x, fs = pc.wav_from_golden(golden)
+    t, f0 = ref.dio(x, fs)
+    assert np.array_equal(t, golden["time_axis"]) and np.array_equal(f0, golden["f0_dio"])
+    f0 = ref.stonemask(x, fs, t, f0)
+    assert np.array_equal(f0, golden["f0_stonemask"])
+    assert np.array_equal(ref.cheaptrick(x, fs, t, f0), golden["sp"])
+    assert np.array_equal(ref.d4c(x, fs, t, f0, int(golden["fft_size"])), golden["ap"])
+
+
+def test_emu_randn_stream(emu, golden):
+    pc.check_randn(emu, golden)
+
+
+def test_emu_golden_cheaptrick_d4c_stonemask(emu, golden):
+    pc.check_golden_cheaptrick_d4c_stonemask(emu, golden)
+
+
+@pytest.mark.parametrize("fs,n,seeds", [(16000, 8000, [1, 2, 3]), (48000, 12000, [4]), (8000, 6000, [5])])
+def test_emu_spectral_stages_on_reference_f0(emu, ref, fs, n, seeds):
+    if fs == 8000:
+        pytest.skip("fs < 15.8 kHz: D4C LoveTrain reads uninitialised memory in the reference (b2 > fft/2)")
+    pc.check_batch_vs_ref(emu, ref, fs, n, seeds, f0_method="ref", ragged=len(seeds) > 1, stages=("sp", "ap"))
+
+
+def test_emu_zero_tail(emu, ref):
+    pc.check_batch_vs_ref(emu, ref, 16000, 8000, [7], f0_method="ref", zero_tail=3000, stages=("sp", "ap"))

@@ -58,6 +58,7 @@ ABI = {
     "world_b200_last_error": (C.c_char_p, [_P]),
     "world_b200_launch_count": (C.c_ulonglong, [_P]),
     "world_b200_frames": (C.c_int, [C.c_int, C.c_int, C.c_double]),
+    "world_b200_randn_stream": (C.c_int, [_P, C.c_uint, _P]),
     "world_b200_dio_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, C.POINTER(DioOption), _P, _P, C.c_int]),
     "world_b200_harvest_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, C.POINTER(HarvestOption), _P, _P, C.c_int]),
     "world_b200_stonemask_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, _P, _P, _IP, C.c_int, _P]),
@@ -177,6 +178,12 @@ class World:
 
     def set_scratch_budget(self, nbytes: int):
         self._check(self.lib.world_b200_set_scratch_budget(self._h, nbytes))
+
+    def randn_stream(self, n_draws, out_u32):
+        """test hook: raw draw sums into a uint32 array/tensor of n_draws elements"""
+        self._use_current_stream()
+        self._check(self.lib.world_b200_randn_stream(self._h, n_draws, _ptr(out_u32)))
+        return out_u32
 
     def frames(self, fs, x_length, frame_period=5.0) -> int:
         return int(self.lib.world_b200_frames(fs, x_length, frame_period))

@@ -346,6 +346,19 @@ int world_b200_harvest_batch(WorldB200 *h, const double *x, int n, int x_stride,
   return harvest_run(&h->c, b, p, time_axis, f0);
 }
 
+// Known-answer hook: the first n_draws randn() draws after randn_reseed(), as the raw 32-bit
+// sums (value = sum / 2^28 - 6), written to a device buffer of n_draws uint32.
+int world_b200_randn_stream(WorldB200 *h, unsigned n_draws, unsigned *out_dev) {
+  if (!h || !out_dev) return WORLD_B200_EINVAL;
+  Ctx *ctx = &h->c;
+  unsigned char *blk = arena_block(ctx, 256);
+  if (!blk) return WORLD_B200_ENOMEM;
+  int rc = dev_memcpy_h2d(ctx, blk, &n_draws, sizeof(unsigned));
+  if (rc) return rc;
+  rng_fill(ctx, reinterpret_cast<unsigned *>(blk), out_dev, 0, n_draws, 1);
+  return dev_check(ctx, "randn_stream");
+}
+
 // ---- option helpers: pure host arithmetic, the reference's expressions verbatim in meaning
 void InitializeDioOption(DioOption *o) {
   o->channels_in_octave = 2.0; o->f0_ceil = 800.0; o->f0_floor = 71.0; o->frame_period = 5;
