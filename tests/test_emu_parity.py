@@ -35,3 +35,24 @@ def test_emu_spectral_stages_on_reference_f0(emu, ref, fs, n, seeds):
 
 def test_emu_zero_tail(emu, ref):
     pc.check_batch_vs_ref(emu, ref, 16000, 8000, [7], f0_method="ref", zero_tail=3000, stages=("sp", "ap"))
+
+
+def test_emu_golden_dio(emu, golden):
+    pc.check_golden_dio(emu, golden)
+
+
+@pytest.mark.parametrize("fs,n,seeds", [(16000, 16000, [11, 12, 13]), (48000, 14400, [14])])
+def test_emu_dio_path_end_to_end(emu, ref, fs, n, seeds):
+    pc.check_batch_vs_ref(emu, ref, fs, n, seeds, f0_method="dio", ragged=len(seeds) > 1)
+
+
+def test_emu_dio_decimated(emu, ref):
+    from synth import synth_batch
+    x = synth_batch([21], 44100, 22050).numpy()
+    o = emu.dio_option(); o.speed = 11
+    ro = ref.dio_option(); ro.speed = 11
+    t, f0, fl = emu.dio(x, 44100, o)
+    emu.synchronize()
+    tr, fr = ref.dio(x[0], 44100, ro)
+    assert np.array_equal(t[0], tr)
+    pc.assert_close(f0[0], fr, "DIO speed=11")

@@ -23,3 +23,25 @@ def test_gpu_spectral_stages_on_reference_f0(gpu_world, ref, fs, n, seeds):
 
 def test_gpu_zero_tail(gpu_world, ref):
     pc.check_batch_vs_ref(gpu_world, ref, 16000, 16000, [9], f0_method="ref", zero_tail=6000, stages=("sp", "ap"))
+
+
+def test_gpu_golden_dio(gpu_world, golden):
+    pc.check_golden_dio(gpu_world, golden)
+
+
+@pytest.mark.parametrize("fs,n,seeds", [(16000, 48000, [11, 12, 13, 14]), (48000, 48000, [15, 16]), (22050, 22050, [17])])
+def test_gpu_dio_path_end_to_end(gpu_world, ref, fs, n, seeds):
+    pc.check_batch_vs_ref(gpu_world, ref, fs, n, seeds, f0_method="dio", ragged=len(seeds) > 1)
+
+
+def test_gpu_dio_decimated(gpu_world, ref):
+    import torch
+    from synth import synth_batch
+    x = synth_batch([21], 44100, 44100)
+    o = gpu_world.dio_option(); o.speed = 11
+    ro = ref.dio_option(); ro.speed = 11
+    t, f0, fl = gpu_world.dio(x.cuda(), 44100, o)
+    gpu_world.synchronize()
+    tr, fr = ref.dio(x[0].numpy(), 44100, ro)
+    assert np.array_equal(t[0].cpu().numpy(), tr)
+    pc.assert_close(f0[0], fr, "DIO speed=11")

@@ -112,3 +112,16 @@ def check_batch_vs_ref(world, ref, fs, n_samples, seeds, f0_method="dio", zero_t
         if ap is not None:
             assert_close(to_np(ap)[u, :fl[u]], ref.d4c(xu, fs, tr, fu, opt.fft_size), f"aperiodicity utt {u}")
     assert flips == 0
+
+
+def check_golden_dio(world, golden):
+    x, fs = wav_from_golden(golden)
+    xb = make(world, x[None, :])
+    t, f0, fl = world.dio(xb, fs)
+    o = world.dio_option(); o.f0_floor = 40.0
+    _, f0_40, _ = world.dio(xb, fs, o)
+    world.synchronize()
+    assert fl[0] == len(golden["time_axis"])
+    assert np.array_equal(to_np(t)[0], golden["time_axis"])
+    assert_close(f0[0], golden["f0_dio"], "DIO f0")
+    assert_close(f0_40[0], golden["f0_dio_floor40"], "DIO f0 (floor 40)")
