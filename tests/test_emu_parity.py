@@ -56,3 +56,24 @@ def test_emu_dio_decimated(emu, ref):
     tr, fr = ref.dio(x[0], 44100, ro)
     assert np.array_equal(t[0], tr)
     pc.assert_close(f0[0], fr, "DIO speed=11")
+
+
+def test_emu_golden_harvest(emu, golden):
+    pc.check_golden_harvest(emu, golden)
+
+
+@pytest.mark.parametrize("fs,n,seeds", [(16000, 12000, [31, 32]), (48000, 9600, [33])])
+def test_emu_harvest_path_end_to_end(emu, ref, fs, n, seeds):
+    pc.check_batch_vs_ref(emu, ref, fs, n, seeds, f0_method="harvest", ragged=len(seeds) > 1)
+
+
+def test_emu_harvest_frame_period_1ms(emu, ref):
+    from synth import synth_batch
+    x = synth_batch([41], 16000, 8000).numpy()
+    o = emu.harvest_option(); o.frame_period = 1.0
+    ro = ref.harvest_option(); ro.frame_period = 1.0
+    t, f0, fl = emu.harvest(x, 16000, o)
+    emu.synchronize()
+    tr, fr = ref.harvest(x[0], 16000, ro)
+    assert np.array_equal(t[0], tr)
+    pc.assert_close(f0[0], fr, "Harvest 1 ms")

@@ -45,3 +45,12 @@ def test_gpu_dio_decimated(gpu_world, ref):
     tr, fr = ref.dio(x[0].numpy(), 44100, ro)
     assert np.array_equal(t[0].cpu().numpy(), tr)
     pc.assert_close(f0[0], fr, "DIO speed=11")
+
+
+def test_gpu_golden_harvest(gpu_world, golden):
+    pc.check_golden_harvest(gpu_world, golden)
+
+
+@pytest.mark.parametrize("fs,n,seeds", [(16000, 48000, [31, 32, 33, 34]), (48000, 48000, [35, 36]), (22050, 22050, [37])])
+def test_gpu_harvest_path_end_to_end(gpu_world, ref, fs, n, seeds):
+    pc.check_batch_vs_ref(gpu_world, ref, fs, n, seeds, f0_method="harvest", ragged=len(seeds) > 1)

@@ -125,3 +125,15 @@ def check_golden_dio(world, golden):
     assert np.array_equal(to_np(t)[0], golden["time_axis"])
     assert_close(f0[0], golden["f0_dio"], "DIO f0")
     assert_close(f0_40[0], golden["f0_dio_floor40"], "DIO f0 (floor 40)")
+
+
+def check_golden_harvest(world, golden):
+    x, fs = wav_from_golden(golden)
+    xb = make(world, x[None, :])
+    t, f0, fl = world.harvest(xb, fs)
+    o = world.harvest_option(); o.f0_floor = 40.0
+    _, f0_40, _ = world.harvest(xb, fs, o)
+    world.synchronize()
+    assert np.array_equal(to_np(t)[0], golden["time_axis"])
+    assert_close(f0[0], golden["f0_harvest"], "Harvest f0")
+    assert_close(f0_40[0], golden["f0_harvest_floor40"], "Harvest f0 (floor 40)")

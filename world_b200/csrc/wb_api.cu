@@ -342,6 +342,9 @@ int world_b200_harvest_batch(WorldB200 *h, const double *x, int n, int x_stride,
   b.x = x; b.n = n; b.x_stride = x_stride; b.fs = fs; b.time_axis = time_axis; b.f0 = f0; b.f_stride = f0_stride;
   rc = upload_lengths(h, n, x_stride, x_lengths, f0_stride, fl.data(), &b);
   if (rc) return rc;
+  std::vector<int> l1(n > 0 ? n : 1);
+  for (int i = 0; i < n; ++i) l1[i] = frames_for(fs, x_lengths ? x_lengths[i] : x_stride, 1.0);
+  b.l1_host = l1.data();
   HarvestParams p = {opt->f0_floor, opt->f0_ceil, opt->frame_period};
   return harvest_run(&h->c, b, p, time_axis, f0);
 }

@@ -195,8 +195,6 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
                          (size_t)fstr * (4 * 8 + 2 * 4) + tmp_stride * 16 + 256;
   int chunk = (int)imin(imin(b.n, 65535), (int)dmax(1.0, (double)ctx->scratch_budget / (double)per_utt));
 #ifndef WB_EMU
-  cudaFuncSetAttribute(band_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sweep);
-  cudaFuncSetAttribute(fir_plain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fir);
 #endif
   for (int u0 = 0; u0 < b.n; u0 += chunk) {
     const int n = imin(chunk, b.n - u0);
@@ -235,7 +233,7 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     fp.out = ylc; fp.out_stride = y_stride; fp.out_origin = padl;
     fp.base_len = ylen; fp.extra_len = 2 * c; fp.taps_rev = (const double *)(blk + o_lc); fp.ntaps = nlc;
     const unsigned tiles = (unsigned)((max_ylen + 2 * c + 2047) / 2048);
-    WB_LAUNCH_COOP(fir_plain_kernel, dim3(tiles, (unsigned)n), 256, smem_fir, ctx->stream, fp);
+    launch_fir_plain(ctx, fp, tiles, (unsigned)n);
 
     SweepParams sp;
     sp.sig = ylc; sp.sig_stride = y_stride; sp.sig_origin = padl + c; sp.y_len = ylen; sp.n_bands = nb;
@@ -247,7 +245,7 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     sp.mode = 0; sp.f0_floor = opt.f0_floor; sp.f0_ceil = opt.f0_ceil;
     sp.cand = (double *)(blk + o_cand); sp.score = (double *)(blk + o_score);
     sp.max_taps = max_taps; sp.status = ctx->status_dev;
-    WB_LAUNCH_COOP(band_sweep_kernel, dim3((unsigned)nb, (unsigned)n), WB_SWEEP_THREADS, smem_sweep, ctx->stream, sp);
+    launch_band_sweep(ctx, sp, (unsigned)n);
 
     DioContourParams cp;
     cp.cand = sp.cand; cp.score = sp.score; cp.n_bands = nb; cp.frame_stride = fstr; cp.f_len = b.f_len + u0;

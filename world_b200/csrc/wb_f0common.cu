@@ -1,0 +1,242 @@
+// wb_f0common.cu -- kernels shared by DIO and Harvest (see wb_f0common.cuh for the design notes).
+#include "wb_internal.h"
+#include "wb_f0common.cuh"
+
+namespace wb {
+
+WB_KERNEL(256, 3) fir_plain_kernel(FirParams p) {
+  WB_DYN_SMEM(double, smem);
+  const int tid = WB_TID, nth = WB_NTH;
+  const int T = 2048, R = 8, G = T / R;
+  const int u = blockIdx.y, n0 = blockIdx.x * T;
+  const int qlen = p.base_len[u] + p.extra_len;
+  if (n0 >= qlen) return;
+  const int ntaps = p.ntaps;
+  const int seg_len = T + ntaps - 1;
+  const int seg_cap = seg_len + 16;
+  double *seg = smem;
+  double *hrev = seg + (seg_cap + (seg_cap >> 3) + 8);
+  const double *in = p.in + (size_t)u * p.in_stride + p.in_origin;
+  double *out = p.out + (size_t)u * p.out_stride + p.out_origin;
+  for (int j = tid; j < ntaps + 8; j += nth) hrev[j] = j < ntaps ? __ldg(&p.taps_rev[j]) : 0.0;
+  const int m0 = n0 - ntaps + 1;
+  for (int i = tid; i < seg_len + 8; i += nth) seg[pad8(i)] = (i < seg_len) ? in[m0 + i] : 0.0;
+  WB_SYNC();
+  for (int g = tid; g < G; g += nth) {
+    const int base = R * g;
+    double acc[8], win[8];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { acc[r] = 0.0; win[r] = seg[pad8(base + r)]; }
+    for (int j0 = 0; j0 < ntaps; j0 += R) {
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) {
+        const double hj = hrev[j0 + jj];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = fma(hj, win[(r + jj) & (R - 1)], acc[r]);
+        win[jj] = seg[pad8(base + R + j0 + jj)];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (n0 + base + r < qlen) out[n0 + base + r] = acc[r];
+  }
+}
+
+// interp1 (matlabfunctions.cpp:157-176) of one event train at time t; edges = fine edge
+// positions (n_edges of them), sample (x, y) pairs are (location, interval) of consecutive edges.
+WB_DEV double train_interp(const double *e, int n_int, double afs, double t) {
+  // k = #{j : loc[j] <= t} clamped to [1, n_int-1]; loc[j] = (e[j] + e[j+1]) / 2 / afs
+  int lo = 0, hi = n_int;  // first j with loc[j] > t
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const double loc = (e[mid] + e[mid + 1]) / 2.0 / afs;
+    if (loc <= t) lo = mid + 1; else hi = mid;
+  }
+  const int k = imin(n_int - 1, imax(1, lo));
+  const double e0 = e[k - 1], e1 = e[k], e2 = e[k + 1];
+  const double x0 = (e0 + e1) / 2.0 / afs, x1 = (e1 + e2) / 2.0 / afs;
+  const double y0 = afs / (e1 - e0), y1 = afs / (e2 - e1);
+  const double s = (t - x0) / (x1 - x0);
+  return y0 + s * (y1 - y0);
+}
+
+// Exclusive scan of G packed counters (4 x 16 bit) held in shared memory, in place; adds the
+// running totals in `carry` (also packed) and returns the new running total to every thread.
+// CUDA path: requires blockDim.x == G (one counter per thread).
+WB_DEV unsigned long long scan_packed(unsigned long long *c, int G, unsigned long long carry,
+                                      unsigned long long *warp_tot /* >= 33 */) {
+#ifdef WB_EMU
+  (void)warp_tot;
+  unsigned long long run = carry;
+  for (int g = 0; g < G; ++g) { const unsigned long long v = c[g]; c[g] = run; run += v; }
+  return run;
+#else
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = G >> 5;
+  const unsigned long long v = c[tid];
+  unsigned long long inc = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  unsigned long long base = carry, all = carry;
+  for (int i = 0; i < nw; ++i) { const unsigned long long t = warp_tot[i]; if (i < w) base += t; all += t; }
+  c[tid] = base + inc - v;
+  __syncthreads();
+  return all;
+#endif
+}
+
+WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
+  WB_DYN_SMEM(double, smem);
+  const int tid = WB_TID, nth = WB_NTH;
+  const int b = blockIdx.x, u = blockIdx.y;
+  const int T = WB_SWEEP_T, R = WB_SWEEP_R, G = T / R;
+  const int ntaps = p.ntaps[b], shift = p.shift[b];
+  const int seg_len = T + ntaps - 1;
+  const int seg_cap = T + p.max_taps + 16;
+  double *seg = smem;                                   // padded: pad8(seg_cap)
+  double *hrev = seg + (seg_cap + (seg_cap >> 3) + 8);  // max_taps + 8
+  double *st = hrev + (p.max_taps + 8);                 // T + 8: [0..1] carry, [2..T+2) this tile
+  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(st + (T + 8));  // G + 40
+
+  const int ylen = p.y_len[u];
+  const double *sig = p.sig + (size_t)u * p.sig_stride + p.sig_origin;
+  double *edges = p.edges + ((size_t)u * p.n_bands + b) * 4 * p.edge_cap;
+  const int cap = (int)p.edge_cap;
+  for (int j = tid; j < ntaps; j += nth) hrev[j] = __ldg(&p.taps_rev[p.tap_off[b] + j]);
+  for (int j = ntaps + tid; j < ntaps + 8; j += nth) hrev[j] = 0.0;
+  if (tid == 0) { st[0] = 0.0; st[1] = 0.0; }
+  int tot[4] = {0, 0, 0, 0};  // running event counts per train (identical in every thread)
+  WB_SYNC();
+
+  // Tile k produces outputs n0..n0+T-1 into st[2..]; events are detected for positions
+  // i = n0-2 .. n0+T-3 (they need s[i], s[i+1], s[i+2]); the last two outputs carry over.
+  for (int n0 = 0; n0 < ylen + 2; n0 += T) {
+    const int m0 = n0 + shift - ntaps + 1;  // seg[i] = s(m0 + i)
+    for (int i = tid; i < seg_len + 8; i += nth) seg[pad8(i)] = (i < seg_len) ? sig[m0 + i] : 0.0;
+    WB_SYNC();
+    for (int g = tid; g < G; g += nth) {
+      const int base = R * g;
+      double acc[WB_SWEEP_R], win[WB_SWEEP_R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) { acc[r] = 0.0; win[r] = seg[pad8(base + r)]; }
+      for (int j0 = 0; j0 < ntaps; j0 += R) {
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj) {
+          const double hj = hrev[j0 + jj];  // zero beyond ntaps
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = fma(hj, win[(r + jj) & (R - 1)], acc[r]);
+          win[jj] = seg[pad8(base + R + j0 + jj)];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) st[2 + base + r] = acc[r];
+    }
+    WB_SYNC();
+    // train 0: s[i] > 0 >= s[i+1]   train 1: s[i] < 0 <= s[i+1]          (i >= 0, i+1 <= ylen-1)
+    // train 2: d[i] > 0 >= d[i+1]   train 3: d[i] < 0 <= d[i+1], d[i] = s[i+1]-s[i]  (i+1 <= ylen-2)
+    for (int g = tid; g < G; g += nth) {
+      unsigned long long c = 0ull;
+      const int base = R * g;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = n0 - 2 + base + r;
+        const double a = st[base + r], bb = st[base + r + 1], cc = st[base + r + 2];
+        const double d0 = bb - a, d1 = cc - bb;
+        if (i >= 0 && i + 1 <= ylen - 1) {
+          c += (0.0 < a && bb <= 0.0) ? 1ull : 0ull;
+          c += (a < 0.0 && 0.0 <= bb) ? (1ull << 16) : 0ull;
+        }
+        if (i >= 0 && i + 1 <= ylen - 2) {
+          c += (0.0 < d0 && d1 <= 0.0) ? (1ull << 32) : 0ull;
+          c += (d0 < 0.0 && 0.0 <= d1) ? (1ull << 48) : 0ull;
+        }
+      }
+      cnt[g] = c;
+    }
+    WB_SYNC();
+    const unsigned long long tile_total = scan_packed(cnt, G, 0ull, cnt + G + 4);  // <= 2048 each: fits 16 bit
+    for (int g = tid; g < G; g += nth) {
+      const unsigned long long o = cnt[g];
+      int o0 = tot[0] + (int)(o & 0xffffull), o1 = tot[1] + (int)((o >> 16) & 0xffffull);
+      int o2 = tot[2] + (int)((o >> 32) & 0xffffull), o3 = tot[3] + (int)((o >> 48) & 0xffffull);
+      const int base = R * g;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = n0 - 2 + base + r;
+        const double a = st[base + r], bb = st[base + r + 1], cc = st[base + r + 2];
+        const double d0 = bb - a, d1 = cc - bb;
+        const double e = (double)(i + 1);
+        if (i >= 0 && i + 1 <= ylen - 1) {
+          if (0.0 < a && bb <= 0.0) { if (o0 < cap) edges[o0] = e - a / (bb - a); ++o0; }
+          if (a < 0.0 && 0.0 <= bb) { if (o1 < cap) edges[(size_t)cap + o1] = e - a / (bb - a); ++o1; }
+        }
+        if (i >= 0 && i + 1 <= ylen - 2) {
+          if (0.0 < d0 && d1 <= 0.0) { if (o2 < cap) edges[2 * (size_t)cap + o2] = e - d0 / (d1 - d0); ++o2; }
+          if (d0 < 0.0 && 0.0 <= d1) { if (o3 < cap) edges[3 * (size_t)cap + o3] = e - d0 / (d1 - d0); ++o3; }
+        }
+      }
+    }
+    tot[0] += (int)(tile_total & 0xffffull); tot[1] += (int)((tile_total >> 16) & 0xffffull);
+    tot[2] += (int)((tile_total >> 32) & 0xffffull); tot[3] += (int)((tile_total >> 48) & 0xffffull);
+    WB_SYNC();
+    if (tid == 0) { st[0] = st[T]; st[1] = st[T + 1]; }
+    WB_SYNC();
+  }
+#ifndef WB_EMU
+  __threadfence_block();
+#endif
+  WB_SYNC();
+  // ---- candidates on the frame grid
+  const int nf = p.n_frames[u];
+  double *cand = p.cand + ((size_t)u * p.n_bands + b) * p.frame_stride;
+  double *score = p.score ? p.score + ((size_t)u * p.n_bands + b) * p.frame_stride : nullptr;
+  int ni[4];
+  bool ok = true;
+  for (int q = 0; q < 4; ++q) {
+    if (tot[q] > cap) { if (tid == 0) atomicOr_status(p.status, 4); ok = false; }
+    ni[q] = tot[q] < 2 ? 0 : tot[q] - 1;  // ZeroCrossingEngine returns count-1 (0 if count<2)
+    if (ni[q] - 2 <= 0) ok = false;       // CheckEvent(n - 2), dio.cpp:475-484
+  }
+  const double bf = p.boundary[b];
+  for (int i = tid; i < nf; i += nth) {
+    double c = 0.0, sc = 100000.0;  // kMaximumValue
+    if (ok) {
+      const double t = i * p.frame_period / 1000.0;
+      const double v0 = train_interp(edges, ni[0], p.afs, t);
+      const double v1 = train_interp(edges + cap, ni[1], p.afs, t);
+      const double v2 = train_interp(edges + 2 * (size_t)cap, ni[2], p.afs, t);
+      const double v3 = train_interp(edges + 3 * (size_t)cap, ni[3], p.afs, t);
+      c = (v0 + v1 + v2 + v3) / 4.0;
+      if (p.mode == 0) {
+        sc = sqrt(((v0 - c) * (v0 - c) + (v1 - c) * (v1 - c) + (v2 - c) * (v2 - c) + (v3 - c) * (v3 - c)) / 3.0);
+        if (c > bf || c < bf / 2.0 || c > p.f0_ceil || c < p.f0_floor) { c = 0.0; sc = 100000.0; }
+      } else {
+        if (c > bf * 1.1 || c < bf * 0.9 || c > p.f0_ceil || c < p.f0_floor) c = 0.0;
+      }
+    }
+    cand[i] = c;
+    if (score) score[i] = sc / (c + kTiny);  // dio.cpp:562-566
+  }
+}
+
+
+void launch_fir_plain(Ctx *ctx, const FirParams &p, unsigned tiles, unsigned n_utts) {
+  const size_t smem = fir_plain_smem_bytes(p.ntaps);
+#ifndef WB_EMU
+  cudaFuncSetAttribute(fir_plain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+  WB_LAUNCH_COOP(fir_plain_kernel, dim3(tiles, n_utts), 256, smem, ctx->stream, p);
+}
+
+void launch_band_sweep(Ctx *ctx, const SweepParams &p, unsigned n_utts) {
+  const size_t smem = sweep_smem_bytes(p.max_taps);
+#ifndef WB_EMU
+  cudaFuncSetAttribute(band_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+  WB_LAUNCH_COOP(band_sweep_kernel, dim3((unsigned)p.n_bands, n_utts), WB_SWEEP_THREADS, smem, ctx->stream, p);
+}
+
+}  // namespace wb

@@ -1,4 +1,687 @@
+// wb_harvest.cu -- Harvest F0 estimation for a batch (replaces Harvest()/HarvestGeneralBody,
+// harvest.cpp:1145-1255).  Algorithm card: SURVEY.md A5.  Everything runs on the 1 ms grid and
+// is subsampled to frame_period at the end, exactly like the reference (harvest.cpp:1237-1251).
+//   K-HVd  harvest_prep_kernel     edge-padded decimation to ~8 kHz + DC removal      (:43-93)
+//   K-HVf  band_sweep_kernel       152 band-pass FIRs + zero-crossing trains + interp1  (:99-343)
+//   K-HVp  harvest_detect_kernel   per-frame candidate pooling over channels           (:348-412)
+//   K-HVr  harvest_refine_kernel   instantaneous-frequency refinement, one warp per 1 ms frame,
+//                                  the +-3 frame overlap (:417-429) done as an index map  (:434-631)
+//          harvest_remove_kernel   RemoveUnreliableCandidates                          (:652-688)
+//   K-HVc  harvest_contour_kernel  SearchF0Base + FixStep1..4 (sequential per utterance) (:693-1043)
+//          harvest_smooth_kernel   zero-lag Butterworth per voiced section + subsample  (:1049-1113, 1246-1251)
+// GetMeanF0's two FFTs per candidate are replaced by a sparse DFT at the <= 6 harmonic bins that
+// FixF0 reads (same linear functional).
 #include "wb_internal.h"
+#include "wb_f0common.cuh"
+#include <vector>
+
 namespace wb {
-int harvest_run(Ctx *ctx, const Batch &, const HarvestParams &, double *, double *) { ctx->last_error = "harvest: not built yet"; return 3; }
+
+#define WB_HV_BASE 32        // >= round(channels / 10): base candidates kept per frame
+#define WB_HV_WARPS 8
+
+// ------------------------------------------------------------------ K-HVd
+struct HvPrepParams {
+  const double *x; const int *x_len; int x_stride; int ratio;
+  double *y; size_t y_stride; int y_origin; int *y_len;
+  double *tmp; size_t tmp_stride;
+};
+
+WB_KERNEL(256, 2) harvest_prep_kernel(HvPrepParams p) {
+  WB_SHARED double red[WB_RED_DOUBLES];
+  const int tid = WB_TID, nth = WB_NTH, u = blockIdx.x;
+  const int n = p.x_len[u];
+  const double *x = p.x + (size_t)u * p.x_stride;
+  double *y = p.y + (size_t)u * p.y_stride + p.y_origin;
+  const int ylen = static_cast<int>(ceil(static_cast<double>(n) / p.ratio));
+  if (p.ratio != 1) {
+    if (tid == 0) {
+      const int lag = static_cast<int>(ceil(140.0 / p.ratio) * p.ratio);
+      double *t1 = p.tmp + (size_t)u * 2 * p.tmp_stride, *t2 = t1 + p.tmp_stride;
+      decimate_one(x, n, lag, p.ratio, t1, t2, lag / p.ratio, ylen, y);
+    }
+    WB_SYNC();
+  } else {
+    for (int i = tid; i < n; i += nth) y[i] = x[i];
+    WB_SYNC();
+  }
+  double s = 0.0;
+  for (int i = tid; i < ylen; i += nth) s += y[i];
+  const double mean = block_sum(s, red) / ylen;
+  for (int i = tid; i < ylen; i += nth) y[i] = y[i] - mean;
+  if (tid == 0) p.y_len[u] = ylen;
 }
+
+// ------------------------------------------------------------------ K-HVp
+struct HvDetectParams {
+  const double *raw; int n_bands; int l1_stride; const int *l1;
+  double *base; int *base_count; int *nc;   // [n][l1_stride][WB_HV_BASE], [n][l1_stride], [n]
+  int n_utts;
+};
+
+WB_KERNEL_PLAIN harvest_detect_kernel(HvDetectParams p) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)p.n_utts * p.l1_stride) return;
+  const int u = (int)(g / p.l1_stride), i = (int)(g % p.l1_stride);
+  if (i >= p.l1[u]) return;
+  const double *raw = p.raw + (size_t)u * p.n_bands * p.l1_stride + i;
+  double *out = p.base + (size_t)g * WB_HV_BASE;
+  int count = 0, prev = 0, st = 0;
+  double sum = 0.0;
+  // vuv[0] = vuv[nb-1] = 0; a section [st, ed) is closed when vuv falls (harvest.cpp:348-385)
+  for (int j = 1; j < p.n_bands; ++j) {
+    const int v = (j == p.n_bands - 1) ? 0 : (raw[(size_t)j * p.l1_stride] > 0 ? 1 : 0);
+    if (v - prev == 1) { st = j; sum = 0.0; }
+    if (v) sum += raw[(size_t)j * p.l1_stride];
+    if (v - prev == -1) {
+      if (j - st >= 10 && count < WB_HV_BASE) out[count++] = sum / (j - st);
+    }
+    prev = v;
+  }
+  for (int c = count; c < WB_HV_BASE; ++c) out[c] = 0.0;
+  p.base_count[g] = count;
+#ifdef WB_EMU
+  if (count > p.nc[u]) p.nc[u] = count;
+#else
+  if (count > 0) atomicMax(&p.nc[u], count);
+#endif
+}
+
+// ------------------------------------------------------------------ K-HVr
+struct HvRefineParams {
+  const double *y; size_t y_stride; int y_origin; const int *y_len; double afs;
+  const double *base; const int *nc; int l1_stride; const int *l1; int max_cand;
+  double f0_floor, f0_ceil;
+  double *cand; double *score;   // [n][l1_stride][max_cand]
+  const double2 *tw;
+  int nwin_max;
+};
+
+#ifdef WB_EMU
+#define WB_LANE 0
+#define WB_LANES 1
+WB_DEV double warp_sum(double v) { return v; }
+#else
+#define WB_LANE ((int)(threadIdx.x & 31))
+#define WB_LANES 32
+WB_DEV double warp_sum(double v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif
+
+WB_DEV double2 hv_tw(const double2 *__restrict__ tw, int idx) {
+  double2 w = __ldg(&tw[idx & (WB_TW_N / 2 - 1)]);
+  if (idx & (WB_TW_N / 2)) { w.x = -w.x; w.y = -w.y; }
+  return w;
+}
+
+// GetRefinedF0 (harvest.cpp:589-617) for one candidate, executed by one warp.
+// wbuf/dbuf: per-warp shared scratch of nwin doubles each.
+WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, double t, double f,
+                          double f0_floor, double f0_ceil, const double2 *__restrict__ tw, double *wbuf,
+                          double *dbuf, double *out_f0, double *out_score) {
+  const int lane = WB_LANE;
+  const int h = static_cast<int>(1.5 * afs / f + 1.0);
+  const int nwin = 2 * h + 1;
+  int lg = 0;
+  while ((2 << lg) <= nwin) ++lg;
+  const int lg_nfft = lg + 2, nfft = 1 << lg_nfft;
+  const double T = (2.0 * h + 1.0) / afs;
+  // base_index[j] = round((t + base_time[0]) * fs + 0.001) + j   (harvest.cpp:434-441)
+  const int basic = round_half_away((t + (-h + 0) / afs) * afs + 0.001);
+  for (int j = lane; j < nwin; j += WB_LANES) {
+    const double tmp = ((basic + j) - 1.0) / afs - t;
+    wbuf[j] = 0.42 + 0.5 * cos(2.0 * kPi * tmp / T) + 0.08 * cos(4.0 * kPi * tmp / T);
+  }
+#ifndef WB_EMU
+  __syncwarp();
+#endif
+  for (int j = lane; j < nwin; j += WB_LANES) {
+    double dw;
+    if (j == 0) dw = -wbuf[1] / 2.0;
+    else if (j == nwin - 1) dw = wbuf[nwin - 2] / 2.0;
+    else dw = -(wbuf[j + 1] - wbuf[j - 1]) / 2.0;
+    const double s = y[imax(0, imin(y_len - 1, basic + j - 1))];
+    dbuf[j] = s * dw;
+  }
+#ifndef WB_EMU
+  __syncwarp();
+#endif
+  for (int j = lane; j < nwin; j += WB_LANES) wbuf[j] = y[imax(0, imin(y_len - 1, basic + j - 1))] * wbuf[j];
+#ifndef WB_EMU
+  __syncwarp();
+#endif
+  const int H = imin(static_cast<int>(afs / 2.0 / f), 6);
+  const int shift = WB_TW_LOG2 - lg_nfft;
+  double numerator = 0.0, denominator = 0.0, score = 0.0;
+  for (int m = 0; m < H; ++m) {
+    const int bin = round_half_away(f * nfft / afs * (m + 1));
+    double mr = 0.0, mi = 0.0, dr = 0.0, di = 0.0;
+    for (int j = lane; j < nwin; j += WB_LANES) {
+      const double2 w = hv_tw(tw, ((bin * j) & (nfft - 1)) << shift);
+      const double a = wbuf[j], d = dbuf[j];
+      mr = fma(a, w.x, mr); mi = fma(a, w.y, mi);
+      dr = fma(d, w.x, dr); di = fma(d, w.y, di);
+    }
+    mr = warp_sum(mr); mi = warp_sum(mi); dr = warp_sum(dr); di = warp_sum(di);
+    const double num = mr * di - mi * dr;
+    const double pw = mr * mr + mi * mi;
+    const double inst = pw == 0.0 ? 0.0 : static_cast<double>(bin) * afs / nfft + num / pw * afs / 2.0 / kPi;
+    const double amp = sqrt(pw);
+    numerator += amp * inst;
+    denominator += amp * (m + 1.0);
+    score += fabs((inst / (m + 1.0) - f) / f);
+  }
+  double rf = numerator / (denominator + kTiny);
+  double rs = 1.0 / (score / H + kTiny);
+  if (rf < f0_floor || rf > f0_ceil || rs < 2.5) { rf = 0.0; rs = 0.0; }
+  *out_f0 = rf;
+  *out_score = rs;
+#ifndef WB_EMU
+  __syncwarp();
+#endif
+}
+
+// candidate of overlapped slot s at frame k (OverlapF0Candidates, harvest.cpp:417-429)
+WB_DEV double hv_slot_candidate(const double *__restrict__ base, int L1, int nc, int k, int s) {
+  const int grp = s / nc, j = s % nc;
+  int src = k;
+  if (grp >= 1 && grp <= 3) src = k - grp;
+  else if (grp >= 4) src = k + (grp - 3);
+  if (src < 0 || src >= L1 || j >= WB_HV_BASE) return 0.0;
+  return base[(size_t)src * WB_HV_BASE + j];
+}
+
+WB_KERNEL(32 * WB_HV_WARPS, 2) harvest_refine_kernel(HvRefineParams p) {
+  WB_DYN_SMEM(double, smem);
+#ifdef WB_EMU
+  const int warp = 0, nwarps = 1;
+#else
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#endif
+  const int lane = WB_LANE;
+  const int u = blockIdx.y;
+  const int L1 = p.l1[u];
+  const int k = blockIdx.x * nwarps + warp;
+  if (k >= L1) return;
+  const int nc = p.nc[u], n_slots = nc * 7;
+  double *wbuf = smem + (size_t)warp * 2 * p.nwin_max, *dbuf = wbuf + p.nwin_max;
+  const double *y = p.y + (size_t)u * p.y_stride + p.y_origin;
+  const double *base = p.base + (size_t)u * p.l1_stride * WB_HV_BASE;
+  double *cand = p.cand + ((size_t)u * p.l1_stride + k) * p.max_cand;
+  double *score = p.score + ((size_t)u * p.l1_stride + k) * p.max_cand;
+  const double t = k * 1 / 1000.0;  // basic frame period 1 ms (harvest.cpp:1203)
+  const int y_len = p.y_len[u];
+  for (int s = 0; s < n_slots; ++s) {
+    const double f = hv_slot_candidate(base, L1, nc, k, s);
+    double rf = 0.0, rs = 0.0;
+    if (f > 0.0) hv_refine_one(y, y_len, p.afs, t, f, p.f0_floor, p.f0_ceil, p.tw, wbuf, dbuf, &rf, &rs);
+    if (lane == 0) { cand[s] = rf; score[s] = rs; }
+  }
+}
+
+// ------------------------------------------------------------------ RemoveUnreliableCandidates
+struct HvRemoveParams {
+  const double *cand_in; const double *score_in; double *cand; double *score;
+  const int *nc; const int *l1; int l1_stride; int max_cand; int n_utts;
+};
+
+WB_DEV double hv_min_rel_error(double reference, const double *row, int n) {
+  double best = 1.0;  // allowed_range of SelectBestF0 in this call (harvest.cpp:657-661)
+  for (int c = 0; c < n; ++c) {
+    const double e = fabs(reference - row[c]) / reference;
+    if (e > best) continue;
+    best = e;
+  }
+  return best;
+}
+
+WB_KERNEL_PLAIN harvest_remove_kernel(HvRemoveParams p) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)p.n_utts * p.l1_stride) return;
+  const int u = (int)(g / p.l1_stride), i = (int)(g % p.l1_stride);
+  const int L1 = p.l1[u];
+  if (i >= L1) return;
+  const int n = p.nc[u] * 7;
+  const double *row = p.cand_in + (size_t)g * p.max_cand;
+  double *oc = p.cand + (size_t)g * p.max_cand, *os = p.score + (size_t)g * p.max_cand;
+  const double *srow = p.score_in + (size_t)g * p.max_cand;
+  for (int j = 0; j < n; ++j) {
+    double c = row[j], s = srow[j];
+    if (i >= 1 && i < L1 - 1 && c != 0) {
+      const double e1 = hv_min_rel_error(c, row + p.max_cand, n);
+      const double e2 = hv_min_rel_error(c, row - p.max_cand, n);
+      if (dmin(e1, e2) > 0.05) { c = 0.0; s = 0.0; }
+    }
+    oc[j] = c; os[j] = s;
+  }
+}
+
+// ------------------------------------------------------------------ K-HVc
+struct HvContourParams {
+  const double *cand; const double *score; const int *nc; const int *l1; int l1_stride; int max_cand;
+  double *work;      // [n][5][l1_stride]: base, s1, s2, s3, s4
+  int *iwork;        // [n][6][l1_stride]: boundary list, section descriptors (off, lo, hi), order
+  double *mc;        // [n][mc_stride] sparse multi-channel storage
+  size_t mc_stride;
+  int *status;
+};
+
+// GetBoundaryList (harvest.cpp:727-743)
+WB_DEV int hv_boundaries(const double *f0, int n, int *list) {
+  int nb = 0, prev = 0;
+  for (int i = 1; i < n; ++i) {
+    const int v = (i == n - 1) ? 0 : (f0[i] > 0 ? 1 : 0);
+    if (v - prev != 0) { list[nb] = i - nb % 2; ++nb; }
+    prev = v;
+  }
+  return nb;
+}
+
+// SelectBestF0 (harvest.cpp:636-650): last candidate among those with the smallest error <= allowed
+WB_DEV double hv_select_best(double reference, const double *row, int n, double allowed) {
+  double best = 0.0, best_err = allowed;
+  for (int c = 0; c < n; ++c) {
+    const double e = fabs(reference - row[c]) / reference;
+    if (e > best_err) continue;
+    best = row[c];
+    best_err = e;
+  }
+  return best;
+}
+
+struct HvSections {
+  double *mc; int *off, *lo, *hi;
+  WB_DEV_MEMBER double get(int s, int j) const { return (j < lo[s] || j > hi[s]) ? 0.0 : mc[off[s] + (j - lo[s])]; }
+  WB_DEV_MEMBER void set(int s, int j, double v) const { if (j >= lo[s] && j <= hi[s]) mc[off[s] + (j - lo[s])] = v; }
+};
+
+// ExtendF0 (harvest.cpp:791-822)
+WB_DEV int hv_extend(const HvSections &S, int s, int origin, int last_point, int shift, const double *cand,
+                     int max_cand, int n_cand, double allowed) {
+  const int threshold = 4;
+  double tmp_f0 = S.get(s, origin);
+  int shifted_origin = origin;
+  const int distance = last_point > origin ? last_point - origin : origin - last_point;
+  int count = 0;
+  for (int i = 0; i <= distance; ++i) {
+    const int target = origin + shift * i + shift;
+    const double v = hv_select_best(tmp_f0, cand + (size_t)target * max_cand, n_cand, allowed);
+    S.set(s, target, v);
+    if (v == 0.0) {
+      ++count;
+    } else {
+      tmp_f0 = v;
+      count = 0;
+      shifted_origin = target;
+    }
+    if (count == threshold) break;
+  }
+  return shifted_origin;
+}
+
+WB_DEV double hv_search_score(double f0, const double *crow, const double *srow, int n) {
+  double score = 0.0;
+  for (int i = 0; i < n; ++i)
+    if (f0 == crow[i] && score < srow[i]) score = srow[i];
+  return score;
+}
+
+WB_KERNEL(128, 4) harvest_contour_kernel(HvContourParams p) {
+  const int tid = WB_TID, nth = WB_NTH, u = blockIdx.x;
+  const int L = p.l1[u], nc7 = p.nc[u] * 7, mcand = p.max_cand;
+  const double *cand = p.cand + (size_t)u * p.l1_stride * mcand;
+  const double *score = p.score + (size_t)u * p.l1_stride * mcand;
+  double *fb = p.work + (size_t)u * 5 * p.l1_stride, *s1 = fb + p.l1_stride, *s2 = s1 + p.l1_stride;
+  double *s3 = s2 + p.l1_stride, *s4 = s3 + p.l1_stride;
+  int *bl = p.iwork + (size_t)u * 6 * p.l1_stride;
+  HvSections S;
+  S.mc = p.mc + (size_t)u * p.mc_stride;
+  S.off = bl + p.l1_stride; S.lo = S.off + p.l1_stride; S.hi = S.lo + p.l1_stride;
+  int *order = S.hi + p.l1_stride;
+
+  // SearchF0Base (:693-705)
+  for (int i = tid; i < L; i += nth) {
+    double best = 0.0, bs = 0.0;
+    const double *c = cand + (size_t)i * mcand, *s = score + (size_t)i * mcand;
+    for (int j = 0; j < nc7; ++j)
+      if (s[j] > bs) { best = c[j]; bs = s[j]; }
+    fb[i] = best;
+  }
+  WB_SYNC();
+  // FixStep1 (:710-722), allowed_range 0.008
+  for (int i = tid; i < L; i += nth) {
+    double v = 0.0;
+    if (i >= 2 && fb[i] != 0.0) {
+      const double reference = fb[i - 1] * 2 - fb[i - 2];
+      v = (fabs((fb[i] - reference) / reference) > 0.008 && fabs((fb[i] - fb[i - 1])) / fb[i - 1] > 0.008) ? 0.0 : fb[i];
+    }
+    s1[i] = v;
+  }
+  WB_SYNC();
+  if (tid != 0) return;
+
+  // FixStep2 (:748-762): voiced sections shorter than 6 frames are removed
+  for (int i = 0; i < L; ++i) s2[i] = s1[i];
+  int nb = hv_boundaries(s1, L, bl);
+  for (int i = 0; i < nb / 2; ++i) {
+    if (bl[i * 2 + 1] - bl[i * 2] >= 6) continue;
+    for (int j = bl[i * 2]; j <= bl[i * 2 + 1]; ++j) s2[j] = 0.0;
+  }
+
+  // FixStep3 (:1000-1025 region): extend sections, select, merge
+  for (int i = 0; i < L; ++i) s3[i] = s2[i];
+  nb = hv_boundaries(s2, L, bl);
+  const int nsec = nb / 2;
+  {
+    size_t used = 0;
+    bool overflow = false;
+    for (int s = 0; s < nsec; ++s) {
+      const int lo = imax(0, bl[2 * s] - 104), hi = imin(L - 1, bl[2 * s + 1] + 104);
+      if (used + (size_t)(hi - lo + 1) > p.mc_stride) { overflow = true; break; }
+      S.off[s] = (int)used; S.lo[s] = lo; S.hi[s] = hi;
+      for (int j = lo; j <= hi; ++j) S.mc[used + (j - lo)] = (j >= bl[2 * s] && j <= bl[2 * s + 1]) ? s2[j] : 0.0;
+      used += (size_t)(hi - lo + 1);
+    }
+    if (overflow) { atomicOr_status(p.status, 4); return; }
+  }
+  // Extend (:858-874)
+  for (int s = 0; s < nsec; ++s) {
+    const int ed = bl[2 * s + 1], st = bl[2 * s];
+    bl[2 * s + 1] = hv_extend(S, s, ed, imin(L - 2, ed + 100), 1, cand, mcand, nc7, 0.18);
+    bl[2 * s] = hv_extend(S, s, st, imax(1, st - 100), -1, cand, mcand, nc7, 0.18);
+  }
+  // ExtendSub (:839-856): note mean_f0 is NOT reset between sections in the reference
+  int nch = 0;
+  {
+    double mean_f0 = 0.0;
+    for (int s = 0; s < nsec; ++s) {
+      const int st = bl[2 * s], ed = bl[2 * s + 1];
+      for (int j = st; j < ed; ++j) mean_f0 += S.get(s, j);
+      mean_f0 /= ed - st;
+      if (2200.0 / mean_f0 < ed - st) {
+        // Swap(count, s): contour and boundary pair
+        int t;
+        t = S.off[nch]; S.off[nch] = S.off[s]; S.off[s] = t;
+        t = S.lo[nch]; S.lo[nch] = S.lo[s]; S.lo[s] = t;
+        t = S.hi[nch]; S.hi[nch] = S.hi[s]; S.hi[s] = t;
+        t = bl[2 * nch]; bl[2 * nch] = bl[2 * s]; bl[2 * s] = t;
+        t = bl[2 * nch + 1]; bl[2 * nch + 1] = bl[2 * s + 1]; bl[2 * s + 1] = t;
+        ++nch;
+      }
+    }
+  }
+  if (nch != 0) {
+    // MergeF0 (:941-973)
+    for (int i = 0; i < nch; ++i) order[i] = i;
+    for (int i = 1; i < nch; ++i)
+      for (int j = i - 1; j >= 0; --j) {
+        if (bl[order[j] * 2] > bl[order[i] * 2]) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+        else break;
+      }
+    // NB: the reference's inner loop compares order[j] with order[i] while i is fixed and does
+    // not follow the moving element; reproduced as written (harvest.cpp:881-893).
+    for (int i = 0; i < L; ++i) s3[i] = S.get(0, i);
+    for (int i = 1; i < nch; ++i) {
+      const int o = order[i];
+      if (bl[o * 2] - bl[1] > 0) {
+        for (int j = bl[o * 2]; j <= bl[o * 2 + 1]; ++j) s3[j] = S.get(o, j);
+        bl[0] = bl[o * 2];
+        bl[1] = bl[o * 2 + 1];
+      } else {
+        // MergeF0Sub (:912-935)
+        const int st1 = bl[0], ed1 = bl[1], st2 = bl[o * 2], ed2 = bl[o * 2 + 1];
+        if (st1 <= st2 && ed1 >= ed2) {
+          bl[1] = ed1;
+        } else {
+          double score1 = 0.0, score2 = 0.0;
+          for (int k = st2; k <= ed1; ++k) {
+            score1 += hv_search_score(s3[k], cand + (size_t)k * mcand, score + (size_t)k * mcand, nc7);
+            score2 += hv_search_score(S.get(o, k), cand + (size_t)k * mcand, score + (size_t)k * mcand, nc7);
+          }
+          if (score1 > score2) { for (int k = ed1; k <= ed2; ++k) s3[k] = S.get(o, k); }
+          else { for (int k = st2; k <= ed2; ++k) s3[k] = S.get(o, k); }
+          bl[1] = ed2;
+        }
+      }
+    }
+  }
+  // FixStep4 (:1000-1022): bridge gaps shorter than 9 frames
+  for (int i = 0; i < L; ++i) s4[i] = s3[i];
+  nb = hv_boundaries(s3, L, bl);
+  for (int i = 0; i < nb / 2 - 1; ++i) {
+    const int distance = bl[(i + 1) * 2] - bl[i * 2 + 1] - 1;
+    if (distance >= 9) continue;
+    const double tmp0 = s3[bl[i * 2 + 1]] + 1;
+    const double tmp1 = s3[bl[(i + 1) * 2]] - 1;
+    const double coefficient = (tmp1 - tmp0) / (distance + 1.0);
+    int count = 1;
+    for (int j = bl[i * 2 + 1] + 1; j <= bl[(i + 1) * 2] - 1; ++j) s4[j] = tmp0 + coefficient * count++;
+  }
+}
+
+// ------------------------------------------------------------------ smoothing + subsampling
+struct HvSmoothParams {
+  const double *work; int l1_stride; const int *l1;  // s4 = work[u][4]
+  double *padded;      // [n][pad_stride]: f0 contour padded by 300 zeros on both sides
+  double *tmp;         // [n][sec_slots][pad_stride] per-section scratch (two buffers per slot)
+  int *blist;          // [n][pad_stride]
+  double *basic;       // [n][l1_stride] smoothed 1 ms contour
+  size_t pad_stride; int sec_slots;
+  const int *f_len; int f_stride; double frame_period;
+  double *time_axis; double *f0;
+};
+
+// FilteringF0 (harvest.cpp:1049-1074) for one section; x is synthesised on the fly:
+// x[i] = f0[st] for i < st, f0[i] inside, f0[ed] beyond.
+WB_DEV void hv_filter_section(const double *f0c, int len, int st, int ed, double *tmp_x, double *yout) {
+  const double b0 = 0.0078202080334971724, b1 = 0.015640416066994345;
+  const double a0 = 1.7347257688092754, a1 = -0.76600660094326412;
+  double w0 = 0.0, w1 = 0.0;
+  for (int i = 0; i < len; ++i) {
+    const double xi = f0c[i < st ? st : (i > ed ? ed : i)];
+    const double wt = xi + a0 * w0 + a1 * w1;
+    tmp_x[len - i - 1] = b0 * wt + b1 * w0 + b0 * w1;
+    w1 = w0; w0 = wt;
+  }
+  w0 = w1 = 0.0;
+  for (int i = 0; i < len; ++i) {
+    const double wt = tmp_x[i] + a0 * w0 + a1 * w1;
+    const int o = len - i - 1;
+    const double v = b0 * wt + b1 * w0 + b0 * w1;
+    if (o >= st && o <= ed) yout[o] = v;
+    w1 = w0; w0 = wt;
+  }
+}
+
+WB_KERNEL(128, 4) harvest_smooth_kernel(HvSmoothParams p) {
+  const int tid = WB_TID, nth = WB_NTH, u = blockIdx.x;
+  WB_SHARED int nb_shared;
+  const int L = p.l1[u], lag = 300, len = L + 2 * lag;
+  const double *s4 = p.work + ((size_t)u * 5 + 4) * p.l1_stride;
+  double *pad = p.padded + (size_t)u * p.pad_stride;
+  double *basic = p.basic + (size_t)u * p.l1_stride;
+  int *bl = p.blist + (size_t)u * p.pad_stride;
+  for (int i = tid; i < len; i += nth) pad[i] = (i >= lag && i < lag + L) ? s4[i - lag] : 0.0;
+  for (int i = tid; i < L; i += nth) basic[i] = 0.0;  // f0[i] = 0 (harvest.cpp:1176-1179)
+  WB_SYNC();
+  if (tid == 0) nb_shared = hv_boundaries(pad, len, bl);
+  WB_SYNC();
+  const int nsec = nb_shared / 2;
+  // sections are independent: thread q filters sections q, q + slots, ... in its own scratch
+  const int slots = imin(p.sec_slots, nth);
+  if (tid < slots) {
+    double *tmp_x = p.tmp + ((size_t)u * p.sec_slots + tid) * 2 * p.pad_stride;
+    double *yout = tmp_x + p.pad_stride;
+    for (int s = tid; s < nsec; s += slots) {
+      const int st = bl[2 * s], ed = bl[2 * s + 1];
+      hv_filter_section(pad, len, st, ed, tmp_x, yout);
+      for (int j = st; j <= ed; ++j) basic[j - lag] = yout[j];
+    }
+  }
+  WB_SYNC();
+  // subsample to the requested frame period (harvest.cpp:1246-1251)
+  const int nf = p.f_len[u];
+  double *f0 = p.f0 + (size_t)u * p.f_stride, *ta = p.time_axis + (size_t)u * p.f_stride;
+  for (int i = tid; i < nf; i += nth) {
+    const double t = i * p.frame_period / 1000.0;
+    ta[i] = t;
+    f0[i] = basic[imin(L - 1, round_half_away(t * 1000.0))];
+  }
+}
+
+int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time_axis_out, double *f0_out) {
+  if (b.n <= 0) return 0;
+  const int fs = b.fs;
+  const int ratio = imax(imin(round_half_away(fs / 8000.0), 12), 1);  // harvest.cpp:1226, :1158
+  const double afs = static_cast<double>(fs) / ratio;
+  const double adj_floor = opt.f0_floor * 0.9, adj_ceil = opt.f0_ceil * 1.1;
+  const int nb = 1 + static_cast<int>(log(adj_ceil / adj_floor) / kLog2 * 40);
+  if (nb < 3 || nb > 1024) { ctx->last_error = "Harvest: bad channel count"; return 3; }
+  const int max_cand = round_half_away(nb / 10.0) * 7;
+  if (max_cand / 7 > WB_HV_BASE) { ctx->last_error = "Harvest: f0 range too wide (more than 325 channels)"; return 3; }
+  std::vector<double> boundary(nb);
+  for (int i = 0; i < nb; ++i) boundary[i] = adj_floor * pow(2.0, (i + 1) / 40.0);
+  // band-pass filters: Nuttall(2 Lh + 1) * cos (GetFilteredSignal, harvest.cpp:99-110)
+  std::vector<int> tap_off(nb), ntaps(nb), shift(nb);
+  std::vector<double> taps;
+  int max_taps = 0;
+  for (int i = 0; i < nb; ++i) {
+    const int lh = round_half_away(afs / boundary[i] * 2.0);
+    const int len = lh * 2 + 1;
+    tap_off[i] = (int)taps.size(); ntaps[i] = len; shift[i] = lh + 1;
+    std::vector<double> w(len);
+    for (int j = 0; j < len; ++j) {
+      const double tmp = j / (len - 1.0);
+      w[j] = 0.355768 - 0.487396 * cos(2.0 * kPi * tmp) + 0.144232 * cos(4.0 * kPi * tmp) -
+             0.012604 * cos(6.0 * kPi * tmp);
+    }
+    for (int j = -lh; j <= lh; ++j) w[j + lh] *= cos(2 * kPi * boundary[i] * j / afs);
+    for (int j = len - 1; j >= 0; --j) taps.push_back(w[j]);
+    for (int j = 0; j < 8; ++j) taps.push_back(0.0);
+    if (len > max_taps) max_taps = len;
+  }
+  const size_t smem_sweep = sweep_smem_bytes(max_taps);
+  const int h_max = static_cast<int>(1.5 * afs / opt.f0_floor + 1.0);
+  const int nwin_max = 2 * h_max + 1 + 2;
+  int lgw = 0;
+  while ((2 << lgw) <= nwin_max) ++lgw;
+  const size_t smem_refine = (size_t)WB_HV_WARPS * 2 * nwin_max * 8;
+  if (smem_sweep > 200 * 1024 || smem_refine > 200 * 1024 || (1 << (lgw + 2)) > WB_TW_N) {
+    ctx->last_error = "Harvest: f0_floor too low for the on-chip filters";
+    return 3;
+  }
+  // sizes on the 1 ms grid (b.l1_host: per-utterance frame counts at 1 ms, from the ABI layer)
+  const int max_ylen = static_cast<int>(ceil(static_cast<double>(b.max_x_len) / ratio));
+  const int l1_stride = static_cast<int>(1000.0 * b.max_x_len / fs / 1.0) + 1;
+  const int T = WB_SWEEP_T;
+  const int padl = max_taps + 16;
+  const size_t y_stride = (size_t)padl + max_ylen + 3 * T + max_taps + 64;
+  const size_t edge_cap = (size_t)max_ylen / 2 + 2;
+  const int lag = static_cast<int>(ceil(140.0 / ratio) * ratio);
+  const size_t tmp_stride = ratio != 1 ? (size_t)b.max_x_len + 2 * lag + 32 : 0;
+  const size_t pad_stride = (size_t)l1_stride + 600 + 8;
+  const size_t mc_stride = (size_t)28 * l1_stride + 1024;
+  const int sec_slots = 16;
+  const size_t per_utt = y_stride * 8 + (size_t)nb * 4 * edge_cap * 8 + (size_t)nb * l1_stride * 8 +
+                         (size_t)l1_stride * (WB_HV_BASE * 8 + 4) + (size_t)l1_stride * max_cand * 8 * 4 +
+                         (size_t)l1_stride * (5 * 8 + 6 * 4 + 8) + mc_stride * 8 + pad_stride * (8 + 4 + sec_slots * 16) +
+                         tmp_stride * 16 + 1024;
+  int chunk = (int)imin(imin(b.n, 65535), (int)dmax(1.0, (double)ctx->scratch_budget / (double)per_utt));
+#ifndef WB_EMU
+  cudaFuncSetAttribute(harvest_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_refine);
+#endif
+  for (int u0 = 0; u0 < b.n; u0 += chunk) {
+    const int n = imin(chunk, b.n - u0);
+    ArenaPlan plan;
+    const size_t o_y = plan.add((size_t)n * y_stride * 8), o_ylen = plan.add((size_t)n * 4);
+    const size_t o_l1 = plan.add((size_t)n * 4), o_nc = plan.add((size_t)n * 4);
+    const size_t o_edges = plan.add((size_t)n * nb * 4 * edge_cap * 8);
+    const size_t o_raw = plan.add((size_t)n * nb * l1_stride * 8);
+    const size_t o_base = plan.add((size_t)n * l1_stride * WB_HV_BASE * 8), o_bcnt = plan.add((size_t)n * l1_stride * 4);
+    const size_t o_c1 = plan.add((size_t)n * l1_stride * max_cand * 8), o_s1 = plan.add((size_t)n * l1_stride * max_cand * 8);
+    const size_t o_c2 = plan.add((size_t)n * l1_stride * max_cand * 8), o_s2 = plan.add((size_t)n * l1_stride * max_cand * 8);
+    const size_t o_work = plan.add((size_t)n * 5 * l1_stride * 8), o_iwork = plan.add((size_t)n * 6 * l1_stride * 4);
+    const size_t o_mc = plan.add((size_t)n * mc_stride * 8);
+    const size_t o_pad = plan.add((size_t)n * pad_stride * 8), o_bl = plan.add((size_t)n * pad_stride * 4);
+    const size_t o_stmp = plan.add((size_t)n * sec_slots * 2 * pad_stride * 8);
+    const size_t o_basic = plan.add((size_t)n * l1_stride * 8);
+    const size_t o_tmp = plan.add((size_t)n * 2 * tmp_stride * 8);
+    const size_t o_taps = plan.add(taps.size() * 8);
+    const size_t o_toff = plan.add(nb * 4), o_nt = plan.add(nb * 4), o_sh = plan.add(nb * 4), o_bd = plan.add(nb * 8);
+    unsigned char *blk = arena_block(ctx, plan.total);
+    if (!blk) return 2;
+    double *y = (double *)(blk + o_y);
+    int *ylen = (int *)(blk + o_ylen), *l1 = (int *)(blk + o_l1), *nc = (int *)(blk + o_nc);
+    int rc = dev_memset(ctx, y, 0, (size_t)n * y_stride * 8);
+    if (!rc) rc = dev_memset(ctx, nc, 0, (size_t)n * 4);
+    if (!rc) rc = dev_memcpy_h2d(ctx, l1, b.l1_host + u0, (size_t)n * 4);
+    if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_taps, taps.data(), taps.size() * 8);
+    if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_toff, tap_off.data(), nb * 4);
+    if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_nt, ntaps.data(), nb * 4);
+    if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_sh, shift.data(), nb * 4);
+    if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_bd, boundary.data(), nb * 8);
+    if (rc) return rc;
+
+    HvPrepParams pp;
+    pp.x = b.x + (size_t)u0 * b.x_stride; pp.x_len = b.x_len + u0; pp.x_stride = b.x_stride; pp.ratio = ratio;
+    pp.y = y; pp.y_stride = y_stride; pp.y_origin = padl; pp.y_len = ylen;
+    pp.tmp = ratio != 1 ? (double *)(blk + o_tmp) : nullptr; pp.tmp_stride = tmp_stride;
+    WB_LAUNCH_COOP(harvest_prep_kernel, dim3((unsigned)n), 256, 0, ctx->stream, pp);
+
+    SweepParams sp;
+    sp.sig = y; sp.sig_stride = y_stride; sp.sig_origin = padl; sp.y_len = ylen; sp.n_bands = nb;
+    sp.taps_rev = (const double *)(blk + o_taps); sp.tap_off = (const int *)(blk + o_toff);
+    sp.ntaps = (const int *)(blk + o_nt); sp.shift = (const int *)(blk + o_sh);
+    sp.boundary = (const double *)(blk + o_bd); sp.afs = afs;
+    sp.edges = (double *)(blk + o_edges); sp.edge_cap = edge_cap;
+    sp.n_frames = l1; sp.frame_stride = l1_stride; sp.frame_period = 1.0;
+    sp.mode = 1; sp.f0_floor = opt.f0_floor; sp.f0_ceil = opt.f0_ceil;
+    sp.cand = (double *)(blk + o_raw); sp.score = nullptr;
+    sp.max_taps = max_taps; sp.status = ctx->status_dev;
+    launch_band_sweep(ctx, sp, (unsigned)n);
+
+    const long long slots = (long long)n * l1_stride;
+    HvDetectParams dp;
+    dp.raw = sp.cand; dp.n_bands = nb; dp.l1_stride = l1_stride; dp.l1 = l1;
+    dp.base = (double *)(blk + o_base); dp.base_count = (int *)(blk + o_bcnt); dp.nc = nc; dp.n_utts = n;
+    WB_LAUNCH_FLAT(harvest_detect_kernel, dim3((unsigned)((slots + 127) / 128)), 128, 0, ctx->stream, dp);
+
+    HvRefineParams rp;
+    rp.y = y; rp.y_stride = y_stride; rp.y_origin = padl; rp.y_len = ylen; rp.afs = afs;
+    rp.base = dp.base; rp.nc = nc; rp.l1_stride = l1_stride; rp.l1 = l1; rp.max_cand = max_cand;
+    rp.f0_floor = opt.f0_floor; rp.f0_ceil = opt.f0_ceil;
+    rp.cand = (double *)(blk + o_c1); rp.score = (double *)(blk + o_s1); rp.tw = ctx->twiddle; rp.nwin_max = nwin_max;
+#ifdef WB_EMU
+    const unsigned refine_blocks = (unsigned)l1_stride;
+#else
+    const unsigned refine_blocks = (unsigned)((l1_stride + WB_HV_WARPS - 1) / WB_HV_WARPS);
+#endif
+    WB_LAUNCH_COOP(harvest_refine_kernel, dim3(refine_blocks, (unsigned)n), 32 * WB_HV_WARPS, smem_refine, ctx->stream, rp);
+
+    HvRemoveParams mp;
+    mp.cand_in = rp.cand; mp.score_in = rp.score; mp.cand = (double *)(blk + o_c2); mp.score = (double *)(blk + o_s2);
+    mp.nc = nc; mp.l1 = l1; mp.l1_stride = l1_stride; mp.max_cand = max_cand; mp.n_utts = n;
+    WB_LAUNCH_FLAT(harvest_remove_kernel, dim3((unsigned)((slots + 127) / 128)), 128, 0, ctx->stream, mp);
+
+    HvContourParams cp;
+    cp.cand = mp.cand; cp.score = mp.score; cp.nc = nc; cp.l1 = l1; cp.l1_stride = l1_stride; cp.max_cand = max_cand;
+    cp.work = (double *)(blk + o_work); cp.iwork = (int *)(blk + o_iwork); cp.mc = (double *)(blk + o_mc);
+    cp.mc_stride = mc_stride; cp.status = ctx->status_dev;
+    WB_LAUNCH_COOP(harvest_contour_kernel, dim3((unsigned)n), 128, 0, ctx->stream, cp);
+
+    HvSmoothParams hp;
+    hp.work = cp.work; hp.l1_stride = l1_stride; hp.l1 = l1; hp.padded = (double *)(blk + o_pad);
+    hp.tmp = (double *)(blk + o_stmp); hp.blist = (int *)(blk + o_bl); hp.basic = (double *)(blk + o_basic);
+    hp.pad_stride = pad_stride; hp.sec_slots = sec_slots; hp.f_len = b.f_len + u0; hp.f_stride = b.f_stride;
+    hp.frame_period = opt.frame_period;
+    hp.time_axis = time_axis_out + (size_t)u0 * b.f_stride; hp.f0 = f0_out + (size_t)u0 * b.f_stride;
+    WB_LAUNCH_COOP(harvest_smooth_kernel, dim3((unsigned)n), 128, 0, ctx->stream, hp);
+    rc = dev_check(ctx, "harvest");
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace wb

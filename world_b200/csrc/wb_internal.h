@@ -63,6 +63,7 @@ struct Batch {
   const int *f_len;         // [n] device
   int f_stride;
   int max_x_len, max_f_len;  // host-known maxima
+  const int *l1_host = nullptr;  // [n] host: frames on the 1 ms grid (Harvest only)
 };
 
 // stage drivers (each: enqueue on ctx->stream, return 0 / error code)

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #define WB_HD __host__ __device__
 #define WB_DEV __device__ __forceinline__
+#define WB_DEV_MEMBER __device__ __forceinline__
 #define WB_KERNEL(bounds_threads, bounds_blocks) \
   __global__ void __launch_bounds__(bounds_threads, bounds_blocks)
 #define WB_KERNEL_PLAIN __global__ void
@@ -54,6 +55,7 @@ extern unsigned char wb_emu_smem[];
 #define WB_EMU_SMEM_BYTES (256 * 1024)
 #define WB_HD
 #define WB_DEV static inline
+#define WB_DEV_MEMBER inline
 #define WB_KERNEL(bounds_threads, bounds_blocks) void
 #define WB_KERNEL_PLAIN void
 #define WB_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(wb_emu_smem)
