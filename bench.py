@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- the WORLD analysis hot path on N B200s (driver contract, see DESIGN.md "Measurement").
+
+One "step" = one pass of {Harvest -> CheapTrick -> D4C} over one batch of synthetic 16 kHz speech
+(default: BASELINE.json configs[2], 1024 utterances x 10 s per GPU; weak scaling over ranks with
+one NCCL all-gather per output array to reassemble the batch, north_star).  Prints ONE JSON line.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--f0 harvest|dio] [--utts U] [--seconds S] [--fs FS]
+
+value      frames/s with inputs and outputs resident in HBM (CUDA events, max over ranks)
+e2e        the same through world_b200_analyze_host(): pinned HOST buffers in, HOST buffers out
+roofline   dominant kernel (largest share of the step, timed live with CUDA events inside the
+           library): algorithmic HBM bytes / kernel time vs the measured copy peak
+cpu_baseline   the compiled reference (oracle/_ref) on this box's host, one thread, bounded sample
+--impl reference   the reference's own CPU implementation on all host cores (rank 0 only)
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "analysis frames/sec (Harvest+CheapTrick+D4C)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--f0", default="harvest", choices=["harvest", "dio"])
+    ap.add_argument("--utts", type=int, default=1024, help="utterances per GPU")
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--fs", type=int, default=16000)
+    ap.add_argument("--cpu-utts", type=int, default=8, help="utterances of the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gather", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    chain = "Harvest+CheapTrick+D4C" if a.f0 == "harvest" else "Dio+StoneMask+CheapTrick+D4C"
+    return f"{a.utts}x{a.seconds:g}s synthetic {a.fs // 1000} kHz batch per GPU, {chain}"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def frames_of(fs, n_samples, frame_period=5.0):
+    return int(1000.0 * n_samples / fs / frame_period) + 1
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes_per_step(kernel, a, n_utts):
+    """Compulsory HBM bytes one step moves through `kernel` (DESIGN.md "Kernels")."""
+    fs = a.fs
+    n = int(a.fs * a.seconds)
+    L = frames_of(fs, n)
+    L1 = frames_of(fs, n, 1.0)
+    fft = 2 ** (1 + int(math.log(3.0 * fs / 71.0 + 1) / math.log(2.0)))
+    bins = fft // 2 + 1
+    hop = 8 * (fs * 5 // 1000)
+    ratio = max(1, int(fs / 8000.0 + 0.5))
+    ylen = math.ceil(n / ratio)
+    table = {
+        # waveform hop once + one output row per frame (4744 B/frame @16 kHz)
+        "ct_frame_kernel": n_utts * L * (hop + 8 * bins),
+        "d4c_body_kernel": n_utts * L * (hop + 8 * bins),
+        "d4c_lovetrain_kernel": n_utts * L * (hop + 16),
+        # decimated waveform once + the candidate map it produces (152 channels x 1 ms frames)
+        "band_sweep_kernel": n_utts * (ylen * 8 + (152 if a.f0 == "harvest" else 7) * (L1 if a.f0 == "harvest" else L) * 8),
+        # candidate map in, refined candidates + scores out (upper bound 105 slots)
+        "harvest_refine_kernel": n_utts * (ylen * 8 + L1 * 21 * 16),
+        "harvest_detect_kernel": n_utts * 152 * L1 * 8,
+        "harvest_remove_kernel": n_utts * L1 * 21 * 32,
+        "harvest_contour_kernel": n_utts * L1 * 21 * 16,
+        "harvest_smooth_kernel": n_utts * L1 * 16,
+        "harvest_prep_kernel": n_utts * n * 8 * 2,
+        "rng_fill_kernel": 0,
+        "stonemask_kernel": n_utts * L * (hop + 16),
+        "fir_plain_kernel": n_utts * n * 16,
+    }
+    return table.get(kernel)
+
+
+def run_reference(a, rank, world):
+    """--impl reference: the unmodified reference (oracle/_ref) on all host cores, rank 0 only."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from refworld import RefWorld, REF_LIB
+    from synth import synth_batch
+    cores = os.cpu_count() or 1
+    ref = RefWorld(REF_LIB)
+    n = int(a.fs * a.seconds)
+    per_step = cores  # one utterance per core per step: a bounded sample of the named batch
+    x = synth_batch(range(1, per_step + 1), a.fs, n, device="cpu").numpy()
+    L = frames_of(a.fs, n)
+
+    def one(u):
+        xu = np.ascontiguousarray(x[u])
+        if a.f0 == "harvest":
+            t, f0 = ref.harvest(xu, a.fs)
+        else:
+            t, f0 = ref.dio(xu, a.fs)
+            f0 = ref.stonemask(xu, a.fs, t, f0)
+        opt = ref.cheaptrick_option(a.fs)
+        ref.cheaptrick(xu, a.fs, t, f0, opt)
+        ref.d4c(xu, a.fs, t, f0, opt.fft_size)
+        return len(f0)
+
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        for _ in range(max(1, min(a.warmup, 1))):
+            list(ex.map(one, range(per_step)))
+        t0 = time.perf_counter()
+        frames = 0
+        for _ in range(a.steps):
+            frames += sum(ex.map(one, range(per_step)))
+        dt = time.perf_counter() - t0
+    value = frames / dt
+    sample = f"{per_step} utterances x {a.seconds:g} s per step ({cores} threads, one utterance each), {a.steps} steps"
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": a.gpus,
+           "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(a), "fs": a.fs, "frame_period_ms": 5.0},
+           "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
+           "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from world_b200.api import World, F0_HARVEST, F0_DIO_STONEMASK
+    from synth import synth_batch
+
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = World(device=local)
+    fs, n = a.fs, int(a.fs * a.seconds)
+    U = a.utts
+    L = frames_of(fs, n)
+    # synthetic batch of this rank (seeds distinct across ranks), built on the device
+    x = torch.empty((U, n), dtype=torch.float64, device=dev)
+    for u0 in range(0, U, 64):
+        u1 = min(U, u0 + 64)
+        x[u0:u1] = synth_batch(range(rank * U + u0 + 1, rank * U + u1 + 1), fs, n, device=dev)
+    opt = w.cheaptrick_option(fs)
+    bins = opt.fft_size // 2 + 1
+    # outputs: with N > 1 each rank writes its shard straight into the gathered arrays
+    free, total = torch.cuda.mem_get_info(dev)
+    gather = world > 1 and not a.no_gather
+    need_full = 2 * world * U * L * bins * 8
+    gather_full = gather and need_full + (24 << 30) < free
+    G = world if gather_full else 1
+    sp_all = torch.empty((G * U, L, bins), dtype=torch.float64, device=dev)
+    ap_all = torch.empty((G * U, L, bins), dtype=torch.float64, device=dev)
+    off = rank * U if gather_full else 0
+    sp, ap = sp_all[off:off + U], ap_all[off:off + U]
+    f0_all = torch.empty((world * U, L), dtype=torch.float64, device=dev)
+    t_all = torch.empty((world * U, L), dtype=torch.float64, device=dev)
+    if world > 1 and free < (60 << 30):
+        w.set_scratch_budget(6 << 30)
+
+    def step():
+        if a.f0 == "harvest":
+            t, f0, fl = w.harvest(x, fs)
+        else:
+            t, f0, fl = w.dio(x, fs)
+            f0 = w.stonemask(x, fs, t, f0)
+        w.cheaptrick(x, fs, t, f0, opt, out=sp)
+        w.d4c(x, fs, t, f0, opt.fft_size, out=ap)
+        if gather:
+            dist.all_gather_into_tensor(f0_all, f0)
+            dist.all_gather_into_tensor(t_all, t)
+            if gather_full:
+                dist.all_gather_into_tensor(sp_all, sp)
+                dist.all_gather_into_tensor(ap_all, ap)
+        return f0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    w.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    w.profile(True)
+    launches0 = w.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        f0_last = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = w.launch_count() - launches0
+    w.profile(False)
+    prof = w.profile_report()
+    clocks = sampler.stop() if rank == 0 else None
+    w.synchronize()
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    frames_step = world * U * L
+    value = frames_step * a.steps / (ms / 1e3)
+
+    # ---- end to end through the host-pointer ABI (pinned host buffers, copies inside the timed region)
+    e2e = None
+    if not a.no_e2e:
+        import psutil
+        need = U * n * 8 + 2 * U * L * bins * 8 + 2 * U * L * 8
+        avail = psutil.virtual_memory().available
+        Ue = U
+        while Ue > 16 and need * Ue / U * 1.3 > avail:
+            Ue //= 2
+        xh = torch.empty((Ue, n), dtype=torch.float64, pin_memory=True)
+        xh.copy_(x[:Ue])
+        th = torch.empty((Ue, L), dtype=torch.float64, pin_memory=True)
+        fh = torch.empty((Ue, L), dtype=torch.float64, pin_memory=True)
+        sph = torch.empty((Ue, L, bins), dtype=torch.float64, pin_memory=True)
+        aph = torch.empty((Ue, L, bins), dtype=torch.float64, pin_memory=True)
+        # free the device-resident outputs of the first phase: analyze_host brings its own buffers
+        del sp, ap, sp_all, ap_all
+        torch.cuda.empty_cache()
+        ao = w.analysis_option(fs, F0_HARVEST if a.f0 == "harvest" else F0_DIO_STONEMASK)
+        w.lib.world_b200_set_stream(w._h, None)
+
+        def e2e_step():
+            w.analyze_host(xh, fs, ao, time_axis=th, f0=fh, spectrogram=sph, aperiodicity=aph, f0_stride=L)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        ke = max(1, min(a.steps, 3))
+        for _ in range(ke):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+            dt = float(tdt.item())
+        e2e = {"value": world * Ue * L * ke / dt, "unit": "frames/s",
+               "h2d_bytes_per_step": int(Ue * n * 8), "d2h_bytes_per_step": int(2 * Ue * L * bins * 8 + 2 * Ue * L * 8),
+               "utts_per_gpu": Ue, "steps": ke,
+               "note": "world_b200_analyze_host: pinned host buffers in/out, upload/compute/download pipelined over chunks"}
+        # the e2e result must be the same numbers the device-resident path produced
+        same = bool(torch.equal(fh, f0_last[:Ue].cpu()))
+        e2e["matches_device_path"] = same
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (timed live above)
+    peak, peak_src = measured_peak_hbm()
+    kernels = {k: {"ms_per_step": v["ms"] / a.steps, "launches_per_step": v["launches"] / a.steps} for k, v in prof.items()}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+    roof = None
+    if dom:
+        nbytes = algorithmic_bytes_per_step(dom, a, U)
+        kms = kernels[dom]["ms_per_step"]
+        achieved = (nbytes / 1e9) / (kms / 1e3) if nbytes else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom)
+        roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": nbytes / max(1.0, kernels[dom]["launches_per_step"]) if nbytes else None,
+                "kernel_ms_per_step": kms, "share_of_step": kms / (ms / a.steps),
+                "note": "FP64-ALU/shared-memory bound path (SURVEY.md 8d): HBM fraction is reported as BASELINE.json asks"}
+
+    # ---- CPU baseline: the compiled reference, one thread, bounded sample of the same batch
+    cpu = None
+    if not a.no_cpu and world == 1:
+        from refworld import RefWorld, REF_LIB, ORACLE_LIB
+        kind, lib = ("reference", REF_LIB) if os.path.exists(REF_LIB) else ("port", ORACLE_LIB)
+        ref = RefWorld(lib)
+        k = max(1, min(a.cpu_utts, U))
+        xs = x[:k].cpu().numpy()
+        t0 = time.perf_counter()
+        fr = 0
+        for u in range(k):
+            xu = np.ascontiguousarray(xs[u])
+            if a.f0 == "harvest":
+                t, f0 = ref.harvest(xu, fs)
+            else:
+                t, f0 = ref.dio(xu, fs)
+                f0 = ref.stonemask(xu, fs, t, f0)
+            o = ref.cheaptrick_option(fs)
+            ref.cheaptrick(xu, fs, t, f0, o)
+            ref.d4c(xu, fs, t, f0, o.fft_size)
+            fr += len(f0)
+        dt = time.perf_counter() - t0
+        cpu = {"value": fr / dt, "unit": "frames/s", "cores": 1, "kind": kind,
+               "sample": f"utterances 1..{k} of the batch ({k} x {a.seconds:g} s), single thread, {dt:.1f} s",
+               "host_cores_available": os.cpu_count()}
+
+    out = {"metric": METRIC if a.f0 == "harvest" else "analysis frames/sec (Dio+StoneMask+CheapTrick+D4C)",
+           "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(a), "fs": fs, "frame_period_ms": 5.0, "frames_per_step": frames_step,
+                      "l2_policy": "inputs+outputs per step (>= 18 GB) exceed the 126 MB L2; no flush needed",
+                      "multi_gpu": ("utterances sharded over ranks, NCCL all-gather of f0/time_axis" +
+                                    ("/spectrogram/aperiodicity" if gather_full else "")) if world > 1 else "single GPU"},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+           "kernels": kernels}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

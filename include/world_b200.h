@@ -58,6 +58,12 @@ const char *world_b200_last_error(const WorldB200 *ctx);
 /* Number of kernels this context has launched so far (bench.py reports it). */
 unsigned long long world_b200_launch_count(const WorldB200 *ctx);
 
+/* Per-kernel device timing (CUDA events on the context's stream around every launch).
+ * profile(ctx, 1) starts collecting; profile_report() synchronises, writes a JSON object
+ * {"<kernel>": {"launches": n, "ms": total}, ...} into buf and clears the collection. */
+int world_b200_profile(WorldB200 *ctx, int enable);
+int world_b200_profile_report(WorldB200 *ctx, char *buf, unsigned long long cap);
+
 /* Test hook: first n_draws values of the reference's randn() stream (matlabfunctions.cpp:237-264)
  * as raw 32-bit sums (value = sum / 2^28 - 6) into a DEVICE buffer of n_draws uint32. */
 int world_b200_randn_stream(WorldB200 *ctx, unsigned n_draws, unsigned *out_dev);

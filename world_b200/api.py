@@ -59,6 +59,8 @@ ABI = {
     "world_b200_launch_count": (C.c_ulonglong, [_P]),
     "world_b200_frames": (C.c_int, [C.c_int, C.c_int, C.c_double]),
     "world_b200_randn_stream": (C.c_int, [_P, C.c_uint, _P]),
+    "world_b200_profile": (C.c_int, [_P, C.c_int]),
+    "world_b200_profile_report": (C.c_int, [_P, C.c_char_p, C.c_ulonglong]),
     "world_b200_dio_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, C.POINTER(DioOption), _P, _P, C.c_int]),
     "world_b200_harvest_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, C.POINTER(HarvestOption), _P, _P, C.c_int]),
     "world_b200_stonemask_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, _P, _P, _IP, C.c_int, _P]),
@@ -178,6 +180,15 @@ class World:
 
     def set_scratch_budget(self, nbytes: int):
         self._check(self.lib.world_b200_set_scratch_budget(self._h, nbytes))
+
+    def profile(self, enable=True):
+        self._check(self.lib.world_b200_profile(self._h, 1 if enable else 0))
+
+    def profile_report(self) -> dict:
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self.lib.world_b200_profile_report(self._h, buf, len(buf)))
+        return json.loads(buf.value.decode())
 
     def randn_stream(self, n_draws, out_u32):
         """test hook: raw draw sums into a uint32 array/tensor of n_draws elements"""

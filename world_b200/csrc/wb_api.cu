@@ -15,6 +15,27 @@ struct WorldB200 {
 namespace wb {
 
 unsigned long long g_launches = 0;
+int g_prof_on = 0;
+
+#ifndef WB_EMU
+namespace {
+struct ProfRec { const char *name; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event() {
+  cudaEvent_t e;
+  if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+void prof_begin(const char *name, cudaStream_t s) {
+  ProfRec r; r.name = name; r.a = prof_event(); r.b = prof_event();
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t s) { cudaEventRecord(g_prof.back().b, s); }
+#endif
 
 #ifndef WB_EMU
 static int cuda_fail(Ctx *ctx, cudaError_t e, const char *what) {
@@ -347,6 +368,43 @@ int world_b200_harvest_batch(WorldB200 *h, const double *x, int n, int x_stride,
   b.l1_host = l1.data();
   HarvestParams p = {opt->f0_floor, opt->f0_ceil, opt->frame_period};
   return harvest_run(&h->c, b, p, time_axis, f0);
+}
+
+// Per-kernel timing: enable, run, then fetch a JSON object {"kernel": {"launches": n, "ms": t}, ...}
+// (CUDA events recorded on the context's stream around every launch; report() synchronises).
+int world_b200_profile(WorldB200 *h, int enable) {
+  if (!h) return WORLD_B200_EINVAL;
+  wb::g_prof_on = enable ? 1 : 0;
+  return 0;
+}
+
+int world_b200_profile_report(WorldB200 *h, char *buf, unsigned long long cap) {
+  if (!h || !buf || cap < 3) return WORLD_B200_EINVAL;
+  std::string out = "{";
+#ifndef WB_EMU
+  int rc = dev_sync(&h->c);
+  if (rc) return rc;
+  std::vector<std::string> names; std::vector<double> ms; std::vector<long> cnt;
+  for (auto &r : g_prof) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    size_t k = 0;
+    for (; k < names.size(); ++k) if (names[k] == r.name) break;
+    if (k == names.size()) { names.push_back(r.name); ms.push_back(0.0); cnt.push_back(0); }
+    ms[k] += t; cnt[k] += 1;
+    g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+  }
+  g_prof.clear();
+  for (size_t k = 0; k < names.size(); ++k) {
+    char item[256];
+    snprintf(item, sizeof item, "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f}", k ? ", " : "", names[k].c_str(), cnt[k], ms[k]);
+    out += item;
+  }
+#endif
+  out += "}";
+  if (out.size() + 1 > cap) return WORLD_B200_EINVAL;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
 }
 
 // Known-answer hook: the first n_draws randn() draws after randn_reseed(), as the raw 32-bit

@@ -35,11 +35,21 @@ typedef cudaStream_t wb_stream_t;
 
 // Cooperative kernels (block-wide phases + barriers) and flat kernels (independent threads)
 // launch the same way on the device.
-namespace wb { extern unsigned long long g_launches; }
-#define WB_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) \
-  (++wb::g_launches, kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
+namespace wb {
+extern unsigned long long g_launches;
+extern int g_prof_on;                       // per-kernel CUDA-event timing (world_b200_profile)
+void prof_begin(const char *name, cudaStream_t s);
+void prof_end(cudaStream_t s);
+}
+#define WB_LAUNCH_COOP(kernel, grid, block, smem, stream, ...)            \
+  do {                                                                    \
+    ++wb::g_launches;                                                     \
+    if (wb::g_prof_on) wb::prof_begin(#kernel, (stream));                 \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);           \
+    if (wb::g_prof_on) wb::prof_end((stream));                            \
+  } while (0)
 #define WB_LAUNCH_FLAT(kernel, grid, block, smem, stream, ...) \
-  (++wb::g_launches, kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
+  WB_LAUNCH_COOP(kernel, grid, block, smem, stream, __VA_ARGS__)
 
 #else
 // ------------------------------------------------------------------- host emulation build
