@@ -13,12 +13,29 @@
 
 namespace wb {
 
+// Event-list capacity per band and train: crossings of a signal band-limited around/below
+// `boundary` cannot be denser than ~boundary per second for long; 2.5x margin, hard bound
+// ylen/2+2 (a negative-going crossing needs two samples).  Overflow raises status bit 4.
+static void plan_edge_caps(const std::vector<double> &boundary, double afs, int max_ylen,
+                           std::vector<int> *cap, std::vector<long long> *off, size_t *stride) {
+  const int nb = (int)boundary.size();
+  cap->resize(nb); off->resize(nb);
+  long long run = 0;
+  for (int i = 0; i < nb; ++i) {
+    const long long hard = (long long)max_ylen / 2 + 2;
+    const long long soft = (long long)(2.5 * boundary[i] * max_ylen / afs) + 64;
+    (*cap)[i] = (int)(soft < hard ? soft : hard);
+    (*off)[i] = run;
+    run += 4LL * (*cap)[i];
+  }
+  *stride = (size_t)run;
+}
+
 struct DioPrepParams {
   const double *x; const int *x_len; int x_stride;
   int ratio;
   double *y; size_t y_stride; int y_origin;   // mean-removed signal, zero padded
   int *y_len;                                  // out: 1 + x_len / ratio
-  double *tmp; size_t tmp_stride;              // decimation scratch (2 rows per utterance) or null
 };
 
 WB_KERNEL(256, 2) dio_prep_kernel(DioPrepParams p) {
@@ -29,12 +46,8 @@ WB_KERNEL(256, 2) dio_prep_kernel(DioPrepParams p) {
   double *y = p.y + (size_t)u * p.y_stride + p.y_origin;
   const int ylen = 1 + n / p.ratio;
   if (p.ratio != 1) {
-    // decimate() leaves (n-1)/r+1 (+ a few mirrored-edge) samples; the rest of y stays zero (dio.cpp:67-73)
-    if (tid == 0) {
-      double *t1 = p.tmp + (size_t)u * 2 * p.tmp_stride, *t2 = t1 + p.tmp_stride;
-      decimate_one(x, n, 0, p.ratio, t1, t2, 0, ylen, y);
-    }
-    WB_SYNC();
+    // launch_decimate() already left (n-1)/r+1 (+ a few mirrored-edge) samples in y; the rest of y
+    // stays zero (dio.cpp:67-73)
   } else {
     for (int i = tid; i < n; i += nth) y[i] = x[i];
     WB_SYNC();
@@ -188,10 +201,11 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
   const int T = WB_SWEEP_T;
   const int padl = imax(max_taps, nlc) + 16;
   const size_t y_stride = (size_t)padl + max_ylen + 2 * c + 3 * T + max_taps + nlc + 64;
-  const size_t edge_cap = (size_t)max_ylen / 2 + 2;
+  std::vector<int> ecap; std::vector<long long> eoff; size_t edge_stride = 0;
+  plan_edge_caps(boundary, afs, max_ylen, &ecap, &eoff, &edge_stride);
   const int fstr = b.f_stride;
   const size_t tmp_stride = ratio != 1 ? (size_t)b.max_x_len + 32 : 0;
-  const size_t per_utt = y_stride * 16 + (size_t)nb * 4 * edge_cap * 8 + (size_t)nb * fstr * 16 +
+  const size_t per_utt = y_stride * 16 + edge_stride * 8 + (size_t)nb * fstr * 16 +
                          (size_t)fstr * (4 * 8 + 2 * 4) + tmp_stride * 16 + 256;
   int chunk = (int)imin(imin(b.n, 65535), (int)dmax(1.0, (double)ctx->scratch_budget / (double)per_utt));
 #ifndef WB_EMU
@@ -201,10 +215,11 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     ArenaPlan plan;
     const size_t o_y = plan.add((size_t)n * y_stride * 8), o_ylc = plan.add((size_t)n * y_stride * 8);
     const size_t o_ylen = plan.add((size_t)n * 4);
-    const size_t o_edges = plan.add((size_t)n * nb * 4 * edge_cap * 8);
+    const size_t o_edges = plan.add((size_t)n * edge_stride * 8);
+    const size_t o_ecap = plan.add(nb * 4), o_eoff = plan.add(nb * 8);
     const size_t o_cand = plan.add((size_t)n * nb * fstr * 8), o_score = plan.add((size_t)n * nb * fstr * 8);
     const size_t o_work = plan.add((size_t)n * 4 * fstr * 8), o_sec = plan.add((size_t)n * 2 * fstr * 4);
-    const size_t o_tmp = plan.add((size_t)n * 2 * tmp_stride * 8);
+    const size_t o_tmp = plan.add((size_t)n * tmp_stride * 8);
     const size_t o_lc = plan.add(lc_rev.size() * 8 + 64), o_taps = plan.add(taps.size() * 8);
     const size_t o_toff = plan.add(nb * 4), o_nt = plan.add(nb * 4), o_sh = plan.add(nb * 4), o_bd = plan.add(nb * 8);
     unsigned char *blk = arena_block(ctx, plan.total);
@@ -219,12 +234,20 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_nt, ntaps.data(), nb * 4);
     if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_sh, shift.data(), nb * 4);
     if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_bd, boundary.data(), nb * 8);
+    if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_ecap, ecap.data(), nb * 4);
+    if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_eoff, eoff.data(), nb * 8);
     if (rc) return rc;
 
     DioPrepParams pp;
     pp.x = b.x + (size_t)u0 * b.x_stride; pp.x_len = b.x_len + u0; pp.x_stride = b.x_stride; pp.ratio = ratio;
     pp.y = y; pp.y_stride = y_stride; pp.y_origin = padl; pp.y_len = ylen;
-    pp.tmp = ratio != 1 ? (double *)(blk + o_tmp) : nullptr; pp.tmp_stride = tmp_stride;
+    if (ratio != 1) {
+      DecimateParams dp;
+      dp.x = pp.x; dp.x_len = pp.x_len; dp.x_stride = pp.x_stride; dp.ratio = ratio; dp.lag = 0;
+      dp.tmp = (double *)(blk + o_tmp); dp.tmp_stride = tmp_stride;
+      dp.y = y; dp.y_stride = y_stride; dp.y_origin = padl; dp.first = 0; dp.n_out_mode = 0;
+      launch_decimate(ctx, dp, b.max_x_len, (unsigned)n);
+    }
     WB_LAUNCH_COOP(dio_prep_kernel, dim3((unsigned)n), 256, 0, ctx->stream, pp);
 
     // ylc(q) = sum_k lc[k] y(q - k), q in [0, ylen + 2c): time index n = q - c
@@ -240,7 +263,8 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     sp.taps_rev = (const double *)(blk + o_taps); sp.tap_off = (const int *)(blk + o_toff);
     sp.ntaps = (const int *)(blk + o_nt); sp.shift = (const int *)(blk + o_sh);
     sp.boundary = (const double *)(blk + o_bd); sp.afs = afs;
-    sp.edges = (double *)(blk + o_edges); sp.edge_cap = edge_cap;
+    sp.edges = (double *)(blk + o_edges); sp.edge_stride = edge_stride;
+    sp.edge_cap = (const int *)(blk + o_ecap); sp.edge_off = (const long long *)(blk + o_eoff);
     sp.n_frames = b.f_len + u0; sp.frame_stride = fstr; sp.frame_period = opt.frame_period;
     sp.mode = 0; sp.f0_floor = opt.f0_floor; sp.f0_ceil = opt.f0_ceil;
     sp.cand = (double *)(blk + o_cand); sp.score = (double *)(blk + o_score);

@@ -103,8 +103,8 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
 
   const int ylen = p.y_len[u];
   const double *sig = p.sig + (size_t)u * p.sig_stride + p.sig_origin;
-  double *edges = p.edges + ((size_t)u * p.n_bands + b) * 4 * p.edge_cap;
-  const int cap = (int)p.edge_cap;
+  double *edges = p.edges + (size_t)u * p.edge_stride + (size_t)p.edge_off[b];
+  const int cap = p.edge_cap[b];
   for (int j = tid; j < ntaps; j += nth) hrev[j] = __ldg(&p.taps_rev[p.tap_off[b] + j]);
   for (int j = ntaps + tid; j < ntaps + 8; j += nth) hrev[j] = 0.0;
   if (tid == 0) { st[0] = 0.0; st[1] = 0.0; }
@@ -222,6 +222,67 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   }
 }
 
+
+// extended input of decimate(): 9 mirrored samples on both sides of the edge-padded signal
+WB_DEV double dec_ext(const double *__restrict__ x, int n, int lag, int nx, int i) {
+#define WB_XIN(k) x[imin(n - 1, imax(0, (k) - lag))]
+  if (i < 9) return 2 * WB_XIN(0) - WB_XIN(9 - i);
+  if (i < 9 + nx) return WB_XIN(i - 9);
+  return 2 * WB_XIN(nx - 1) - WB_XIN(nx - 2 - (i - (9 + nx)));
+#undef WB_XIN
+}
+
+// pass 0: tmp[i] = forward IIR of ext;  pass 1: backward IIR over tmp, decimated into y
+template <int kPass>
+WB_KERNEL_PLAIN decimate_pass_kernel(DecimateParams p) {
+  const int u = blockIdx.y;
+  const int n = p.x_len[u];
+  const int nx = n + 2 * p.lag, nt = nx + 18;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long begin = g * WB_DEC_BLOCK;
+  if (begin >= nt) return;
+  const int end = (int)(begin + WB_DEC_BLOCK < nt ? begin + WB_DEC_BLOCK : nt);
+  const int start = (int)(begin - WB_DEC_WARM > 0 ? begin - WB_DEC_WARM : 0);
+  const double *x = p.x + (size_t)u * p.x_stride;
+  double *tmp = p.tmp + (size_t)u * p.tmp_stride;
+  double a[3], b[2];
+  decimate_coefficients(p.ratio, a, b);
+  double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+  if (kPass == 0) {
+    for (int i = start; i < end; ++i) {
+      const double wt = dec_ext(x, n, p.lag, nx, i) + a[0] * w0 + a[1] * w1 + a[2] * w2;
+      if (i >= begin) tmp[i] = b[0] * wt + b[1] * w0 + b[1] * w1 + b[0] * w2;
+      w2 = w1; w1 = w0; w0 = wt;
+    }
+  } else {
+    // second filter runs over the reversed forward output; its result, reversed again, is tmp1 of
+    // decimate(): final[j] with j = nt - 1 - i.  y[k] = final[nbeg + k r + 8]  (matlabfunctions.cpp:196-200)
+    const int nout = (nx - 1) / p.ratio + 1;
+    const int nbeg = p.ratio - p.ratio * nout + nx;
+    const int n_out = p.n_out_mode == 0 ? 1 + n / p.ratio : static_cast<int>(ceil(static_cast<double>(n) / p.ratio));
+    double *y = p.y + (size_t)u * p.y_stride + p.y_origin;
+    for (int i = start; i < end; ++i) {
+      const double wt = tmp[nt - 1 - i] + a[0] * w0 + a[1] * w1 + a[2] * w2;
+      if (i >= begin) {
+        const int j = nt - 1 - i - 8;          // = nbeg + k r  for a kept sample
+        const int d = j - nbeg;
+        if (d >= 0 && j < nx + 9 && d % p.ratio == 0) {
+          const int k = d / p.ratio - p.first;
+          if (k >= 0 && k < n_out) y[k] = b[0] * wt + b[1] * w0 + b[1] * w1 + b[0] * w2;
+        }
+      }
+      w2 = w1; w1 = w0; w0 = wt;
+    }
+  }
+}
+
+void launch_decimate(Ctx *ctx, const DecimateParams &p, int max_x_len, unsigned n_utts) {
+  const long long nt = (long long)max_x_len + 2 * p.lag + 18;
+  const long long threads = (nt + WB_DEC_BLOCK - 1) / WB_DEC_BLOCK;
+  const unsigned blocks = (unsigned)((threads + 63) / 64);
+  WB_LAUNCH_FLAT(decimate_pass_kernel<0>, dim3(blocks, n_utts), 64, 0, ctx->stream, p);
+  WB_LAUNCH_FLAT(decimate_pass_kernel<1>, dim3(blocks, n_utts), 64, 0, ctx->stream, p);
+}
 
 void launch_fir_plain(Ctx *ctx, const FirParams &p, unsigned tiles, unsigned n_utts) {
   const size_t smem = fir_plain_smem_bytes(p.ntaps);

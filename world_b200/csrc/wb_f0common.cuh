@@ -17,6 +17,8 @@
 
 namespace wb {
 
+struct Ctx;
+
 #define WB_SWEEP_T 2048      // outputs per tile
 #define WB_SWEEP_R 8         // outputs per thread group (register tile)
 #define WB_SWEEP_THREADS 256 // = T / R
@@ -55,41 +57,6 @@ WB_HD inline void decimate_coefficients(int r, double a[3], double b[2]) {
   }
 }
 
-// One thread decimates one (virtually edge-padded) signal:  xin(i) = x[clamp(i - lag, 0, n-1)]
-// for i in [0, n + 2 lag)  (harvest.cpp:43-66; lag = 0 gives plain decimate()).
-// tmp1/tmp2: scratch of n + 2 lag + 18 doubles each.  Writes out[0..n_out) = decimated samples
-// starting at decimated index `first`; returns how many decimated samples exist.
-WB_DEV int decimate_one(const double *__restrict__ x, int n, int lag, int r, double *tmp1, double *tmp2,
-                        int first, int n_out, double *out) {
-  const int kNFact = 9;
-  const int nx = n + 2 * lag;
-  const int nt = nx + 2 * kNFact;
-#define WB_XIN(i) x[imin(n - 1, imax(0, (i) - lag))]
-  for (int i = 0; i < kNFact; ++i) tmp1[i] = 2 * WB_XIN(0) - WB_XIN(kNFact - i);
-  for (int i = kNFact; i < kNFact + nx; ++i) tmp1[i] = WB_XIN(i - kNFact);
-  for (int i = kNFact + nx; i < nt; ++i) tmp1[i] = 2 * WB_XIN(nx - 1) - WB_XIN(nx - 2 - (i - (kNFact + nx)));
-#undef WB_XIN
-  double a[3], b[2];
-  decimate_coefficients(r, a, b);
-  for (int pass = 0; pass < 2; ++pass) {
-    double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-    for (int i = 0; i < nt; ++i) {
-      const double wt = tmp1[i] + a[0] * w0 + a[1] * w1 + a[2] * w2;
-      tmp2[i] = b[0] * wt + b[1] * w0 + b[1] * w1 + b[0] * w2;
-      w2 = w1; w1 = w0; w0 = wt;
-    }
-    for (int i = 0; i < nt; ++i) tmp1[i] = tmp2[nt - i - 1];
-  }
-  const int nout = (nx - 1) / r + 1;
-  const int nbeg = r - r * nout + nx;
-  int count = 0;
-  for (int i = nbeg; i < nx + kNFact; i += r, ++count) {
-    const int k = count - first;
-    if (k >= 0 && k < n_out) out[k] = tmp1[i + kNFact - 1];
-  }
-  return count;
-}
-
 // ------------------------------------------------------------------------------ plain FIR
 // out(q) = sum_k h[k] * in(q - k), q in [0, q_len[u]); `in` is zero padded on both sides.
 // grid (tiles, utterances); same register tiling as the band sweep.
@@ -113,7 +80,8 @@ struct SweepParams {
   const double *taps_rev; const int *tap_off; const int *ntaps; const int *shift;  // per band
   const double *boundary;                                // per band boundary f0
   double afs;                                            // sampling rate of sig
-  double *edges; size_t edge_cap;                        // [(u*nb+b)*4+train][edge_cap] fine edges
+  double *edges; size_t edge_stride;                     // per utterance; band b: 4 trains of edge_cap[b] at edge_off[b]
+  const int *edge_cap; const long long *edge_off;
   const int *n_frames; int frame_stride; double frame_period;  // frame grid: t_i = i*frame_period/1000
   int mode;                                              // 0 = DIO (candidate + score), 1 = Harvest
   double f0_floor, f0_ceil;
@@ -128,8 +96,25 @@ WB_HD inline size_t sweep_smem_bytes(int max_taps) {
          (size_t)(WB_SWEEP_T / WB_SWEEP_R + 40) * 8;
 }
 
+// ------------------------------------------------------------------------------ blocked decimate
+// GPU restatement of decimate(): the zero-phase IIR (poles |z| <= 0.89 for every supported
+// ratio) forgets its state to below 1e-19 within 384 samples, so each thread filters one block of
+// DEC_BLOCK samples after a DEC_WARM sample run-in from zero state (the first block starts at
+// sample 0 from zero state exactly like the reference).  Forward pass -> tmp, backward pass picks
+// every r-th sample straight into the output.
+#define WB_DEC_BLOCK 256
+#define WB_DEC_WARM 512
+struct DecimateParams {
+  const double *x; const int *x_len; int x_stride;
+  int ratio, lag;              // virtual edge padding of `lag` samples on both sides (Harvest), 0 for DIO
+  double *tmp; size_t tmp_stride;   // forward-filtered extended signal, n + 2 lag + 18 per utterance
+  double *y; size_t y_stride; int y_origin;
+  int first;                   // decimated index of y[0]
+  int n_out_mode;              // 0: 1 + n / r samples (DIO), 1: ceil(n / r) samples (Harvest)
+};
+
 // launchers (wb_f0common.cu)
-struct Ctx;
+void launch_decimate(Ctx *ctx, const DecimateParams &p, int max_x_len, unsigned n_utts);
 void launch_fir_plain(Ctx *ctx, const FirParams &p, unsigned tiles, unsigned n_utts);
 void launch_band_sweep(Ctx *ctx, const SweepParams &p, unsigned n_utts);
 

@@ -17,6 +17,24 @@
 
 namespace wb {
 
+// Event-list capacity per band and train: crossings of a signal band-limited around/below
+// `boundary` cannot be denser than ~boundary per second for long; 2.5x margin, hard bound
+// ylen/2+2 (a negative-going crossing needs two samples).  Overflow raises status bit 4.
+static void plan_edge_caps(const std::vector<double> &boundary, double afs, int max_ylen,
+                           std::vector<int> *cap, std::vector<long long> *off, size_t *stride) {
+  const int nb = (int)boundary.size();
+  cap->resize(nb); off->resize(nb);
+  long long run = 0;
+  for (int i = 0; i < nb; ++i) {
+    const long long hard = (long long)max_ylen / 2 + 2;
+    const long long soft = (long long)(2.5 * boundary[i] * max_ylen / afs) + 64;
+    (*cap)[i] = (int)(soft < hard ? soft : hard);
+    (*off)[i] = run;
+    run += 4LL * (*cap)[i];
+  }
+  *stride = (size_t)run;
+}
+
 #define WB_HV_BASE 32        // >= round(channels / 10): base candidates kept per frame
 #define WB_HV_WARPS 8
 
@@ -24,7 +42,6 @@ namespace wb {
 struct HvPrepParams {
   const double *x; const int *x_len; int x_stride; int ratio;
   double *y; size_t y_stride; int y_origin; int *y_len;
-  double *tmp; size_t tmp_stride;
 };
 
 WB_KERNEL(256, 2) harvest_prep_kernel(HvPrepParams p) {
@@ -35,12 +52,7 @@ WB_KERNEL(256, 2) harvest_prep_kernel(HvPrepParams p) {
   double *y = p.y + (size_t)u * p.y_stride + p.y_origin;
   const int ylen = static_cast<int>(ceil(static_cast<double>(n) / p.ratio));
   if (p.ratio != 1) {
-    if (tid == 0) {
-      const int lag = static_cast<int>(ceil(140.0 / p.ratio) * p.ratio);
-      double *t1 = p.tmp + (size_t)u * 2 * p.tmp_stride, *t2 = t1 + p.tmp_stride;
-      decimate_one(x, n, lag, p.ratio, t1, t2, lag / p.ratio, ylen, y);
-    }
-    WB_SYNC();
+    // launch_decimate() already wrote the decimated samples (harvest.cpp:43-66)
   } else {
     for (int i = tid; i < n; i += nth) y[i] = x[i];
     WB_SYNC();
@@ -118,6 +130,9 @@ WB_DEV double2 hv_tw(const double2 *__restrict__ tw, int idx) {
 
 // GetRefinedF0 (harvest.cpp:589-617) for one candidate, executed by one warp.
 // wbuf/dbuf: per-warp shared scratch of nwin doubles each.
+// Lane layout of the sparse DFT: lane = 8*c + m handles harmonic m (H <= 6 of the 8 slots) over
+// the samples j = c, c+4, c+8, ...; two xor-shuffles fold the four sample classes, then the
+// harmonics are combined in index order exactly like FixF0 (harvest.cpp:509-535).
 WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, double t, double f,
                           double f0_floor, double f0_ceil, const double2 *__restrict__ tw, double *wbuf,
                           double *dbuf, double *out_f0, double *out_score) {
@@ -130,9 +145,11 @@ WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, d
   const double T = (2.0 * h + 1.0) / afs;
   // base_index[j] = round((t + base_time[0]) * fs + 0.001) + j   (harvest.cpp:434-441)
   const int basic = round_half_away((t + (-h + 0) / afs) * afs + 0.001);
+  // Blackman window (harvest.cpp:446-456); cos(2a) = 2 cos(a)^2 - 1 saves the second cosine
   for (int j = lane; j < nwin; j += WB_LANES) {
     const double tmp = ((basic + j) - 1.0) / afs - t;
-    wbuf[j] = 0.42 + 0.5 * cos(2.0 * kPi * tmp / T) + 0.08 * cos(4.0 * kPi * tmp / T);
+    const double c1 = cos(2.0 * kPi * tmp / T);
+    wbuf[j] = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
   }
 #ifndef WB_EMU
   __syncwarp();
@@ -142,8 +159,7 @@ WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, d
     if (j == 0) dw = -wbuf[1] / 2.0;
     else if (j == nwin - 1) dw = wbuf[nwin - 2] / 2.0;
     else dw = -(wbuf[j + 1] - wbuf[j - 1]) / 2.0;
-    const double s = y[imax(0, imin(y_len - 1, basic + j - 1))];
-    dbuf[j] = s * dw;
+    dbuf[j] = y[imax(0, imin(y_len - 1, basic + j - 1))] * dw;
   }
 #ifndef WB_EMU
   __syncwarp();
@@ -154,25 +170,49 @@ WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, d
 #endif
   const int H = imin(static_cast<int>(afs / 2.0 / f), 6);
   const int shift = WB_TW_LOG2 - lg_nfft;
+  double amp_l = 0.0, inst_l = 0.0;  // this lane's harmonic (CUDA) / current harmonic (emulation)
   double numerator = 0.0, denominator = 0.0, score = 0.0;
+#ifdef WB_EMU
   for (int m = 0; m < H; ++m) {
-    const int bin = round_half_away(f * nfft / afs * (m + 1));
+    const int c0 = 0, cstep = 1;
+#else
+  {
+    const int m = lane & 7, c0 = lane >> 3, cstep = 4;
+#endif
     double mr = 0.0, mi = 0.0, dr = 0.0, di = 0.0;
-    for (int j = lane; j < nwin; j += WB_LANES) {
-      const double2 w = hv_tw(tw, ((bin * j) & (nfft - 1)) << shift);
-      const double a = wbuf[j], d = dbuf[j];
-      mr = fma(a, w.x, mr); mi = fma(a, w.y, mi);
-      dr = fma(d, w.x, dr); di = fma(d, w.y, di);
+    const int bin = round_half_away(f * nfft / afs * (m + 1));
+    if (m < H) {
+      for (int j = c0; j < nwin; j += cstep) {
+        const double2 w = hv_tw(tw, ((bin * j) & (nfft - 1)) << shift);
+        const double a = wbuf[j], d = dbuf[j];
+        mr = fma(a, w.x, mr); mi = fma(a, w.y, mi);
+        dr = fma(d, w.x, dr); di = fma(d, w.y, di);
+      }
     }
-    mr = warp_sum(mr); mi = warp_sum(mi); dr = warp_sum(dr); di = warp_sum(di);
+#ifndef WB_EMU
+    mr += __shfl_xor_sync(0xffffffffu, mr, 8);  mi += __shfl_xor_sync(0xffffffffu, mi, 8);
+    dr += __shfl_xor_sync(0xffffffffu, dr, 8);  di += __shfl_xor_sync(0xffffffffu, di, 8);
+    mr += __shfl_xor_sync(0xffffffffu, mr, 16); mi += __shfl_xor_sync(0xffffffffu, mi, 16);
+    dr += __shfl_xor_sync(0xffffffffu, dr, 16); di += __shfl_xor_sync(0xffffffffu, di, 16);
+#endif
     const double num = mr * di - mi * dr;
     const double pw = mr * mr + mi * mi;
-    const double inst = pw == 0.0 ? 0.0 : static_cast<double>(bin) * afs / nfft + num / pw * afs / 2.0 / kPi;
-    const double amp = sqrt(pw);
-    numerator += amp * inst;
-    denominator += amp * (m + 1.0);
-    score += fabs((inst / (m + 1.0) - f) / f);
+    inst_l = pw == 0.0 ? 0.0 : static_cast<double>(bin) * afs / nfft + num / pw * afs / 2.0 / kPi;
+    amp_l = sqrt(pw);
+#ifdef WB_EMU
+    numerator += amp_l * inst_l;
+    denominator += amp_l * (m + 1.0);
+    score += fabs((inst_l / (m + 1.0) - f) / f);
   }
+#else
+  }
+  for (int m = 0; m < H; ++m) {
+    const double am = __shfl_sync(0xffffffffu, amp_l, m), im = __shfl_sync(0xffffffffu, inst_l, m);
+    numerator += am * im;
+    denominator += am * (m + 1.0);
+    score += fabs((im / (m + 1.0) - f) / f);
+  }
+#endif
   double rf = numerator / (denominator + kTiny);
   double rs = 1.0 / (score / H + kTiny);
   if (rf < f0_floor || rf > f0_ceil || rs < 2.5) { rf = 0.0; rs = 0.0; }
@@ -268,15 +308,37 @@ struct HvContourParams {
   int *status;
 };
 
-// GetBoundaryList (harvest.cpp:727-743)
-WB_DEV int hv_boundaries(const double *f0, int n, int *list) {
-  int nb = 0, prev = 0;
-  for (int i = 1; i < n; ++i) {
+// GetBoundaryList (harvest.cpp:727-743), block-cooperative: every thread scans a contiguous
+// chunk, chunk counts are prefix-summed, boundaries are written in order.  list[k] = i - k % 2.
+// `cnt` is shared scratch of nthreads + 1 ints.  Returns the number of boundaries to all threads.
+WB_DEV int hv_boundaries(const double *f0, int n, int *list, int *cnt) {
+  const int tid = WB_TID, nth = WB_NTH;
+  const int chunk = (n - 1 + nth - 1) / nth;  // positions 1 .. n-1
+  const int lo = imin(n, 1 + tid * chunk), hi = imin(n, lo + chunk);
+  int c = 0;
+  for (int i = lo; i < hi; ++i) {
     const int v = (i == n - 1) ? 0 : (f0[i] > 0 ? 1 : 0);
-    if (v - prev != 0) { list[nb] = i - nb % 2; ++nb; }
-    prev = v;
+    const int pv = (i - 1 == 0) ? 0 : (f0[i - 1] > 0 ? 1 : 0);
+    c += (v != pv);
   }
-  return nb;
+  WB_SYNC();
+  cnt[tid] = c;
+  WB_SYNC();
+  if (tid == 0) {
+    int run = 0;
+    for (int t = 0; t < nth; ++t) { const int v = cnt[t]; cnt[t] = run; run += v; }
+    cnt[nth] = run;
+  }
+  WB_SYNC();
+  int k = cnt[tid];
+  for (int i = lo; i < hi; ++i) {
+    const int v = (i == n - 1) ? 0 : (f0[i] > 0 ? 1 : 0);
+    const int pv = (i - 1 == 0) ? 0 : (f0[i - 1] > 0 ? 1 : 0);
+    if (v != pv) { list[k] = i - k % 2; ++k; }
+  }
+  const int total = cnt[nth];
+  WB_SYNC();
+  return total;
 }
 
 // SelectBestF0 (harvest.cpp:636-650): last candidate among those with the smallest error <= allowed
@@ -291,24 +353,18 @@ WB_DEV double hv_select_best(double reference, const double *row, int n, double 
   return best;
 }
 
-struct HvSections {
-  double *mc; int *off, *lo, *hi;
-  WB_DEV_MEMBER double get(int s, int j) const { return (j < lo[s] || j > hi[s]) ? 0.0 : mc[off[s] + (j - lo[s])]; }
-  WB_DEV_MEMBER void set(int s, int j, double v) const { if (j >= lo[s] && j <= hi[s]) mc[off[s] + (j - lo[s])] = v; }
-};
-
-// ExtendF0 (harvest.cpp:791-822)
-WB_DEV int hv_extend(const HvSections &S, int s, int origin, int last_point, int shift, const double *cand,
+// ExtendF0 (harvest.cpp:791-822) on one section's window `w` (w[j - lo] = contour at frame j)
+WB_DEV int hv_extend(double *w, int lo, int hi, int origin, int last_point, int shift, const double *cand,
                      int max_cand, int n_cand, double allowed) {
   const int threshold = 4;
-  double tmp_f0 = S.get(s, origin);
+  double tmp_f0 = w[origin - lo];
   int shifted_origin = origin;
   const int distance = last_point > origin ? last_point - origin : origin - last_point;
   int count = 0;
   for (int i = 0; i <= distance; ++i) {
     const int target = origin + shift * i + shift;
     const double v = hv_select_best(tmp_f0, cand + (size_t)target * max_cand, n_cand, allowed);
-    S.set(s, target, v);
+    if (target >= lo && target <= hi) w[target - lo] = v;
     if (v == 0.0) {
       ++count;
     } else {
@@ -329,6 +385,8 @@ WB_DEV double hv_search_score(double f0, const double *crow, const double *srow,
 }
 
 WB_KERNEL(128, 4) harvest_contour_kernel(HvContourParams p) {
+  WB_SHARED int cnt[130];
+  WB_SHARED int sh_nch;
   const int tid = WB_TID, nth = WB_NTH, u = blockIdx.x;
   const int L = p.l1[u], nc7 = p.nc[u] * 7, mcand = p.max_cand;
   const double *cand = p.cand + (size_t)u * p.l1_stride * mcand;
@@ -336,10 +394,8 @@ WB_KERNEL(128, 4) harvest_contour_kernel(HvContourParams p) {
   double *fb = p.work + (size_t)u * 5 * p.l1_stride, *s1 = fb + p.l1_stride, *s2 = s1 + p.l1_stride;
   double *s3 = s2 + p.l1_stride, *s4 = s3 + p.l1_stride;
   int *bl = p.iwork + (size_t)u * 6 * p.l1_stride;
-  HvSections S;
-  S.mc = p.mc + (size_t)u * p.mc_stride;
-  S.off = bl + p.l1_stride; S.lo = S.off + p.l1_stride; S.hi = S.lo + p.l1_stride;
-  int *order = S.hi + p.l1_stride;
+  double *mc = p.mc + (size_t)u * p.mc_stride;
+  int *off = bl + p.l1_stride, *wlo = off + p.l1_stride, *whi = wlo + p.l1_stride, *order = whi + p.l1_stride;
 
   // SearchF0Base (:693-705)
   for (int i = tid; i < L; i += nth) {
@@ -358,99 +414,121 @@ WB_KERNEL(128, 4) harvest_contour_kernel(HvContourParams p) {
       v = (fabs((fb[i] - reference) / reference) > 0.008 && fabs((fb[i] - fb[i - 1])) / fb[i - 1] > 0.008) ? 0.0 : fb[i];
     }
     s1[i] = v;
+    s2[i] = v;
   }
   WB_SYNC();
-  if (tid != 0) return;
-
   // FixStep2 (:748-762): voiced sections shorter than 6 frames are removed
-  for (int i = 0; i < L; ++i) s2[i] = s1[i];
-  int nb = hv_boundaries(s1, L, bl);
-  for (int i = 0; i < nb / 2; ++i) {
+  int nb = hv_boundaries(s1, L, bl, cnt);
+  for (int i = tid; i < nb / 2; i += nth) {
     if (bl[i * 2 + 1] - bl[i * 2] >= 6) continue;
     for (int j = bl[i * 2]; j <= bl[i * 2 + 1]; ++j) s2[j] = 0.0;
   }
+  WB_SYNC();
 
-  // FixStep3 (:1000-1025 region): extend sections, select, merge
-  for (int i = 0; i < L; ++i) s3[i] = s2[i];
-  nb = hv_boundaries(s2, L, bl);
+  // FixStep3 (:978-995): extend sections, select, merge
+  for (int i = tid; i < L; i += nth) s3[i] = s2[i];
+  nb = hv_boundaries(s2, L, bl, cnt);
   const int nsec = nb / 2;
-  {
+  if (tid == 0) {
     size_t used = 0;
-    bool overflow = false;
+    int okay = 1;
     for (int s = 0; s < nsec; ++s) {
       const int lo = imax(0, bl[2 * s] - 104), hi = imin(L - 1, bl[2 * s + 1] + 104);
-      if (used + (size_t)(hi - lo + 1) > p.mc_stride) { overflow = true; break; }
-      S.off[s] = (int)used; S.lo[s] = lo; S.hi[s] = hi;
-      for (int j = lo; j <= hi; ++j) S.mc[used + (j - lo)] = (j >= bl[2 * s] && j <= bl[2 * s + 1]) ? s2[j] : 0.0;
+      if (used + (size_t)(hi - lo + 1) > p.mc_stride) { okay = 0; break; }
+      off[s] = (int)used; wlo[s] = lo; whi[s] = hi;
       used += (size_t)(hi - lo + 1);
     }
-    if (overflow) { atomicOr_status(p.status, 4); return; }
+    sh_nch = okay ? 0 : -1;
+    if (!okay) atomicOr_status(p.status, 4);
   }
-  // Extend (:858-874)
-  for (int s = 0; s < nsec; ++s) {
-    const int ed = bl[2 * s + 1], st = bl[2 * s];
-    bl[2 * s + 1] = hv_extend(S, s, ed, imin(L - 2, ed + 100), 1, cand, mcand, nc7, 0.18);
-    bl[2 * s] = hv_extend(S, s, st, imax(1, st - 100), -1, cand, mcand, nc7, 0.18);
+  WB_SYNC();
+  if (sh_nch < 0) return;
+  // sections are independent until ExtendSub: one thread per section fills its window and runs
+  // both ExtendF0 calls (Extend, :858-874)
+  for (int s = tid; s < nsec; s += nth) {
+    const int st = bl[2 * s], ed = bl[2 * s + 1], lo = wlo[s], hi = whi[s];
+    double *w = mc + off[s];
+    for (int j = lo; j <= hi; ++j) w[j - lo] = (j >= st && j <= ed) ? s2[j] : 0.0;
+    const int new_ed = hv_extend(w, lo, hi, ed, imin(L - 2, ed + 100), 1, cand, mcand, nc7, 0.18);
+    const int new_st = hv_extend(w, lo, hi, st, imax(1, st - 100), -1, cand, mcand, nc7, 0.18);
+    bl[2 * s + 1] = new_ed;
+    bl[2 * s] = new_st;
   }
-  // ExtendSub (:839-856): note mean_f0 is NOT reset between sections in the reference
-  int nch = 0;
-  {
+  WB_SYNC();
+  if (tid == 0) {
+    // ExtendSub (:839-856): note mean_f0 is NOT reset between sections in the reference
+    int nch = 0;
     double mean_f0 = 0.0;
     for (int s = 0; s < nsec; ++s) {
       const int st = bl[2 * s], ed = bl[2 * s + 1];
-      for (int j = st; j < ed; ++j) mean_f0 += S.get(s, j);
+      const double *w = mc + off[s] - wlo[s];
+      for (int j = st; j < ed; ++j) mean_f0 += w[j];
       mean_f0 /= ed - st;
       if (2200.0 / mean_f0 < ed - st) {
-        // Swap(count, s): contour and boundary pair
-        int t;
-        t = S.off[nch]; S.off[nch] = S.off[s]; S.off[s] = t;
-        t = S.lo[nch]; S.lo[nch] = S.lo[s]; S.lo[s] = t;
-        t = S.hi[nch]; S.hi[nch] = S.hi[s]; S.hi[s] = t;
+        int t;  // Swap(count, s): contour and boundary pair
+        t = off[nch]; off[nch] = off[s]; off[s] = t;
+        t = wlo[nch]; wlo[nch] = wlo[s]; wlo[s] = t;
+        t = whi[nch]; whi[nch] = whi[s]; whi[s] = t;
         t = bl[2 * nch]; bl[2 * nch] = bl[2 * s]; bl[2 * s] = t;
         t = bl[2 * nch + 1]; bl[2 * nch + 1] = bl[2 * s + 1]; bl[2 * s + 1] = t;
         ++nch;
       }
     }
+    sh_nch = nch;
   }
+  WB_SYNC();
+  const int nch = sh_nch;
   if (nch != 0) {
-    // MergeF0 (:941-973)
-    for (int i = 0; i < nch; ++i) order[i] = i;
-    for (int i = 1; i < nch; ++i)
-      for (int j = i - 1; j >= 0; --j) {
-        if (bl[order[j] * 2] > bl[order[i] * 2]) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
-        else break;
-      }
-    // NB: the reference's inner loop compares order[j] with order[i] while i is fixed and does
-    // not follow the moving element; reproduced as written (harvest.cpp:881-893).
-    for (int i = 0; i < L; ++i) s3[i] = S.get(0, i);
-    for (int i = 1; i < nch; ++i) {
-      const int o = order[i];
-      if (bl[o * 2] - bl[1] > 0) {
-        for (int j = bl[o * 2]; j <= bl[o * 2 + 1]; ++j) s3[j] = S.get(o, j);
-        bl[0] = bl[o * 2];
-        bl[1] = bl[o * 2 + 1];
-      } else {
-        // MergeF0Sub (:912-935)
-        const int st1 = bl[0], ed1 = bl[1], st2 = bl[o * 2], ed2 = bl[o * 2 + 1];
-        if (st1 <= st2 && ed1 >= ed2) {
-          bl[1] = ed1;
-        } else {
-          double score1 = 0.0, score2 = 0.0;
-          for (int k = st2; k <= ed1; ++k) {
-            score1 += hv_search_score(s3[k], cand + (size_t)k * mcand, score + (size_t)k * mcand, nc7);
-            score2 += hv_search_score(S.get(o, k), cand + (size_t)k * mcand, score + (size_t)k * mcand, nc7);
-          }
-          if (score1 > score2) { for (int k = ed1; k <= ed2; ++k) s3[k] = S.get(o, k); }
-          else { for (int k = st2; k <= ed2; ++k) s3[k] = S.get(o, k); }
-          bl[1] = ed2;
+    // MergeF0 (:941-973); merged starts as channel 0 over the whole axis
+    {
+      const int lo = wlo[0], hi = whi[0];
+      const double *w = mc + off[0] - lo;
+      for (int i = tid; i < L; i += nth) s3[i] = (i < lo || i > hi) ? 0.0 : w[i];
+    }
+    WB_SYNC();
+    if (tid == 0) {
+      for (int i = 0; i < nch; ++i) order[i] = i;
+      // MakeSortedOrder exactly as written in the reference (:881-893): the inner loop keeps
+      // comparing against position i while elements move
+      for (int i = 1; i < nch; ++i)
+        for (int j = i - 1; j >= 0; --j) {
+          if (bl[order[j] * 2] > bl[order[i] * 2]) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+          else break;
         }
+      for (int i = 1; i < nch; ++i) {
+        const int o = order[i];
+        const int lo = wlo[o], hi = whi[o];
+        const double *w = mc + off[o] - lo;
+#define WB_CH(j) (((j) < lo || (j) > hi) ? 0.0 : w[(j)])
+        if (bl[o * 2] - bl[1] > 0) {
+          for (int j = bl[o * 2]; j <= bl[o * 2 + 1]; ++j) s3[j] = WB_CH(j);
+          bl[0] = bl[o * 2];
+          bl[1] = bl[o * 2 + 1];
+        } else {
+          // MergeF0Sub (:912-935)
+          const int st1 = bl[0], ed1 = bl[1], st2 = bl[o * 2], ed2 = bl[o * 2 + 1];
+          if (st1 <= st2 && ed1 >= ed2) {
+            bl[1] = ed1;
+          } else {
+            double score1 = 0.0, score2 = 0.0;
+            for (int k = st2; k <= ed1; ++k) {
+              score1 += hv_search_score(s3[k], cand + (size_t)k * mcand, score + (size_t)k * mcand, nc7);
+              score2 += hv_search_score(WB_CH(k), cand + (size_t)k * mcand, score + (size_t)k * mcand, nc7);
+            }
+            if (score1 > score2) { for (int k = ed1; k <= ed2; ++k) s3[k] = WB_CH(k); }
+            else { for (int k = st2; k <= ed2; ++k) s3[k] = WB_CH(k); }
+            bl[1] = ed2;
+          }
+        }
+#undef WB_CH
       }
     }
+    WB_SYNC();
   }
   // FixStep4 (:1000-1022): bridge gaps shorter than 9 frames
-  for (int i = 0; i < L; ++i) s4[i] = s3[i];
-  nb = hv_boundaries(s3, L, bl);
-  for (int i = 0; i < nb / 2 - 1; ++i) {
+  for (int i = tid; i < L; i += nth) s4[i] = s3[i];
+  nb = hv_boundaries(s3, L, bl, cnt);
+  for (int i = tid; i < nb / 2 - 1; i += nth) {
     const int distance = bl[(i + 1) * 2] - bl[i * 2 + 1] - 1;
     if (distance >= 9) continue;
     const double tmp0 = s3[bl[i * 2 + 1]] + 1;
@@ -465,39 +543,43 @@ WB_KERNEL(128, 4) harvest_contour_kernel(HvContourParams p) {
 struct HvSmoothParams {
   const double *work; int l1_stride; const int *l1;  // s4 = work[u][4]
   double *padded;      // [n][pad_stride]: f0 contour padded by 300 zeros on both sides
-  double *tmp;         // [n][sec_slots][pad_stride] per-section scratch (two buffers per slot)
+  double *tmp;         // [n][sec_slots][seg_cap] per-thread section scratch
   int *blist;          // [n][pad_stride]
   double *basic;       // [n][l1_stride] smoothed 1 ms contour
-  size_t pad_stride; int sec_slots;
+  size_t pad_stride; int sec_slots; int seg_cap;
   const int *f_len; int f_stride; double frame_period;
   double *time_axis; double *f0;
 };
 
-// FilteringF0 (harvest.cpp:1049-1074) for one section; x is synthesised on the fly:
-// x[i] = f0[st] for i < st, f0[i] inside, f0[ed] beyond.
-WB_DEV void hv_filter_section(const double *f0c, int len, int st, int ed, double *tmp_x, double *yout) {
+// FilteringF0 (harvest.cpp:1049-1074) for one section.  The reference filters the whole padded
+// contour (edge-held outside [st, ed]) forward and backward from zero state.  The filter's poles
+// have |z| = 0.875, so a zero-state start WB_HV_RUNIN samples before the section is
+// indistinguishable (0.875^640 < 1e-37) from the reference's start at sample 0; both passes are
+// restricted to [st - RUNIN, ed + RUNIN].  tmp_x holds the reversed forward output of that span.
+#define WB_HV_RUNIN 640
+WB_DEV void hv_filter_section(const double *f0c, int len, int st, int ed, double *tmp_x, double *basic, int lag) {
   const double b0 = 0.0078202080334971724, b1 = 0.015640416066994345;
   const double a0 = 1.7347257688092754, a1 = -0.76600660094326412;
+  const int lo = imax(0, st - WB_HV_RUNIN), hi = imin(len - 1, ed + WB_HV_RUNIN);
   double w0 = 0.0, w1 = 0.0;
-  for (int i = 0; i < len; ++i) {
+  for (int i = lo; i <= hi; ++i) {
     const double xi = f0c[i < st ? st : (i > ed ? ed : i)];
     const double wt = xi + a0 * w0 + a1 * w1;
-    tmp_x[len - i - 1] = b0 * wt + b1 * w0 + b0 * w1;
+    tmp_x[hi - i] = b0 * wt + b1 * w0 + b0 * w1;
     w1 = w0; w0 = wt;
   }
   w0 = w1 = 0.0;
-  for (int i = 0; i < len; ++i) {
+  for (int i = 0; i <= hi - lo; ++i) {
     const double wt = tmp_x[i] + a0 * w0 + a1 * w1;
-    const int o = len - i - 1;
-    const double v = b0 * wt + b1 * w0 + b0 * w1;
-    if (o >= st && o <= ed) yout[o] = v;
+    const int o = hi - i;
+    if (o >= st && o <= ed) basic[o - lag] = b0 * wt + b1 * w0 + b0 * w1;
     w1 = w0; w0 = wt;
   }
 }
 
 WB_KERNEL(128, 4) harvest_smooth_kernel(HvSmoothParams p) {
+  WB_SHARED int cnt[130];
   const int tid = WB_TID, nth = WB_NTH, u = blockIdx.x;
-  WB_SHARED int nb_shared;
   const int L = p.l1[u], lag = 300, len = L + 2 * lag;
   const double *s4 = p.work + ((size_t)u * 5 + 4) * p.l1_stride;
   double *pad = p.padded + (size_t)u * p.pad_stride;
@@ -506,19 +588,12 @@ WB_KERNEL(128, 4) harvest_smooth_kernel(HvSmoothParams p) {
   for (int i = tid; i < len; i += nth) pad[i] = (i >= lag && i < lag + L) ? s4[i - lag] : 0.0;
   for (int i = tid; i < L; i += nth) basic[i] = 0.0;  // f0[i] = 0 (harvest.cpp:1176-1179)
   WB_SYNC();
-  if (tid == 0) nb_shared = hv_boundaries(pad, len, bl);
-  WB_SYNC();
-  const int nsec = nb_shared / 2;
+  const int nsec = hv_boundaries(pad, len, bl, cnt) / 2;
   // sections are independent: thread q filters sections q, q + slots, ... in its own scratch
   const int slots = imin(p.sec_slots, nth);
   if (tid < slots) {
-    double *tmp_x = p.tmp + ((size_t)u * p.sec_slots + tid) * 2 * p.pad_stride;
-    double *yout = tmp_x + p.pad_stride;
-    for (int s = tid; s < nsec; s += slots) {
-      const int st = bl[2 * s], ed = bl[2 * s + 1];
-      hv_filter_section(pad, len, st, ed, tmp_x, yout);
-      for (int j = st; j <= ed; ++j) basic[j - lag] = yout[j];
-    }
+    double *tmp_x = p.tmp + ((size_t)u * p.sec_slots + tid) * p.seg_cap;
+    for (int s = tid; s < nsec; s += slots) hv_filter_section(pad, len, bl[2 * s], bl[2 * s + 1], tmp_x, basic, lag);
   }
   WB_SYNC();
   // subsample to the requested frame period (harvest.cpp:1246-1251)
@@ -578,15 +653,17 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
   const int T = WB_SWEEP_T;
   const int padl = max_taps + 16;
   const size_t y_stride = (size_t)padl + max_ylen + 3 * T + max_taps + 64;
-  const size_t edge_cap = (size_t)max_ylen / 2 + 2;
+  std::vector<int> ecap; std::vector<long long> eoff; size_t edge_stride = 0;
+  plan_edge_caps(boundary, afs, max_ylen, &ecap, &eoff, &edge_stride);
   const int lag = static_cast<int>(ceil(140.0 / ratio) * ratio);
   const size_t tmp_stride = ratio != 1 ? (size_t)b.max_x_len + 2 * lag + 32 : 0;
   const size_t pad_stride = (size_t)l1_stride + 600 + 8;
   const size_t mc_stride = (size_t)28 * l1_stride + 1024;
-  const int sec_slots = 16;
-  const size_t per_utt = y_stride * 8 + (size_t)nb * 4 * edge_cap * 8 + (size_t)nb * l1_stride * 8 +
+  const int sec_slots = 32;
+  const int seg_cap = l1_stride + 600 + 8;  // a section span never exceeds the padded contour
+  const size_t per_utt = y_stride * 8 + edge_stride * 8 + (size_t)nb * l1_stride * 8 +
                          (size_t)l1_stride * (WB_HV_BASE * 8 + 4) + (size_t)l1_stride * max_cand * 8 * 4 +
-                         (size_t)l1_stride * (5 * 8 + 6 * 4 + 8) + mc_stride * 8 + pad_stride * (8 + 4 + sec_slots * 16) +
+                         (size_t)l1_stride * (5 * 8 + 6 * 4 + 8) + mc_stride * 8 + pad_stride * (8 + 4) + (size_t)sec_slots * seg_cap * 8 +
                          tmp_stride * 16 + 1024;
   int chunk = (int)imin(imin(b.n, 65535), (int)dmax(1.0, (double)ctx->scratch_budget / (double)per_utt));
 #ifndef WB_EMU
@@ -597,7 +674,8 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     ArenaPlan plan;
     const size_t o_y = plan.add((size_t)n * y_stride * 8), o_ylen = plan.add((size_t)n * 4);
     const size_t o_l1 = plan.add((size_t)n * 4), o_nc = plan.add((size_t)n * 4);
-    const size_t o_edges = plan.add((size_t)n * nb * 4 * edge_cap * 8);
+    const size_t o_edges = plan.add((size_t)n * edge_stride * 8);
+    const size_t o_ecap = plan.add(nb * 4), o_eoff = plan.add(nb * 8);
     const size_t o_raw = plan.add((size_t)n * nb * l1_stride * 8);
     const size_t o_base = plan.add((size_t)n * l1_stride * WB_HV_BASE * 8), o_bcnt = plan.add((size_t)n * l1_stride * 4);
     const size_t o_c1 = plan.add((size_t)n * l1_stride * max_cand * 8), o_s1 = plan.add((size_t)n * l1_stride * max_cand * 8);
@@ -605,9 +683,9 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     const size_t o_work = plan.add((size_t)n * 5 * l1_stride * 8), o_iwork = plan.add((size_t)n * 6 * l1_stride * 4);
     const size_t o_mc = plan.add((size_t)n * mc_stride * 8);
     const size_t o_pad = plan.add((size_t)n * pad_stride * 8), o_bl = plan.add((size_t)n * pad_stride * 4);
-    const size_t o_stmp = plan.add((size_t)n * sec_slots * 2 * pad_stride * 8);
+    const size_t o_stmp = plan.add((size_t)n * sec_slots * seg_cap * 8);
     const size_t o_basic = plan.add((size_t)n * l1_stride * 8);
-    const size_t o_tmp = plan.add((size_t)n * 2 * tmp_stride * 8);
+    const size_t o_tmp = plan.add((size_t)n * tmp_stride * 8);
     const size_t o_taps = plan.add(taps.size() * 8);
     const size_t o_toff = plan.add(nb * 4), o_nt = plan.add(nb * 4), o_sh = plan.add(nb * 4), o_bd = plan.add(nb * 8);
     unsigned char *blk = arena_block(ctx, plan.total);
@@ -622,12 +700,20 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_nt, ntaps.data(), nb * 4);
     if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_sh, shift.data(), nb * 4);
     if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_bd, boundary.data(), nb * 8);
+    if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_ecap, ecap.data(), nb * 4);
+    if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_eoff, eoff.data(), nb * 8);
     if (rc) return rc;
 
     HvPrepParams pp;
     pp.x = b.x + (size_t)u0 * b.x_stride; pp.x_len = b.x_len + u0; pp.x_stride = b.x_stride; pp.ratio = ratio;
     pp.y = y; pp.y_stride = y_stride; pp.y_origin = padl; pp.y_len = ylen;
-    pp.tmp = ratio != 1 ? (double *)(blk + o_tmp) : nullptr; pp.tmp_stride = tmp_stride;
+    if (ratio != 1) {
+      DecimateParams dp;
+      dp.x = pp.x; dp.x_len = pp.x_len; dp.x_stride = pp.x_stride; dp.ratio = ratio; dp.lag = lag;
+      dp.tmp = (double *)(blk + o_tmp); dp.tmp_stride = tmp_stride;
+      dp.y = y; dp.y_stride = y_stride; dp.y_origin = padl; dp.first = lag / ratio; dp.n_out_mode = 1;
+      launch_decimate(ctx, dp, b.max_x_len, (unsigned)n);
+    }
     WB_LAUNCH_COOP(harvest_prep_kernel, dim3((unsigned)n), 256, 0, ctx->stream, pp);
 
     SweepParams sp;
@@ -635,7 +721,8 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     sp.taps_rev = (const double *)(blk + o_taps); sp.tap_off = (const int *)(blk + o_toff);
     sp.ntaps = (const int *)(blk + o_nt); sp.shift = (const int *)(blk + o_sh);
     sp.boundary = (const double *)(blk + o_bd); sp.afs = afs;
-    sp.edges = (double *)(blk + o_edges); sp.edge_cap = edge_cap;
+    sp.edges = (double *)(blk + o_edges); sp.edge_stride = edge_stride;
+    sp.edge_cap = (const int *)(blk + o_ecap); sp.edge_off = (const long long *)(blk + o_eoff);
     sp.n_frames = l1; sp.frame_stride = l1_stride; sp.frame_period = 1.0;
     sp.mode = 1; sp.f0_floor = opt.f0_floor; sp.f0_ceil = opt.f0_ceil;
     sp.cand = (double *)(blk + o_raw); sp.score = nullptr;
@@ -674,7 +761,7 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     HvSmoothParams hp;
     hp.work = cp.work; hp.l1_stride = l1_stride; hp.l1 = l1; hp.padded = (double *)(blk + o_pad);
     hp.tmp = (double *)(blk + o_stmp); hp.blist = (int *)(blk + o_bl); hp.basic = (double *)(blk + o_basic);
-    hp.pad_stride = pad_stride; hp.sec_slots = sec_slots; hp.f_len = b.f_len + u0; hp.f_stride = b.f_stride;
+    hp.pad_stride = pad_stride; hp.sec_slots = sec_slots; hp.seg_cap = seg_cap; hp.f_len = b.f_len + u0; hp.f_stride = b.f_stride;
     hp.frame_period = opt.frame_period;
     hp.time_axis = time_axis_out + (size_t)u0 * b.f_stride; hp.f0 = f0_out + (size_t)u0 * b.f_stride;
     WB_LAUNCH_COOP(harvest_smooth_kernel, dim3((unsigned)n), 128, 0, ctx->stream, hp);

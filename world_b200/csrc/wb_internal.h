@@ -24,7 +24,7 @@ struct Ctx {
   double2 *twiddle = nullptr;        // [WB_TW_N/2] exp(-j 2 pi k / WB_TW_N)
   uint32_t *rng_jump = nullptr;      // [WB_RNG_NJ][32][16] uint4
   Arena arena;
-  size_t scratch_budget = (size_t)12 << 30;  // bytes of scratch a stage may use per chunk
+  size_t scratch_budget = (size_t)24 << 30;  // bytes of scratch a stage may use per chunk
   int sm_count = 148;
   int *status_dev = nullptr;         // sticky device-side error word
   std::string last_error;
