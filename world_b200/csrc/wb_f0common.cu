@@ -42,17 +42,23 @@ WB_KERNEL(256, 3) fir_plain_kernel(FirParams p) {
   }
 }
 
-// interp1 (matlabfunctions.cpp:157-176) of one event train at time t; edges = fine edge
-// positions (n_edges of them), sample (x, y) pairs are (location, interval) of consecutive edges.
-WB_DEV double train_interp(const double *e, int n_int, double afs, double t) {
-  // k = #{j : loc[j] <= t} clamped to [1, n_int-1]; loc[j] = (e[j] + e[j+1]) / 2 / afs
-  int lo = 0, hi = n_int;  // first j with loc[j] > t
+// interp1 (matlabfunctions.cpp:157-176) of one event train at time t.  e = fine edge positions;
+// the (x, y) samples interp1 sees are (location, interval) of consecutive edges:
+// x_j = (e_j + e_{j+1}) / 2 / afs, y_j = afs / (e_{j+1} - e_j), j < n_int.
+// `lo` narrows the search: the caller guarantees #{j : x_j <= t} >= lo.
+WB_DEV double train_location(const double *e, int j, double afs) { return (e[j] + e[j + 1]) / 2.0 / afs; }
+
+WB_DEV int train_count(const double *e, int lo, int n_int, double afs, double t) {
+  int hi = n_int;  // first j in [lo, n_int) with x_j > t
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    const double loc = (e[mid] + e[mid + 1]) / 2.0 / afs;
-    if (loc <= t) lo = mid + 1; else hi = mid;
+    if (train_location(e, mid, afs) <= t) lo = mid + 1; else hi = mid;
   }
-  const int k = imin(n_int - 1, imax(1, lo));
+  return lo;
+}
+
+WB_DEV double train_interp(const double *e, int lo, int n_int, double afs, double t) {
+  const int k = imin(n_int - 1, imax(1, train_count(e, lo, n_int, afs, t)));
   const double e0 = e[k - 1], e1 = e[k], e2 = e[k + 1];
   const double x0 = (e0 + e1) / 2.0 / afs, x1 = (e1 + e2) / 2.0 / afs;
   const double y0 = afs / (e1 - e0), y1 = afs / (e2 - e1);
@@ -88,6 +94,26 @@ WB_DEV unsigned long long scan_packed(unsigned long long *c, int G, unsigned lon
 #endif
 }
 
+// One frame of one band: interp1 of the four trains, mean, (DIO) score, range checks
+// (dio.cpp:441-465, 562-566 / harvest.cpp:240-254).
+WB_DEV void sweep_candidate(const SweepParams &p, const double *edges, int cap, const int *lo_j, const int *tot,
+                            int i, double bf, double *cand, double *score) {
+  const double t = i * p.frame_period / 1000.0;
+  const double v0 = train_interp(edges, lo_j[0], tot[0] - 1, p.afs, t);
+  const double v1 = train_interp(edges + cap, lo_j[1], tot[1] - 1, p.afs, t);
+  const double v2 = train_interp(edges + 2 * (size_t)cap, lo_j[2], tot[2] - 1, p.afs, t);
+  const double v3 = train_interp(edges + 3 * (size_t)cap, lo_j[3], tot[3] - 1, p.afs, t);
+  double c = (v0 + v1 + v2 + v3) / 4.0, sc = 0.0;
+  if (p.mode == 0) {
+    sc = sqrt(((v0 - c) * (v0 - c) + (v1 - c) * (v1 - c) + (v2 - c) * (v2 - c) + (v3 - c) * (v3 - c)) / 3.0);
+    if (c > bf || c < bf / 2.0 || c > p.f0_ceil || c < p.f0_floor) { c = 0.0; sc = 100000.0; }
+  } else {
+    if (c > bf * 1.1 || c < bf * 0.9 || c > p.f0_ceil || c < p.f0_floor) c = 0.0;
+  }
+  cand[i] = c;
+  if (score) score[i] = sc / (c + kTiny);  // dio.cpp:562-566
+}
+
 WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   WB_DYN_SMEM(double, smem);
   const int tid = WB_TID, nth = WB_NTH;
@@ -109,6 +135,12 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   for (int j = ntaps + tid; j < ntaps + 8; j += nth) hrev[j] = 0.0;
   if (tid == 0) { st[0] = 0.0; st[1] = 0.0; }
   int tot[4] = {0, 0, 0, 0};  // running event counts per train (identical in every thread)
+  int lo_j[4] = {0, 0, 0, 0}; // per train: intervals below this index lie before every unfinished frame
+  int next_frame = 0;         // frames [0, next_frame) are done
+  const int nf = p.n_frames[u];
+  double *cand = p.cand + ((size_t)u * p.n_bands + b) * p.frame_stride;
+  double *score = p.score ? p.score + ((size_t)u * p.n_bands + b) * p.frame_stride : nullptr;
+  const double bf = p.boundary[b];
   WB_SYNC();
 
   // Tile k produces outputs n0..n0+T-1 into st[2..]; events are detected for positions
@@ -181,47 +213,56 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
     }
     tot[0] += (int)(tile_total & 0xffffull); tot[1] += (int)((tile_total >> 16) & 0xffffull);
     tot[2] += (int)((tile_total >> 32) & 0xffffull); tot[3] += (int)((tile_total >> 48) & 0xffffull);
+#ifndef WB_EMU
+    __threadfence_block();
+#endif
     WB_SYNC();
     if (tid == 0) { st[0] = st[T]; st[1] = st[T + 1]; }
+    // ---- streaming candidates: every frame whose time lies before the last complete interval of
+    // all four trains can be interpolated now; its events are the most recent ones (cache hot).
+    bool can = true;
+    double t_safe = 0.0;
+    for (int q = 0; q < 4; ++q) {
+      if (tot[q] > cap || tot[q] < 2) { can = false; break; }
+      const double loc = train_location(edges + (size_t)q * cap, tot[q] - 2, p.afs);
+      t_safe = (q == 0 || loc < t_safe) ? loc : t_safe;
+    }
+    if (can) {
+      // first frame index with t_i >= t_safe (t_i = i * frame_period / 1000.0, monotone in i)
+      int i_safe = (int)(t_safe * 1000.0 / p.frame_period);
+      if (i_safe < 0) i_safe = 0;
+      while (i_safe > 0 && !((i_safe - 1) * p.frame_period / 1000.0 < t_safe)) --i_safe;
+      while (i_safe < nf && (i_safe * p.frame_period / 1000.0 < t_safe)) ++i_safe;
+      if (i_safe > nf) i_safe = nf;
+      if (i_safe > next_frame) {
+        for (int i = next_frame + tid; i < i_safe; i += nth)
+          sweep_candidate(p, edges, cap, lo_j, tot, i, bf, cand, score);
+        // all later frames have t >= t_safe: their interval counts are at least those of t_safe
+        for (int q = 0; q < 4; ++q) {
+          const int c = train_count(edges + (size_t)q * cap, lo_j[q], tot[q] - 1, p.afs, (i_safe - 1) * p.frame_period / 1000.0);
+          lo_j[q] = imax(lo_j[q], c);
+        }
+        next_frame = i_safe;
+      }
+    }
     WB_SYNC();
   }
-#ifndef WB_EMU
-  __threadfence_block();
-#endif
-  WB_SYNC();
-  // ---- candidates on the frame grid
-  const int nf = p.n_frames[u];
-  double *cand = p.cand + ((size_t)u * p.n_bands + b) * p.frame_stride;
-  double *score = p.score ? p.score + ((size_t)u * p.n_bands + b) * p.frame_stride : nullptr;
-  int ni[4];
+  // ---- frames after the last complete interval (interp1 extrapolates from the last two samples)
   bool ok = true;
   for (int q = 0; q < 4; ++q) {
     if (tot[q] > cap) { if (tid == 0) atomicOr_status(p.status, 4); ok = false; }
-    ni[q] = tot[q] < 2 ? 0 : tot[q] - 1;  // ZeroCrossingEngine returns count-1 (0 if count<2)
-    if (ni[q] - 2 <= 0) ok = false;       // CheckEvent(n - 2), dio.cpp:475-484
+    const int ni = tot[q] < 2 ? 0 : tot[q] - 1;  // ZeroCrossingEngine returns count-1 (0 if count<2)
+    if (ni - 2 <= 0) ok = false;                 // CheckEvent(n - 2), dio.cpp:475-484
   }
-  const double bf = p.boundary[b];
-  for (int i = tid; i < nf; i += nth) {
-    double c = 0.0, sc = 100000.0;  // kMaximumValue
-    if (ok) {
-      const double t = i * p.frame_period / 1000.0;
-      const double v0 = train_interp(edges, ni[0], p.afs, t);
-      const double v1 = train_interp(edges + cap, ni[1], p.afs, t);
-      const double v2 = train_interp(edges + 2 * (size_t)cap, ni[2], p.afs, t);
-      const double v3 = train_interp(edges + 3 * (size_t)cap, ni[3], p.afs, t);
-      c = (v0 + v1 + v2 + v3) / 4.0;
-      if (p.mode == 0) {
-        sc = sqrt(((v0 - c) * (v0 - c) + (v1 - c) * (v1 - c) + (v2 - c) * (v2 - c) + (v3 - c) * (v3 - c)) / 3.0);
-        if (c > bf || c < bf / 2.0 || c > p.f0_ceil || c < p.f0_floor) { c = 0.0; sc = 100000.0; }
-      } else {
-        if (c > bf * 1.1 || c < bf * 0.9 || c > p.f0_ceil || c < p.f0_floor) c = 0.0;
-      }
+  if (ok) {
+    for (int i = next_frame + tid; i < nf; i += nth) sweep_candidate(p, edges, cap, lo_j, tot, i, bf, cand, score);
+  } else {
+    for (int i = tid; i < nf; i += nth) {
+      cand[i] = 0.0;
+      if (score) score[i] = 100000.0 / (0.0 + kTiny);
     }
-    cand[i] = c;
-    if (score) score[i] = sc / (c + kTiny);  // dio.cpp:562-566
   }
 }
-
 
 // extended input of decimate(): 9 mirrored samples on both sides of the edge-padded signal
 WB_DEV double dec_ext(const double *__restrict__ x, int n, int lag, int nx, int i) {

@@ -36,7 +36,7 @@ static void plan_edge_caps(const std::vector<double> &boundary, double afs, int 
 }
 
 #define WB_HV_BASE 32        // >= round(channels / 10): base candidates kept per frame
-#define WB_HV_WARPS 8
+#define WB_HV_WARPS 4
 
 // ------------------------------------------------------------------ K-HVd
 struct HvPrepParams {
@@ -129,13 +129,15 @@ WB_DEV double2 hv_tw(const double2 *__restrict__ tw, int idx) {
 }
 
 // GetRefinedF0 (harvest.cpp:589-617) for one candidate, executed by one warp.
-// wbuf/dbuf: per-warp shared scratch of nwin doubles each.
+// wbuf / xbuf / dbuf: per-warp shared scratch of nwin doubles each (window, x*window, x*dwindow).
+// Loops are unrolled by four independent iterations per lane to keep several cosines / table
+// gathers in flight (the kernel is latency bound otherwise).
 // Lane layout of the sparse DFT: lane = 8*c + m handles harmonic m (H <= 6 of the 8 slots) over
 // the samples j = c, c+4, c+8, ...; two xor-shuffles fold the four sample classes, then the
 // harmonics are combined in index order exactly like FixF0 (harvest.cpp:509-535).
 WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, double t, double f,
                           double f0_floor, double f0_ceil, const double2 *__restrict__ tw, double *wbuf,
-                          double *dbuf, double *out_f0, double *out_score) {
+                          double *xbuf, double *dbuf, double *out_f0, double *out_score) {
   const int lane = WB_LANE;
   const int h = static_cast<int>(1.5 * afs / f + 1.0);
   const int nwin = 2 * h + 1;
@@ -146,25 +148,35 @@ WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, d
   // base_index[j] = round((t + base_time[0]) * fs + 0.001) + j   (harvest.cpp:434-441)
   const int basic = round_half_away((t + (-h + 0) / afs) * afs + 0.001);
   // Blackman window (harvest.cpp:446-456); cos(2a) = 2 cos(a)^2 - 1 saves the second cosine
-  for (int j = lane; j < nwin; j += WB_LANES) {
-    const double tmp = ((basic + j) - 1.0) / afs - t;
-    const double c1 = cos(2.0 * kPi * tmp / T);
-    wbuf[j] = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
+  for (int j0 = 0; j0 < nwin; j0 += 4 * WB_LANES) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + q * WB_LANES + lane;
+      if (j < nwin) {
+        const double tmp = ((basic + j) - 1.0) / afs - t;
+        const double c1 = cos(2.0 * kPi * tmp / T);
+        wbuf[j] = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
+      }
+    }
   }
 #ifndef WB_EMU
   __syncwarp();
 #endif
-  for (int j = lane; j < nwin; j += WB_LANES) {
-    double dw;
-    if (j == 0) dw = -wbuf[1] / 2.0;
-    else if (j == nwin - 1) dw = wbuf[nwin - 2] / 2.0;
-    else dw = -(wbuf[j + 1] - wbuf[j - 1]) / 2.0;
-    dbuf[j] = y[imax(0, imin(y_len - 1, basic + j - 1))] * dw;
+  for (int j0 = 0; j0 < nwin; j0 += 4 * WB_LANES) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + q * WB_LANES + lane;
+      if (j < nwin) {
+        double dw;
+        if (j == 0) dw = -wbuf[1] / 2.0;
+        else if (j == nwin - 1) dw = wbuf[nwin - 2] / 2.0;
+        else dw = -(wbuf[j + 1] - wbuf[j - 1]) / 2.0;
+        const double s = y[imax(0, imin(y_len - 1, basic + j - 1))];
+        xbuf[j] = s * wbuf[j];
+        dbuf[j] = s * dw;
+      }
+    }
   }
-#ifndef WB_EMU
-  __syncwarp();
-#endif
-  for (int j = lane; j < nwin; j += WB_LANES) wbuf[j] = y[imax(0, imin(y_len - 1, basic + j - 1))] * wbuf[j];
 #ifndef WB_EMU
   __syncwarp();
 #endif
@@ -182,11 +194,17 @@ WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, d
     double mr = 0.0, mi = 0.0, dr = 0.0, di = 0.0;
     const int bin = round_half_away(f * nfft / afs * (m + 1));
     if (m < H) {
-      for (int j = c0; j < nwin; j += cstep) {
-        const double2 w = hv_tw(tw, ((bin * j) & (nfft - 1)) << shift);
-        const double a = wbuf[j], d = dbuf[j];
-        mr = fma(a, w.x, mr); mi = fma(a, w.y, mi);
-        dr = fma(d, w.x, dr); di = fma(d, w.y, di);
+      for (int j0 = c0; j0 < nwin; j0 += 4 * cstep) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = j0 + q * cstep;
+          if (j < nwin) {
+            const double2 w = hv_tw(tw, ((bin * j) & (nfft - 1)) << shift);
+            const double a = xbuf[j], d = dbuf[j];
+            mr = fma(a, w.x, mr); mi = fma(a, w.y, mi);
+            dr = fma(d, w.x, dr); di = fma(d, w.y, di);
+          }
+        }
       }
     }
 #ifndef WB_EMU
@@ -233,7 +251,7 @@ WB_DEV double hv_slot_candidate(const double *__restrict__ base, int L1, int nc,
   return base[(size_t)src * WB_HV_BASE + j];
 }
 
-WB_KERNEL(32 * WB_HV_WARPS, 2) harvest_refine_kernel(HvRefineParams p) {
+WB_KERNEL(32 * WB_HV_WARPS, 4) harvest_refine_kernel(HvRefineParams p) {
   WB_DYN_SMEM(double, smem);
 #ifdef WB_EMU
   const int warp = 0, nwarps = 1;
@@ -246,18 +264,30 @@ WB_KERNEL(32 * WB_HV_WARPS, 2) harvest_refine_kernel(HvRefineParams p) {
   const int k = blockIdx.x * nwarps + warp;
   if (k >= L1) return;
   const int nc = p.nc[u], n_slots = nc * 7;
-  double *wbuf = smem + (size_t)warp * 2 * p.nwin_max, *dbuf = wbuf + p.nwin_max;
+  double *wbuf = smem + (size_t)warp * 3 * p.nwin_max, *xbuf = wbuf + p.nwin_max, *dbuf = xbuf + p.nwin_max;
   const double *y = p.y + (size_t)u * p.y_stride + p.y_origin;
   const double *base = p.base + (size_t)u * p.l1_stride * WB_HV_BASE;
   double *cand = p.cand + ((size_t)u * p.l1_stride + k) * p.max_cand;
   double *score = p.score + ((size_t)u * p.l1_stride + k) * p.max_cand;
   const double t = k * 1 / 1000.0;  // basic frame period 1 ms (harvest.cpp:1203)
   const int y_len = p.y_len[u];
-  for (int s = 0; s < n_slots; ++s) {
-    const double f = hv_slot_candidate(base, L1, nc, k, s);
-    double rf = 0.0, rs = 0.0;
-    if (f > 0.0) hv_refine_one(y, y_len, p.afs, t, f, p.f0_floor, p.f0_ceil, p.tw, wbuf, dbuf, &rf, &rs);
-    if (lane == 0) { cand[s] = rf; score[s] = rs; }
+  // the frame's slots are fetched WB_LANES at a time (one per lane) and handed round by shuffle
+  for (int s0 = 0; s0 < n_slots; s0 += WB_LANES) {
+    const double f_mine = (s0 + lane < n_slots) ? hv_slot_candidate(base, L1, nc, k, s0 + lane) : 0.0;
+    double rf_mine = 0.0, rs_mine = 0.0;
+    for (int q = 0; q < WB_LANES && s0 + q < n_slots; ++q) {
+#ifdef WB_EMU
+      const double f = f_mine;
+#else
+      const double f = __shfl_sync(0xffffffffu, f_mine, q);
+#endif
+      if (f > 0.0) {
+        double rf, rs;
+        hv_refine_one(y, y_len, p.afs, t, f, p.f0_floor, p.f0_ceil, p.tw, wbuf, xbuf, dbuf, &rf, &rs);
+        if (lane == q) { rf_mine = rf; rs_mine = rs; }
+      }
+    }
+    if (s0 + lane < n_slots) { cand[s0 + lane] = rf_mine; score[s0 + lane] = rs_mine; }
   }
 }
 
@@ -642,7 +672,7 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
   const int nwin_max = 2 * h_max + 1 + 2;
   int lgw = 0;
   while ((2 << lgw) <= nwin_max) ++lgw;
-  const size_t smem_refine = (size_t)WB_HV_WARPS * 2 * nwin_max * 8;
+  const size_t smem_refine = (size_t)WB_HV_WARPS * 3 * nwin_max * 8;
   if (smem_sweep > 200 * 1024 || smem_refine > 200 * 1024 || (1 << (lgw + 2)) > WB_TW_N) {
     ctx->last_error = "Harvest: f0_floor too low for the on-chip filters";
     return 3;
