@@ -63,25 +63,33 @@ WB_DEV int block_sum_int(int v, double *red) {
 #endif
 }
 
-// Inclusive prefix sum over a shared array a[0..n) in place (order: tree, see header note).
-// Each thread owns a contiguous chunk; chunk totals are scanned by thread 0.
-WB_DEV void block_inclusive_scan(double *a, int n, double *red_big /* >= nthreads+1 */) {
+// Inclusive prefix sum over a shared array a[0..n) in place (order: blocked tree, see header note).
+// Each thread owns a contiguous chunk; chunk totals are scanned with warp shuffles.
+// red_big: >= nthreads + 33 doubles of shared scratch.
+WB_DEV void block_inclusive_scan(double *a, int n, double *red_big) {
   const int tid = WB_TID, nth = WB_NTH;
   const int chunk = (n + nth - 1) / nth;
   const int lo = imin(n, tid * chunk), hi = imin(n, lo + chunk);
   double s = 0.0;
   for (int i = lo; i < hi; ++i) { s += a[i]; a[i] = s; }
-  WB_SYNC();
-  red_big[tid] = s;
-  WB_SYNC();
-  if (tid == 0) {
-    double run = 0.0;
-    for (int t = 0; t < nth; ++t) { double c = red_big[t]; red_big[t] = run; run += c; }
+#ifdef WB_EMU
+  (void)red_big;
+#else
+  // exclusive scan of the per-thread totals
+  double inc = s;
+  const int lane = tid & 31, w = tid >> 5, nw = (nth + 31) >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
   }
-  WB_SYNC();
-  const double base = red_big[tid];
-  if (tid > 0)
+  __syncthreads();
+  if (lane == 31) red_big[w] = inc;
+  __syncthreads();
+  double base = inc - s;
+  for (int i = 0; i < w && i < nw; ++i) base += red_big[i];
+  if (base != 0.0 || tid > 0)
     for (int i = lo; i < hi; ++i) a[i] += base;
+#endif
   WB_SYNC();
 }
 

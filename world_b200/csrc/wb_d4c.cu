@@ -135,13 +135,19 @@ WB_KERNEL(128, 4) d4c_lovetrain_kernel(D4cParams p) {
   }
 }
 
-// k-th largest (1-based) of the non-negative doubles a[0..n): bisection on the bit pattern.
+// k-th largest (1-based) of the non-negative doubles a[0..n): bisection on the IEEE bit pattern,
+// two bits per round (three pivots counted at once), one barrier per round (the per-warp count
+// slots alternate between two halves of `red`, so a round never overwrites what a slow warp of
+// the previous round still reads).  red: >= 2 * 2 * 33 ints.
 WB_DEV double select_kth_largest(const double *a, int n, int kth, double *red) {
   const int tid = WB_TID, nth = WB_NTH;
   unsigned long long pat = 0ull;
-  for (int bit = 62; bit >= 0; --bit) {
-    const unsigned long long cand = pat | (1ull << bit);
-    int c = 0;
+  int round = 0;
+  for (int bit = 62; bit >= 0; bit -= 2, ++round) {
+    const bool two = bit >= 1;
+    const unsigned long long hi_bit = 1ull << bit, lo_bit = two ? (1ull << (bit - 1)) : 0ull;
+    const unsigned long long p01 = pat | lo_bit, p10 = pat | hi_bit, p11 = pat | hi_bit | lo_bit;
+    int c01 = 0, c10 = 0, c11 = 0;
     for (int j = tid; j < n; j += nth) {
       const double v = a[j];
       unsigned long long bits;
@@ -150,11 +156,29 @@ WB_DEV double select_kth_largest(const double *a, int n, int kth, double *red) {
 #else
       bits = (unsigned long long)__double_as_longlong(v);
 #endif
-      c += (bits >= cand) ? 1 : 0;
+      c01 += (bits >= p01) ? 1 : 0;
+      c10 += (bits >= p10) ? 1 : 0;
+      c11 += (bits >= p11) ? 1 : 0;
     }
-    c = block_sum_int(c, red);
-    if (c >= kth) pat = cand;
+#ifndef WB_EMU
+    int *ired = reinterpret_cast<int *>(red) + (round & 1) * 2 * 33;
+    const int packed = __reduce_add_sync(0xffffffffu, c01 | (c10 << 16));
+    c11 = __reduce_add_sync(0xffffffffu, c11);
+    const int lane = tid & 31, w = tid >> 5, nw = (nth + 31) >> 5;
+    if (lane == 0) { ired[w] = packed; ired[33 + w] = c11; }
+    __syncthreads();
+    int sp = 0, s11 = 0;
+    for (int i = 0; i < nw; ++i) { sp += ired[i]; s11 += ired[33 + i]; }
+    c01 = sp & 0xffff; c10 = sp >> 16; c11 = s11;
+#endif
+    // largest pattern whose ">= count" still reaches kth
+    if (two && c11 >= kth) pat = p11;
+    else if (c10 >= kth) pat = p10;
+    else if (two && c01 >= kth) pat = p01;
   }
+#ifndef WB_EMU
+  __syncthreads();
+#endif
   double r;
 #ifdef WB_EMU
   memcpy(&r, &pat, 8);

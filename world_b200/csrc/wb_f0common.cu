@@ -125,7 +125,7 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   double *seg = smem;                                   // padded: pad8(seg_cap)
   double *hrev = seg + (seg_cap + (seg_cap >> 3) + 8);  // max_taps + 8
   double *st = hrev + (p.max_taps + 8);                 // T + 8: [0..1] carry, [2..T+2) this tile
-  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(st + (T + 8));  // G + 40
+  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(st + (T + 8 + ((T + 8) >> 3) + 8));  // G + 40
 
   const int ylen = p.y_len[u];
   const double *sig = p.sig + (size_t)u * p.sig_stride + p.sig_origin;
@@ -164,7 +164,7 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
         }
       }
 #pragma unroll
-      for (int r = 0; r < R; ++r) st[2 + base + r] = acc[r];
+      for (int r = 0; r < R; ++r) st[pad8(2 + base + r)] = acc[r];
     }
     WB_SYNC();
     // train 0: s[i] > 0 >= s[i+1]   train 1: s[i] < 0 <= s[i+1]          (i >= 0, i+1 <= ylen-1)
@@ -175,7 +175,7 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int i = n0 - 2 + base + r;
-        const double a = st[base + r], bb = st[base + r + 1], cc = st[base + r + 2];
+        const double a = st[pad8(base + r)], bb = st[pad8(base + r + 1)], cc = st[pad8(base + r + 2)];
         const double d0 = bb - a, d1 = cc - bb;
         if (i >= 0 && i + 1 <= ylen - 1) {
           c += (0.0 < a && bb <= 0.0) ? 1ull : 0ull;
@@ -198,7 +198,7 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int i = n0 - 2 + base + r;
-        const double a = st[base + r], bb = st[base + r + 1], cc = st[base + r + 2];
+        const double a = st[pad8(base + r)], bb = st[pad8(base + r + 1)], cc = st[pad8(base + r + 2)];
         const double d0 = bb - a, d1 = cc - bb;
         const double e = (double)(i + 1);
         if (i >= 0 && i + 1 <= ylen - 1) {
@@ -217,7 +217,7 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
     __threadfence_block();
 #endif
     WB_SYNC();
-    if (tid == 0) { st[0] = st[T]; st[1] = st[T + 1]; }
+    if (tid == 0) { st[pad8(0)] = st[pad8(T)]; st[pad8(1)] = st[pad8(T + 1)]; }
     // ---- streaming candidates: every frame whose time lies before the last complete interval of
     // all four trains can be interpolated now; its events are the most recent ones (cache hot).
     bool can = true;

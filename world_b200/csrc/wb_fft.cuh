@@ -29,6 +29,9 @@ WB_DEV unsigned bit_reverse(unsigned v, int bits) {
 }
 
 // In-place forward complex FFT of z[0..2^lg) (natural order in, natural order out).
+// Bit reversal, then decimation-in-time stages taken two at a time as radix-4 butterflies held in
+// registers (half the shared-memory passes and barriers of radix-2; one table twiddle per
+// butterfly, the second one is its square), plus one radix-2 stage when lg is odd.
 // Ends with a barrier.
 WB_DEV void cfft_forward(double2 *z, int lg, const double2 *__restrict__ tw) {
   const int tid = WB_TID, nth = WB_NTH;
@@ -38,9 +41,9 @@ WB_DEV void cfft_forward(double2 *z, int lg, const double2 *__restrict__ tw) {
     if (i < j) { const double2 a = z[i]; z[i] = z[j]; z[j] = a; }
   }
   WB_SYNC();
-  // first stage (twiddle 1) and second stage (twiddles 1, -j) fused: radix-4 on 4 neighbours
   int s = 1;
   if (lg >= 2) {
+    // stages 1+2: twiddles are 1 and -j
     for (int q = tid; q < (n >> 2); q += nth) {
       double2 *p = z + 4 * q;
       const double2 a = p[0], b = p[1], c = p[2], d = p[3];
@@ -48,7 +51,6 @@ WB_DEV void cfft_forward(double2 *z, int lg, const double2 *__restrict__ tw) {
       const double2 ab1 = make_double2(a.x - b.x, a.y - b.y);
       const double2 cd0 = make_double2(c.x + d.x, c.y + d.y);
       const double2 cd1 = make_double2(c.x - d.x, c.y - d.y);
-      // (-j) * cd1 = (cd1.y, -cd1.x)
       p[0] = make_double2(ab0.x + cd0.x, ab0.y + cd0.y);
       p[2] = make_double2(ab0.x - cd0.x, ab0.y - cd0.y);
       p[1] = make_double2(ab1.x + cd1.y, ab1.y - cd1.x);
@@ -57,7 +59,32 @@ WB_DEV void cfft_forward(double2 *z, int lg, const double2 *__restrict__ tw) {
     WB_SYNC();
     s = 3;
   }
-  for (; s <= lg; ++s) {
+  for (; s + 1 <= lg; s += 2) {
+    // stages s and s+1: quarter = 2^(s-1); group of 4*quarter elements
+    const int quarter = 1 << (s - 1);
+    const int tws = WB_TW_LOG2 - (s + 1);
+    for (int q = tid; q < (n >> 2); q += nth) {
+      const int j = q & (quarter - 1);
+      const int i0 = ((q >> (s - 1)) << (s + 1)) + j;
+      const int i1 = i0 + quarter, i2 = i1 + quarter, i3 = i2 + quarter;
+      const double2 b = __ldg(&tw[j << tws]);                       // exp(-j 2 pi j / (4 quarter))
+      const double2 a = make_double2(fma(b.x, b.x, -(b.y * b.y)), 2.0 * b.x * b.y);  // its square
+      const double2 z0 = z[i0], z1 = z[i1], z2 = z[i2], z3 = z[i3];
+      const double t1r = fma(a.x, z1.x, -(a.y * z1.y)), t1i = fma(a.x, z1.y, a.y * z1.x);
+      const double t3r = fma(a.x, z3.x, -(a.y * z3.y)), t3i = fma(a.x, z3.y, a.y * z3.x);
+      const double u0r = z0.x + t1r, u0i = z0.y + t1i, u1r = z0.x - t1r, u1i = z0.y - t1i;
+      const double u2r = z2.x + t3r, u2i = z2.y + t3i, u3r = z2.x - t3r, u3i = z2.y - t3i;
+      const double v2r = fma(b.x, u2r, -(b.y * u2i)), v2i = fma(b.x, u2i, b.y * u2r);   // b * u2
+      const double w3r = fma(b.x, u3r, -(b.y * u3i)), w3i = fma(b.x, u3i, b.y * u3r);   // b * u3
+      // (-j b) u3 = (w3i, -w3r)
+      z[i0] = make_double2(u0r + v2r, u0i + v2i);
+      z[i2] = make_double2(u0r - v2r, u0i - v2i);
+      z[i1] = make_double2(u1r + w3i, u1i - w3r);
+      z[i3] = make_double2(u1r - w3i, u1i + w3r);
+    }
+    WB_SYNC();
+  }
+  if (s <= lg) {
     const int half = 1 << (s - 1);
     const int tws = WB_TW_LOG2 - s;
     for (int b = tid; b < (n >> 1); b += nth) {

@@ -194,16 +194,27 @@ WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, d
     double mr = 0.0, mi = 0.0, dr = 0.0, di = 0.0;
     const int bin = round_half_away(f * nfft / afs * (m + 1));
     if (m < H) {
+      // twiddles exp(-j 2 pi bin j / nfft) by rotation: four interleaved chains (one per unrolled
+      // slot) start from exact table values and advance by exp(-j 2 pi bin 4 cstep / nfft); a
+      // chain is <= nwin / (4 cstep) steps long, so the accumulated rounding stays ~1e-15.
+      // (A table gather per sample made this kernel L1-LSU bound: profiles/r1c.)
+      const double2 rot = hv_tw(tw, ((bin * 4 * cstep) & (nfft - 1)) << shift);
+      double2 wq[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) wq[q] = hv_tw(tw, ((bin * (c0 + q * cstep)) & (nfft - 1)) << shift);
       for (int j0 = c0; j0 < nwin; j0 += 4 * cstep) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j = j0 + q * cstep;
           if (j < nwin) {
-            const double2 w = hv_tw(tw, ((bin * j) & (nfft - 1)) << shift);
+            const double2 w = wq[q];
             const double a = xbuf[j], d = dbuf[j];
             mr = fma(a, w.x, mr); mi = fma(a, w.y, mi);
             dr = fma(d, w.x, dr); di = fma(d, w.y, di);
           }
+          const double nx = fma(wq[q].x, rot.x, -(wq[q].y * rot.y));
+          const double ny = fma(wq[q].x, rot.y, wq[q].y * rot.x);
+          wq[q].x = nx; wq[q].y = ny;
         }
       }
     }
