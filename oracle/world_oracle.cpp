@@ -1,0 +1,344 @@
+// oracle/world_oracle.cpp -- CPU restatement of the WORLD analysis path.  TEST INFRASTRUCTURE ONLY.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this library; the
+// product (world_b200/) never links, loads or calls it.  It restates, in plain single-threaded
+// C++ and with its own textbook radix-2 FFT, what the reference computes, each function citing the
+// reference lines it follows (mmorise/World @ d625e76).  It exists beside oracle/_ref (the
+// unmodified reference compiled from /root/reference) so that the checker does not depend on the
+// reference tree being present, and so that the algorithm cards of SURVEY.md App. A are executable.
+//
+// Pinning: the reference ships no golden outputs.  This restatement is pinned against
+// tests/golden/vaiueo2d.npz (generated from oracle/_ref on the reference's own fixture) and against
+// oracle/_ref directly on synthetic batches, by tests/test_oracle.py.
+//
+// Restated here: randn, interp1Q, interp1, DCCorrection, LinearSmoothing, NuttallWindow, the FFT
+// conventions, StoneMask, CheapTrick, D4C, and the option / sizing helpers.
+// NOT restated (checked against oracle/_ref only): Dio, Harvest.
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+namespace {
+
+const double kPi = 3.1415926535897932384;        // constantnumbers.h:18
+const double kTiny = 0.000000000001;             // kMySafeGuardMinimum :19
+const double kEps = 0.00000000000000022204460492503131;  // :20
+const double kLog2 = 0.69314718055994529;        // :24
+
+int RoundHalfAway(double x) { return x > 0 ? (int)(x + 0.5) : (int)(x - 0.5); }  // matlabfunctions.cpp:206-208
+
+// ---- randn: xorshift128, 12 steps per draw (matlabfunctions.cpp:237-264)
+struct Rng {
+  uint32_t x, y, z, w;
+  Rng() : x(123456789), y(362436069), z(521288629), w(88675123) {}
+  double Next() {
+    uint32_t acc = 0;
+    for (int i = 0; i < 12; ++i) {
+      uint32_t t = x ^ (x << 11);
+      x = y; y = z; z = w;
+      w = (w ^ (w >> 19)) ^ (t ^ (t >> 8));
+      acc += w >> 4;
+    }
+    return acc / 268435456.0 - 6.0;
+  }
+};
+
+// ---- FFT: r2c convention of fft.cpp:49-60 (X[k] = sum x[n] exp(-j 2 pi k n / N)), textbook
+// iterative radix-2 on a complex copy of the real input.
+void RealFFT(const std::vector<double> &x, std::vector<double> *re, std::vector<double> *im) {
+  const int n = (int)x.size();
+  std::vector<double> ar(x), ai(n, 0.0);
+  for (int i = 1, j = 0; i < n; ++i) {
+    int bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) std::swap(ar[i], ar[j]);
+  }
+  for (int len = 2; len <= n; len <<= 1) {
+    const double ang = -2.0 * kPi / len;
+    for (int i = 0; i < n; i += len)
+      for (int k = 0; k < len / 2; ++k) {
+        const double wr = cos(ang * k), wi = sin(ang * k);
+        const int a = i + k, b = i + k + len / 2;
+        const double tr = ar[b] * wr - ai[b] * wi, ti = ar[b] * wi + ai[b] * wr;
+        ar[b] = ar[a] - tr; ai[b] = ai[a] - ti;
+        ar[a] += tr; ai[a] += ti;
+      }
+  }
+  re->assign(ar.begin(), ar.begin() + n / 2 + 1);
+  im->assign(ai.begin(), ai.begin() + n / 2 + 1);
+}
+
+// ---- interp1Q (matlabfunctions.cpp:214-235)
+double Interp1QAt(double x0, double dx, const std::vector<double> &y, int ny, double xi) {
+  const double r = (xi - x0) / dx;
+  const int base = (int)r;
+  const double dy = base + 1 < ny ? y[base + 1] - y[base] : 0.0;
+  return y[base] + dy * (r - base);
+}
+
+// ---- interp1 + histc for sorted query points (matlabfunctions.cpp:136-176)
+double Interp1At(const std::vector<double> &x, const std::vector<double> &y, double xi) {
+  const int n = (int)x.size();
+  int k = 0;
+  while (k < n && x[k] <= xi) ++k;
+  k = std::min(n - 1, std::max(1, k));
+  const double s = (xi - x[k - 1]) / (x[k] - x[k - 1]);
+  return y[k - 1] + s * (y[k] - y[k - 1]);
+}
+
+// ---- DCCorrection (common.cpp:56-75), in place
+void DCCorrect(std::vector<double> *spec, double f0, int fs, int fft_size) {
+  const int upper = 2 + (int)(f0 * fft_size / fs);
+  std::vector<double> rep(upper - 1);
+  for (int i = 0; i < upper - 1; ++i)
+    rep[i] = Interp1QAt(f0, -(double)fs / fft_size, *spec, upper + 1, (double)i * fs / fft_size);
+  for (int i = 0; i < upper - 1; ++i) (*spec)[i] += rep[i];
+}
+
+// ---- LinearSmoothing (common.cpp:27-46, 77-111): index-order running sum is essential (App. B4)
+void LinearSmooth(const std::vector<double> &in, double width, int fs, int fft_size, std::vector<double> *out) {
+  const int half = fft_size / 2;
+  const int boundary = (int)(width * fft_size / fs) + 1;
+  const int n = half + boundary * 2 + 1;
+  std::vector<double> seg(n);
+  for (int i = 0; i < n; ++i) {
+    double v;
+    if (i < boundary) v = in[boundary - i];
+    else if (i < half + boundary) v = in[i - boundary];
+    else v = in[half - (i - (half + boundary))];
+    seg[i] = v * fs / fft_size + (i ? seg[i - 1] : 0.0);
+  }
+  const double origin = -(boundary - 0.5) * fs / fft_size, dx = (double)fs / fft_size;
+  std::vector<double> res(half + 1);
+  for (int i = 0; i <= half; ++i) {
+    const double lo = (double)i / fft_size * fs - width / 2.0, hi = lo + width;
+    res[i] = (Interp1QAt(origin, dx, seg, n, hi) - Interp1QAt(origin, dx, seg, n, lo)) / width;
+  }
+  *out = res;
+}
+
+double SampleAt(const double *x, int n, int idx) { return x[std::min(n - 1, std::max(0, idx))]; }
+
+}  // namespace
+
+extern "C" {
+
+typedef struct { double q1; double f0_floor; int fft_size; } CheapTrickOption;   // cheaptrick.h:16-20
+typedef struct { double threshold; } D4COption;                                   // d4c.h:16-18
+
+int GetFFTSizeForCheapTrick(int fs, const CheapTrickOption *o) {                  // cheaptrick.cpp:191-194
+  return (int)pow(2.0, 1.0 + (int)(log(3.0 * fs / o->f0_floor + 1) / kLog2));
+}
+double GetF0FloorForCheapTrick(int fs, int fft_size) { return 3.0 * fs / (fft_size - 3.0); }  // :196-198
+void InitializeCheapTrickOption(int fs, CheapTrickOption *o) {                    // :231-240
+  o->q1 = -0.15; o->f0_floor = 71.0; o->fft_size = GetFFTSizeForCheapTrick(fs, o);
+}
+void InitializeD4COption(D4COption *o) { o->threshold = 0.85; }                   // d4c.cpp:405-407
+int GetSamplesForDIO(int fs, int n, double fp) { return (int)(1000.0 * n / fs / fp) + 1; }      // dio.cpp:639-641
+int GetSamplesForHarvest(int fs, int n, double fp) { return (int)(1000.0 * n / fs / fp) + 1; }  // harvest.cpp:1219-1221
+
+// ---- CheapTrick (cheaptrick.cpp:200-229; card SURVEY.md A1)
+void CheapTrick(const double *x, int x_length, int fs, const double *t, const double *f0, int f0_length,
+                const CheapTrickOption *opt, double **spectrogram) {
+  const int N = opt->fft_size, half = N / 2;
+  const double floor_f0 = GetF0FloorForCheapTrick(fs, N);
+  Rng rng;                                                          // :205-206
+  for (int i = 0; i < f0_length; ++i) {
+    const double f = f0[i] <= floor_f0 ? 500.0 : f0[i];             // :218
+    const int h = RoundHalfAway(1.5 * fs / f);                      // :115
+    const int origin = RoundHalfAway(t[i] * fs + 0.001);            // :92
+    std::vector<double> w(2 * h + 1), v(N, 0.0);
+    double e = 0.0;
+    for (int j = 0; j <= 2 * h; ++j) {                              // :97-106
+      const double pos = (j - h) / 1.5 / fs;
+      w[j] = 0.5 * cos(kPi * pos * f) + 0.5;
+      e += w[j] * w[j];
+    }
+    e = sqrt(e);
+    double s1 = 0.0, s2 = 0.0;
+    for (int j = 0; j <= 2 * h; ++j) {                              // :126-137
+      w[j] /= e;
+      v[j] = SampleAt(x, x_length, origin + j - h) * w[j] + rng.Next() * kTiny;
+      s1 += v[j]; s2 += w[j];
+    }
+    for (int j = 0; j <= 2 * h; ++j) v[j] -= w[j] * (s1 / s2);
+    std::vector<double> re, im, p(half + 1);
+    RealFFT(v, &re, &im);                                           // :71-78
+    for (int k = 0; k <= half; ++k) p[k] = re[k] * re[k] + im[k] * im[k];
+    DCCorrect(&p, f, fs, N);                                        // :81
+    LinearSmooth(p, f * 2.0 / 3.0, fs, N, &p);                      // :176-177
+    std::vector<double> l(N);
+    for (int k = 0; k <= half; ++k) {                               // :147-151, :39-42
+      p[k] += fabs(rng.Next()) * kEps;
+      l[k] = log(p[k]);
+    }
+    for (int k = 1; k < half; ++k) l[N - k] = l[k];
+    RealFFT(l, &re, &im);                                           // :43
+    std::vector<double> c(N);
+    for (int k = 0; k <= half; ++k) {                               // :28-37, :45-49
+      double sl = 1.0, cl = (1.0 - 2.0 * opt->q1) + 2.0 * opt->q1;
+      if (k > 0) {
+        const double q = (double)k / fs;
+        sl = sin(kPi * f * q) / (kPi * f * q);
+        cl = (1.0 - 2.0 * opt->q1) + 2.0 * opt->q1 * cos(2.0 * kPi * q * f);
+      }
+      c[k] = re[k] * sl * cl / N;
+    }
+    for (int k = 1; k < half; ++k) c[N - k] = c[k];
+    RealFFT(c, &re, &im);   // c2r of a real even spectrum == Re r2c(mirror)   (:50, fft.cpp:26-35)
+    for (int k = 0; k <= half; ++k) spectrogram[i][k] = exp(re[k]);  // :52-53
+  }
+}
+
+// ---- D4C helpers (d4c.cpp:21-83): F0-adaptive window + noise + weighted mean removal
+static int D4CWindowed(const double *x, int n, int fs, double f, double pos, int type, double ratio, Rng *rng,
+                       std::vector<double> *v) {
+  const int h = RoundHalfAway(ratio * fs / f / 2.0);
+  const int origin = RoundHalfAway(pos * fs + 0.001);
+  std::vector<double> w(2 * h + 1);
+  double s1 = 0.0, s2 = 0.0;
+  for (int j = 0; j <= 2 * h; ++j) {
+    const double p = (2.0 * (j - h) / ratio) / fs;
+    w[j] = type == 1 ? 0.5 * cos(kPi * p * f) + 0.5 : 0.42 + 0.5 * cos(kPi * p * f) + 0.08 * cos(kPi * p * f * 2);
+    (*v)[j] = SampleAt(x, n, origin + j - h) * w[j] + rng->Next() * 0.000001;
+    s1 += (*v)[j]; s2 += w[j];
+  }
+  for (int j = 0; j <= 2 * h; ++j) (*v)[j] -= w[j] * (s1 / s2);
+  return 2 * h + 1;
+}
+
+// ---- D4C (d4c.cpp:342-403; card SURVEY.md A2)
+void D4C(const double *x, int x_length, int fs, const double *t, const double *f0, int f0_length, int fft_size,
+         const D4COption *opt, double **aperiodicity) {
+  const int bins = fft_size / 2 + 1;
+  Rng rng;
+  for (int i = 0; i < f0_length; ++i)
+    for (int k = 0; k < bins; ++k) aperiodicity[i][k] = 1.0 - kTiny;                  // :323-328
+  const int Nd = (int)pow(2.0, 1.0 + (int)(log(4.0 * fs / 47.0 + 1) / kLog2));       // :350-352
+  const int Nl = (int)pow(2.0, 1.0 + (int)(log(3.0 * fs / 40.0 + 1) / kLog2));       // :262-264
+  const int n_ap = (int)(std::min(15000.0, fs / 2.0 - 3000.0) / 3000.0);             // :357-359
+  const int wlen = (int)(3000.0 * Nd / fs) * 2 + 1;                                   // :362-363
+  std::vector<double> nuttall(wlen);
+  for (int i = 0; i < wlen; ++i) {                                                    // common.cpp:113-121
+    const double u = i / (wlen - 1.0);
+    nuttall[i] = 0.355768 - 0.487396 * cos(2.0 * kPi * u) + 0.144232 * cos(4.0 * kPi * u) - 0.012604 * cos(6.0 * kPi * u);
+  }
+  // pass A: LoveTrain (:260-285, :227-252)
+  const int b0 = (int)ceil(100.0 * Nl / fs), b1 = (int)ceil(4000.0 * Nl / fs), b2 = (int)ceil(7900.0 * Nl / fs);
+  std::vector<double> ap0(f0_length, 0.0), re, im;
+  for (int i = 0; i < f0_length; ++i) {
+    if (f0[i] == 0.0) continue;
+    std::vector<double> v(Nl, 0.0);
+    D4CWindowed(x, x_length, fs, std::max(f0[i], 40.0), t[i], 2, 3.0, &rng, &v);
+    RealFFT(v, &re, &im);
+    double lo = 0.0, hi = 0.0;
+    for (int k = b0 + 1; k <= std::min(b2, Nl / 2); ++k) {
+      const double p = re[k] * re[k] + im[k] * im[k];
+      hi += p;
+      if (k == b1) lo = hi;
+    }
+    ap0[i] = lo / hi;
+  }
+  // pass B (:385-395, :293-321)
+  std::vector<double> axis(n_ap + 2), coarse(n_ap + 2);
+  for (int i = 0; i <= n_ap; ++i) axis[i] = i * 3000.0;
+  axis[n_ap + 1] = fs / 2.0;
+  coarse[0] = -60.0; coarse[n_ap + 1] = -kTiny;
+  const int half = Nd / 2, bd = RoundHalfAway(Nd * 8.0 / wlen), hw = wlen / 2;
+  for (int i = 0; i < f0_length; ++i) {
+    if (f0[i] == 0 || ap0[i] <= opt->threshold) continue;
+    const double f = std::max(47.0, f0[i]);
+    std::vector<double> cent(half + 1, 0.0);
+    for (int pass = 0; pass < 2; ++pass) {                                            // GetCentroid :90-120
+      std::vector<double> v(Nd, 0.0), r2, i2;
+      const int nw = D4CWindowed(x, x_length, fs, f, pass == 0 ? t[i] - 0.25 / f : t[i] + 0.25 / f, 2, 4.0, &rng, &v);
+      double pw = 0.0;
+      for (int j = 0; j < nw; ++j) pw += v[j] * v[j];
+      for (int j = 0; j < nw; ++j) v[j] /= sqrt(pw);
+      RealFFT(v, &re, &im);
+      for (int j = 0; j < Nd; ++j) v[j] *= j + 1.0;
+      RealFFT(v, &r2, &i2);
+      for (int k = 0; k <= half; ++k) cent[k] += r2[k] * re[k] + im[k] * i2[k];
+    }
+    DCCorrect(&cent, f, fs, Nd);                                                      // :137-140
+    std::vector<double> v(Nd, 0.0), pwr(half + 1);                                    // :149-166
+    D4CWindowed(x, x_length, fs, f, t[i], 1, 4.0, &rng, &v);
+    RealFFT(v, &re, &im);
+    for (int k = 0; k <= half; ++k) pwr[k] = re[k] * re[k] + im[k] * im[k];
+    DCCorrect(&pwr, f, fs, Nd);
+    LinearSmooth(pwr, f, fs, Nd, &pwr);
+    std::vector<double> g(half + 1), g2;                                              // :172-188
+    for (int k = 0; k <= half; ++k) g[k] = cent[k] / pwr[k];
+    LinearSmooth(g, f / 2.0, fs, Nd, &g);
+    LinearSmooth(g, f, fs, Nd, &g2);
+    for (int k = 0; k <= half; ++k) g[k] -= g2[k];
+    for (int b = 0; b < n_ap; ++b) {                                                  // :194-225
+      const int center = (int)(3000.0 * (b + 1) * Nd / fs);
+      std::vector<double> u(Nd, 0.0), ps(half + 1);
+      for (int j = 0; j <= hw * 2; ++j) u[j] = g[center - hw + j] * nuttall[j];
+      RealFFT(u, &re, &im);
+      for (int k = 0; k <= half; ++k) ps[k] = re[k] * re[k] + im[k] * im[k];
+      std::sort(ps.begin(), ps.end());
+      for (int k = 1; k <= half; ++k) ps[k] += ps[k - 1];
+      coarse[b + 1] = std::min(0.0, 10 * log10(ps[half - bd - 1] / ps[half]) + (f - 100) / 50.0);  // :314-316
+    }
+    for (int k = 0; k < bins; ++k)                                                    // :330-338
+      aperiodicity[i][k] = pow(10.0, Interp1At(axis, coarse, (double)k * fs / fft_size) / 20.0);
+  }
+}
+
+// ---- StoneMask (stonemask.cpp:212-218; card SURVEY.md A4)
+static double FixF0(const std::vector<double> &pw, const std::vector<double> &num, int N, int fs, double f, int H) {
+  double numer = 0.0, denom = 0.0;                                                    // :96-118
+  for (int m = 0; m < H; ++m) {
+    const int k = std::min(RoundHalfAway(f * N / fs * (m + 1)), N / 2);
+    const double inst = pw[k] == 0.0 ? 0.0 : (double)k * fs / N + num[k] / pw[k] * fs / 2.0 / kPi;
+    const double amp = sqrt(pw[k]);
+    numer += amp * inst;
+    denom += amp * (m + 1);
+  }
+  return numer / (denom + kTiny);
+}
+
+void StoneMask(const double *x, int x_length, int fs, const double *t, const double *f0, int f0_length,
+               double *refined) {
+  for (int i = 0; i < f0_length; ++i) {
+    const double f = f0[i];
+    if (f <= 40.0 || f > fs / 12.0) { refined[i] = 0.0; continue; }                   // :187-188
+    const int h = (int)(1.5 * fs / f + 1.0), n = 2 * h + 1;
+    const int N = (int)pow(2.0, 2.0 + (int)(log(n * 1.0) / kLog2));                    // :195-196
+    const double T = (2.0 * h + 1.0) / fs;
+    std::vector<int> raw(n);
+    std::vector<double> w(n), dw(n), a(N, 0.0), d(N, 0.0);
+    for (int j = 0; j < n; ++j) {                                                     // :24-43
+      raw[j] = RoundHalfAway((t[i] + (double)(j - h) / fs) * fs);
+      const double tau = (raw[j] - 1.0) / fs - t[i];
+      w[j] = 0.42 + 0.5 * cos(2.0 * kPi * tau / T) + 0.08 * cos(4.0 * kPi * tau / T);
+    }
+    dw[0] = -w[1] / 2.0;                                                              // :49-55
+    for (int j = 1; j < n - 1; ++j) dw[j] = -(w[j + 1] - w[j - 1]) / 2.0;
+    dw[n - 1] = w[n - 2] / 2.0;
+    for (int j = 0; j < n; ++j) {                                                     // :61-88
+      const double s = SampleAt(x, x_length, raw[j] - 1);
+      a[j] = s * w[j]; d[j] = s * dw[j];
+    }
+    std::vector<double> mr, mi, dr, di, pw(N / 2 + 1), num(N / 2 + 1);
+    RealFFT(a, &mr, &mi);
+    RealFFT(d, &dr, &di);
+    for (int k = 0; k <= N / 2; ++k) {                                                // :159-164
+      num[k] = mr[k] * di[k] - mi[k] * dr[k];
+      pw[k] = mr[k] * mr[k] + mi[k] * mi[k];
+    }
+    double mean = 0.0;
+    const double tent = FixF0(pw, num, N, fs, f, 2);                                  // :123-132
+    if (!(tent <= 0.0 || tent > f * 2)) mean = FixF0(pw, num, N, fs, tent, 6);
+    if (fabs(mean - f) > f * 0.2) mean = f;                                           // :203
+    refined[i] = mean;
+  }
+}
+
+}  // extern "C"

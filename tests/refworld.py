@@ -39,12 +39,16 @@ class RefWorld:
         L.GetFFTSizeForCheapTrick.restype = C.c_int
         L.GetF0FloorForCheapTrick.restype = C.c_double
         L.GetF0FloorForCheapTrick.argtypes = [C.c_int, C.c_int]
-        L.Dio.argtypes = [_P, C.c_int, C.c_int, C.POINTER(DioOption), _P, _P]
-        L.Harvest.argtypes = [_P, C.c_int, C.c_int, C.POINTER(HarvestOption), _P, _P]
+        self.has_f0 = hasattr(L, "Dio") and hasattr(L, "Harvest")  # the CPU restatement has no Dio/Harvest
+        if self.has_f0:
+            L.Dio.argtypes = [_P, C.c_int, C.c_int, C.POINTER(DioOption), _P, _P]
+            L.Harvest.argtypes = [_P, C.c_int, C.c_int, C.POINTER(HarvestOption), _P, _P]
+            L.Dio.restype = None
+            L.Harvest.restype = None
         L.StoneMask.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]
         L.CheapTrick.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.POINTER(CheapTrickOption), _P]
         L.D4C.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.POINTER(D4COption), _P]
-        for f in (L.Dio, L.Harvest, L.StoneMask, L.CheapTrick, L.D4C):
+        for f in (L.StoneMask, L.CheapTrick, L.D4C):
             f.restype = None
 
     # options

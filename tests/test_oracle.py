@@ -1,0 +1,50 @@
+"""Pins the CPU restatement (oracle/world_oracle.cpp) against the golden vectors generated from the
+unmodified reference, and against the compiled reference itself on synthetic speech.
+The restatement uses an independent FFT and libstdc++'s sort, so agreement is to rounding
+(<= 1e-10 on sp), not bit-exact."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import test_parity_common as pc
+from refworld import RefWorld, ORACLE_LIB, rel_err
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def port():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "libworld_oracle.so"])
+    return RefWorld(ORACLE_LIB)
+
+
+def test_port_matches_golden_vectors(port, golden):
+    x, fs = pc.wav_from_golden(golden)
+    t = golden["time_axis"]
+    sm = port.stonemask(x, fs, t, golden["f0_dio"])
+    assert rel_err(sm, golden["f0_stonemask"]).max() < 1e-9
+    f0 = golden["f0_stonemask"]
+    sp = port.cheaptrick(x, fs, t, f0)
+    ap = port.d4c(x, fs, t, f0, int(golden["fft_size"]))
+    assert rel_err(sp, golden["sp"]).max() < 1e-8
+    assert rel_err(ap, golden["ap"]).max() < 1e-8
+
+
+def test_port_matches_reference_on_synthetic(port, ref):
+    from synth import synth_batch
+    for fs, n, seed in ((16000, 12000, 51), (48000, 14400, 52)):
+        x = synth_batch([seed], fs, n).numpy()[0]
+        t, f0 = ref.dio(x, fs)
+        f0r = ref.stonemask(x, fs, t, f0)
+        assert rel_err(port.stonemask(x, fs, t, f0), f0r).max() < 1e-9
+        o = ref.cheaptrick_option(fs)
+        assert rel_err(port.cheaptrick(x, fs, t, f0r, o), ref.cheaptrick(x, fs, t, f0r, o)).max() < 1e-8
+        assert rel_err(port.d4c(x, fs, t, f0r, o.fft_size), ref.d4c(x, fs, t, f0r, o.fft_size)).max() < 1e-8
+
+
+def test_port_sizing_helpers(port, ref):
+    for fs in (8000, 16000, 22050, 44100, 48000):
+        assert port.cheaptrick_option(fs).fft_size == ref.cheaptrick_option(fs).fft_size
+        assert port.frames(fs, 12345) == ref.frames(fs, 12345)

@@ -12,6 +12,7 @@
 // a hop), 16 B of f0/time, (2h+1 + fft/2+1)*4 B of materialised draws, (fft/2+1)*8 B written.
 #include "wb_internal.h"
 #include "wb_spectral.cuh"
+#include <stdlib.h>
 
 namespace wb {
 
@@ -196,7 +197,9 @@ int cheaptrick_run(Ctx *ctx, const Batch &b, double q1, int fft_size, double *sp
     p.draws = draws; p.draw_stride = draw_stride_full; p.draw_off = offs;
     p.out = spectrogram + (size_t)u0 * b.f_stride * bins;
     p.tw = ctx->twiddle; p.status = ctx->status_dev;
-    WB_LAUNCH_COOP(ct_frame_kernel, dim3((unsigned)b.max_f_len, (unsigned)n), 128, smem, ctx->stream, p);
+    int ct_threads = 128;
+    if (const char *e = getenv("WB_CT_THREADS")) ct_threads = atoi(e);
+    WB_LAUNCH_COOP(ct_frame_kernel, dim3((unsigned)b.max_f_len, (unsigned)n), ct_threads, smem, ctx->stream, p);
     int rc = dev_check(ctx, "cheaptrick");
     if (rc) return rc;
   }
