@@ -42,24 +42,28 @@ WB_KERNEL(256, 3) fir_plain_kernel(FirParams p) {
   }
 }
 
-// interp1 (matlabfunctions.cpp:157-176) of one event train at time t.  e = fine edge positions;
-// the (x, y) samples interp1 sees are (location, interval) of consecutive edges:
-// x_j = (e_j + e_{j+1}) / 2 / afs, y_j = afs / (e_{j+1} - e_j), j < n_int.
-// `lo` narrows the search: the caller guarantees #{j : x_j <= t} >= lo.
-WB_DEV double train_location(const double *e, int j, double afs) { return (e[j] + e[j + 1]) / 2.0 / afs; }
+// interp1 (matlabfunctions.cpp:157-176) of one event train at time t.  Fine edge positions e_j live
+// in global memory (complete list) and, for the most recent WB_RING of them, in a shared-memory ring
+// (the searches below almost always stay inside the ring).  The (x, y) samples interp1 sees are
+// (location, interval) of consecutive edges: x_j = (e_j + e_{j+1}) / 2 / afs, y_j = afs / (e_{j+1} - e_j).
+#define WB_RING 512
+struct Train { const double *g; const double *ring; int from; };  // ring holds indices >= from
+WB_DEV double tr_get(const Train &t, int i) { return i >= t.from ? t.ring[i & (WB_RING - 1)] : t.g[i]; }
+WB_DEV double train_location(const Train &t, int j, double afs) { return (tr_get(t, j) + tr_get(t, j + 1)) / 2.0 / afs; }
 
-WB_DEV int train_count(const double *e, int lo, int n_int, double afs, double t) {
-  int hi = n_int;  // first j in [lo, n_int) with x_j > t
+// first j in [lo, n_int) with x_j > t   (the caller guarantees #{j : x_j <= t} >= lo)
+WB_DEV int train_count(const Train &tr, int lo, int n_int, double afs, double t) {
+  int hi = n_int;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (train_location(e, mid, afs) <= t) lo = mid + 1; else hi = mid;
+    if (train_location(tr, mid, afs) <= t) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
 
-WB_DEV double train_interp(const double *e, int lo, int n_int, double afs, double t) {
-  const int k = imin(n_int - 1, imax(1, train_count(e, lo, n_int, afs, t)));
-  const double e0 = e[k - 1], e1 = e[k], e2 = e[k + 1];
+WB_DEV double train_interp(const Train &tr, int lo, int n_int, double afs, double t) {
+  const int k = imin(n_int - 1, imax(1, train_count(tr, lo, n_int, afs, t)));
+  const double e0 = tr_get(tr, k - 1), e1 = tr_get(tr, k), e2 = tr_get(tr, k + 1);
   const double x0 = (e0 + e1) / 2.0 / afs, x1 = (e1 + e2) / 2.0 / afs;
   const double y0 = afs / (e1 - e0), y1 = afs / (e2 - e1);
   const double s = (t - x0) / (x1 - x0);
@@ -96,13 +100,13 @@ WB_DEV unsigned long long scan_packed(unsigned long long *c, int G, unsigned lon
 
 // One frame of one band: interp1 of the four trains, mean, (DIO) score, range checks
 // (dio.cpp:441-465, 562-566 / harvest.cpp:240-254).
-WB_DEV void sweep_candidate(const SweepParams &p, const double *edges, int cap, const int *lo_j, const int *tot,
+WB_DEV void sweep_candidate(const SweepParams &p, const Train *tr, const int *lo_j, const int *tot,
                             int i, double bf, double *cand, double *score) {
   const double t = i * p.frame_period / 1000.0;
-  const double v0 = train_interp(edges, lo_j[0], tot[0] - 1, p.afs, t);
-  const double v1 = train_interp(edges + cap, lo_j[1], tot[1] - 1, p.afs, t);
-  const double v2 = train_interp(edges + 2 * (size_t)cap, lo_j[2], tot[2] - 1, p.afs, t);
-  const double v3 = train_interp(edges + 3 * (size_t)cap, lo_j[3], tot[3] - 1, p.afs, t);
+  const double v0 = train_interp(tr[0], lo_j[0], tot[0] - 1, p.afs, t);
+  const double v1 = train_interp(tr[1], lo_j[1], tot[1] - 1, p.afs, t);
+  const double v2 = train_interp(tr[2], lo_j[2], tot[2] - 1, p.afs, t);
+  const double v3 = train_interp(tr[3], lo_j[3], tot[3] - 1, p.afs, t);
   double c = (v0 + v1 + v2 + v3) / 4.0, sc = 0.0;
   if (p.mode == 0) {
     sc = sqrt(((v0 - c) * (v0 - c) + (v1 - c) * (v1 - c) + (v2 - c) * (v2 - c) + (v3 - c) * (v3 - c)) / 3.0);
@@ -126,6 +130,7 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   double *hrev = seg + (seg_cap + (seg_cap >> 3) + 8);  // max_taps + 8
   double *st = hrev + (p.max_taps + 8);                 // T + 8: [0..1] carry, [2..T+2) this tile
   unsigned long long *cnt = reinterpret_cast<unsigned long long *>(st + (T + 8 + ((T + 8) >> 3) + 8));  // G + 40
+  double *ring = reinterpret_cast<double *>(cnt + (G + 40));                                           // 4 * WB_RING
 
   const int ylen = p.y_len[u];
   const double *sig = p.sig + (size_t)u * p.sig_stride + p.sig_origin;
@@ -134,6 +139,8 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   for (int j = tid; j < ntaps; j += nth) hrev[j] = __ldg(&p.taps_rev[p.tap_off[b] + j]);
   for (int j = ntaps + tid; j < ntaps + 8; j += nth) hrev[j] = 0.0;
   if (tid == 0) { st[0] = 0.0; st[1] = 0.0; }
+  Train tr[4];
+  for (int q = 0; q < 4; ++q) { tr[q].g = edges + (size_t)q * cap; tr[q].ring = ring + q * WB_RING; tr[q].from = 0; }
   int tot[4] = {0, 0, 0, 0};  // running event counts per train (identical in every thread)
   int lo_j[4] = {0, 0, 0, 0}; // per train: intervals below this index lie before every unfinished frame
   int next_frame = 0;         // frames [0, next_frame) are done
@@ -190,6 +197,11 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
     }
     WB_SYNC();
     const unsigned long long tile_total = scan_packed(cnt, G, 0ull, cnt + G + 4);  // <= 2048 each: fits 16 bit
+    int keep[4];  // after this tile the ring holds event indices >= keep[q]
+    keep[0] = imax(0, tot[0] + (int)(tile_total & 0xffffull) - WB_RING);
+    keep[1] = imax(0, tot[1] + (int)((tile_total >> 16) & 0xffffull) - WB_RING);
+    keep[2] = imax(0, tot[2] + (int)((tile_total >> 32) & 0xffffull) - WB_RING);
+    keep[3] = imax(0, tot[3] + (int)((tile_total >> 48) & 0xffffull) - WB_RING);
     for (int g = tid; g < G; g += nth) {
       const unsigned long long o = cnt[g];
       int o0 = tot[0] + (int)(o & 0xffffull), o1 = tot[1] + (int)((o >> 16) & 0xffffull);
@@ -202,17 +214,38 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
         const double d0 = bb - a, d1 = cc - bb;
         const double e = (double)(i + 1);
         if (i >= 0 && i + 1 <= ylen - 1) {
-          if (0.0 < a && bb <= 0.0) { if (o0 < cap) edges[o0] = e - a / (bb - a); ++o0; }
-          if (a < 0.0 && 0.0 <= bb) { if (o1 < cap) edges[(size_t)cap + o1] = e - a / (bb - a); ++o1; }
+          if (0.0 < a && bb <= 0.0) {
+            const double v = e - a / (bb - a);
+            if (o0 < cap) edges[o0] = v;
+            if (o0 >= keep[0]) ring[o0 & (WB_RING - 1)] = v;
+            ++o0;
+          }
+          if (a < 0.0 && 0.0 <= bb) {
+            const double v = e - a / (bb - a);
+            if (o1 < cap) edges[(size_t)cap + o1] = v;
+            if (o1 >= keep[1]) ring[WB_RING + (o1 & (WB_RING - 1))] = v;
+            ++o1;
+          }
         }
         if (i >= 0 && i + 1 <= ylen - 2) {
-          if (0.0 < d0 && d1 <= 0.0) { if (o2 < cap) edges[2 * (size_t)cap + o2] = e - d0 / (d1 - d0); ++o2; }
-          if (d0 < 0.0 && 0.0 <= d1) { if (o3 < cap) edges[3 * (size_t)cap + o3] = e - d0 / (d1 - d0); ++o3; }
+          if (0.0 < d0 && d1 <= 0.0) {
+            const double v = e - d0 / (d1 - d0);
+            if (o2 < cap) edges[2 * (size_t)cap + o2] = v;
+            if (o2 >= keep[2]) ring[2 * WB_RING + (o2 & (WB_RING - 1))] = v;
+            ++o2;
+          }
+          if (d0 < 0.0 && 0.0 <= d1) {
+            const double v = e - d0 / (d1 - d0);
+            if (o3 < cap) edges[3 * (size_t)cap + o3] = v;
+            if (o3 >= keep[3]) ring[3 * WB_RING + (o3 & (WB_RING - 1))] = v;
+            ++o3;
+          }
         }
       }
     }
     tot[0] += (int)(tile_total & 0xffffull); tot[1] += (int)((tile_total >> 16) & 0xffffull);
     tot[2] += (int)((tile_total >> 32) & 0xffffull); tot[3] += (int)((tile_total >> 48) & 0xffffull);
+    for (int q = 0; q < 4; ++q) tr[q].from = keep[q];
 #ifndef WB_EMU
     __threadfence_block();
 #endif
@@ -224,7 +257,7 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
     double t_safe = 0.0;
     for (int q = 0; q < 4; ++q) {
       if (tot[q] > cap || tot[q] < 2) { can = false; break; }
-      const double loc = train_location(edges + (size_t)q * cap, tot[q] - 2, p.afs);
+      const double loc = train_location(tr[q], tot[q] - 2, p.afs);
       t_safe = (q == 0 || loc < t_safe) ? loc : t_safe;
     }
     if (can) {
@@ -236,10 +269,10 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
       if (i_safe > nf) i_safe = nf;
       if (i_safe > next_frame) {
         for (int i = next_frame + tid; i < i_safe; i += nth)
-          sweep_candidate(p, edges, cap, lo_j, tot, i, bf, cand, score);
+          sweep_candidate(p, tr, lo_j, tot, i, bf, cand, score);
         // all later frames have t >= t_safe: their interval counts are at least those of t_safe
         for (int q = 0; q < 4; ++q) {
-          const int c = train_count(edges + (size_t)q * cap, lo_j[q], tot[q] - 1, p.afs, (i_safe - 1) * p.frame_period / 1000.0);
+          const int c = train_count(tr[q], lo_j[q], tot[q] - 1, p.afs, (i_safe - 1) * p.frame_period / 1000.0);
           lo_j[q] = imax(lo_j[q], c);
         }
         next_frame = i_safe;
@@ -255,7 +288,7 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
     if (ni - 2 <= 0) ok = false;                 // CheckEvent(n - 2), dio.cpp:475-484
   }
   if (ok) {
-    for (int i = next_frame + tid; i < nf; i += nth) sweep_candidate(p, edges, cap, lo_j, tot, i, bf, cand, score);
+    for (int i = next_frame + tid; i < nf; i += nth) sweep_candidate(p, tr, lo_j, tot, i, bf, cand, score);
   } else {
     for (int i = tid; i < nf; i += nth) {
       cand[i] = 0.0;
