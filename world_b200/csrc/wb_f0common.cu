@@ -51,12 +51,25 @@ struct Train { const double *g; const double *ring; int from; };  // ring holds 
 WB_DEV double tr_get(const Train &t, int i) { return i >= t.from ? t.ring[i & (WB_RING - 1)] : t.g[i]; }
 WB_DEV double train_location(const Train &t, int j, double afs) { return (tr_get(t, j) + tr_get(t, j + 1)) / 2.0 / afs; }
 
+// x_j <= t, exactly as the reference evaluates it ((e_j + e_{j+1}) / 2.0 / afs <= t), but without
+// the division in the common case: the quotient is within a few ulp of s / (2 afs), so unless
+// s and 2 afs t agree to ~1e-13 relative the comparison of the products decides; only near ties
+// is the reference expression evaluated.
+WB_DEV bool location_le(const Train &tr, int j, double afs, double t, double two_afs_t) {
+  const double s = tr_get(tr, j) + tr_get(tr, j + 1);
+  const double margin = 1e-13 * (fabs(s) + fabs(two_afs_t));
+  if (s < two_afs_t - margin) return true;
+  if (s > two_afs_t + margin) return false;
+  return s / 2.0 / afs <= t;
+}
+
 // first j in [lo, n_int) with x_j > t   (the caller guarantees #{j : x_j <= t} >= lo)
 WB_DEV int train_count(const Train &tr, int lo, int n_int, double afs, double t) {
   int hi = n_int;
+  const double two_afs_t = 2.0 * afs * t;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (train_location(tr, mid, afs) <= t) lo = mid + 1; else hi = mid;
+    if (location_le(tr, mid, afs, t, two_afs_t)) lo = mid + 1; else hi = mid;
   }
   return lo;
 }

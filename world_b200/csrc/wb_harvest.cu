@@ -168,14 +168,17 @@ WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, d
   const double T = (2.0 * h + 1.0) / afs;
   // base_index[j] = round((t + base_time[0]) * fs + 0.001) + j   (harvest.cpp:434-441)
   const int basic = round_half_away((t + (-h + 0) / afs) * afs + 0.001);
-  // Blackman window (harvest.cpp:446-456); cos(2a) = 2 cos(a)^2 - 1 saves the second cosine
+  // Blackman window (harvest.cpp:446-456); cos(2a) = 2 cos(a)^2 - 1 saves the second cosine, and
+  // the two per-sample divisions (by afs and by T) become multiplications by reciprocals: the
+  // window only has to be accurate to rounding, it feeds no integer decision.
+  const double inv_afs = 1.0 / afs, w_scale = 2.0 * kPi / T;
   for (int j0 = 0; j0 < nwin; j0 += 4 * WB_LANES) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int j = j0 + q * WB_LANES + lane;
       if (j < nwin) {
-        const double tmp = ((basic + j) - 1.0) / afs - t;
-        const double c1 = hv_cos_small(2.0 * kPi * tmp / T);
+        const double tmp = ((basic + j) - 1.0) * inv_afs - t;
+        const double c1 = hv_cos_small(w_scale * tmp);
         wbuf[j] = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
       }
     }
