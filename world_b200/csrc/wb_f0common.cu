@@ -172,15 +172,18 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
     for (int g = tid; g < G; g += nth) {
       const int base = R * g;
       double acc[WB_SWEEP_R], win[WB_SWEEP_R];
+      // pad8(8 (g+1) + 8 it + jj) = 9 (g+1) + 9 it + jj: one running pointer, immediate offsets
+      const double *sp = seg + 9 * (g + 1);
+      const double *hp = hrev;
 #pragma unroll
-      for (int r = 0; r < R; ++r) { acc[r] = 0.0; win[r] = seg[pad8(base + r)]; }
-      for (int j0 = 0; j0 < ntaps; j0 += R) {
+      for (int r = 0; r < R; ++r) { acc[r] = 0.0; win[r] = seg[9 * g + r]; }
+      for (int j0 = 0; j0 < ntaps; j0 += R, sp += 9, hp += R) {
 #pragma unroll
         for (int jj = 0; jj < R; ++jj) {
-          const double hj = hrev[j0 + jj];  // zero beyond ntaps
+          const double hj = hp[jj];  // zero beyond ntaps
 #pragma unroll
           for (int r = 0; r < R; ++r) acc[r] = fma(hj, win[(r + jj) & (R - 1)], acc[r]);
-          win[jj] = seg[pad8(base + R + j0 + jj)];
+          win[jj] = sp[jj];
         }
       }
 #pragma unroll

@@ -206,7 +206,7 @@ WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, d
 #endif
   const int H = imin(static_cast<int>(afs / 2.0 / f), 6);
   const int shift = WB_TW_LOG2 - lg_nfft;
-  double amp_l = 0.0, inst_l = 0.0;  // this lane's harmonic (CUDA) / current harmonic (emulation)
+  double amp_l = 0.0, inst_l = 0.0;
   double numerator = 0.0, denominator = 0.0, score = 0.0;
 #ifdef WB_EMU
   for (int m = 0; m < H; ++m) {
@@ -252,18 +252,21 @@ WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, d
     const double pw = mr * mr + mi * mi;
     inst_l = pw == 0.0 ? 0.0 : static_cast<double>(bin) * afs / nfft + num / pw * afs / 2.0 / kPi;
     amp_l = sqrt(pw);
+    // this harmonic's three FixF0 terms (harvest.cpp:521-527); summed in harmonic order below
+    const double t_num = amp_l * inst_l;
+    const double t_den = amp_l * (m + 1.0);
+    const double t_sc = fabs((inst_l / (m + 1.0) - f) / f);
 #ifdef WB_EMU
-    numerator += amp_l * inst_l;
-    denominator += amp_l * (m + 1.0);
-    score += fabs((inst_l / (m + 1.0) - f) / f);
+    numerator += t_num;
+    denominator += t_den;
+    score += t_sc;
   }
 #else
-  }
-  for (int m = 0; m < H; ++m) {
-    const double am = __shfl_sync(0xffffffffu, amp_l, m), im = __shfl_sync(0xffffffffu, inst_l, m);
-    numerator += am * im;
-    denominator += am * (m + 1.0);
-    score += fabs((im / (m + 1.0) - f) / f);
+    for (int mm = 0; mm < H; ++mm) {
+      numerator += __shfl_sync(0xffffffffu, t_num, mm);
+      denominator += __shfl_sync(0xffffffffu, t_den, mm);
+      score += __shfl_sync(0xffffffffu, t_sc, mm);
+    }
   }
 #endif
   double rf = numerator / (denominator + kTiny);
