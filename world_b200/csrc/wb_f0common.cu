@@ -42,46 +42,56 @@ WB_KERNEL(256, 3) fir_plain_kernel(FirParams p) {
   }
 }
 
-// interp1 (matlabfunctions.cpp:157-176) of one event train at time t.  Fine edge positions e_j live
-// in global memory (complete list) and, for the most recent WB_RING of them, in a shared-memory ring
-// (the searches below almost always stay inside the ring).  The (x, y) samples interp1 sees are
-// (location, interval) of consecutive edges: x_j = (e_j + e_{j+1}) / 2 / afs, y_j = afs / (e_{j+1} - e_j).
+// ---------------------------------------------------------------------------------------------
+// Event trains of one (utterance, band).  Fine edge positions e_j are appended to global lists
+// (complete, for the rare look-back) and to shared-memory rings; every pair of consecutive edges
+// defines the (location, interval) sample interp1 sees (matlabfunctions.cpp:157-176 through
+// dio.cpp:357-393 / harvest.cpp:162-198):  x_j = (e_j + e_{j+1}) / 2 / afs,  y_j = afs / (e_{j+1} - e_j).
+// x_j and y_j are evaluated ONCE per interval (same expressions as the reference) and kept in rings.
+#ifndef WB_RING
 #define WB_RING 512
-struct Train { const double *g; const double *ring; int from; };  // ring holds indices >= from
-WB_DEV double tr_get(const Train &t, int i) { return i >= t.from ? t.ring[i & (WB_RING - 1)] : t.g[i]; }
-WB_DEV double train_location(const Train &t, int j, double afs) { return (tr_get(t, j) + tr_get(t, j + 1)) / 2.0 / afs; }
-
-// x_j <= t, exactly as the reference evaluates it ((e_j + e_{j+1}) / 2.0 / afs <= t), but without
-// the division in the common case: the quotient is within a few ulp of s / (2 afs), so unless
-// s and 2 afs t agree to ~1e-13 relative the comparison of the products decides; only near ties
-// is the reference expression evaluated.
-WB_DEV bool location_le(const Train &tr, int j, double afs, double t, double two_afs_t) {
-  const double s = tr_get(tr, j) + tr_get(tr, j + 1);
-  const double margin = 1e-13 * (fabs(s) + fabs(two_afs_t));
-  if (s < two_afs_t - margin) return true;
-  if (s > two_afs_t + margin) return false;
-  return s / 2.0 / afs <= t;
+#endif
+#define WB_FCHUNK 256  // frames finalised per round (= WB_SWEEP_THREADS)
+struct Trains {
+  const double *g[4];   // global edge lists
+  double *er, *xr, *yr; // shared rings [4][WB_RING]: edges, interval locations, interval values
+  int efrom[4];         // edge ring holds indices >= efrom
+  int ifrom[4];         // interval rings hold indices >= ifrom
+  double afs;
+};
+WB_DEV double edge_at(const Trains &T, int q, int i) {
+  return i >= T.efrom[q] ? T.er[q * WB_RING + (i & (WB_RING - 1))] : T.g[q][i];
+}
+WB_DEV double loc_at(const Trains &T, int q, int j) {
+  return j >= T.ifrom[q] ? T.xr[q * WB_RING + (j & (WB_RING - 1))] : (edge_at(T, q, j) + edge_at(T, q, j + 1)) / 2.0 / T.afs;
+}
+WB_DEV double val_at(const Trains &T, int q, int j) {
+  return j >= T.ifrom[q] ? T.yr[q * WB_RING + (j & (WB_RING - 1))] : T.afs / (edge_at(T, q, j + 1) - edge_at(T, q, j));
 }
 
-// first j in [lo, n_int) with x_j > t   (the caller guarantees #{j : x_j <= t} >= lo)
-WB_DEV int train_count(const Train &tr, int lo, int n_int, double afs, double t) {
-  int hi = n_int;
-  const double two_afs_t = 2.0 * afs * t;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (location_le(tr, mid, afs, t, two_afs_t)) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
-WB_DEV double train_interp(const Train &tr, int lo, int n_int, double afs, double t) {
-  const int k = imin(n_int - 1, imax(1, train_count(tr, lo, n_int, afs, t)));
-  const double e0 = tr_get(tr, k - 1), e1 = tr_get(tr, k), e2 = tr_get(tr, k + 1);
-  const double x0 = (e0 + e1) / 2.0 / afs, x1 = (e1 + e2) / 2.0 / afs;
-  const double y0 = afs / (e1 - e0), y1 = afs / (e2 - e1);
+// interp1 at time t given count = #{j : x_j <= t}: k = clamp(count, 1, n_int-1) picks the segment
+WB_DEV double train_value(const Trains &T, int q, int count, int n_int, double t) {
+  const int k = imin(n_int - 1, imax(1, count));
+  const double x0 = loc_at(T, q, k - 1), x1 = loc_at(T, q, k);
+  const double y0 = val_at(T, q, k - 1), y1 = val_at(T, q, k);
   const double s = (t - x0) / (x1 - x0);
   return y0 + s * (y1 - y0);
 }
+
+// smallest frame index i with t_i >= x, t_i = i * frame_period / 1000.0 (the reference's expression)
+WB_DEV int first_frame_at_or_after(double x, double frame_period) {
+  int g = (int)ceil(x * 1000.0 / frame_period);
+  if (g < 0) g = 0;
+  while (g > 0 && !((g - 1) * frame_period / 1000.0 < x)) --g;
+  while (g * frame_period / 1000.0 < x) ++g;
+  return g;
+}
+
+#ifdef WB_EMU
+static inline void smem_add_u64(unsigned long long *p, unsigned long long v) { *p += v; }
+#else
+__device__ __forceinline__ void smem_add_u64(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
+#endif
 
 // Exclusive scan of G packed counters (4 x 16 bit) held in shared memory, in place; adds the
 // running totals in `carry` (also packed) and returns the new running total to every thread.
@@ -111,15 +121,9 @@ WB_DEV unsigned long long scan_packed(unsigned long long *c, int G, unsigned lon
 #endif
 }
 
-// One frame of one band: interp1 of the four trains, mean, (DIO) score, range checks
-// (dio.cpp:441-465, 562-566 / harvest.cpp:240-254).
-WB_DEV void sweep_candidate(const SweepParams &p, const Train *tr, const int *lo_j, const int *tot,
-                            int i, double bf, double *cand, double *score) {
-  const double t = i * p.frame_period / 1000.0;
-  const double v0 = train_interp(tr[0], lo_j[0], tot[0] - 1, p.afs, t);
-  const double v1 = train_interp(tr[1], lo_j[1], tot[1] - 1, p.afs, t);
-  const double v2 = train_interp(tr[2], lo_j[2], tot[2] - 1, p.afs, t);
-  const double v3 = train_interp(tr[3], lo_j[3], tot[3] - 1, p.afs, t);
+// One frame of one band from the four interpolated values (dio.cpp:441-465, 562-566 / harvest.cpp:240-254)
+WB_DEV void sweep_store_candidate(const SweepParams &p, double v0, double v1, double v2, double v3, int i, double bf,
+                                  double *cand, double *score) {
   double c = (v0 + v1 + v2 + v3) / 4.0, sc = 0.0;
   if (p.mode == 0) {
     sc = sqrt(((v0 - c) * (v0 - c) + (v1 - c) * (v1 - c) + (v2 - c) * (v2 - c) + (v3 - c) * (v3 - c)) / 3.0);
@@ -129,6 +133,43 @@ WB_DEV void sweep_candidate(const SweepParams &p, const Train *tr, const int *lo
   }
   cand[i] = c;
   if (score) score[i] = sc / (c + kTiny);  // dio.cpp:562-566
+}
+
+// Finalises frames [f_begin, f_end): for every train the intervals still ahead of the frame cursor
+// (indices lo_j .. ni-1) are binned by the first frame they precede-or-equal; a packed block scan
+// turns the bins into per-frame interval counts, i.e. interp1's segment index, without any search.
+// lo_j advances past the intervals consumed.  Block-cooperative; ends with a barrier.
+WB_DEV void finalize_frames(const SweepParams &p, const Trains &T, int *lo_j, const int *ni, int f_begin, int f_end,
+                            unsigned long long *marks, unsigned long long *orig, unsigned long long *scan_tmp,
+                            double bf, double *cand, double *score) {
+  const int tid = WB_TID, nth = WB_NTH;
+  for (int c0 = f_begin; c0 < f_end; c0 += WB_FCHUNK) {
+    const int c1 = imin(f_end, c0 + WB_FCHUNK);
+    for (int i = tid; i < WB_FCHUNK; i += nth) marks[i] = 0ull;
+    WB_SYNC();
+    for (int q = 0; q < 4; ++q)
+      for (int j = lo_j[q] + tid; j < ni[q]; j += nth) {
+        int m = first_frame_at_or_after(loc_at(T, q, j), p.frame_period);
+        if (m < c0) m = c0;
+        if (m < c1) smem_add_u64(&marks[m - c0], 1ull << (16 * q));
+      }
+    WB_SYNC();
+    for (int i = tid; i < WB_FCHUNK; i += nth) orig[i] = marks[i];
+    WB_SYNC();
+    const unsigned long long all = scan_packed(marks, WB_FCHUNK, 0ull, scan_tmp);
+    for (int i = tid; i < c1 - c0; i += nth) {
+      const unsigned long long inc = marks[i] + orig[i];
+      const double t = (c0 + i) * p.frame_period / 1000.0;
+      const double v0 = train_value(T, 0, lo_j[0] + (int)(inc & 0xffffull), ni[0], t);
+      const double v1 = train_value(T, 1, lo_j[1] + (int)((inc >> 16) & 0xffffull), ni[1], t);
+      const double v2 = train_value(T, 2, lo_j[2] + (int)((inc >> 32) & 0xffffull), ni[2], t);
+      const double v3 = train_value(T, 3, lo_j[3] + (int)((inc >> 48) & 0xffffull), ni[3], t);
+      sweep_store_candidate(p, v0, v1, v2, v3, c0 + i, bf, cand, score);
+    }
+    lo_j[0] += (int)(all & 0xffffull); lo_j[1] += (int)((all >> 16) & 0xffffull);
+    lo_j[2] += (int)((all >> 32) & 0xffffull); lo_j[3] += (int)((all >> 48) & 0xffffull);
+    WB_SYNC();
+  }
 }
 
 WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
@@ -143,7 +184,9 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   double *hrev = seg + (seg_cap + (seg_cap >> 3) + 8);  // max_taps + 8
   double *st = hrev + (p.max_taps + 8);                 // T + 8: [0..1] carry, [2..T+2) this tile
   unsigned long long *cnt = reinterpret_cast<unsigned long long *>(st + (T + 8 + ((T + 8) >> 3) + 8));  // G + 40
-  double *ring = reinterpret_cast<double *>(cnt + (G + 40));                                           // 4 * WB_RING
+  double *ring = reinterpret_cast<double *>(cnt + (G + 40));                                           // 3 * 4 * WB_RING
+  unsigned long long *marks = reinterpret_cast<unsigned long long *>(ring + 12 * WB_RING);             // WB_FCHUNK
+  unsigned long long *orig = marks + WB_FCHUNK;                                                        // WB_FCHUNK
 
   const int ylen = p.y_len[u];
   const double *sig = p.sig + (size_t)u * p.sig_stride + p.sig_origin;
@@ -152,8 +195,10 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   for (int j = tid; j < ntaps; j += nth) hrev[j] = __ldg(&p.taps_rev[p.tap_off[b] + j]);
   for (int j = ntaps + tid; j < ntaps + 8; j += nth) hrev[j] = 0.0;
   if (tid == 0) { st[0] = 0.0; st[1] = 0.0; }
-  Train tr[4];
-  for (int q = 0; q < 4; ++q) { tr[q].g = edges + (size_t)q * cap; tr[q].ring = ring + q * WB_RING; tr[q].from = 0; }
+  Trains tr;
+  tr.er = ring; tr.xr = ring + 4 * WB_RING; tr.yr = ring + 8 * WB_RING; tr.afs = p.afs;
+  for (int q = 0; q < 4; ++q) { tr.g[q] = edges + (size_t)q * cap; tr.efrom[q] = 0; tr.ifrom[q] = 0; }
+  int ni[4] = {0, 0, 0, 0};   // intervals known so far per train (= max(0, events - 1))
   int tot[4] = {0, 0, 0, 0};  // running event counts per train (identical in every thread)
   int lo_j[4] = {0, 0, 0, 0}; // per train: intervals below this index lie before every unfinished frame
   int next_frame = 0;         // frames [0, next_frame) are done
@@ -261,36 +306,37 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
     }
     tot[0] += (int)(tile_total & 0xffffull); tot[1] += (int)((tile_total >> 16) & 0xffffull);
     tot[2] += (int)((tile_total >> 32) & 0xffffull); tot[3] += (int)((tile_total >> 48) & 0xffffull);
-    for (int q = 0; q < 4; ++q) tr[q].from = keep[q];
+    for (int q = 0; q < 4; ++q) tr.efrom[q] = keep[q];
 #ifndef WB_EMU
     __threadfence_block();
 #endif
     WB_SYNC();
     if (tid == 0) { st[pad8(0)] = st[pad8(T)]; st[pad8(1)] = st[pad8(T + 1)]; }
-    // ---- streaming candidates: every frame whose time lies before the last complete interval of
-    // all four trains can be interpolated now; its events are the most recent ones (cache hot).
+    // ---- new intervals of this tile -> location / value rings
     bool can = true;
-    double t_safe = 0.0;
     for (int q = 0; q < 4; ++q) {
-      if (tot[q] > cap || tot[q] < 2) { can = false; break; }
-      const double loc = train_location(tr[q], tot[q] - 2, p.afs);
-      t_safe = (q == 0 || loc < t_safe) ? loc : t_safe;
+      if (tot[q] > cap) { can = false; continue; }
+      const int n_new = imax(0, tot[q] - 1);
+      const int from = imax(0, n_new - WB_RING);
+      for (int j = imax(ni[q], from) + tid; j < n_new; j += nth) {
+        const double e0 = edge_at(tr, q, j), e1 = edge_at(tr, q, j + 1);
+        tr.xr[q * WB_RING + (j & (WB_RING - 1))] = (e0 + e1) / 2.0 / p.afs;
+        tr.yr[q * WB_RING + (j & (WB_RING - 1))] = p.afs / (e1 - e0);
+      }
+      ni[q] = n_new;
+      tr.ifrom[q] = from;
+      if (n_new < 1) can = false;
     }
+    WB_SYNC();
+    // ---- streaming candidates: every frame whose time lies before the last complete interval of
+    // all four trains can be interpolated now.
     if (can) {
-      // first frame index with t_i >= t_safe (t_i = i * frame_period / 1000.0, monotone in i)
-      int i_safe = (int)(t_safe * 1000.0 / p.frame_period);
-      if (i_safe < 0) i_safe = 0;
-      while (i_safe > 0 && !((i_safe - 1) * p.frame_period / 1000.0 < t_safe)) --i_safe;
-      while (i_safe < nf && (i_safe * p.frame_period / 1000.0 < t_safe)) ++i_safe;
+      double t_safe = loc_at(tr, 0, ni[0] - 1);
+      for (int q = 1; q < 4; ++q) t_safe = dmin(t_safe, loc_at(tr, q, ni[q] - 1));
+      int i_safe = first_frame_at_or_after(t_safe, p.frame_period);  // frames below have t_i < t_safe
       if (i_safe > nf) i_safe = nf;
       if (i_safe > next_frame) {
-        for (int i = next_frame + tid; i < i_safe; i += nth)
-          sweep_candidate(p, tr, lo_j, tot, i, bf, cand, score);
-        // all later frames have t >= t_safe: their interval counts are at least those of t_safe
-        for (int q = 0; q < 4; ++q) {
-          const int c = train_count(tr[q], lo_j[q], tot[q] - 1, p.afs, (i_safe - 1) * p.frame_period / 1000.0);
-          lo_j[q] = imax(lo_j[q], c);
-        }
+        finalize_frames(p, tr, lo_j, ni, next_frame, i_safe, marks, orig, cnt + G + 4, bf, cand, score);
         next_frame = i_safe;
       }
     }
@@ -300,11 +346,11 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   bool ok = true;
   for (int q = 0; q < 4; ++q) {
     if (tot[q] > cap) { if (tid == 0) atomicOr_status(p.status, 4); ok = false; }
-    const int ni = tot[q] < 2 ? 0 : tot[q] - 1;  // ZeroCrossingEngine returns count-1 (0 if count<2)
-    if (ni - 2 <= 0) ok = false;                 // CheckEvent(n - 2), dio.cpp:475-484
+    const int n_int = tot[q] < 2 ? 0 : tot[q] - 1;  // ZeroCrossingEngine returns count-1 (0 if count<2)
+    if (n_int - 2 <= 0) ok = false;                 // CheckEvent(n - 2), dio.cpp:475-484
   }
   if (ok) {
-    for (int i = next_frame + tid; i < nf; i += nth) sweep_candidate(p, tr, lo_j, tot, i, bf, cand, score);
+    finalize_frames(p, tr, lo_j, ni, next_frame, nf, marks, orig, cnt + G + 4, bf, cand, score);
   } else {
     for (int i = tid; i < nf; i += nth) {
       cand[i] = 0.0;
