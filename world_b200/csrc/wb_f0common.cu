@@ -1,6 +1,7 @@
 // wb_f0common.cu -- kernels shared by DIO and Harvest (see wb_f0common.cuh for the design notes).
 #include "wb_internal.h"
 #include "wb_f0common.cuh"
+#include <stdlib.h>
 
 namespace wb {
 
@@ -235,10 +236,19 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
       for (int r = 0; r < R; ++r) st[pad8(2 + base + r)] = acc[r];
     }
     WB_SYNC();
+    if (p.debug_skip >= 2) { WB_SYNC(); continue; }
     // train 0: s[i] > 0 >= s[i+1]   train 1: s[i] < 0 <= s[i+1]          (i >= 0, i+1 <= ylen-1)
     // train 2: d[i] > 0 >= d[i+1]   train 3: d[i] < 0 <= d[i+1], d[i] = s[i+1]-s[i]  (i+1 <= ylen-2)
+    // Pass 1 marks events (bit 4 r + q of a per-group mask) and counts them; a packed scan gives
+    // every group its offsets; pass 2 compacts the event POSITIONS into per-train lists (no
+    // arithmetic); pass 3 walks the dense lists and evaluates the fine edge (one division per
+    // event, all lanes busy) -- high bands have an event every few samples, so doing the division
+    // inside the divergent per-position branches cost more than the FIR itself (r1h experiment).
+    unsigned *emask = reinterpret_cast<unsigned *>(marks);  // G words (marks is idle here)
+    int *elist = reinterpret_cast<int *>(seg);              // 4 x (T/2) positions (seg is idle after the FIR)
     for (int g = tid; g < G; g += nth) {
       unsigned long long c = 0ull;
+      unsigned m = 0u;
       const int base = R * g;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -246,62 +256,55 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
         const double a = st[pad8(base + r)], bb = st[pad8(base + r + 1)], cc = st[pad8(base + r + 2)];
         const double d0 = bb - a, d1 = cc - bb;
         if (i >= 0 && i + 1 <= ylen - 1) {
-          c += (0.0 < a && bb <= 0.0) ? 1ull : 0ull;
-          c += (a < 0.0 && 0.0 <= bb) ? (1ull << 16) : 0ull;
+          if (0.0 < a && bb <= 0.0) { c += 1ull; m |= 1u << (4 * r); }
+          if (a < 0.0 && 0.0 <= bb) { c += 1ull << 16; m |= 2u << (4 * r); }
         }
         if (i >= 0 && i + 1 <= ylen - 2) {
-          c += (0.0 < d0 && d1 <= 0.0) ? (1ull << 32) : 0ull;
-          c += (d0 < 0.0 && 0.0 <= d1) ? (1ull << 48) : 0ull;
+          if (0.0 < d0 && d1 <= 0.0) { c += 1ull << 32; m |= 4u << (4 * r); }
+          if (d0 < 0.0 && 0.0 <= d1) { c += 1ull << 48; m |= 8u << (4 * r); }
         }
       }
       cnt[g] = c;
+      emask[g] = m;
     }
     WB_SYNC();
     const unsigned long long tile_total = scan_packed(cnt, G, 0ull, cnt + G + 4);  // <= 2048 each: fits 16 bit
-    int keep[4];  // after this tile the ring holds event indices >= keep[q]
-    keep[0] = imax(0, tot[0] + (int)(tile_total & 0xffffull) - WB_RING);
-    keep[1] = imax(0, tot[1] + (int)((tile_total >> 16) & 0xffffull) - WB_RING);
-    keep[2] = imax(0, tot[2] + (int)((tile_total >> 32) & 0xffffull) - WB_RING);
-    keep[3] = imax(0, tot[3] + (int)((tile_total >> 48) & 0xffffull) - WB_RING);
+    int tcount[4], keep[4];  // events of this tile; after it the ring holds event indices >= keep[q]
+    for (int q = 0; q < 4; ++q) {
+      tcount[q] = (int)((tile_total >> (16 * q)) & 0xffffull);
+      keep[q] = imax(0, tot[q] + tcount[q] - WB_RING);
+    }
     for (int g = tid; g < G; g += nth) {
       const unsigned long long o = cnt[g];
-      int o0 = tot[0] + (int)(o & 0xffffull), o1 = tot[1] + (int)((o >> 16) & 0xffffull);
-      int o2 = tot[2] + (int)((o >> 32) & 0xffffull), o3 = tot[3] + (int)((o >> 48) & 0xffffull);
-      const int base = R * g;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int i = n0 - 2 + base + r;
-        const double a = st[pad8(base + r)], bb = st[pad8(base + r + 1)], cc = st[pad8(base + r + 2)];
-        const double d0 = bb - a, d1 = cc - bb;
-        const double e = (double)(i + 1);
-        if (i >= 0 && i + 1 <= ylen - 1) {
-          if (0.0 < a && bb <= 0.0) {
-            const double v = e - a / (bb - a);
-            if (o0 < cap) edges[o0] = v;
-            if (o0 >= keep[0]) ring[o0 & (WB_RING - 1)] = v;
-            ++o0;
-          }
-          if (a < 0.0 && 0.0 <= bb) {
-            const double v = e - a / (bb - a);
-            if (o1 < cap) edges[(size_t)cap + o1] = v;
-            if (o1 >= keep[1]) ring[WB_RING + (o1 & (WB_RING - 1))] = v;
-            ++o1;
-          }
+      int off[4] = {(int)(o & 0xffffull), (int)((o >> 16) & 0xffffull), (int)((o >> 32) & 0xffffull), (int)((o >> 48) & 0xffffull)};
+      unsigned m = emask[g];
+      while (m) {
+#ifdef WB_EMU
+        const int bit = __builtin_ctz(m);
+#else
+        const int bit = __ffs((int)m) - 1;
+#endif
+        m &= m - 1u;
+        const int q = bit & 3, r = bit >> 2;
+        elist[q * (T / 2) + off[q]] = R * g + r;  // position relative to n0 - 2
+        ++off[q];
+      }
+    }
+    WB_SYNC();
+    for (int q = 0; q < 4; ++q) {
+      for (int e = tid; e < tcount[q]; e += nth) {
+        const int pos = elist[q * (T / 2) + e];
+        const double a = st[pad8(pos)], bb = st[pad8(pos + 1)];
+        double v;
+        if (q < 2) {
+          v = (double)(n0 - 2 + pos + 1) - a / (bb - a);
+        } else {
+          const double d0 = bb - a, d1 = st[pad8(pos + 2)] - bb;
+          v = (double)(n0 - 2 + pos + 1) - d0 / (d1 - d0);
         }
-        if (i >= 0 && i + 1 <= ylen - 2) {
-          if (0.0 < d0 && d1 <= 0.0) {
-            const double v = e - d0 / (d1 - d0);
-            if (o2 < cap) edges[2 * (size_t)cap + o2] = v;
-            if (o2 >= keep[2]) ring[2 * WB_RING + (o2 & (WB_RING - 1))] = v;
-            ++o2;
-          }
-          if (d0 < 0.0 && 0.0 <= d1) {
-            const double v = e - d0 / (d1 - d0);
-            if (o3 < cap) edges[3 * (size_t)cap + o3] = v;
-            if (o3 >= keep[3]) ring[3 * WB_RING + (o3 & (WB_RING - 1))] = v;
-            ++o3;
-          }
-        }
+        const int o = tot[q] + e;
+        if (o < cap) edges[(size_t)q * cap + o] = v;
+        if (o >= keep[q]) ring[q * WB_RING + (o & (WB_RING - 1))] = v;
       }
     }
     tot[0] += (int)(tile_total & 0xffffull); tot[1] += (int)((tile_total >> 16) & 0xffffull);
@@ -312,6 +315,7 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
 #endif
     WB_SYNC();
     if (tid == 0) { st[pad8(0)] = st[pad8(T)]; st[pad8(1)] = st[pad8(T + 1)]; }
+    if (p.debug_skip >= 1) { WB_SYNC(); continue; }
     // ---- new intervals of this tile -> location / value rings
     bool can = true;
     for (int q = 0; q < 4; ++q) {
@@ -428,7 +432,10 @@ void launch_fir_plain(Ctx *ctx, const FirParams &p, unsigned tiles, unsigned n_u
   WB_LAUNCH_COOP(fir_plain_kernel, dim3(tiles, n_utts), 256, smem, ctx->stream, p);
 }
 
-void launch_band_sweep(Ctx *ctx, const SweepParams &p, unsigned n_utts) {
+void launch_band_sweep(Ctx *ctx, const SweepParams &p_in, unsigned n_utts) {
+  SweepParams p = p_in;
+  p.debug_skip = 0;
+  if (const char *e = getenv("WB_SWEEP_DEBUG")) p.debug_skip = atoi(e);
   const size_t smem = sweep_smem_bytes(p.max_taps);
 #ifndef WB_EMU
   cudaFuncSetAttribute(band_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -88,6 +88,7 @@ struct SweepParams {
   double *cand; double *score;                           // [(u*nb+b)][frame_stride]
   int max_taps;
   int *status;
+  int debug_skip;   // experiments only: 1 = no candidate phase, 2 = no event phase either
 };
 
 WB_HD inline size_t sweep_smem_bytes(int max_taps) {
