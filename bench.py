@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--slices", type=int, default=4,
+                    help="utterance slices per step: F0 of slice s+1 overlaps CheapTrick/D4C of slice s on a second stream")
     return ap.parse_args()
 
 
@@ -254,14 +256,42 @@ def main():
     if world > 1 and free < (60 << 30):
         w.set_scratch_budget(6 << 30)
 
+    # Two contexts on two streams: the F0 estimator of slice s+1 (FP64 bound) runs concurrently with
+    # CheapTrick + D4C of slice s (shared-memory / barrier bound); slices are contiguous utterance ranges.
+    n_slices = max(1, min(a.slices, U))
+    w2 = World(device=local) if n_slices > 1 else w
+    side = torch.cuda.Stream(device=dev) if n_slices > 1 else None
+    bounds = [U * i // n_slices for i in range(n_slices + 1)]
+    t_loc = torch.zeros((U, L), dtype=torch.float64, device=dev)
+    f0_loc = torch.zeros((U, L), dtype=torch.float64, device=dev)
+    if world > 1 and free < (60 << 30):
+        w2.set_scratch_budget(6 << 30)
+
     def step():
-        if a.f0 == "harvest":
-            t, f0, fl = w.harvest(x, fs)
-        else:
-            t, f0, fl = w.dio(x, fs)
-            f0 = w.stonemask(x, fs, t, f0)
-        w.cheaptrick(x, fs, t, f0, opt, out=sp)
-        w.d4c(x, fs, t, f0, opt.fft_size, out=ap)
+        main = torch.cuda.current_stream(dev)
+        for si in range(n_slices):
+            b0, b1 = bounds[si], bounds[si + 1]
+            xs = x[b0:b1]
+            if a.f0 == "harvest":
+                t, f0, fl = w.harvest(xs, fs)
+            else:
+                t, f0, fl = w.dio(xs, fs)
+                f0 = w.stonemask(xs, fs, t, f0)
+            t_loc[b0:b1].copy_(t); f0_loc[b0:b1].copy_(f0)
+            if side is None:
+                w.cheaptrick(xs, fs, t, f0, opt, out=sp[b0:b1])
+                w.d4c(xs, fs, t, f0, opt.fft_size, out=ap[b0:b1])
+            else:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ev)
+                    t.record_stream(side); f0.record_stream(side)
+                    w2.cheaptrick(xs, fs, t, f0, opt, out=sp[b0:b1])
+                    w2.d4c(xs, fs, t, f0, opt.fft_size, out=ap[b0:b1])
+        if side is not None:
+            main.wait_stream(side)
+        t, f0 = t_loc, f0_loc
         if gather:
             dist.all_gather_into_tensor(f0_all, f0)
             dist.all_gather_into_tensor(t_all, t)
@@ -407,7 +437,7 @@ def main():
                       "l2_policy": "inputs+outputs per step (>= 18 GB) exceed the 126 MB L2; no flush needed",
                       "multi_gpu": ("utterances sharded over ranks, NCCL all-gather of f0/time_axis" +
                                     ("/spectrogram/aperiodicity" if gather_full else "")) if world > 1 else "single GPU"},
-           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+           "clocks": clocks, "e2e": e2e, "slices": n_slices, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
            "kernels": kernels}
     print(json.dumps(out), flush=True)
     if world > 1:
