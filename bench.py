@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
-    ap.add_argument("--slices", type=int, default=4,
+    ap.add_argument("--slices", type=int, default=1,
                     help="utterance slices per step: F0 of slice s+1 overlaps CheapTrick/D4C of slice s on a second stream")
     return ap.parse_args()
 
@@ -396,12 +396,36 @@ def main():
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(dom)
+            per_utt = json.load(open(tp)).get(dom, {}).get("dram_bytes_per_utt")
+            if per_utt:
+                traffic = per_utt * U / max(1.0, kernels[dom]["launches_per_step"])
         roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": nbytes / max(1.0, kernels[dom]["launches_per_step"]) if nbytes else None,
                 "kernel_ms_per_step": kms, "share_of_step": kms / (ms / a.steps),
                 "note": "FP64-ALU/shared-memory bound path (SURVEY.md 8d): HBM fraction is reported as BASELINE.json asks"}
+
+    # ---- FP64 view of the two FP64-bound kernels (the binding roofline)
+    fp64 = None
+    try:
+        peak64 = w.fp64_peak()
+        ratio = max(1, int(fs / 8000.0 + 0.5))
+        ylen = math.ceil(n / ratio)
+        fir_flops = None
+        if a.f0 == "harvest":
+            afs = fs / ratio
+            taps = 0
+            for i in range(152):
+                bnd = 71.0 * 0.9 * 2.0 ** ((i + 1) / 40.0)
+                taps += 2 * int(afs / bnd * 2.0 + 0.5) + 1
+            fir_flops = 2.0 * taps * ylen * U  # one FMA per tap and output sample
+        fp64 = {"peak_tflops": peak64, "peak_source": "world_b200_fp64_peak (8 DFMA chains/thread, CUDA events)"}
+        if fir_flops and "band_sweep_kernel" in kernels:
+            t_s = kernels["band_sweep_kernel"]["ms_per_step"] / 1e3
+            fp64["band_sweep_fir_tflops"] = fir_flops / t_s / 1e12
+            fp64["band_sweep_frac"] = fir_flops / t_s / 1e12 / peak64
+    except Exception as e:  # never let the extra figure break the bench line
+        fp64 = {"error": str(e)[:100]}
 
     # ---- CPU baseline: the compiled reference, one thread, bounded sample of the same batch
     cpu = None
@@ -437,7 +461,7 @@ def main():
                       "l2_policy": "inputs+outputs per step (>= 18 GB) exceed the 126 MB L2; no flush needed",
                       "multi_gpu": ("utterances sharded over ranks, NCCL all-gather of f0/time_axis" +
                                     ("/spectrogram/aperiodicity" if gather_full else "")) if world > 1 else "single GPU"},
-           "clocks": clocks, "e2e": e2e, "slices": n_slices, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+           "clocks": clocks, "e2e": e2e, "slices": n_slices, "gpu_launches": int(launches), "roofline": roof, "fp64": fp64, "cpu_baseline": cpu,
            "kernels": kernels}
     print(json.dumps(out), flush=True)
     if world > 1:

@@ -64,6 +64,10 @@ unsigned long long world_b200_launch_count(const WorldB200 *ctx);
 int world_b200_profile(WorldB200 *ctx, int enable);
 int world_b200_profile_report(WorldB200 *ctx, char *buf, unsigned long long cap);
 
+/* Measured FP64 FMA peak of the device in TFLOP/s (8 independent DFMA chains per thread, CUDA
+ * events): the roofline the analysis path is bound by (no FP64 figure exists in MEASURED_PEAKS). */
+int world_b200_fp64_peak(WorldB200 *ctx, double *tflops);
+
 /* Test hook: first n_draws values of the reference's randn() stream (matlabfunctions.cpp:237-264)
  * as raw 32-bit sums (value = sum / 2^28 - 6) into a DEVICE buffer of n_draws uint32. */
 int world_b200_randn_stream(WorldB200 *ctx, unsigned n_draws, unsigned *out_dev);

@@ -77,3 +77,7 @@ def test_emu_harvest_frame_period_1ms(emu, ref):
     tr, fr = ref.harvest(x[0], 16000, ro)
     assert np.array_equal(t[0], tr)
     pc.assert_close(f0[0], fr, "Harvest 1 ms")
+
+
+def test_emu_edge_cases(emu, ref):
+    pc.check_edge_cases(emu, ref)

@@ -54,3 +54,71 @@ def test_gpu_golden_harvest(gpu_world, golden):
 @pytest.mark.parametrize("fs,n,seeds", [(16000, 48000, [31, 32, 33, 34]), (48000, 48000, [35, 36]), (22050, 22050, [37])])
 def test_gpu_harvest_path_end_to_end(gpu_world, ref, fs, n, seeds):
     pc.check_batch_vs_ref(gpu_world, ref, fs, n, seeds, f0_method="harvest", ragged=len(seeds) > 1)
+
+
+def test_gpu_edge_cases(gpu_world, ref):
+    pc.check_edge_cases(gpu_world, ref)
+
+
+def test_gpu_long_48k_utterance(gpu_world, ref):
+    """BASELINE configs[3] shape: 48 kHz, CheapTrick fft 2048 + D4C fft 4096 (long-FFT shared-memory path)."""
+    import torch
+    from synth import synth_batch
+    fs, n = 48000, 48000 * 6
+    x = synth_batch([71], fs, n)
+    xh = x[0].numpy()
+    tr, fr = ref.dio(xh, fs)
+    fr = ref.stonemask(xh, fs, tr, fr)
+    xb = x.cuda()
+    t, f0, fl = gpu_world.dio(xb, fs)
+    f0 = gpu_world.stonemask(xb, fs, t, f0)
+    opt = gpu_world.cheaptrick_option(fs)
+    assert opt.fft_size == 2048
+    sp = gpu_world.cheaptrick(xb, fs, t, f0, opt)
+    ap = gpu_world.d4c(xb, fs, t, f0, opt.fft_size)
+    gpu_world.synchronize()
+    assert np.array_equal(t[0].cpu().numpy(), tr)
+    pc.assert_close(f0[0], fr, "f0 48k")
+    fu = np.ascontiguousarray(f0[0].cpu().numpy())
+    pc.assert_close(sp[0], ref.cheaptrick(xh, fs, tr, fu, opt), "sp 48k")
+    pc.assert_close(ap[0], ref.d4c(xh, fs, tr, fu, opt.fft_size), "ap 48k")
+
+
+def test_gpu_legacy_api_and_analyze_host(gpu_world, ref, golden):
+    """The reference's own entry points (host pointers, double**) and the one-call host pipeline."""
+    import ctypes as C
+    from world_b200 import api
+    lib = gpu_world.lib
+    x, fs = pc.wav_from_golden(golden)
+    n = len(x)
+    L = lib.GetSamplesForDIO(fs, n, 5.0)
+    t = np.zeros(L); f0 = np.zeros(L); f0r = np.zeros(L)
+    do = api.DioOption(); lib.InitializeDioOption(C.byref(do))
+    lib.Dio(x.ctypes.data, n, fs, C.byref(do), t.ctypes.data, f0.ctypes.data)
+    lib.StoneMask(x.ctypes.data, n, fs, t.ctypes.data, f0.ctypes.data, L, f0r.ctypes.data)
+    co = api.CheapTrickOption(); lib.InitializeCheapTrickOption(fs, C.byref(co))
+    bins = co.fft_size // 2 + 1
+    sp = np.zeros((L, bins)); ap = np.zeros((L, bins))
+    rows = (C.c_void_p * L)(*[sp[i].ctypes.data for i in range(L)])
+    lib.CheapTrick(x.ctypes.data, n, fs, t.ctypes.data, f0r.ctypes.data, L, C.byref(co), rows)
+    rows2 = (C.c_void_p * L)(*[ap[i].ctypes.data for i in range(L)])
+    d4 = api.D4COption(); lib.InitializeD4COption(C.byref(d4))
+    lib.D4C(x.ctypes.data, n, fs, t.ctypes.data, f0r.ctypes.data, L, co.fft_size, C.byref(d4), rows2)
+    assert np.array_equal(t, golden["time_axis"])
+    pc.assert_close(f0, golden["f0_dio"], "legacy Dio")
+    pc.assert_close(f0r, golden["f0_stonemask"], "legacy StoneMask")
+    pc.assert_close(sp, ref.cheaptrick(x, fs, t, f0r), "legacy CheapTrick")
+    pc.assert_close(ap, ref.d4c(x, fs, t, f0r, co.fft_size), "legacy D4C")
+    fh = np.zeros(L); th = np.zeros(L)
+    ho = api.HarvestOption(); lib.InitializeHarvestOption(C.byref(ho))
+    lib.Harvest(x.ctypes.data, n, fs, C.byref(ho), th.ctypes.data, fh.ctypes.data)
+    pc.assert_close(fh, golden["f0_harvest"], "legacy Harvest")
+    # one-call host pipeline on a small batch (both F0 methods)
+    xb = np.ascontiguousarray(np.stack([x, x[::-1]]))
+    for method, key in ((api.F0_DIO_STONEMASK, "f0_stonemask"), (api.F0_HARVEST, "f0_harvest")):
+        ao = gpu_world.analysis_option(fs, method)
+        ta, fa, spa, apa, fl = gpu_world.analyze_host(xb, fs, ao)
+        assert np.array_equal(ta[0], golden["time_axis"])
+        pc.assert_close(fa[0], golden[key], "analyze_host f0")
+        pc.assert_close(spa[0], ref.cheaptrick(x, fs, ta[0], np.ascontiguousarray(fa[0])), "analyze_host sp")
+        pc.assert_close(apa[0], ref.d4c(x, fs, ta[0], np.ascontiguousarray(fa[0]), co.fft_size), "analyze_host ap")

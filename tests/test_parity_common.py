@@ -137,3 +137,45 @@ def check_golden_harvest(world, golden):
     assert np.array_equal(to_np(t)[0], golden["time_axis"])
     assert_close(f0[0], golden["f0_harvest"], "Harvest f0")
     assert_close(f0_40[0], golden["f0_harvest_floor40"], "Harvest f0 (floor 40)")
+
+
+def check_edge_cases(world, ref):
+    """Silence, very short and ragged utterances, non-default frame periods."""
+    from synth import synth_batch
+    fs = 16000
+    x = synth_batch([61, 62, 63], fs, 8000).numpy()
+    x[1, :] = 0.0                      # digital silence: f0 = 0 everywhere, randn-only frames downstream
+    lens = [8000, 8000, 900]           # third utterance is shorter than most analysis windows
+    xb = make(world, x)
+    for method in ("dio", "harvest"):
+        for fp in (5.0, 10.0, 2.5):
+            if method == "dio":
+                o = world.dio_option(); o.frame_period = fp
+                ro = ref.dio_option(); ro.frame_period = fp
+                t, f0, fl = world.dio(xb, fs, o, x_lengths=lens)
+            else:
+                o = world.harvest_option(); o.frame_period = fp
+                ro = ref.harvest_option(); ro.frame_period = fp
+                t, f0, fl = world.harvest(xb, fs, o, x_lengths=lens)
+            world.synchronize()
+            for u in range(3):
+                xu = x[u, :lens[u]]
+                tr, fr = (ref.dio(xu, fs, ro) if method == "dio" else ref.harvest(xu, fs, ro))
+                assert fl[u] == len(tr)
+                assert np.array_equal(to_np(t)[u, :fl[u]], tr)
+                assert_close(to_np(f0)[u, :fl[u]], fr, f"{method} fp={fp} utt {u}")
+    # spectral stages on the silent and the short utterance (reference f0)
+    fl = [ref.frames(fs, l) for l in lens]
+    tn = np.zeros((3, max(fl))); fn = np.zeros((3, max(fl)))
+    for u in range(3):
+        tr, fr = ref.dio(x[u, :lens[u]], fs)
+        tn[u, :fl[u]] = tr; fn[u, :fl[u]] = ref.stonemask(x[u, :lens[u]], fs, tr, fr)
+    t, f0 = make(world, tn), make(world, fn)
+    opt = world.cheaptrick_option(fs)
+    sp = world.cheaptrick(xb, fs, t, f0, opt, x_lengths=lens, f0_lengths=fl)
+    ap = world.d4c(xb, fs, t, f0, opt.fft_size, x_lengths=lens, f0_lengths=fl)
+    world.synchronize()
+    for u in range(3):
+        xu = x[u, :lens[u]]
+        assert_close(to_np(sp)[u, :fl[u]], ref.cheaptrick(xu, fs, tn[u, :fl[u]], fn[u, :fl[u]], opt), f"sp edge utt {u}")
+        assert_close(to_np(ap)[u, :fl[u]], ref.d4c(xu, fs, tn[u, :fl[u]], fn[u, :fl[u]], opt.fft_size), f"ap edge utt {u}")

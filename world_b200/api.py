@@ -59,6 +59,7 @@ ABI = {
     "world_b200_launch_count": (C.c_ulonglong, [_P]),
     "world_b200_frames": (C.c_int, [C.c_int, C.c_int, C.c_double]),
     "world_b200_randn_stream": (C.c_int, [_P, C.c_uint, _P]),
+    "world_b200_fp64_peak": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "world_b200_profile": (C.c_int, [_P, C.c_int]),
     "world_b200_profile_report": (C.c_int, [_P, C.c_char_p, C.c_ulonglong]),
     "world_b200_dio_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, C.POINTER(DioOption), _P, _P, C.c_int]),
@@ -180,6 +181,11 @@ class World:
 
     def set_scratch_budget(self, nbytes: int):
         self._check(self.lib.world_b200_set_scratch_budget(self._h, nbytes))
+
+    def fp64_peak(self) -> float:
+        v = C.c_double(0.0)
+        self._check(self.lib.world_b200_fp64_peak(self._h, C.byref(v)))
+        return v.value
 
     def profile(self, enable=True):
         self._check(self.lib.world_b200_profile(self._h, 1 if enable else 0))

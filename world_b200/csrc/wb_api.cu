@@ -407,6 +407,48 @@ int world_b200_profile_report(WorldB200 *h, char *buf, unsigned long long cap) {
   return 0;
 }
 
+// FP64 FMA peak of this device (the roofline the path is actually bound by; MEASURED_PEAKS.json
+// has no FP64 figure): 8 independent DFMA chains per thread, timed with CUDA events.
+#ifndef WB_EMU
+__global__ void fp64_peak_kernel(double *out, int iters) {
+  double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000000001, c = 0.5;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+#endif
+
+int world_b200_fp64_peak(WorldB200 *h, double *tflops) {
+  if (!h || !tflops) return WORLD_B200_EINVAL;
+  *tflops = 0.0;
+#ifndef WB_EMU
+  Ctx *ctx = &h->c;
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 15;
+  unsigned char *blk = arena_block(ctx, (size_t)blocks * threads * 8);
+  if (!blk) return WORLD_B200_ENOMEM;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(a, ctx->stream);
+    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double *)blk, iters);
+    cudaEventRecord(b, ctx->stream);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  *tflops = (double)blocks * threads * iters * 8 * 2 / (best * 1e-3) / 1e12;
+  return dev_check(ctx, "fp64_peak");
+#else
+  return 0;
+#endif
+}
+
 // Known-answer hook: the first n_draws randn() draws after randn_reseed(), as the raw 32-bit
 // sums (value = sum / 2^28 - 6), written to a device buffer of n_draws uint32.
 int world_b200_randn_stream(WorldB200 *h, unsigned n_draws, unsigned *out_dev) {

@@ -333,6 +333,7 @@ WB_KERNEL(32 * WB_HV_WARPS, 4) harvest_refine_kernel(HvRefineParams p) {
 struct HvRemoveParams {
   const double *cand_in; const double *score_in; double *cand; double *score;
   const int *nc; const int *l1; int l1_stride; int max_cand; int n_utts;
+  double *f0_base;   // [n][5][l1_stride] work rows of the contour kernel; row 0 = SearchF0Base result
 };
 
 // min(1, min_c |reference - row[c]| / reference): SelectBestF0's error with allowed_range 1.0
@@ -355,6 +356,7 @@ WB_KERNEL_PLAIN harvest_remove_kernel(HvRemoveParams p) {
   const double *row = p.cand_in + (size_t)g * p.max_cand;
   double *oc = p.cand + (size_t)g * p.max_cand, *os = p.score + (size_t)g * p.max_cand;
   const double *srow = p.score_in + (size_t)g * p.max_cand;
+  double best = 0.0, best_score = 0.0;  // SearchF0Base (harvest.cpp:693-705) on the cleaned candidates
   for (int j = 0; j < n; ++j) {
     double c = row[j], s = srow[j];
     if (i >= 1 && i < L1 - 1 && c != 0) {
@@ -363,7 +365,9 @@ WB_KERNEL_PLAIN harvest_remove_kernel(HvRemoveParams p) {
       if (dmin(e1, e2) > 0.05) { c = 0.0; s = 0.0; }
     }
     oc[j] = c; os[j] = s;
+    if (s > best_score) { best = c; best_score = s; }
   }
+  p.f0_base[(size_t)u * 5 * p.l1_stride + i] = best;
 }
 
 // ------------------------------------------------------------------ K-HVc
@@ -465,15 +469,7 @@ WB_KERNEL(128, 4) harvest_contour_kernel(HvContourParams p) {
   double *mc = p.mc + (size_t)u * p.mc_stride;
   int *off = bl + p.l1_stride, *wlo = off + p.l1_stride, *whi = wlo + p.l1_stride, *order = whi + p.l1_stride;
 
-  // SearchF0Base (:693-705)
-  for (int i = tid; i < L; i += nth) {
-    double best = 0.0, bs = 0.0;
-    const double *c = cand + (size_t)i * mcand, *s = score + (size_t)i * mcand;
-    for (int j = 0; j < nc7; ++j)
-      if (s[j] > bs) { best = c[j]; bs = s[j]; }
-    fb[i] = best;
-  }
-  WB_SYNC();
+  // SearchF0Base (:693-705) was evaluated by harvest_remove_kernel while it held the rows: fb[]
   // FixStep1 (:710-722), allowed_range 0.008
   for (int i = tid; i < L; i += nth) {
     double v = 0.0;
@@ -818,6 +814,7 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     HvRemoveParams mp;
     mp.cand_in = rp.cand; mp.score_in = rp.score; mp.cand = (double *)(blk + o_c2); mp.score = (double *)(blk + o_s2);
     mp.nc = nc; mp.l1 = l1; mp.l1_stride = l1_stride; mp.max_cand = max_cand; mp.n_utts = n;
+    mp.f0_base = (double *)(blk + o_work);
     WB_LAUNCH_FLAT(harvest_remove_kernel, dim3((unsigned)((slots + 127) / 128)), 128, 0, ctx->stream, mp);
 
     HvContourParams cp;
