@@ -289,7 +289,7 @@ WB_DEV double hv_slot_candidate(const double *__restrict__ base, int L1, int nc,
   return base[(size_t)src * WB_HV_BASE + j];
 }
 
-WB_KERNEL(32 * WB_HV_WARPS, 4) harvest_refine_kernel(HvRefineParams p) {
+WB_KERNEL(32 * WB_HV_WARPS, 6) harvest_refine_kernel(HvRefineParams p) {
   WB_DYN_SMEM(double, smem);
 #ifdef WB_EMU
   const int warp = 0, nwarps = 1;
