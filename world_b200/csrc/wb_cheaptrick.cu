@@ -76,6 +76,7 @@ WB_KERNEL(128, 4) ct_frame_kernel(CtParams p) {
 
   // ---- F0-adaptive Hanning window, normalised to unit energy (cheaptrick.cpp:97-106)
   double sq = 0.0;
+  WB_UNROLL4
   for (int j = tid; j < nwin; j += nth) {
     const double pos = (j - h) / 1.5 / fs;
     const double w = 0.5 * cos(kPi * pos * f) + 0.5;
@@ -85,6 +86,7 @@ WB_KERNEL(128, 4) ct_frame_kernel(CtParams p) {
   const double norm = sqrt(block_sum(sq, red));
   // ---- windowed waveform + 1e-12 * randn, weighted-mean removal (:126-137)
   double s1 = 0.0, s2 = 0.0;
+  WB_UNROLL4
   for (int j = tid; j < nwin; j += nth) {
     const double w = ext[j] / norm;
     ext[j] = w;
@@ -96,6 +98,7 @@ WB_KERNEL(128, 4) ct_frame_kernel(CtParams p) {
   }
   block_sum2(s1, s2, red);
   const double coef = s1 / s2;
+  WB_UNROLL4
   for (int j = tid; j < N + 2; j += nth) buf[j] = (j < nwin) ? buf[j] - ext[j] * coef : 0.0;
   WB_SYNC();
 
@@ -103,6 +106,7 @@ WB_KERNEL(128, 4) ct_frame_kernel(CtParams p) {
   rfft_forward(buf, p.lg_fft, p.tw);
   {
     const double2 *z = reinterpret_cast<const double2 *>(buf);
+    WB_UNROLL4
     for (int k = tid; k <= half; k += nth) { const double2 c = z[k]; ext[k] = c.x * c.x + c.y * c.y; }
   }
   WB_SYNC();
@@ -112,6 +116,7 @@ WB_KERNEL(128, 4) ct_frame_kernel(CtParams p) {
     return;
   }
   // ---- + |randn| * eps (:147-151), log, mirror (:39-42)
+  WB_UNROLL4
   for (int k = tid; k <= half; k += nth) {
     const double v = ext[k] + fabs(randn_value(draw[nwin + k])) * kEps;
     const double l = log(v);
@@ -123,6 +128,7 @@ WB_KERNEL(128, 4) ct_frame_kernel(CtParams p) {
   // ---- liftering in the cepstrum domain (:28-37, 45-49)
   {
     const double2 *z = reinterpret_cast<const double2 *>(buf);
+    WB_UNROLL4
     for (int k = tid; k <= half; k += nth) {
       double sl = 1.0, cl = (1.0 - 2.0 * p.q1) + 2.0 * p.q1;
       if (k > 0) {
@@ -134,6 +140,7 @@ WB_KERNEL(128, 4) ct_frame_kernel(CtParams p) {
     }
   }
   WB_SYNC();
+  WB_UNROLL4
   for (int k = tid; k <= half; k += nth) {
     const double v = ext[k];
     buf[k] = v;
@@ -143,6 +150,7 @@ WB_KERNEL(128, 4) ct_frame_kernel(CtParams p) {
   rfft_forward(buf, p.lg_fft, p.tw);
   {
     const double2 *z = reinterpret_cast<const double2 *>(buf);
+    WB_UNROLL4
     for (int k = tid; k <= half; k += nth) row[k] = exp(z[k].x);
   }
 }

@@ -59,6 +59,7 @@ WB_DEV int d4c_windowed(const double *__restrict__ x, int x_len, int fs, double 
   const int nwin = 2 * h + 1;
   const int origin = round_half_away(pos * fs + 0.001);
   double s1 = 0.0, s2 = 0.0;
+  WB_UNROLL4
   for (int j = tid; j < nwin; j += nth) {
     const double position = (2.0 * (j - h) / ratio) / fs;
     double w;
@@ -75,6 +76,7 @@ WB_DEV int d4c_windowed(const double *__restrict__ x, int x_len, int fs, double 
   }
   block_sum2(s1, s2, red);
   const double coef = s1 / s2;
+  WB_UNROLL4
   for (int j = tid; j < nwin; j += nth)
     dst_v[(size_t)j * stride] = dst_v[(size_t)j * stride] - dst_w[(size_t)j * stride] * coef;
   WB_SYNC();
@@ -108,6 +110,7 @@ WB_KERNEL(128, 4) d4c_lovetrain_kernel(D4cParams p) {
   const double *x = p.x + (size_t)u * p.x_stride;
   const unsigned *draw = p.draws + (size_t)u * p.draw_stride + p.off_a[fidx];
   const int nwin = d4c_windowed(x, p.x_len[u], p.fs, f, p.time_axis[fidx], 2, 3.0, draw, buf, win, 1, red);
+  WB_UNROLL4
   for (int j = nwin + tid; j < N + 2; j += nth) buf[j] = 0.0;
   WB_SYNC();
   rfft_forward(buf, p.lt_lg, p.tw);
@@ -149,6 +152,7 @@ WB_DEV double select_kth_largest(const double *a, int n, int kth, double *red) {
     const unsigned long long hi_bit = 1ull << bit, lo_bit = two ? (1ull << (bit - 1)) : 0ull;
     const unsigned long long p01 = pat | lo_bit, p10 = pat | hi_bit, p11 = pat | hi_bit | lo_bit;
     int c01 = 0, c10 = 0, c11 = 0;
+    WB_UNROLL4
     for (int j = tid; j < n; j += nth) {
       const double v = a[j];
       unsigned long long bits;
@@ -219,8 +223,10 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
     const int nwin = d4c_windowed(x, x_len, fs, f, pos, 2, 4.0, draw, zb, zb + 1, 2, red);
     draw += nwin;
     double sq = 0.0;
+    WB_UNROLL4
     for (int j = tid; j < nwin; j += nth) sq += z[j].x * z[j].x;
     const double rt = sqrt(block_sum(sq, red));
+    WB_UNROLL4
     for (int j = tid; j < N; j += nth) {
       if (j < nwin) {
         const double v = z[j].x / rt;
@@ -231,6 +237,7 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
     }
     WB_SYNC();
     cfft_forward(z, p.d_lg, p.tw);
+    WB_UNROLL4
     for (int k = tid; k <= half; k += nth) {
       double2 A, B;
       split_pair(z, N, k, A, B);
@@ -244,9 +251,11 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
   // ---- smoothed power spectrum (d4c.cpp:149-166)
   {
     const int nwin = d4c_windowed(x, x_len, fs, f, t, 1, 4.0, draw, zb, zb + N + 2, 1, red);
+    WB_UNROLL4
     for (int j = nwin + tid; j < N + 2; j += nth) zb[j] = 0.0;
     WB_SYNC();
     rfft_forward(zb, p.d_lg, p.tw);
+    WB_UNROLL4
     for (int k = tid; k <= half; k += nth) { const double2 c = z[k]; pw[k] = c.x * c.x + c.y * c.y; }
     WB_SYNC();
     dc_correction(pw, f, fs, N, zb);
@@ -256,6 +265,7 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
     }
   }
   // ---- static group delay (d4c.cpp:172-188): g = cent / pw, two smoothers
+  WB_UNROLL4
   for (int k = tid; k <= half; k += nth) pw[k] = cent[k] / pw[k];
   WB_SYNC();
   bool ok = linear_smoothing<false>(pw, f / 2.0, fs, N, pw, zb, red_big);
@@ -264,6 +274,7 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
     if (tid == 0) atomicOr_status(p.status, 2);
     return;
   }
+  WB_UNROLL4
   for (int k = tid; k <= half; k += nth) pw[k] = pw[k] - cent[k];
   WB_SYNC();
 
@@ -271,11 +282,13 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
   const int half_w = p.win_len / 2;
   for (int b = 0; b < p.n_ap; ++b) {
     const int center = static_cast<int>(3000.0 * (b + 1) * N / fs);
+    WB_UNROLL4
     for (int j = tid; j < N + 2; j += nth)
       zb[j] = (j <= half_w * 2) ? pw[center - half_w + j] * __ldg(&p.nuttall[j]) : 0.0;
     WB_SYNC();
     rfft_forward(zb, p.d_lg, p.tw);
     double tot = 0.0;
+    WB_UNROLL4
     for (int k = tid; k <= half; k += nth) {
       const double2 c = z[k];
       const double v = c.x * c.x + c.y * c.y;
@@ -287,6 +300,7 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
     const double kth = select_kth_largest(cent, half + 1, p.bd + 1, red);
     double below = 0.0;
     int n_below = 0;
+    WB_UNROLL4
     for (int k = tid; k <= half; k += nth)
       if (cent[k] < kth) { below += cent[k]; ++n_below; }
     below = block_sum(below, red);
@@ -305,6 +319,7 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
   const int bins = p.ct_fft_size / 2 + 1;
   double *row = p.out + fidx * (size_t)bins;
   const int nx = p.n_ap + 2;
+  WB_UNROLL4
   for (int k = tid; k < bins; k += nth) {
     const double xi = static_cast<double>(k) * fs / p.ct_fft_size;
     int idx = 0;  // number of axis points <= xi

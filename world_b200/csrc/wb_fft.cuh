@@ -36,6 +36,7 @@ WB_DEV unsigned bit_reverse(unsigned v, int bits) {
 WB_DEV void cfft_forward(double2 *z, int lg, const double2 *__restrict__ tw) {
   const int tid = WB_TID, nth = WB_NTH;
   const int n = 1 << lg;
+  WB_UNROLL4
   for (int i = tid; i < n; i += nth) {
     const int j = (int)bit_reverse((unsigned)i, lg);
     if (i < j) { const double2 a = z[i]; z[i] = z[j]; z[j] = a; }
@@ -44,6 +45,7 @@ WB_DEV void cfft_forward(double2 *z, int lg, const double2 *__restrict__ tw) {
   int s = 1;
   if (lg >= 2) {
     // stages 1+2: twiddles are 1 and -j
+    WB_UNROLL4
     for (int q = tid; q < (n >> 2); q += nth) {
       double2 *p = z + 4 * q;
       const double2 a = p[0], b = p[1], c = p[2], d = p[3];
@@ -63,6 +65,7 @@ WB_DEV void cfft_forward(double2 *z, int lg, const double2 *__restrict__ tw) {
     // stages s and s+1: quarter = 2^(s-1); group of 4*quarter elements
     const int quarter = 1 << (s - 1);
     const int tws = WB_TW_LOG2 - (s + 1);
+    WB_UNROLL4
     for (int q = tid; q < (n >> 2); q += nth) {
       const int j = q & (quarter - 1);
       const int i0 = ((q >> (s - 1)) << (s + 1)) + j;
@@ -87,6 +90,7 @@ WB_DEV void cfft_forward(double2 *z, int lg, const double2 *__restrict__ tw) {
   if (s <= lg) {
     const int half = 1 << (s - 1);
     const int tws = WB_TW_LOG2 - s;
+    WB_UNROLL4
     for (int b = tid; b < (n >> 1); b += nth) {
       const int j = b & (half - 1);
       const int i0 = ((b >> (s - 1)) << s) + j;
@@ -110,6 +114,7 @@ WB_DEV void rfft_forward(double *buf, int lg, const double2 *__restrict__ tw) {
   const int m = 1 << (lg - 1);
   cfft_forward(z, lg - 1, tw);
   const int tws = WB_TW_LOG2 - lg;
+  WB_UNROLL4
   for (int k = tid; k <= (m >> 1); k += nth) {
     if (k == 0) {
       const double2 z0 = z[0];

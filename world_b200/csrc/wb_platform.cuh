@@ -28,6 +28,7 @@
   type *name = reinterpret_cast<type *>(wb_dyn_smem_)
 #define WB_SHARED __shared__
 #define WB_SYNC() __syncthreads()
+#define WB_UNROLL4  /* r1k experiment: "unroll 4" cost registers and occupancy (CheapTrick 99 -> 113 ms); kept empty */
 #define WB_TID ((int)threadIdx.x)
 #define WB_NTH ((int)blockDim.x)
 #define WB_CONST_TABLE __device__
@@ -71,6 +72,7 @@ extern unsigned char wb_emu_smem[];
 #define WB_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(wb_emu_smem)
 #define WB_SHARED static
 #define WB_SYNC() ((void)0)
+#define WB_UNROLL4
 #define WB_TID ((int)threadIdx.x)
 #define WB_NTH ((int)blockDim.x)
 #define WB_CONST_TABLE

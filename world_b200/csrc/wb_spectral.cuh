@@ -27,11 +27,13 @@ WB_DEV void dc_correction(double *spec, double f0, int fs, int fft_size, double 
   const int upper_limit = 2 + static_cast<int>(f0 * fft_size / fs);
   const int n_rep = upper_limit - 1;
   const double dx = -static_cast<double>(fs) / fft_size;
+  WB_UNROLL4
   for (int i = tid; i < n_rep; i += nth) {
     const double xi = static_cast<double>(i) * fs / fft_size;
     tmp[i] = interp1q_at(f0, dx, spec, upper_limit + 1, xi);
   }
   WB_SYNC();
+  WB_UNROLL4
   for (int i = tid; i < n_rep; i += nth) spec[i] = spec[i] + tmp[i];
   WB_SYNC();
 }
@@ -53,6 +55,7 @@ WB_DEV bool linear_smoothing(const double *in, double width, int fs, int fft_siz
   if (boundary > half || n_ext > smoothing_capacity(fft_size)) return false;
 
   // mirror-extend and scale:  seg[i] = ext[i] * fs / fft_size   (common.cpp:30-41)
+  WB_UNROLL4
   for (int i = tid; i < n_ext; i += nth) {
     double v;
     if (i < boundary) v = in[boundary - i];
@@ -72,6 +75,7 @@ WB_DEV bool linear_smoothing(const double *in, double width, int fs, int fft_siz
   }
   const double origin = -(boundary - 0.5) * fs / fft_size;
   const double dx = static_cast<double>(fs) / fft_size;
+  WB_UNROLL4
   for (int i = tid; i <= half; i += nth) {
     const double lo_x = static_cast<double>(i) / fft_size * fs - width / 2.0;
     const double hi_x = lo_x + width;
