@@ -47,7 +47,7 @@ WB_KERNEL_PLAIN ct_count_kernel(const double *__restrict__ f0, const int *__rest
   counts[g] = c;
 }
 
-WB_KERNEL(128, 4) ct_frame_kernel(CtParams p) {
+WB_KERNEL(128, 8) ct_frame_kernel(CtParams p) {
   WB_DYN_SMEM(double, smem);
   const int tid = WB_TID, nth = WB_NTH;
   const int u = blockIdx.y, i = blockIdx.x;
