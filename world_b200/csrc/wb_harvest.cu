@@ -211,31 +211,22 @@ WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, d
 #ifdef WB_EMU
   for (int m = 0; m < H; ++m) {
     const int c0 = 0, cstep = 1;
-    const bool lane_active = true;
 #else
   {
-    // lane = 6 c + m: harmonic m (H <= 6) over the samples j = c, c+5, c+10, ...; lanes 30, 31 idle
-    const int m = lane % 6, c0 = lane / 6, cstep = 5;
-    const bool lane_active = lane < 30;
+    const int m = lane & 7, c0 = lane >> 3, cstep = 4;
 #endif
     double mr = 0.0, mi = 0.0, dr = 0.0, di = 0.0;
     const int bin = round_half_away(f * nfft / afs * (m + 1));
-    if (m < H && lane_active) {
-      // twiddles w_j = exp(-j 2 pi bin j / nfft) along four interleaved chains (one per unrolled
-      // slot), each advanced by D = 4 cstep samples with the three-term recurrence
-      // w_{j+D} = 2 cos(2 pi bin D / nfft) w_j - w_{j-D}: two FMAs per step, started from two exact
-      // table values; a chain is <= nwin / D steps long and bin D / nfft is far from 0, so the
-      // accumulated rounding stays ~1e-14.  (A table gather per sample made this kernel L1-LSU
-      // bound, profiles/r1c; a complex rotation costs four operations per step.)
-      const int D = 4 * cstep;
-      const double k2 = 2.0 * hv_tw(tw, ((bin * D) & (nfft - 1)) << shift).x;
-      double2 wq[4], wp[4];
+    if (m < H) {
+      // twiddles exp(-j 2 pi bin j / nfft) by rotation: four interleaved chains (one per unrolled
+      // slot) start from exact table values and advance by exp(-j 2 pi bin 4 cstep / nfft); a
+      // chain is <= nwin / (4 cstep) steps long, so the accumulated rounding stays ~1e-15.
+      // (A table gather per sample made this kernel L1-LSU bound: profiles/r1c.)
+      const double2 rot = hv_tw(tw, ((bin * 4 * cstep) & (nfft - 1)) << shift);
+      double2 wq[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        wq[q] = hv_tw(tw, ((bin * (c0 + q * cstep)) & (nfft - 1)) << shift);
-        wp[q] = hv_tw(tw, ((bin * (c0 + q * cstep - D)) & (nfft - 1)) << shift);
-      }
-      for (int j0 = c0; j0 < nwin; j0 += D) {
+      for (int q = 0; q < 4; ++q) wq[q] = hv_tw(tw, ((bin * (c0 + q * cstep)) & (nfft - 1)) << shift);
+      for (int j0 = c0; j0 < nwin; j0 += 4 * cstep) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j = j0 + q * cstep;
@@ -245,24 +236,17 @@ WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, d
             mr = fma(a, w.x, mr); mi = fma(a, w.y, mi);
             dr = fma(d, w.x, dr); di = fma(d, w.y, di);
           }
-          const double nx = fma(k2, wq[q].x, -wp[q].x);
-          const double ny = fma(k2, wq[q].y, -wp[q].y);
-          wp[q] = wq[q];
+          const double nx = fma(wq[q].x, rot.x, -(wq[q].y * rot.y));
+          const double ny = fma(wq[q].x, rot.y, wq[q].y * rot.x);
           wq[q].x = nx; wq[q].y = ny;
         }
       }
     }
 #ifndef WB_EMU
-    {  // fold the five sample classes: lanes m, m+6, m+12, m+18, m+24 -> lane m
-      double v[4] = {mr, mi, dr, di};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const double a1 = v[k] + __shfl_down_sync(0xffffffffu, v[k], 6);
-        const double b1 = a1 + __shfl_down_sync(0xffffffffu, a1, 12);
-        v[k] = b1 + __shfl_down_sync(0xffffffffu, v[k], 24);
-      }
-      mr = v[0]; mi = v[1]; dr = v[2]; di = v[3];
-    }
+    mr += __shfl_xor_sync(0xffffffffu, mr, 8);  mi += __shfl_xor_sync(0xffffffffu, mi, 8);
+    dr += __shfl_xor_sync(0xffffffffu, dr, 8);  di += __shfl_xor_sync(0xffffffffu, di, 8);
+    mr += __shfl_xor_sync(0xffffffffu, mr, 16); mi += __shfl_xor_sync(0xffffffffu, mi, 16);
+    dr += __shfl_xor_sync(0xffffffffu, dr, 16); di += __shfl_xor_sync(0xffffffffu, di, 16);
 #endif
     const double num = mr * di - mi * dr;
     const double pw = mr * mr + mi * mi;
