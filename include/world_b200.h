@@ -30,6 +30,7 @@
 #include "world/cheaptrick.h"
 #include "world/d4c.h"
 #include "world/stonemask.h"
+#include "world/synthesis.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -99,6 +100,14 @@ int world_b200_d4c_batch(WorldB200 *ctx, const double *x, int n_utts, int x_stri
                          const int *x_lengths, int fs, const double *time_axis,
                          const double *f0, const int *f0_lengths, int f0_stride, int fft_size,
                          const D4COption *option, double *aperiodicity);
+
+/* Synthesis() over a batch (synthesis.h:30) -- SURVEY.md 8 row f1.  f0 [n][f0_stride], spectrogram /
+ * aperiodicity [n][f0_stride][fft_size/2+1], y [n][y_stride] (all DEVICE); f0_lengths / y_lengths are
+ * host arrays (NULL = full rows).  frame_period in ms. */
+int world_b200_synthesis_batch(WorldB200 *ctx, const double *f0, const int *f0_lengths, int n_utts,
+                               int f0_stride, const double *spectrogram, const double *aperiodicity,
+                               int fft_size, double frame_period, int fs, const int *y_lengths,
+                               int y_stride, double *y);
 
 /* ---- whole analysis chain, host pointers ---------------------------------------------- */
 #define WORLD_B200_F0_DIO_STONEMASK 0

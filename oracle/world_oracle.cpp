@@ -13,7 +13,7 @@
 //
 // Restated here: randn, interp1Q, interp1, DCCorrection, LinearSmoothing, NuttallWindow, the FFT
 // conventions, StoneMask, CheapTrick, D4C, and the option / sizing helpers.
-// NOT restated (checked against oracle/_ref only): Dio, Harvest.
+// NOT restated (checked against oracle/_ref only): Dio, Harvest, Synthesis.
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>

@@ -104,6 +104,15 @@ class RefWorld:
         self.lib.CheapTrick(x.ctypes.data, len(x), fs, t.ctypes.data, f0.ctypes.data, len(f0), C.byref(opt), rows)
         return sp
 
+    def synthesis(self, f0, sp, ap, fft_size, frame_period, fs, y_length):
+        f0 = np.ascontiguousarray(f0); sp = np.ascontiguousarray(sp); ap = np.ascontiguousarray(ap)
+        y = np.zeros(y_length)
+        self.lib.Synthesis.restype = None
+        self.lib.Synthesis.argtypes = [_P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int, C.c_int, _P]
+        self.lib.Synthesis(f0.ctypes.data, len(f0), self._rows(sp), self._rows(ap), fft_size, frame_period, fs,
+                           y_length, y.ctypes.data)
+        return y
+
     def d4c(self, x, fs, t, f0, fft_size, opt=None):
         x = np.ascontiguousarray(x, dtype=np.float64)
         t = np.ascontiguousarray(t); f0 = np.ascontiguousarray(f0)

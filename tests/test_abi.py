@@ -29,7 +29,7 @@ def test_headers_declare_the_reference_api():
     for required in ["Dio", "Harvest", "StoneMask", "CheapTrick", "D4C", "InitializeDioOption",
                      "InitializeHarvestOption", "InitializeCheapTrickOption", "InitializeD4COption",
                      "GetSamplesForDIO", "GetSamplesForHarvest", "GetFFTSizeForCheapTrick",
-                     "GetF0FloorForCheapTrick", "world_b200_cheaptrick_batch", "world_b200_d4c_batch",
+                     "GetF0FloorForCheapTrick", "Synthesis", "world_b200_synthesis_batch", "world_b200_cheaptrick_batch", "world_b200_d4c_batch",
                      "world_b200_dio_batch", "world_b200_harvest_batch", "world_b200_stonemask_batch",
                      "world_b200_analyze_host"]:
         assert required in names

@@ -81,3 +81,7 @@ def test_emu_harvest_frame_period_1ms(emu, ref):
 
 def test_emu_edge_cases(emu, ref):
     pc.check_edge_cases(emu, ref)
+
+
+def test_emu_synthesis(emu, ref, golden):
+    pc.check_synthesis(emu, ref, golden)

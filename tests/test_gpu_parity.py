@@ -122,3 +122,20 @@ def test_gpu_legacy_api_and_analyze_host(gpu_world, ref, golden):
         pc.assert_close(fa[0], golden[key], "analyze_host f0")
         pc.assert_close(spa[0], ref.cheaptrick(x, fs, ta[0], np.ascontiguousarray(fa[0])), "analyze_host sp")
         pc.assert_close(apa[0], ref.d4c(x, fs, ta[0], np.ascontiguousarray(fa[0]), co.fft_size), "analyze_host ap")
+
+
+def test_gpu_synthesis(gpu_world, ref, golden):
+    pc.check_synthesis(gpu_world, ref, golden)
+
+
+def test_gpu_legacy_synthesis(gpu_world, ref, golden):
+    import ctypes as C
+    x, fs = pc.wav_from_golden(golden)
+    f0 = np.ascontiguousarray(golden["f0_harvest"]); t = golden["time_axis"]
+    sp = ref.cheaptrick(x, fs, t, f0); ap = ref.d4c(x, fs, t, f0, 1024)
+    y = np.zeros(len(x))
+    rows_s = (C.c_void_p * len(f0))(*[sp[i].ctypes.data for i in range(len(f0))])
+    rows_a = (C.c_void_p * len(f0))(*[ap[i].ctypes.data for i in range(len(f0))])
+    gpu_world.lib.Synthesis(f0.ctypes.data, len(f0), rows_s, rows_a, 1024, 5.0, fs, len(x), y.ctypes.data)
+    yr = ref.synthesis(f0, sp, ap, 1024, 5.0, fs, len(x))
+    assert np.abs(y - yr).max() <= 1e-9 * np.abs(yr).max()

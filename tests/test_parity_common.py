@@ -179,3 +179,35 @@ def check_edge_cases(world, ref):
         xu = x[u, :lens[u]]
         assert_close(to_np(sp)[u, :fl[u]], ref.cheaptrick(xu, fs, tn[u, :fl[u]], fn[u, :fl[u]], opt), f"sp edge utt {u}")
         assert_close(to_np(ap)[u, :fl[u]], ref.d4c(xu, fs, tn[u, :fl[u]], fn[u, :fl[u]], opt.fft_size), f"ap edge utt {u}")
+
+
+def check_synthesis(world, ref, golden):
+    """batched Synthesis() vs the reference (relative to the waveform peak)."""
+    from synth import synth_batch
+    x, fs = wav_from_golden(golden)
+    fft = int(golden["fft_size"])
+    f0 = golden["f0_stonemask"]; sp = golden["sp"]; ap = golden["ap"]
+    yr = ref.synthesis(f0, sp, ap, fft, 5.0, fs, len(x))
+    y = world.synthesis(make(world, f0[None]), make(world, sp[None]), make(world, ap[None]), fft, 5.0, fs, len(x))
+    world.synchronize()
+    assert np.abs(to_np(y)[0] - yr).max() <= 1e-9 * np.abs(yr).max()
+    # ragged synthetic batch, parameters from the reference analysis
+    fs2, n = 16000, 12000
+    xs = synth_batch([81, 82], fs2, n).numpy()
+    lens = [12000, 9000]
+    L = [ref.frames(fs2, l) for l in lens]
+    opt = ref.cheaptrick_option(fs2)
+    bins = opt.fft_size // 2 + 1
+    F = np.zeros((2, max(L))); S = np.ones((2, max(L), bins)); A = np.ones((2, max(L), bins))
+    refs = []
+    for u in range(2):
+        xu = xs[u, :lens[u]]
+        t, f = ref.harvest(xu, fs2)
+        s_ = ref.cheaptrick(xu, fs2, t, f, opt); a_ = ref.d4c(xu, fs2, t, f, opt.fft_size)
+        F[u, :L[u]] = f; S[u, :L[u]] = s_; A[u, :L[u]] = a_
+        refs.append(ref.synthesis(f, s_, a_, opt.fft_size, 5.0, fs2, lens[u]))
+    y = world.synthesis(make(world, F), make(world, S), make(world, A), opt.fft_size, 5.0, fs2, n, f0_lengths=L,
+                        y_lengths=lens)
+    world.synchronize()
+    for u in range(2):
+        assert np.abs(to_np(y)[u, :lens[u]] - refs[u]).max() <= 1e-9 * np.abs(refs[u]).max(), f"synthesis utt {u}"

@@ -69,6 +69,8 @@ ABI = {
                                               C.POINTER(CheapTrickOption), _P]),
     "world_b200_d4c_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, _P, _P, _IP, C.c_int, C.c_int,
                                        C.POINTER(D4COption), _P]),
+    "world_b200_synthesis_batch": (C.c_int, [_P, _P, _IP, C.c_int, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int, _IP,
+                                             C.c_int, _P]),
     "world_b200_default_analysis_option": (None, [C.c_int, C.c_int, C.POINTER(AnalysisOption)]),
     "world_b200_analyze_host": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, C.POINTER(AnalysisOption),
                                           _P, _P, C.c_int, _P, _P]),
@@ -78,6 +80,7 @@ ABI = {
     "StoneMask": (None, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     "CheapTrick": (None, [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.POINTER(CheapTrickOption), _P]),
     "D4C": (None, [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.POINTER(D4COption), _P]),
+    "Synthesis": (None, [_P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int, C.c_int, _P]),
     "InitializeDioOption": (None, [C.POINTER(DioOption)]),
     "InitializeHarvestOption": (None, [C.POINTER(HarvestOption)]),
     "InitializeCheapTrickOption": (None, [C.c_int, C.POINTER(CheapTrickOption)]),
@@ -294,6 +297,19 @@ class World:
         self._check(self.lib.world_b200_d4c_batch(self._h, _ptr(x), n, stride, xl, fs, _ptr(time_axis), _ptr(f0),
                                                   fl, f0.shape[1], fft_size, C.byref(option), _ptr(out)))
         return out
+
+    def synthesis(self, f0, spectrogram, aperiodicity, fft_size, frame_period, fs, y_length, f0_lengths=None,
+                  y_lengths=None):
+        """Batched Synthesis(): f0 [n, L], spectrogram / aperiodicity [n, L, bins] -> y [n, y_length]."""
+        n = f0.shape[0]
+        y = self._zeros(f0, (n, y_length))
+        fl, k1 = _int_array(f0_lengths, n)
+        yl, k2 = _int_array(y_lengths, n)
+        self._use_current_stream()
+        self._check(self.lib.world_b200_synthesis_batch(self._h, _ptr(f0), fl, n, f0.shape[1], _ptr(spectrogram),
+                                                        _ptr(aperiodicity), fft_size, frame_period, fs, yl, y_length,
+                                                        _ptr(y)))
+        return y
 
     def analysis_option(self, fs, f0_method=F0_HARVEST) -> AnalysisOption:
         o = AnalysisOption()

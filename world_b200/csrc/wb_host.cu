@@ -257,4 +257,31 @@ void D4C(const double *x, int x_length, int fs, const double *temporal_positions
   dev_free(rows);
 }
 
+void Synthesis(const double *f0, int f0_length, const double *const *spectrogram, const double *const *aperiodicity,
+               int fft_size, double frame_period, int fs, int y_length, double *y) {
+  std::lock_guard<std::mutex> lock(g_legacy_mutex);
+  WorldB200 *h = legacy_ctx();
+  if (!h) return;
+  Ctx *ctx = ctx_of(h);
+  const int bins = fft_size / 2 + 1;
+  std::vector<double> flat((size_t)f0_length * bins);
+  double *d_f0 = (double *)dev_malloc(ctx, (size_t)f0_length * 8);
+  double *d_sp = (double *)dev_malloc(ctx, flat.size() * 8), *d_ap = (double *)dev_malloc(ctx, flat.size() * 8);
+  double *d_y = (double *)dev_malloc(ctx, (size_t)y_length * 8);
+  int rc = (d_f0 && d_sp && d_ap && d_y) ? 0 : WORLD_B200_ENOMEM;
+  if (!rc) rc = dev_memcpy_h2d(ctx, d_f0, f0, (size_t)f0_length * 8);
+  for (int pass = 0; pass < 2 && !rc; ++pass) {
+    const double *const *rows = pass == 0 ? spectrogram : aperiodicity;
+    for (int i = 0; i < f0_length; ++i) memcpy(flat.data() + (size_t)i * bins, rows[i], (size_t)bins * 8);
+    rc = dev_memcpy_h2d(ctx, pass == 0 ? d_sp : d_ap, flat.data(), flat.size() * 8);
+    if (!rc) rc = dev_sync(ctx);  // flat is reused
+  }
+  if (!rc) rc = world_b200_synthesis_batch(h, d_f0, nullptr, 1, f0_length, d_sp, d_ap, fft_size, frame_period, fs,
+                                           nullptr, y_length, d_y);
+  if (!rc) rc = dev_memcpy_d2h(ctx, y, d_y, (size_t)y_length * 8);
+  if (!rc) rc = world_b200_synchronize(h);
+  report(h, "Synthesis", rc);
+  dev_free(d_f0); dev_free(d_sp); dev_free(d_ap); dev_free(d_y);
+}
+
 }  // extern "C"
