@@ -253,8 +253,10 @@ def main():
     sp, ap = sp_all[off:off + U], ap_all[off:off + U]
     f0_all = torch.empty((world * U, L), dtype=torch.float64, device=dev)
     t_all = torch.empty((world * U, L), dtype=torch.float64, device=dev)
-    if world > 1 and free < (60 << 30):
-        w.set_scratch_budget(6 << 30)
+    # scratch budget follows what is left after the (possibly gathered) outputs are resident
+    free_now, _ = torch.cuda.mem_get_info(dev)
+    budget = int(min(24 << 30, max(2 << 30, free_now * 0.45)))
+    w.set_scratch_budget(budget)
 
     # Two contexts on two streams: the F0 estimator of slice s+1 (FP64 bound) runs concurrently with
     # CheapTrick + D4C of slice s (shared-memory / barrier bound); slices are contiguous utterance ranges.
@@ -264,8 +266,9 @@ def main():
     bounds = [U * i // n_slices for i in range(n_slices + 1)]
     t_loc = torch.zeros((U, L), dtype=torch.float64, device=dev)
     f0_loc = torch.zeros((U, L), dtype=torch.float64, device=dev)
-    if world > 1 and free < (60 << 30):
-        w2.set_scratch_budget(6 << 30)
+    if w2 is not w:
+        w2.set_scratch_budget(budget // 2)
+        w.set_scratch_budget(budget // 2)
 
     def step():
         main = torch.cuda.current_stream(dev)
