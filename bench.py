@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--reserve-gb", type=float, default=0.0,
+                    help="test hook: hold this much extra device memory (emulates the gathered arrays of a larger world)")
     ap.add_argument("--slices", type=int, default=1,
                     help="utterance slices per step: F0 of slice s+1 overlaps CheapTrick/D4C of slice s on a second stream")
     return ap.parse_args()
@@ -253,6 +255,7 @@ def main():
     sp, ap = sp_all[off:off + U], ap_all[off:off + U]
     f0_all = torch.empty((world * U, L), dtype=torch.float64, device=dev)
     t_all = torch.empty((world * U, L), dtype=torch.float64, device=dev)
+    reserve = torch.empty(int(a.reserve_gb * (1 << 30)), dtype=torch.uint8, device=dev) if a.reserve_gb > 0 else None
     # scratch budget follows what is left after the (possibly gathered) outputs are resident
     free_now, _ = torch.cuda.mem_get_info(dev)
     budget = int(min(24 << 30, max(2 << 30, free_now * 0.45)))
