@@ -50,7 +50,7 @@ WB_KERNEL(256, 3) fir_plain_kernel(FirParams p) {
 // dio.cpp:357-393 / harvest.cpp:162-198):  x_j = (e_j + e_{j+1}) / 2 / afs,  y_j = afs / (e_{j+1} - e_j).
 // x_j and y_j are evaluated ONCE per interval (same expressions as the reference) and kept in rings.
 #ifndef WB_RING
-#define WB_RING 512
+#define WB_RING 256   // location / value rings per train; older intervals are recomputed from the global edge lists
 #endif
 #define WB_FCHUNK 256  // frames finalised per round (= WB_SWEEP_THREADS)
 struct Trains {
@@ -61,7 +61,8 @@ struct Trains {
   double afs;
 };
 WB_DEV double edge_at(const Trains &T, int q, int i) {
-  return i >= T.efrom[q] ? T.er[q * WB_RING + (i & (WB_RING - 1))] : T.g[q][i];
+  (void)T.efrom; (void)T.er;   // edges are read back from global memory (L2): an edge ring cost a CTA per SM
+  return T.g[q][i];
 }
 WB_DEV double loc_at(const Trains &T, int q, int j) {
   return j >= T.ifrom[q] ? T.xr[q * WB_RING + (j & (WB_RING - 1))] : (edge_at(T, q, j) + edge_at(T, q, j + 1)) / 2.0 / T.afs;
@@ -185,8 +186,8 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   double *hrev = seg + (seg_cap + (seg_cap >> 3) + 8);  // max_taps + 8
   double *st = hrev + (p.max_taps + 8);                 // T + 8: [0..1] carry, [2..T+2) this tile
   unsigned long long *cnt = reinterpret_cast<unsigned long long *>(st + (T + 8 + ((T + 8) >> 3) + 8));  // G + 40
-  double *ring = reinterpret_cast<double *>(cnt + (G + 40));                                           // 3 * 4 * WB_RING
-  unsigned long long *marks = reinterpret_cast<unsigned long long *>(ring + 12 * WB_RING);             // WB_FCHUNK
+  double *ring = reinterpret_cast<double *>(cnt + (G + 40));                                           // 2 * 4 * WB_RING
+  unsigned long long *marks = reinterpret_cast<unsigned long long *>(ring + 8 * WB_RING);              // WB_FCHUNK
   unsigned long long *orig = marks + WB_FCHUNK;                                                        // WB_FCHUNK
 
   const int ylen = p.y_len[u];
@@ -197,7 +198,7 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   for (int j = ntaps + tid; j < ntaps + 8; j += nth) hrev[j] = 0.0;
   if (tid == 0) { st[0] = 0.0; st[1] = 0.0; }
   Trains tr;
-  tr.er = ring; tr.xr = ring + 4 * WB_RING; tr.yr = ring + 8 * WB_RING; tr.afs = p.afs;
+  tr.er = nullptr; tr.xr = ring; tr.yr = ring + 4 * WB_RING; tr.afs = p.afs;
   for (int q = 0; q < 4; ++q) { tr.g[q] = edges + (size_t)q * cap; tr.efrom[q] = 0; tr.ifrom[q] = 0; }
   int ni[4] = {0, 0, 0, 0};   // intervals known so far per train (= max(0, events - 1))
   int tot[4] = {0, 0, 0, 0};  // running event counts per train (identical in every thread)
@@ -304,7 +305,6 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
         }
         const int o = tot[q] + e;
         if (o < cap) edges[(size_t)q * cap + o] = v;
-        if (o >= keep[q]) ring[q * WB_RING + (o & (WB_RING - 1))] = v;
       }
     }
     tot[0] += (int)(tile_total & 0xffffull); tot[1] += (int)((tile_total >> 16) & 0xffffull);

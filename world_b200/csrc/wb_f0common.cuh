@@ -94,7 +94,7 @@ struct SweepParams {
 WB_HD inline size_t sweep_smem_bytes(int max_taps) {
   const int seg = WB_SWEEP_T + max_taps + 16;
   return (size_t)(seg + (seg >> 3) + 8) * 8 + (size_t)(max_taps + 8) * 8 + (size_t)(WB_SWEEP_T + 8 + ((WB_SWEEP_T + 8) >> 3) + 8) * 8 +
-         (size_t)(WB_SWEEP_T / WB_SWEEP_R + 40) * 8 + 12 * 512 * 8 + 2 * 256 * 8;
+         (size_t)(WB_SWEEP_T / WB_SWEEP_R + 40) * 8 + 8 * 256 * 8 + 2 * 256 * 8;
 }
 
 // ------------------------------------------------------------------------------ blocked decimate
