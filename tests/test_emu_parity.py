@@ -85,3 +85,7 @@ def test_emu_edge_cases(emu, ref):
 
 def test_emu_synthesis(emu, ref, golden):
     pc.check_synthesis(emu, ref, golden)
+
+
+def test_emu_fft_known_answers(emu):
+    pc.check_fft_known_answers(emu)

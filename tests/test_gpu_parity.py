@@ -139,3 +139,7 @@ def test_gpu_legacy_synthesis(gpu_world, ref, golden):
     gpu_world.lib.Synthesis(f0.ctypes.data, len(f0), rows_s, rows_a, 1024, 5.0, fs, len(x), y.ctypes.data)
     yr = ref.synthesis(f0, sp, ap, 1024, 5.0, fs, len(x))
     assert np.abs(y - yr).max() <= 1e-9 * np.abs(yr).max()
+
+
+def test_gpu_fft_known_answers(gpu_world):
+    pc.check_fft_known_answers(gpu_world)

@@ -211,3 +211,18 @@ def check_synthesis(world, ref, golden):
     world.synchronize()
     for u in range(2):
         assert np.abs(to_np(y)[u, :lens[u]] - refs[u]).max() <= 1e-9 * np.abs(refs[u]).max(), f"synthesis utt {u}"
+
+
+def check_fft_known_answers(world):
+    """The shared-memory FFT against numpy's (conventions of SURVEY.md App. A0), every size it serves."""
+    rng = np.random.RandomState(7)
+    for lg in range(2, 14):
+        n = 1 << lg
+        x = rng.standard_normal(n)
+        out = make(world, np.zeros(n + 2))
+        world.rfft_test(make(world, x), out)
+        world.synchronize()
+        got = to_np(out).reshape(-1, 2)
+        want = np.fft.rfft(x)
+        err = np.abs(got[:, 0] + 1j * got[:, 1] - want).max() / np.abs(want).max()
+        assert err < 1e-13, f"rfft n={n}: {err:.2e}"

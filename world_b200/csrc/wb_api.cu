@@ -449,6 +449,31 @@ int world_b200_fp64_peak(WorldB200 *h, double *tflops) {
 #endif
 }
 
+// Known-answer hook for the shared-memory FFT: r2c of n = 2^lg reals (n/2+1 complex out), one CTA.
+namespace wb {
+WB_KERNEL(128, 1) rfft_test_kernel(const double *x, int n, int lg, double *out, const double2 *tw) {
+  WB_DYN_SMEM(double, buf);
+  for (int i = WB_TID; i < n + 2; i += WB_NTH) buf[i] = i < n ? x[i] : 0.0;
+  WB_SYNC();
+  rfft_forward(buf, lg, tw);
+  for (int i = WB_TID; i < n + 2; i += WB_NTH) out[i] = buf[i];
+}
+}  // namespace wb
+
+int world_b200_rfft_test(WorldB200 *h, const double *x_dev, int n, double *out_dev) {
+  if (!h || !x_dev || !out_dev) return WORLD_B200_EINVAL;
+  int lg = 0;
+  while ((1 << lg) < n) ++lg;
+  if ((1 << lg) != n || n < 4 || n > WB_TW_N) return WORLD_B200_EINVAL;
+  Ctx *ctx = &h->c;
+  const size_t smem = (size_t)(n + 2) * 8;
+#ifndef WB_EMU
+  cudaFuncSetAttribute(rfft_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+  WB_LAUNCH_COOP(rfft_test_kernel, dim3(1), 128, smem, ctx->stream, x_dev, n, lg, out_dev, ctx->twiddle);
+  return dev_check(ctx, "rfft_test");
+}
+
 // Known-answer hook: the first n_draws randn() draws after randn_reseed(), as the raw 32-bit
 // sums (value = sum / 2^28 - 6), written to a device buffer of n_draws uint32.
 int world_b200_randn_stream(WorldB200 *h, unsigned n_draws, unsigned *out_dev) {

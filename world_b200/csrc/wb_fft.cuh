@@ -28,82 +28,105 @@ WB_DEV unsigned bit_reverse(unsigned v, int bits) {
 #endif
 }
 
+WB_DEV double2 cmul(double2 a, double2 b) {
+  return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+WB_DEV double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+WB_DEV double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+WB_DEV double2 mul_mj(double2 a) { return make_double2(a.y, -a.x); }  // (-j) * a
+
+// DIT stages s, s+1 as one radix-4 pass (quarter = 2^(s-1)); one table twiddle, the other is its square.
+WB_DEV void fft_pass_radix4(double2 *z, int n, int s, const double2 *__restrict__ tw) {
+  const int tid = WB_TID, nth = WB_NTH;
+  const int quarter = 1 << (s - 1);
+  const int tws = WB_TW_LOG2 - (s + 1);
+  for (int q = tid; q < (n >> 2); q += nth) {
+    const int j = q & (quarter - 1);
+    const int i0 = ((q >> (s - 1)) << (s + 1)) + j;
+    const int i1 = i0 + quarter, i2 = i1 + quarter, i3 = i2 + quarter;
+    const double2 b = __ldg(&tw[j << tws]);  // exp(-j 2 pi j / (4 quarter))
+    const double2 a = cmul(b, b);
+    const double2 z0 = z[i0], z1 = z[i1], z2 = z[i2], z3 = z[i3];
+    const double2 t1 = cmul(a, z1), t3 = cmul(a, z3);
+    const double2 u0 = cadd(z0, t1), u1 = csub(z0, t1), u2 = cadd(z2, t3), u3 = csub(z2, t3);
+    const double2 v2 = cmul(b, u2), w3 = mul_mj(cmul(b, u3));
+    z[i0] = cadd(u0, v2); z[i2] = csub(u0, v2);
+    z[i1] = cadd(u1, w3); z[i3] = csub(u1, w3);
+  }
+  WB_SYNC();
+}
+
+// DIT stages s, s+1, s+2 as one radix-8 pass held in registers (q = 2^(s-1), elements i0 + k q):
+// a third of the shared-memory passes of radix-2.  One table twiddle c = W_{8q}^j; b = c^2, a = c^4;
+// the remaining factors are the constants W_8^k.
+WB_DEV void fft_pass_radix8(double2 *z, int n, int s, const double2 *__restrict__ tw) {
+  const int tid = WB_TID, nth = WB_NTH;
+  const int q = 1 << (s - 1);
+  const int tws = WB_TW_LOG2 - (s + 2);
+  const double r = 0.70710678118654752440;
+  for (int t = tid; t < (n >> 3); t += nth) {
+    const int j = t & (q - 1);
+    const int i0 = ((t >> (s - 1)) << (s + 2)) + j;
+    const double2 c = __ldg(&tw[j << tws]);
+    const double2 b = cmul(c, c);
+    const double2 a = cmul(b, b);
+    double2 x0 = z[i0], x1 = z[i0 + q], x2 = z[i0 + 2 * q], x3 = z[i0 + 3 * q];
+    double2 x4 = z[i0 + 4 * q], x5 = z[i0 + 5 * q], x6 = z[i0 + 6 * q], x7 = z[i0 + 7 * q];
+    // stage s: (0,1) (2,3) (4,5) (6,7), twiddle a
+    double2 t1 = cmul(a, x1), t3 = cmul(a, x3), t5 = cmul(a, x5), t7 = cmul(a, x7);
+    const double2 y0 = cadd(x0, t1), y1 = csub(x0, t1), y2 = cadd(x2, t3), y3 = csub(x2, t3);
+    const double2 y4 = cadd(x4, t5), y5 = csub(x4, t5), y6 = cadd(x6, t7), y7 = csub(x6, t7);
+    // stage s+1: (0,2) (4,6) twiddle b; (1,3) (5,7) twiddle -j b
+    const double2 u2 = cmul(b, y2), u6 = cmul(b, y6), u3 = mul_mj(cmul(b, y3)), u7 = mul_mj(cmul(b, y7));
+    const double2 w0 = cadd(y0, u2), w2 = csub(y0, u2), w1 = cadd(y1, u3), w3 = csub(y1, u3);
+    const double2 w4 = cadd(y4, u6), w6 = csub(y4, u6), w5 = cadd(y5, u7), w7 = csub(y5, u7);
+    // stage s+2: (k, k+4) twiddle c W_8^k
+    const double2 v4 = cmul(c, w4);
+    const double2 c5 = cmul(c, w5), v5 = make_double2((c5.x + c5.y) * r, (c5.y - c5.x) * r);
+    const double2 v6 = mul_mj(cmul(c, w6));
+    const double2 c7 = cmul(c, w7), v7 = make_double2((c7.y - c7.x) * r, -(c7.x + c7.y) * r);
+    z[i0] = cadd(w0, v4);         z[i0 + 4 * q] = csub(w0, v4);
+    z[i0 + q] = cadd(w1, v5);     z[i0 + 5 * q] = csub(w1, v5);
+    z[i0 + 2 * q] = cadd(w2, v6); z[i0 + 6 * q] = csub(w2, v6);
+    z[i0 + 3 * q] = cadd(w3, v7); z[i0 + 7 * q] = csub(w3, v7);
+  }
+  WB_SYNC();
+}
+
+WB_DEV void fft_pass_radix2(double2 *z, int n, int s, const double2 *__restrict__ tw) {
+  const int tid = WB_TID, nth = WB_NTH;
+  const int half = 1 << (s - 1);
+  const int tws = WB_TW_LOG2 - s;
+  for (int b = tid; b < (n >> 1); b += nth) {
+    const int j = b & (half - 1);
+    const int i0 = ((b >> (s - 1)) << s) + j;
+    const double2 w = __ldg(&tw[j << tws]);
+    const double2 u = z[i0], v = cmul(w, z[i0 + half]);
+    z[i0] = cadd(u, v);
+    z[i0 + half] = csub(u, v);
+  }
+  WB_SYNC();
+}
+
 // In-place forward complex FFT of z[0..2^lg) (natural order in, natural order out).
-// Bit reversal, then decimation-in-time stages taken two at a time as radix-4 butterflies held in
-// registers (half the shared-memory passes and barriers of radix-2; one table twiddle per
-// butterfly, the second one is its square), plus one radix-2 stage when lg is odd.
-// Ends with a barrier.
+// Bit reversal, then decimation-in-time stages grouped into radix-8 passes held in registers (plus
+// one or two radix-4 passes, or a radix-2 pass for lg < 2, to make the stage count come out):
+// lg = 9 (CheapTrick) takes 3 passes, lg = 10 / 11 (D4C) take 4.  Ends with a barrier.
 WB_DEV void cfft_forward(double2 *z, int lg, const double2 *__restrict__ tw) {
   const int tid = WB_TID, nth = WB_NTH;
   const int n = 1 << lg;
-  WB_UNROLL4
   for (int i = tid; i < n; i += nth) {
     const int j = (int)bit_reverse((unsigned)i, lg);
     if (i < j) { const double2 a = z[i]; z[i] = z[j]; z[j] = a; }
   }
   WB_SYNC();
   int s = 1;
-  if (lg >= 2) {
-    // stages 1+2: twiddles are 1 and -j
-    WB_UNROLL4
-    for (int q = tid; q < (n >> 2); q += nth) {
-      double2 *p = z + 4 * q;
-      const double2 a = p[0], b = p[1], c = p[2], d = p[3];
-      const double2 ab0 = make_double2(a.x + b.x, a.y + b.y);
-      const double2 ab1 = make_double2(a.x - b.x, a.y - b.y);
-      const double2 cd0 = make_double2(c.x + d.x, c.y + d.y);
-      const double2 cd1 = make_double2(c.x - d.x, c.y - d.y);
-      p[0] = make_double2(ab0.x + cd0.x, ab0.y + cd0.y);
-      p[2] = make_double2(ab0.x - cd0.x, ab0.y - cd0.y);
-      p[1] = make_double2(ab1.x + cd1.y, ab1.y - cd1.x);
-      p[3] = make_double2(ab1.x - cd1.y, ab1.y + cd1.x);
-    }
-    WB_SYNC();
-    s = 3;
-  }
-  for (; s + 1 <= lg; s += 2) {
-    // stages s and s+1: quarter = 2^(s-1); group of 4*quarter elements
-    const int quarter = 1 << (s - 1);
-    const int tws = WB_TW_LOG2 - (s + 1);
-    WB_UNROLL4
-    for (int q = tid; q < (n >> 2); q += nth) {
-      const int j = q & (quarter - 1);
-      const int i0 = ((q >> (s - 1)) << (s + 1)) + j;
-      const int i1 = i0 + quarter, i2 = i1 + quarter, i3 = i2 + quarter;
-      const double2 b = __ldg(&tw[j << tws]);                       // exp(-j 2 pi j / (4 quarter))
-      const double2 a = make_double2(fma(b.x, b.x, -(b.y * b.y)), 2.0 * b.x * b.y);  // its square
-      const double2 z0 = z[i0], z1 = z[i1], z2 = z[i2], z3 = z[i3];
-      const double t1r = fma(a.x, z1.x, -(a.y * z1.y)), t1i = fma(a.x, z1.y, a.y * z1.x);
-      const double t3r = fma(a.x, z3.x, -(a.y * z3.y)), t3i = fma(a.x, z3.y, a.y * z3.x);
-      const double u0r = z0.x + t1r, u0i = z0.y + t1i, u1r = z0.x - t1r, u1i = z0.y - t1i;
-      const double u2r = z2.x + t3r, u2i = z2.y + t3i, u3r = z2.x - t3r, u3i = z2.y - t3i;
-      const double v2r = fma(b.x, u2r, -(b.y * u2i)), v2i = fma(b.x, u2i, b.y * u2r);   // b * u2
-      const double w3r = fma(b.x, u3r, -(b.y * u3i)), w3i = fma(b.x, u3i, b.y * u3r);   // b * u3
-      // (-j b) u3 = (w3i, -w3r)
-      z[i0] = make_double2(u0r + v2r, u0i + v2i);
-      z[i2] = make_double2(u0r - v2r, u0i - v2i);
-      z[i1] = make_double2(u1r + w3i, u1i - w3r);
-      z[i3] = make_double2(u1r - w3i, u1i + w3r);
-    }
-    WB_SYNC();
-  }
-  if (s <= lg) {
-    const int half = 1 << (s - 1);
-    const int tws = WB_TW_LOG2 - s;
-    WB_UNROLL4
-    for (int b = tid; b < (n >> 1); b += nth) {
-      const int j = b & (half - 1);
-      const int i0 = ((b >> (s - 1)) << s) + j;
-      const int i1 = i0 + half;
-      const double2 w = __ldg(&tw[j << tws]);
-      const double2 u = z[i0], v = z[i1];
-      const double tr = fma(w.x, v.x, -(w.y * v.y));
-      const double ti = fma(w.x, v.y, w.y * v.x);
-      z[i0] = make_double2(u.x + tr, u.y + ti);
-      z[i1] = make_double2(u.x - tr, u.y - ti);
-    }
-    WB_SYNC();
-  }
+  if (lg == 1) { fft_pass_radix2(z, n, 1, tw); return; }
+  // number of radix-4 passes so that the rest is a multiple of three stages
+  int n4 = (lg % 3 == 0) ? 0 : ((lg % 3 == 2) ? 1 : 2);
+  if (lg < 4 && lg % 3 == 1) n4 = lg / 2;  // lg = 1 handled above; (lg = 4 -> two radix-4 passes)
+  for (int k = 0; k < n4; ++k, s += 2) fft_pass_radix4(z, n, s, tw);
+  for (; s + 2 <= lg; s += 3) fft_pass_radix8(z, n, s, tw);
 }
 
 // Forward real FFT of buf[0..N), N = 2^lg >= 4, in place: on return buf holds N/2+1 complex
