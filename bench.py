@@ -369,8 +369,11 @@ def main():
         barrier()
         t0 = time.perf_counter()
         ke = max(1, min(a.steps, 3))
+        e2e_steps_ms = []
         for _ in range(ke):
+            t1 = time.perf_counter()
             e2e_step()
+            e2e_steps_ms.append((time.perf_counter() - t1) * 1e3)
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -379,7 +382,7 @@ def main():
             dt = float(tdt.item())
         e2e = {"value": world * Ue * L * ke / dt, "unit": "frames/s",
                "h2d_bytes_per_step": int(Ue * n * 8), "d2h_bytes_per_step": int(2 * Ue * L * bins * 8 + 2 * Ue * L * 8),
-               "utts_per_gpu": Ue, "steps": ke,
+               "utts_per_gpu": Ue, "steps": ke, "ms_per_step_rank0": e2e_steps_ms,
                "note": "world_b200_analyze_host: pinned host buffers in/out, upload/compute/download pipelined over chunks"}
         # the e2e result must be the same numbers the device-resident path produced
         same = bool(torch.equal(fh, f0_last[:Ue].cpu()))

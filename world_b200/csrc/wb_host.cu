@@ -45,7 +45,11 @@ extern "C" int world_b200_analyze_host(WorldB200 *h, const double *x, int n_utts
   // chunk so that two sets of device buffers (double buffering) stay within ~1/3 of the budget
   const size_t per_utt = (size_t)x_stride * 8 + (size_t)f0_stride * (16 + 2 * (size_t)bins * 8);
   int chunk = (int)dmax(1.0, dmin((double)n_utts, (double)(ctx->scratch_budget / 3) / (double)(2 * per_utt)));
-  if (chunk > 256) chunk = 256;
+  // small chunks keep the un-overlapped tail (download of the last chunk) short; 96 utterances still
+  // fill the GPU (the per-utterance kernels see 96 CTAs, the frame kernels ~200 k)
+  int cap = 96;
+  if (const char *e = getenv("WB_HOST_CHUNK")) cap = atoi(e) > 0 ? atoi(e) : cap;
+  if (chunk > cap) chunk = cap;
 
 #ifndef WB_EMU
   cudaStream_t s_compute = ctx->stream, s_in = nullptr, s_out = nullptr;
