@@ -66,8 +66,20 @@ WB_DEV bool linear_smoothing(const double *in, double width, int fs, int fft_siz
   WB_SYNC();
   if (kSequential) {
     if (tid == 0) {
+      // index-order running sum: eight loads in flight, then eight dependent adds (the chain is the
+      // DADD latency, not load + add + store per element)
       double run = seg[0];
-      for (int i = 1; i < n_ext; ++i) { run = seg[i] + run; seg[i] = run; }
+      int i = 1;
+      for (; i + 8 <= n_ext; i += 8) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = seg[i + k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { run = v[k] + run; v[k] = run; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) seg[i + k] = v[k];
+      }
+      for (; i < n_ext; ++i) { run = seg[i] + run; seg[i] = run; }
     }
     WB_SYNC();
   } else {
