@@ -15,7 +15,7 @@ def synth_batch(seeds, fs, n_samples, device="cpu", zero_tail=0):
     n = len(seeds)
     base = np.empty(n); rate = np.empty(n)
     for i, s in enumerate(seeds):
-        r = np.random.RandomState(1000003 * int(s) + 17)
+        r = np.random.RandomState((1000003 * int(s) + 17) % (1 << 32))
         base[i] = r.uniform(90.0, 250.0)
         rate[i] = r.uniform(0.3, 0.8)
     dev = torch.device(device)

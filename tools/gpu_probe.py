@@ -16,7 +16,7 @@ def true_f0(seeds, fs, n_frames, frame_period=5.0):
     out = np.zeros((len(seeds), n_frames))
     t = np.arange(n_frames) * frame_period / 1000.0
     for i, s in enumerate(seeds):
-        r = np.random.RandomState(1000003 * int(s) + 17)
+        r = np.random.RandomState((1000003 * int(s) + 17) % (1 << 32))
         base = r.uniform(90.0, 250.0); rate = r.uniform(0.3, 0.8)
         f = base * (1.0 + 0.25 * np.sin(2 * math.pi * rate * t))
         f[np.mod(t, 1.0) >= 0.75] = 0.0
