@@ -82,3 +82,38 @@ def test_option_defaults_and_sizes_match_reference(ref):
     assert [getattr(hopt, f) for f, _ in hopt._fields_] == [getattr(r, f) for f, _ in r._fields_]
     o = api.D4COption(); lib.InitializeD4COption(ctypes.byref(o))
     assert o.threshold == ref.d4c_option().threshold
+
+
+CUDA_INC = "/usr/local/cuda/include"
+CUDA_LIB = "/usr/local/cuda/lib64"
+
+
+def build_cpp_overload_program(out):
+    from world_b200 import api
+    libdir = os.path.dirname(api.DEFAULT_LIB)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", INC, "-I", CUDA_INC,
+                           os.path.join(ROOT, "tests", "cpp", "batch_overloads.cpp"), "-o", str(out),
+                           "-L", libdir, "-lworld_b200", "-L", CUDA_LIB, "-lcudart",
+                           f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{CUDA_LIB}"])
+    return str(out)
+
+
+def test_cpp_batched_overloads_compile_and_fail_loudly_without_gpu(tmp_path):
+    """include/world_b200.hpp (the 'N waveforms at once' overloads of the reference's C API) compiles
+    next to the legacy headers, links against the library, and without a device reports an error
+    instead of computing anything on the CPU."""
+    exe = build_cpp_overload_program(tmp_path / "batch_overloads")
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "no CPU path" in r.stderr
+
+
+@pytest.mark.gpu
+def test_gpu_cpp_batched_overloads_equal_single_utterance_api(tmp_path):
+    exe = build_cpp_overload_program(tmp_path / "batch_overloads")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("OK")
