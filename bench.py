@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--fs", type=int, default=16000)
     ap.add_argument("--cpu-utts", type=int, default=8, help="utterances of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-coded", action="store_true", help="skip the int16-in / coded-out variant of the e2e leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--reserve-gb", type=float, default=0.0,
@@ -387,6 +388,36 @@ def main():
         # the e2e result must be the same numbers the device-resident path produced
         same = bool(torch.equal(fh, f0_last[:Ue].cpu()))
         e2e["matches_device_path"] = same
+        # the same chain with the ingest (int16 PCM in) and the codec (60 mel-cepstral dimensions + band
+        # aperiodicities out) fused in on the device -- SURVEY.md 8 rows f2/f3: what crosses PCIe shrinks
+        if not a.no_coded:
+            dims = 60
+            n_ap = max(1, w.number_of_aperiodicities(fs))
+            del sph, aph
+            ph = torch.empty((Ue, n), dtype=torch.int16, pin_memory=True)
+            ph.copy_((xh * 32767.0).round().to(torch.int16))
+            csh = torch.empty((Ue, L, dims), dtype=torch.float64, pin_memory=True)
+            cah = torch.empty((Ue, L, n_ap), dtype=torch.float64, pin_memory=True)
+
+            def coded_step():
+                w.analyze_coded_host(ph, 16, fs, ao, dims, time_axis=th, f0=fh, coded_sp=csh, coded_ap=cah, f0_stride=L)
+
+            coded_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                coded_step()
+            barrier()
+            dtc = time.perf_counter() - t0
+            if world > 1:
+                tdt = torch.tensor([dtc], dtype=torch.float64, device=dev)
+                dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+                dtc = float(tdt.item())
+            e2e["coded"] = {"value": world * Ue * L * ke / dtc, "unit": "frames/s",
+                            "h2d_bytes_per_step": int(Ue * n * 2),
+                            "d2h_bytes_per_step": int(Ue * L * (dims + n_ap) * 8 + 2 * Ue * L * 8),
+                            "note": "world_b200_analyze_coded_host: int16 PCM in, CodeSpectralEnvelope(60) + "
+                                    "CodeAperiodicity rows out; input is the 16-bit quantisation of the same waveforms"}
 
     if rank != 0:
         if world > 1:

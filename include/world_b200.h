@@ -31,6 +31,7 @@
 #include "world/d4c.h"
 #include "world/stonemask.h"
 #include "world/synthesis.h"
+#include "world/codec.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -113,6 +114,32 @@ int world_b200_synthesis_batch(WorldB200 *ctx, const double *f0, const int *f0_l
                                int fft_size, double frame_period, int fs, const int *y_lengths,
                                int y_stride, double *y);
 
+/* ---- codec over a batch (codec.h:20-92) -- SURVEY.md 8 row f2; all DEVICE pointers ------ */
+/* aperiodicity [n][f0_stride][fft_size/2+1] -> coded [n][f0_stride][GetNumberOfAperiodicities(fs)]. */
+int world_b200_code_aperiodicity_batch(WorldB200 *ctx, const double *aperiodicity, int n_utts,
+                                       const int *f0_lengths, int f0_stride, int fs, int fft_size,
+                                       double *coded_aperiodicity);
+int world_b200_decode_aperiodicity_batch(WorldB200 *ctx, const double *coded_aperiodicity, int n_utts,
+                                         const int *f0_lengths, int f0_stride, int fs, int fft_size,
+                                         double *aperiodicity);
+/* spectrogram [n][f0_stride][fft_size/2+1] -> coded [n][f0_stride][number_of_dimensions]. */
+int world_b200_code_spectral_envelope_batch(WorldB200 *ctx, const double *spectrogram, int n_utts,
+                                            const int *f0_lengths, int f0_stride, int fs, int fft_size,
+                                            int number_of_dimensions, double *coded_spectral_envelope);
+int world_b200_decode_spectral_envelope_batch(WorldB200 *ctx, const double *coded_spectral_envelope,
+                                              int n_utts, const int *f0_lengths, int f0_stride, int fs,
+                                              int fft_size, int number_of_dimensions, double *spectrogram);
+
+/* ---- ingest (tools/audioio.cpp:217-252) -- SURVEY.md 8 row f3 --------------------------- */
+/* Host-only: locates the sample data of a mono PCM RIFF/WAVE image held in memory, with the
+ * acceptance rules of the reference's wavread (16-byte fmt chunk, format 1, one channel). */
+int world_b200_wav_parse(const unsigned char *bytes, unsigned long long size, int *fs, int *nbit,
+                         int *n_samples, unsigned long long *data_offset);
+/* Little-endian signed PCM of nbit in {8, 16, 24, 32}, rows [n][x_stride] samples (DEVICE), to the
+ * doubles wavread produces: sample / 2^(nbit-1), exact.  x_lengths NULL = full rows. */
+int world_b200_pcm_to_double_batch(WorldB200 *ctx, const void *pcm, int nbit, int n_utts, int x_stride,
+                                   const int *x_lengths, double *x);
+
 /* ---- whole analysis chain, host pointers ---------------------------------------------- */
 #define WORLD_B200_F0_DIO_STONEMASK 0
 #define WORLD_B200_F0_HARVEST 1
@@ -129,11 +156,22 @@ void world_b200_default_analysis_option(int fs, int f0_method, WorldB200Analysis
 
 /* {Dio+StoneMask | Harvest} -> CheapTrick -> D4C for n_utts host waveforms; outputs are host
  * arrays laid out as described above.  Input upload, compute and result download are pipelined
- * over utterance chunks.  Any output pointer may be NULL to skip its download. */
+ * over utterance chunks.  Any output pointer may be NULL to skip its download.  Whole padded rows
+ * are downloaded: frames beyond an utterance's own count come back as zeros. */
 int world_b200_analyze_host(WorldB200 *ctx, const double *x, int n_utts, int x_stride,
                             const int *x_lengths, int fs, const WorldB200AnalysisOption *option,
                             double *time_axis, double *f0, int f0_stride, double *spectrogram,
                             double *aperiodicity);
+
+/* The same chain with the ingest and the codec fused in on the device: x holds samples of `nbit`
+ * bits (0 = doubles as above; 8/16/24/32 = little-endian PCM as in a WAV data chunk), and the
+ * results that cross PCIe are the coded rows -- coded_spectral_envelope [n][f0_stride]
+ * [number_of_dimensions], coded_aperiodicity [n][f0_stride][GetNumberOfAperiodicities(fs)] -- about
+ * 8.4 times (16 kHz, 60 dimensions) fewer device-to-host bytes than the full rows. */
+int world_b200_analyze_coded_host(WorldB200 *ctx, const void *x, int nbit, int n_utts, int x_stride,
+                                  const int *x_lengths, int fs, const WorldB200AnalysisOption *option,
+                                  int number_of_dimensions, double *time_axis, double *f0, int f0_stride,
+                                  double *coded_spectral_envelope, double *coded_aperiodicity);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,8 @@
 // oracle/_ref directly on synthetic batches, by tests/test_oracle.py.
 //
 // Restated here: randn, interp1Q, interp1, DCCorrection, LinearSmoothing, NuttallWindow, the FFT
-// conventions, StoneMask, CheapTrick, D4C, and the option / sizing helpers.
+// conventions, StoneMask, CheapTrick, D4C, the option / sizing helpers, and (rows f2 / f3 of SURVEY.md 8)
+// the codec of codec.cpp and the PCM sample conversion of tools/audioio.cpp.
 // NOT restated (checked against oracle/_ref only): Dio, Harvest, Synthesis.
 #include <math.h>
 #include <stdint.h>
@@ -338,6 +339,104 @@ void StoneMask(const double *x, int x_length, int fs, const double *t, const dou
     if (!(tent <= 0.0 || tent > f * 2)) mean = FixF0(pw, num, N, fs, tent, 6);
     if (fabs(mean - f) > f * 0.2) mean = f;                                           // :203
     refined[i] = mean;
+  }
+}
+
+// ---- codec (codec.cpp).  The "DCT" there is one real FFT of the even/odd re-ordered mel spectrum
+// times a unit phasor; the inverse is written out here as the plain sum it stands for.
+static double MelOf(double f) { return 1127.01048 * log(f / 700.0 + 1.0); }        // codec.cpp:60-62, constantnumbers.h:45-46
+static double HzOf(double m) { return 700.0 * (exp(m / 1127.01048) - 1.0); }      // :67-69
+
+int GetNumberOfAperiodicities(int fs) {                                            // :216-219
+  return (int)(std::min(15000.0, fs / 2.0 - 3000.0) / 3000.0);
+}
+
+void CodeAperiodicity(const double *const *ap, int f0_length, int fs, int fft_size, double **coded) {  // :221-240
+  const int n_ap = GetNumberOfAperiodicities(fs), bins = fft_size / 2 + 1;
+  std::vector<double> db(bins);
+  for (int i = 0; i < f0_length; ++i) {
+    for (int j = 0; j < bins; ++j) db[j] = 20 * log10(ap[i][j]);
+    for (int b = 0; b < n_ap; ++b) coded[i][b] = Interp1QAt(0, (double)fs / fft_size, db, bins, 3000.0 * (b + 1.0));
+  }
+}
+
+void DecodeAperiodicity(const double *const *coded, int f0_length, int fs, int fft_size, double **ap) {  // :242-272
+  const int n_ap = GetNumberOfAperiodicities(fs), bins = fft_size / 2 + 1;
+  std::vector<double> axis(n_ap + 2), val(n_ap + 2);
+  for (int i = 0; i <= n_ap; ++i) axis[i] = i * 3000.0;
+  axis[n_ap + 1] = fs / 2.0;
+  val[0] = -60.0;
+  val[n_ap + 1] = -kTiny;
+  for (int i = 0; i < f0_length; ++i) {
+    double mean = 0.0;
+    for (int b = 0; b < n_ap; ++b) { mean += coded[i][b]; val[b + 1] = coded[i][b]; }
+    mean /= n_ap;
+    for (int j = 0; j < bins; ++j)
+      ap[i][j] = mean > -0.5 ? 1.0 - kTiny                                          // unvoiced frame (:21-41, :263-264)
+                             : pow(10.0, Interp1At(axis, val, (double)fs / fft_size * j) / 20.0);
+  }
+}
+
+void CodeSpectralEnvelope(const double *const *sp, int f0_length, int fs, int fft_size, int dims, double **coded) {  // :274-301
+  const int M = fft_size / 2;
+  const double floor_mel = MelOf(40.0), ceil_mel = MelOf(std::min(fs / 2.0, 20000.0));
+  std::vector<double> lin_axis(M + 1), lg(M + 1), v(M), re, im;
+  for (int j = 0; j <= M; ++j) lin_axis[j] = MelOf((double)j * fs / fft_size);      // :177-180
+  for (int i = 0; i < f0_length; ++i) {
+    for (int j = 0; j <= M; ++j) lg[j] = log(sp[i][j]);
+    std::vector<double> mel(M);
+    for (int m = 0; m < M; ++m) mel[m] = Interp1At(lin_axis, lg, (ceil_mel - floor_mel) * m / M + floor_mel);  // :121-122, :169-170
+    for (int m = 0; m < M / 2; ++m) { v[m] = mel[2 * m]; v[m + M / 2] = mel[M - 2 * m - 1]; }                   // :77-81
+    RealFFT(v, &re, &im);
+    for (int d = 0; d < dims; ++d) {                                                                            // :85-88, :171-175
+      double wr = 2.0 * cos(d * kPi / fft_size) / sqrt((double)fft_size);
+      const double wi = 2.0 * sin(d * kPi / fft_size) / sqrt((double)fft_size);
+      if (d == 0) wr /= sqrt(2.0);
+      coded[i][d] = (re[d] * wr - im[d] * wi) / sqrt((double)M);
+    }
+  }
+}
+
+void DecodeSpectralEnvelope(const double *const *coded, int f0_length, int fs, int fft_size, int dims, double **sp) {  // :303-324
+  const int M = fft_size / 2;
+  const double floor_mel = MelOf(40.0), ceil_mel = MelOf(std::min(fs / 2.0, 20000.0));
+  std::vector<double> axis(M + 2), mel(M + 2), out(M);
+  axis[0] = 0;
+  for (int m = 0; m < M; ++m) axis[m + 1] = HzOf((ceil_mel - floor_mel) * m / M + floor_mel);                    // :202-206
+  axis[M + 1] = fs / 2.0;
+  for (int i = 0; i < f0_length; ++i) {
+    // Re conj(FFT(a)) = Re FFT(a) with a[d] = c[d] (wr - j wi) sqrt(M), zero beyond dims (:97-109, fft.cpp:36-46)
+    for (int n = 0; n < M; ++n) {
+      double acc = 0.0;
+      for (int d = 0; d < dims; ++d) {
+        double wr = cos(d * kPi / fft_size) * sqrt((double)fft_size);
+        const double wi = sin(d * kPi / fft_size) * sqrt((double)fft_size);
+        if (d == 0) wr /= sqrt(2.0);
+        const double ar = coded[i][d] * wr * sqrt((double)M), ai = -coded[i][d] * wi * sqrt((double)M);
+        const double ang = -2.0 * kPi * d * n / M;
+        acc += ar * cos(ang) - ai * sin(ang);
+      }
+      out[n] = acc;
+    }
+    for (int m = 0; m < M / 2; ++m) { mel[1 + 2 * m] = out[m]; mel[2 + 2 * m] = out[M - m - 1]; }               // :111-115
+    mel[0] = mel[1];
+    mel[M + 1] = mel[M];
+    for (int j = 0; j <= M; ++j) sp[i][j] = exp(Interp1At(axis, mel, (double)j * fs / fft_size) / M);           // :150-154
+  }
+}
+
+// ---- wavread's sample conversion (tools/audioio.cpp:236-249): little-endian signed PCM -> [-1, 1)
+void OraclePcmToDouble(const unsigned char *pcm, int nbit, int n, double *x) {
+  const int nb = nbit / 8;
+  const double zero_line = pow(2.0, nbit - 1);
+  for (int i = 0; i < n; ++i) {
+    const unsigned char *s = pcm + (size_t)i * nb;
+    double tmp = 0.0, bias = 0.0;
+    unsigned char top = s[nb - 1];
+    if (top >= 128) { bias = zero_line; top &= 0x7F; }
+    tmp = top;
+    for (int j = nb - 2; j >= 0; --j) tmp = tmp * 256.0 + s[j];
+    x[i] = (tmp - bias) / zero_line;
   }
 }
 

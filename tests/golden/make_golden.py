@@ -51,6 +51,16 @@ def main():
     for _ in range(1000000):
         ref.lib.randn(st)
     out["randn_at_1e6"] = np.array([ref.lib.randn(st) for _ in range(8)])
+    # codec (codec.cpp:221-324) on the DIO-path envelope / aperiodicity, 40 mel-cepstral dimensions
+    dims = 40
+    csp = ref.code_spectral_envelope(sp, fs, ct.fft_size, dims)
+    cap = ref.code_aperiodicity(ap, fs, ct.fft_size)
+    out.update(coded_dims=np.int32(dims), coded_sp=csp, coded_ap=cap,
+               decoded_sp_rows=ref.decode_spectral_envelope(csp, fs, ct.fft_size, dims)[::4],
+               decoded_ap_rows=ref.decode_aperiodicity(cap, fs, ct.fft_size)[::4])
+    # the fixture through the reference's own wavread must be what read_wav() gives
+    xr, fsr, nbit = ref.wavread(WAV)
+    assert fsr == fs and nbit == 16 and np.array_equal(xr, x)
     path = os.path.join(ROOT, "tests", "golden", "vaiueo2d.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

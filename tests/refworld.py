@@ -50,6 +50,16 @@ class RefWorld:
         L.D4C.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.POINTER(D4COption), _P]
         for f in (L.StoneMask, L.CheapTrick, L.D4C):
             f.restype = None
+        self.has_codec = hasattr(L, "CodeSpectralEnvelope")
+        if self.has_codec:
+            L.GetNumberOfAperiodicities.restype = C.c_int
+            L.GetNumberOfAperiodicities.argtypes = [C.c_int]
+            for f in (L.CodeAperiodicity, L.DecodeAperiodicity):
+                f.restype = None
+                f.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P]
+            for f in (L.CodeSpectralEnvelope, L.DecodeSpectralEnvelope):
+                f.restype = None
+                f.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P]
 
     # options
     def dio_option(self):
@@ -121,6 +131,37 @@ class RefWorld:
         rows = self._rows(ap)
         self.lib.D4C(x.ctypes.data, len(x), fs, t.ctypes.data, f0.ctypes.data, len(f0), fft_size, C.byref(opt), rows)
         return ap
+
+
+    # codec.h
+    def number_of_aperiodicities(self, fs):
+        return self.lib.GetNumberOfAperiodicities(fs)
+
+    def _codec(self, fn, src, out_w, *args):
+        src = np.ascontiguousarray(src, dtype=np.float64)
+        out = np.zeros((src.shape[0], out_w))
+        fn(self._rows(src), src.shape[0], *args, self._rows(out))
+        return out
+
+    def code_aperiodicity(self, ap, fs, fft_size):
+        return self._codec(self.lib.CodeAperiodicity, ap, max(1, self.number_of_aperiodicities(fs)), fs, fft_size)
+
+    def decode_aperiodicity(self, coded, fs, fft_size):
+        return self._codec(self.lib.DecodeAperiodicity, coded, fft_size // 2 + 1, fs, fft_size)
+
+    def code_spectral_envelope(self, sp, fs, fft_size, dims):
+        return self._codec(self.lib.CodeSpectralEnvelope, sp, dims, fs, fft_size, dims)
+
+    def decode_spectral_envelope(self, coded, fs, fft_size, dims):
+        return self._codec(self.lib.DecodeSpectralEnvelope, coded, fft_size // 2 + 1, fs, fft_size, dims)
+
+    def wavread(self, path):
+        """the reference's own wavread (tools/audioio.cpp:217-252); only in oracle/_ref"""
+        self.lib.GetAudioLength.restype = C.c_int
+        n = self.lib.GetAudioLength(path.encode())
+        x = np.zeros(max(n, 1)); fs = C.c_int(); nbit = C.c_int()
+        self.lib.wavread(path.encode(), C.byref(fs), C.byref(nbit), x.ctypes.data)
+        return x[:n], fs.value, nbit.value
 
 
 def rel_err(got, want, floor=0.0):

@@ -31,7 +31,11 @@ def test_headers_declare_the_reference_api():
                      "GetSamplesForDIO", "GetSamplesForHarvest", "GetFFTSizeForCheapTrick",
                      "GetF0FloorForCheapTrick", "Synthesis", "world_b200_synthesis_batch", "world_b200_cheaptrick_batch", "world_b200_d4c_batch",
                      "world_b200_dio_batch", "world_b200_harvest_batch", "world_b200_stonemask_batch",
-                     "world_b200_analyze_host"]:
+                     "world_b200_analyze_host", "GetNumberOfAperiodicities", "CodeAperiodicity", "DecodeAperiodicity",
+                     "CodeSpectralEnvelope", "DecodeSpectralEnvelope", "world_b200_code_spectral_envelope_batch",
+                     "world_b200_code_aperiodicity_batch", "world_b200_decode_spectral_envelope_batch",
+                     "world_b200_decode_aperiodicity_batch", "world_b200_pcm_to_double_batch", "world_b200_wav_parse",
+                     "world_b200_analyze_coded_host"]:
         assert required in names
 
 

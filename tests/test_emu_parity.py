@@ -89,3 +89,15 @@ def test_emu_synthesis(emu, ref, golden):
 
 def test_emu_fft_known_answers(emu):
     pc.check_fft_known_answers(emu)
+
+
+def test_emu_codec(emu, ref, golden):
+    pc.check_codec(emu, ref, golden)
+
+
+def test_emu_ingest(emu, ref, golden, tmp_path):
+    pc.check_ingest(emu, golden, ref, tmp_path)
+
+
+def test_emu_analyze_coded_host(emu, golden):
+    pc.check_analyze_coded(emu, golden)

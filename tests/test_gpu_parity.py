@@ -143,3 +143,37 @@ def test_gpu_legacy_synthesis(gpu_world, ref, golden):
 
 def test_gpu_fft_known_answers(gpu_world):
     pc.check_fft_known_answers(gpu_world)
+
+
+def test_gpu_codec(gpu_world, ref, golden):
+    pc.check_codec(gpu_world, ref, golden)
+
+
+def test_gpu_ingest(gpu_world, ref, golden, tmp_path):
+    pc.check_ingest(gpu_world, golden, ref, tmp_path)
+
+
+def test_gpu_analyze_coded_host(gpu_world, golden):
+    from world_b200 import api
+    pc.check_analyze_coded(gpu_world, golden, api.F0_DIO_STONEMASK)
+
+
+def test_gpu_legacy_codec(gpu_world, ref, golden):
+    """codec.h entry points with the reference's calling convention (row pointers, host memory)."""
+    import ctypes as C
+    lib = gpu_world.lib
+    fs, fft, dims = int(golden["fs"]), int(golden["fft_size"]), int(golden["coded_dims"])
+    sp = np.ascontiguousarray(golden["sp"]); ap = np.ascontiguousarray(golden["ap"])
+    L = sp.shape[0]
+    rows = lambda a: (C.c_void_p * a.shape[0])(*[a[i].ctypes.data for i in range(a.shape[0])])
+    n_ap = lib.GetNumberOfAperiodicities(fs)
+    assert n_ap == ref.number_of_aperiodicities(fs)
+    csp = np.zeros((L, dims)); cap = np.zeros((L, n_ap)); dsp = np.zeros_like(sp); dap = np.zeros_like(ap)
+    lib.CodeSpectralEnvelope(rows(sp), L, fs, fft, dims, rows(csp))
+    lib.CodeAperiodicity(rows(ap), L, fs, fft, rows(cap))
+    lib.DecodeSpectralEnvelope(rows(csp), L, fs, fft, dims, rows(dsp))
+    lib.DecodeAperiodicity(rows(cap), L, fs, fft, rows(dap))
+    pc.assert_close_signed(csp, golden["coded_sp"], "legacy CodeSpectralEnvelope")
+    pc.assert_close_signed(cap, golden["coded_ap"], "legacy CodeAperiodicity")
+    pc.assert_close(dsp[::4], golden["decoded_sp_rows"], "legacy DecodeSpectralEnvelope")
+    pc.assert_close(dap[::4], golden["decoded_ap_rows"], "legacy DecodeAperiodicity")

@@ -48,3 +48,27 @@ def test_port_sizing_helpers(port, ref):
     for fs in (8000, 16000, 22050, 44100, 48000):
         assert port.cheaptrick_option(fs).fft_size == ref.cheaptrick_option(fs).fft_size
         assert port.frames(fs, 12345) == ref.frames(fs, 12345)
+
+
+def test_port_codec_matches_golden_and_reference(port, ref, golden):
+    """rows f2 / f3: the restated codec and PCM conversion against the reference's outputs."""
+    import ctypes as C
+    fs, fft, dims = int(golden["fs"]), int(golden["fft_size"]), int(golden["coded_dims"])
+    assert port.has_codec and port.number_of_aperiodicities(fs) == golden["coded_ap"].shape[1]
+    csp = port.code_spectral_envelope(golden["sp"], fs, fft, dims)
+    cap = port.code_aperiodicity(golden["ap"], fs, fft)
+    pc.assert_close_signed(csp, golden["coded_sp"], "port CodeSpectralEnvelope", tol=1e-9)
+    pc.assert_close_signed(cap, golden["coded_ap"], "port CodeAperiodicity", tol=1e-9)
+    assert rel_err(port.decode_spectral_envelope(golden["coded_sp"], fs, fft, dims)[::4], golden["decoded_sp_rows"]).max() < 1e-9
+    assert rel_err(port.decode_aperiodicity(golden["coded_ap"], fs, fft)[::4], golden["decoded_ap_rows"]).max() < 1e-9
+    for fs2, fft2, d in ((16000, 1024, 60), (48000, 2048, 24), (8000, 512, 129)):
+        rng = np.random.default_rng(fs2)
+        sp = np.exp(rng.normal(size=(5, fft2 // 2 + 1)) * 3 - 8)
+        want = ref.code_spectral_envelope(sp, fs2, fft2, d)
+        pc.assert_close_signed(port.code_spectral_envelope(sp, fs2, fft2, d), want, "port code sp", tol=1e-9)
+        assert rel_err(port.decode_spectral_envelope(want, fs2, fft2, d), ref.decode_spectral_envelope(want, fs2, fft2, d)).max() < 1e-9
+        assert port.number_of_aperiodicities(fs2) == ref.number_of_aperiodicities(fs2)
+    pcm = np.ascontiguousarray(golden["pcm"])
+    x = np.zeros(len(pcm))
+    port.lib.OraclePcmToDouble(pcm.ctypes.data_as(C.c_void_p), 16, len(pcm), x.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(x, pc.wav_from_golden(golden)[0])

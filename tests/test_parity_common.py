@@ -1,6 +1,8 @@
 """Shared parity checks; the same assertions run against the host emulation (CPU, -m "not gpu")
 and against the CUDA library (-m gpu).  Tolerance: BASELINE.json's north_star -- 1e-6 relative
 for f0 / spectrogram / aperiodicity, frame counts and time_axis bit-exact."""
+import os
+
 import numpy as np
 
 from refworld import rel_err
@@ -226,3 +228,146 @@ def check_fft_known_answers(world):
         want = np.fft.rfft(x)
         err = np.abs(got[:, 0] + 1j * got[:, 1] - want).max() / np.abs(want).max()
         assert err < 1e-13, f"rfft n={n}: {err:.2e}"
+
+
+# ---------------------------------------------------------------- codec (row f2) and ingest (row f3)
+def assert_close_signed(got, want, what, tol=TOL):
+    """Cepstral coefficients and dB values pass through zero, so the relative bound is taken against
+    max(|want|, 1e-4 * max|want| of the whole array): 1e-6 of anything that is not numerically zero."""
+    want = np.asarray(want)
+    r = rel_err(to_np(got), want, floor=1e-4 * np.abs(want).max())
+    assert r.max() <= tol, f"{what}: max rel err {r.max():.3e}"
+
+
+def check_codec(world, ref, golden):
+    fs, fft, dims = int(golden["fs"]), int(golden["fft_size"]), int(golden["coded_dims"])
+    sp, ap = make(world, golden["sp"][None]), make(world, golden["ap"][None])
+    csp = world.code_spectral_envelope(sp, fs, fft, dims)
+    cap = world.code_aperiodicity(ap, fs, fft)
+    dsp = world.decode_spectral_envelope(make(world, golden["coded_sp"][None]), fs, fft, dims)
+    dap = world.decode_aperiodicity(make(world, golden["coded_ap"][None]), fs, fft)
+    world.synchronize()
+    assert world.number_of_aperiodicities(fs) == golden["coded_ap"].shape[1]
+    assert_close_signed(csp[0], golden["coded_sp"], "coded spectral envelope (golden)")
+    assert_close_signed(cap[0], golden["coded_ap"], "coded aperiodicity (golden)")
+    assert_close(to_np(dsp)[0][::4], golden["decoded_sp_rows"], "decoded spectral envelope (golden)")
+    assert_close(to_np(dap)[0][::4], golden["decoded_ap_rows"], "decoded aperiodicity (golden)")
+    # other rates / sizes / dimensions against the compiled reference, ragged batch of three
+    for fs2, fft2 in [(16000, 1024), (48000, 2048), (8000, 512), (44100, 2048), (16000, 4096)]:
+        rng = np.random.default_rng(fs2 + fft2)
+        bins, lens = fft2 // 2 + 1, [9, 4, 0]
+        sp2 = np.exp(rng.normal(size=(3, 9, bins)) * 3 - 8)
+        ap2 = np.clip(rng.uniform(size=(3, 9, bins)), 1e-3, 1 - 1e-12)
+        ap2[0, 2] = 1 - 1e-12                                   # an unvoiced frame (decodes to the constant)
+        n_ap = ref.number_of_aperiodicities(fs2)
+        assert world.number_of_aperiodicities(fs2) == n_ap
+        for d in (1, 24, 60, fft2 // 4 + 1):
+            a = world.code_spectral_envelope(make(world, sp2), fs2, fft2, d, f0_lengths=lens)
+            world.synchronize()
+            a = to_np(a)
+            want = [ref.code_spectral_envelope(sp2[u, :lens[u]], fs2, fft2, d) for u in range(2)]
+            back = np.zeros((3, 9, d))
+            for u in range(2):
+                assert_close_signed(a[u, :lens[u]], want[u], f"CodeSpectralEnvelope fs={fs2} d={d} utt {u}")
+                assert not a[u, lens[u]:].any()                # padded frames are never written
+                back[u, :lens[u]] = want[u]
+            assert not a[2].any()
+            b = world.decode_spectral_envelope(make(world, back), fs2, fft2, d, f0_lengths=lens)
+            world.synchronize()
+            for u in range(2):
+                assert_close(to_np(b)[u, :lens[u]], ref.decode_spectral_envelope(want[u], fs2, fft2, d),
+                             f"DecodeSpectralEnvelope fs={fs2} d={d} utt {u}")
+        if n_ap > 0:
+            a = world.code_aperiodicity(make(world, ap2), fs2, fft2, f0_lengths=lens)
+            world.synchronize()
+            coded = np.zeros((3, 9, n_ap))
+            for u in range(2):
+                coded[u, :lens[u]] = ref.code_aperiodicity(ap2[u, :lens[u]], fs2, fft2)
+                assert_close_signed(to_np(a)[u, :lens[u]], coded[u, :lens[u]], f"CodeAperiodicity fs={fs2} utt {u}")
+        else:
+            coded = np.zeros((3, 9, 1))
+        b = world.decode_aperiodicity(make(world, coded), fs2, fft2, f0_lengths=lens)
+        world.synchronize()
+        for u in range(2):
+            want_ap = ref.decode_aperiodicity(coded[u, :lens[u]], fs2, fft2)
+            assert_close(to_np(b)[u, :lens[u]], want_ap, f"DecodeAperiodicity fs={fs2} utt {u}")
+
+
+def wav_image(pcm_bytes, fs, nbit, extra_chunk=b""):
+    """RIFF/WAVE image like the reference's wavwrite (tools/audioio.cpp:121-171), optionally with
+    another chunk between fmt and data (the case wavread's scan for "data" exists for)."""
+    import struct
+    fmt = struct.pack("<4sIHHIIHH", b"fmt ", 16, 1, 1, fs, fs * nbit // 8, nbit // 8, nbit)
+    body = b"WAVE" + fmt + extra_chunk + b"data" + struct.pack("<I", len(pcm_bytes)) + pcm_bytes
+    return b"RIFF" + struct.pack("<I", len(body)) + body
+
+
+def check_ingest(world, golden, ref=None, tmp_path=None):
+    pcm16 = np.ascontiguousarray(golden["pcm"])
+    fs = int(golden["fs"])
+    # WAV header walk
+    for extra in (b"", b"LIST" + (10).to_bytes(4, "little") + b"INFOdummy!"):
+        img = wav_image(pcm16.tobytes(), fs, 16, extra)
+        got = world.wav_parse(img)
+        assert got[:3] == (fs, 16, len(pcm16)) and img[got[3]:got[3] + 4] == pcm16.tobytes()[:4]
+        if ref is not None and ref.has_codec and tmp_path is not None:
+            p = os.path.join(str(tmp_path), "a.wav")
+            open(p, "wb").write(img)
+            xr, fsr, nbit = ref.wavread(p)
+            assert (fsr, nbit, len(xr)) == got[:3]
+    for bad in (b"RIFX" + bytes(60), wav_image(b"", fs, 16)[:30], wav_image(pcm16.tobytes(), fs, 16).replace(b"fmt ", b"fmtx")):
+        try:
+            world.wav_parse(bad)
+            raise AssertionError("malformed WAV accepted")
+        except Exception as e:
+            assert "WAV" in str(e)
+    # sample conversion: exact for every width, ragged rows untouched beyond their length
+    rng = np.random.default_rng(5)
+    for nbit in (8, 16, 24, 32):
+        nb = nbit // 8
+        raw = rng.integers(0, 256, size=(3, 1000 * nb), dtype=np.uint8)
+        raw[0, :nb] = 0
+        raw[0, nb:2 * nb] = 255                                   # -1 LSB
+        raw[0, 2 * nb:3 * nb - 1] = 0; raw[0, 3 * nb - 1] = 128   # most negative
+        raw[0, 3 * nb:4 * nb - 1] = 255; raw[0, 4 * nb - 1] = 127 # most positive
+        lens = [1000, 999, 1]
+        x = world.pcm_to_double(make(world, raw, dtype=np.uint8), nbit, x_lengths=lens)
+        world.synchronize()
+        vals = np.zeros((3, 1000), dtype=np.int64)
+        for j in range(nb):
+            vals += raw[:, j::nb].astype(np.int64) << (8 * j)
+        vals = np.where(vals >= 1 << (nbit - 1), vals - (1 << nbit), vals)
+        want = vals.astype(np.float64) / float(1 << (nbit - 1))
+        for u in range(3):
+            assert np.array_equal(to_np(x)[u, :lens[u]], want[u, :lens[u]])
+            assert not to_np(x)[u, lens[u]:].any()
+        assert want[0, 2] == -1.0 and want[0, 1] == -1.0 / (1 << (nbit - 1))
+    x = world.pcm_to_double(make(world, pcm16[None].view(np.uint8), dtype=np.uint8), 16)
+    world.synchronize()
+    assert np.array_equal(to_np(x)[0], wav_from_golden(golden)[0])
+
+
+def check_analyze_coded(world, golden, f0_method=0):
+    """int16 in, coded rows out, through the one-call host API; against the goldens of the DIO path."""
+    import numpy as np
+    pcm16 = np.ascontiguousarray(golden["pcm"])
+    fs, dims = int(golden["fs"]), int(golden["coded_dims"])
+    n = 3
+    stride = len(pcm16) + 64
+    rows = np.zeros((n, stride), dtype=np.int16)
+    lens = [len(pcm16), len(pcm16) - 777, len(pcm16)]
+    for u in range(n):
+        rows[u, :lens[u]] = pcm16[:lens[u]]
+    opt = world.analysis_option(fs, f0_method)
+    t, f0, csp, cap, fl = world.analyze_coded_host(rows, 16, fs, opt, dims, x_lengths=lens)
+    for u in (0, 2):
+        assert fl[u] == len(golden["time_axis"])
+        assert np.array_equal(t[u, :fl[u]], golden["time_axis"])
+        assert_close(f0[u, :fl[u]], golden["f0_stonemask"], "f0 via analyze_coded_host")
+        assert_close_signed(csp[u, :fl[u]], golden["coded_sp"], "coded sp via analyze_coded_host")
+        assert_close_signed(cap[u, :fl[u]], golden["coded_ap"], "coded ap via analyze_coded_host")
+    assert fl[1] < fl[0] and not csp[1, fl[1]:].any()
+    # and the same call on doubles (nbit 0) gives the same numbers
+    xd = rows.astype(np.float64) / 32768.0
+    t2, f02, csp2, cap2, _ = world.analyze_coded_host(xd, 0, fs, opt, dims, x_lengths=lens)
+    assert np.array_equal(csp2, csp) and np.array_equal(cap2, cap) and np.array_equal(f02, f0)

@@ -90,6 +90,20 @@ ABI = {
     "GetSamplesForHarvest": (C.c_int, [C.c_int, C.c_int, C.c_double]),
     "GetFFTSizeForCheapTrick": (C.c_int, [C.c_int, C.POINTER(CheapTrickOption)]),
     "GetF0FloorForCheapTrick": (C.c_double, [C.c_int, C.c_int]),
+    # codec (row f2) and ingest (row f3)
+    "world_b200_code_aperiodicity_batch": (C.c_int, [_P, _P, C.c_int, _IP, C.c_int, C.c_int, C.c_int, _P]),
+    "world_b200_decode_aperiodicity_batch": (C.c_int, [_P, _P, C.c_int, _IP, C.c_int, C.c_int, C.c_int, _P]),
+    "world_b200_code_spectral_envelope_batch": (C.c_int, [_P, _P, C.c_int, _IP, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "world_b200_decode_spectral_envelope_batch": (C.c_int, [_P, _P, C.c_int, _IP, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "world_b200_wav_parse": (C.c_int, [_P, C.c_ulonglong, _IP, _IP, _IP, C.POINTER(C.c_ulonglong)]),
+    "world_b200_pcm_to_double_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _IP, _P]),
+    "world_b200_analyze_coded_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _IP, C.c_int,
+                                                C.POINTER(AnalysisOption), C.c_int, _P, _P, C.c_int, _P, _P]),
+    "GetNumberOfAperiodicities": (C.c_int, [C.c_int]),
+    "CodeAperiodicity": (None, [_P, C.c_int, C.c_int, C.c_int, _P]),
+    "DecodeAperiodicity": (None, [_P, C.c_int, C.c_int, C.c_int, _P]),
+    "CodeSpectralEnvelope": (None, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "DecodeSpectralEnvelope": (None, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
 
 
@@ -346,3 +360,85 @@ class World:
                                                      _ptr(time_axis), _ptr(f0), f0_stride, _ptr(spectrogram),
                                                      _ptr(aperiodicity)))
         return time_axis, f0, spectrogram, aperiodicity, fl
+
+    # -- codec (codec.h) and ingest ----------------------------------------------------------
+    def number_of_aperiodicities(self, fs) -> int:
+        return int(self.lib.GetNumberOfAperiodicities(fs))
+
+    def _codec(self, fn, src, out_width, fs, fft_size, f0_lengths, dims=None):
+        n, stride = src.shape[0], src.shape[1]
+        out = self._zeros(src, (n, stride, out_width))
+        fl, keep = _int_array(f0_lengths, n)
+        self._use_current_stream()
+        args = [self._h, _ptr(src), n, fl, stride, fs, fft_size]
+        if dims is not None:
+            args.append(dims)
+        self._check(fn(*args, _ptr(out)))
+        return out
+
+    def code_aperiodicity(self, aperiodicity, fs, fft_size, f0_lengths=None):
+        return self._codec(self.lib.world_b200_code_aperiodicity_batch, aperiodicity,
+                           max(1, self.number_of_aperiodicities(fs)), fs, fft_size, f0_lengths)
+
+    def decode_aperiodicity(self, coded, fs, fft_size, f0_lengths=None):
+        return self._codec(self.lib.world_b200_decode_aperiodicity_batch, coded, fft_size // 2 + 1, fs, fft_size,
+                           f0_lengths)
+
+    def code_spectral_envelope(self, spectrogram, fs, fft_size, number_of_dimensions, f0_lengths=None):
+        return self._codec(self.lib.world_b200_code_spectral_envelope_batch, spectrogram, number_of_dimensions, fs,
+                           fft_size, f0_lengths, number_of_dimensions)
+
+    def decode_spectral_envelope(self, coded, fs, fft_size, number_of_dimensions, f0_lengths=None):
+        return self._codec(self.lib.world_b200_decode_spectral_envelope_batch, coded, fft_size // 2 + 1, fs,
+                           fft_size, f0_lengths, number_of_dimensions)
+
+    def wav_parse(self, data: bytes):
+        """Host only: (fs, nbit, n_samples, data_offset) of a mono PCM WAV image."""
+        fs, nbit, ns, off = C.c_int(), C.c_int(), C.c_int(), C.c_ulonglong()
+        buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
+        rc = self.lib.world_b200_wav_parse(buf, len(data), C.byref(fs), C.byref(nbit), C.byref(ns), C.byref(off))
+        if rc != 0:
+            raise WorldError(f"not a mono PCM WAV image the reference's wavread accepts (code {rc})")
+        return fs.value, nbit.value, ns.value, off.value
+
+    def pcm_to_double(self, pcm, nbit, x_lengths=None):
+        """pcm: [n, stride * nbit/8] uint8 (or [n, stride] int16 for nbit 16) on the device -> doubles."""
+        n = pcm.shape[0]
+        stride = pcm.shape[1] * pcm.element_size() // (nbit // 8) if hasattr(pcm, "element_size") \
+            else pcm.shape[1] * pcm.itemsize // (nbit // 8)
+        if self.xp == "torch":
+            x = self.torch.zeros((n, stride), dtype=self.torch.float64, device=pcm.device)
+        else:
+            import numpy as np
+            x = np.zeros((n, stride))
+        xl, keep = _int_array(x_lengths, n)
+        self._use_current_stream()
+        self._check(self.lib.world_b200_pcm_to_double_batch(self._h, _ptr(pcm), nbit, n, stride, xl, _ptr(x)))
+        return x
+
+    def analyze_coded_host(self, x_host, nbit, fs, option: AnalysisOption, number_of_dimensions, x_lengths=None,
+                           time_axis=None, f0=None, coded_sp=None, coded_ap=None, f0_stride=None):
+        """Whole chain with device-side ingest (nbit 0 = float64 rows, 16 = int16 rows, ...) and codec;
+        only the coded rows are downloaded."""
+        import numpy as np
+        n = x_host.shape[0]
+        item = x_host.element_size() if hasattr(x_host, "element_size") else x_host.itemsize
+        stride = x_host.shape[1] * item // (nbit // 8 if nbit else 8)
+        frame_period = option.dio.frame_period if option.f0_method == F0_DIO_STONEMASK else option.harvest.frame_period
+        lens = [stride] * n if x_lengths is None else [int(v) for v in x_lengths]
+        fl = [self.frames(fs, v, frame_period) for v in lens]
+        f0_stride = f0_stride or max(fl)
+        n_ap = self.number_of_aperiodicities(fs)
+        if time_axis is None:
+            time_axis = np.zeros((n, f0_stride))
+        if f0 is None:
+            f0 = np.zeros((n, f0_stride))
+        if coded_sp is None:
+            coded_sp = np.zeros((n, f0_stride, number_of_dimensions))
+        if coded_ap is None:
+            coded_ap = np.zeros((n, f0_stride, max(1, n_ap)))
+        xl, keep = _int_array(x_lengths, n)
+        self._check(self.lib.world_b200_analyze_coded_host(self._h, _ptr(x_host), nbit, n, stride, xl, fs,
+                                                           C.byref(option), number_of_dimensions, _ptr(time_axis),
+                                                           _ptr(f0), f0_stride, _ptr(coded_sp), _ptr(coded_ap)))
+        return time_axis, f0, coded_sp, coded_ap, fl
