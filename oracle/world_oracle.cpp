@@ -13,8 +13,9 @@
 //
 // Restated here: randn, interp1Q, interp1, DCCorrection, LinearSmoothing, NuttallWindow, the FFT
 // conventions, StoneMask, CheapTrick, D4C, the option / sizing helpers, and (rows f2 / f3 of SURVEY.md 8)
-// the codec of codec.cpp and the PCM sample conversion of tools/audioio.cpp.
-// NOT restated (checked against oracle/_ref only): Dio, Harvest, Synthesis.
+// the codec of codec.cpp and the PCM sample conversion of tools/audioio.cpp; Dio (with decimate) as
+// direct time-domain filtering instead of the reference's FFT convolutions.
+// NOT restated (checked against oracle/_ref only): Harvest, Synthesis.
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -440,4 +441,211 @@ void OraclePcmToDouble(const unsigned char *pcm, int nbit, int n, double *x) {
   }
 }
 
+// ---- decimate (matlabfunctions.cpp:178-204) with FilterForDecimate's IIR (:27-125)
+static void DecimateCoefficients(int r, double a[3], double b[2]) {
+  static const double kTable[11][5] = {   // rows r = 2 .. 12: a0 a1 a2 b0 b1
+    {0.041156734567757189, -0.42599112459189636, 0.041037215479961225, 0.16797464681802227, 0.50392394045406674},
+    {0.95039378983237421, -0.67429146741526791, 0.15412211621346475, 0.071221945171178636, 0.21366583551353591},
+    {1.4499664446880227, -0.98943497080950582, 0.24578252340690215, 0.036710750339322612, 0.11013225101796784},
+    {1.7610939654280557, -1.2554914843859768, 0.3237186507788215, 0.021334858522387423, 0.06400457556716227},
+    {1.9715352749512141, -1.4686795689225347, 0.3893908434965701, 0.013469181309343825, 0.040407543928031475},
+    {2.1225239019534703, -1.6395144861046302, 0.44469707800587366, 0.0090366882681608418, 0.027110064804482525},
+    {2.2357462340187593, -1.7780899984041358, 0.49152555365968692, 0.0063522763407111993, 0.019056829022133598},
+    {2.3236003491759578, -1.8921545617463598, 0.53148928133729068, 0.0046331164041389372, 0.013899349212416812},
+    {2.3936475118069387, -1.9873904075111861, 0.5658879979027055, 0.0034818622251927556, 0.010445586675578267},
+    {2.450743295230728, -2.06794904601978, 0.59574774438332101, 0.0026822508007163792, 0.0080467524021491377},
+    {2.4981398605924205, -2.1368928194784025, 0.62187513816221485, 0.0021097275904709001, 0.0063291827714127002}};
+  for (int i = 0; i < 3; ++i) a[i] = (r >= 2 && r <= 12) ? kTable[r - 2][i] : 0.0;
+  for (int i = 0; i < 2; ++i) b[i] = (r >= 2 && r <= 12) ? kTable[r - 2][3 + i] : 0.0;
+}
+
+static void IirPass(const std::vector<double> &in, int r, std::vector<double> *out) {   // :113-122
+  double a[3], b[2], w0 = 0.0, w1 = 0.0, w2 = 0.0;
+  DecimateCoefficients(r, a, b);
+  out->resize(in.size());
+  for (size_t i = 0; i < in.size(); ++i) {
+    const double wt = in[i] + a[0] * w0 + a[1] * w1 + a[2] * w2;
+    (*out)[i] = b[0] * wt + b[1] * w0 + b[1] * w1 + b[0] * w2;
+    w2 = w1; w1 = w0; w0 = wt;
+  }
+}
+
+static void Decimate(const double *x, int n, int r, std::vector<double> *y) {
+  const int pad = 9;
+  std::vector<double> ext(n + 2 * pad), tmp;
+  for (int i = 0; i < pad; ++i) ext[i] = 2 * x[0] - x[pad - i];                       // odd reflection at both ends
+  for (int i = 0; i < n; ++i) ext[pad + i] = x[i];
+  for (int i = 0; i < pad; ++i) ext[pad + n + i] = 2 * x[n - 1] - x[n - 2 - i];
+  for (int pass = 0; pass < 2; ++pass) {                                              // forward, then backward: zero phase
+    IirPass(ext, r, &tmp);
+    for (size_t i = 0; i < ext.size(); ++i) ext[i] = tmp[ext.size() - 1 - i];
+  }
+  const int nout = (n - 1) / r + 1, nbeg = r - r * nout + n;
+  y->clear();
+  for (int i = nbeg; i < n + pad; i += r) y->push_back(ext[i + pad - 1]);
+}
+
+// ---- DIO (dio.cpp).  The reference filters by FFT; every product there is a circular convolution that
+// the chosen fft_size keeps free of wrap-around (:590-592), so the same signals are linear convolutions.
+typedef struct { double f0_floor, f0_ceil, channels_in_octave, frame_period; int speed; double allowed_range; } DioOption;  // dio.h:16-23
+
+void InitializeDioOption(DioOption *o) {                                            // dio.cpp:650-663
+  o->channels_in_octave = 2.0; o->f0_ceil = 800.0; o->f0_floor = 71.0;
+  o->frame_period = 5; o->speed = 1; o->allowed_range = 0.1;
+}
+
+// ZeroCrossingEngine (:357-401): negative-going crossings, linearly interpolated; interval i lies
+// between crossings i and i+1.  Returns the number of intervals.
+static int CrossingIntervals(const std::vector<double> &s, int n, double fs, std::vector<double> *loc, std::vector<double> *f) {
+  std::vector<double> fine;
+  for (int i = 0; i + 1 < n; ++i)
+    if (0.0 < s[i] && s[i + 1] <= 0.0) fine.push_back((i + 1) - s[i] / (s[i + 1] - s[i]));
+  loc->clear(); f->clear();
+  if (fine.size() < 2) return 0;
+  for (size_t i = 0; i + 1 < fine.size(); ++i) {
+    f->push_back(fs / (fine[i + 1] - fine[i]));
+    loc->push_back((fine[i] + fine[i + 1]) / 2.0 / fs);
+  }
+  return (int)f->size();
+}
+
+// interp1 as the reference evaluates it for a whole sorted query vector (matlabfunctions.cpp:136-176)
+static void Interp1Vec(const std::vector<double> &x, const std::vector<double> &y, const double *xi, int n, std::vector<double> *yi) {
+  yi->resize(n);
+  for (int i = 0; i < n; ++i) (*yi)[i] = Interp1At(x, y, xi[i]);
+}
+
+static double DioSelect(double cur, double past, const std::vector<std::vector<double> > &cand, int idx, double allowed) {  // :197-216
+  const double ref = (cur * 3.0 - past) / 2.0;
+  double best = cand[0][idx], err = fabs(ref - best);
+  for (size_t b = 1; b < cand.size(); ++b)
+    if (fabs(ref - cand[b][idx]) < err) { err = fabs(ref - cand[b][idx]); best = cand[b][idx]; }
+  return fabs(1.0 - best / ref) > allowed ? 0.0 : best;
+}
+
+void Dio(const double *x, int x_length, int fs, const DioOption *o, double *t, double *f0) {   // :643-648, :578-635
+  const int nb = 1 + (int)(log(o->f0_ceil / o->f0_floor) / kLog2 * o->channels_in_octave);
+  std::vector<double> boundary(nb);
+  for (int i = 0; i < nb; ++i) boundary[i] = o->f0_floor * pow(2.0, (i + 1) / o->channels_in_octave);
+  const int ratio = std::max(std::min(o->speed, 12), 1);
+  const int ylen = 1 + x_length / ratio;
+  const double afs = (double)fs / ratio;
+  const int L = GetSamplesForDIO(fs, x_length, o->frame_period);
+  for (int i = 0; i < L; ++i) t[i] = i * o->frame_period / 1000.0;
+
+  // GetSpectrumForEstimation (:61-106): decimate, remove the mean over y_length, low-cut filter
+  std::vector<double> y(ylen, 0.0), dec;
+  if (ratio != 1) { Decimate(x, x_length, ratio, &dec); for (size_t i = 0; i < dec.size() && (int)i < ylen; ++i) y[i] = dec[i]; }
+  else for (int i = 0; i < x_length; ++i) y[i] = x[i];
+  double mean = 0.0;
+  for (int i = 0; i < ylen; ++i) mean += y[i];
+  mean /= ylen;
+  for (int i = 0; i < ylen; ++i) y[i] -= mean;
+  // DesignLowCutFilter (:40-53): delta minus a unit-sum Hann bump of 2c+1 points, centred on lag 0
+  const int c = RoundHalfAway(afs / 50.0), N = 2 * c + 1;
+  std::vector<double> lc(N);
+  double sum = 0.0;
+  for (int i = 1; i <= N; ++i) { lc[i - 1] = 0.5 - 0.5 * cos(i * 2.0 * kPi / (N + 1)); sum += lc[i - 1]; }
+  for (int i = 0; i < N; ++i) lc[i] = -lc[i] / sum;
+  lc[c] += 1.0;
+  // s[n], n in [-c, ylen + c): stored with offset c
+  std::vector<double> s(ylen + 2 * c, 0.0);
+  for (int n = -c; n < ylen + c; ++n) {
+    double acc = 0.0;
+    for (int k = -c; k <= c; ++k) { const int m = n - k; if (m >= 0 && m < ylen) acc += lc[k + c] * y[m]; }
+    s[n + c] = acc;
+  }
+
+  std::vector<std::vector<double> > cand(nb, std::vector<double>(L)), score(nb, std::vector<double>(L));
+  std::vector<double> filt(ylen), work, loc[4], itv[4], yi[4];
+  for (int b = 0; b < nb; ++b) {
+    // GetFilteredSignal (:296-343): Nuttall window of 4h points as low-pass, delay 2h removed
+    const int h = RoundHalfAway(afs / boundary[b] / 2.0), M = 4 * h;
+    std::vector<double> w(M);
+    for (int i = 0; i < M; ++i) {
+      const double u = i / (M - 1.0);
+      w[i] = 0.355768 - 0.487396 * cos(2.0 * kPi * u) + 0.144232 * cos(4.0 * kPi * u) - 0.012604 * cos(6.0 * kPi * u);
+    }
+    for (int i = 0; i < ylen; ++i) {
+      double acc = 0.0;
+      for (int k = 0; k < M; ++k) { const int m = i + 2 * h - k; if (m >= -c && m < ylen + c) acc += w[k] * s[m + c]; }
+      filt[i] = acc;
+    }
+    // GetFourZeroCrossingIntervals (:410-444): crossings of s, -s, and of the two signs of the difference
+    int cnt[4];
+    cnt[0] = CrossingIntervals(filt, ylen, afs, &loc[0], &itv[0]);
+    work.assign(filt.begin(), filt.end());
+    for (int i = 0; i < ylen; ++i) work[i] = -work[i];
+    cnt[1] = CrossingIntervals(work, ylen, afs, &loc[1], &itv[1]);
+    for (int i = 0; i + 1 < ylen; ++i) work[i] = work[i] - work[i + 1];
+    cnt[2] = CrossingIntervals(work, ylen - 1, afs, &loc[2], &itv[2]);
+    for (int i = 0; i + 1 < ylen; ++i) work[i] = -work[i];
+    cnt[3] = CrossingIntervals(work, ylen - 1, afs, &loc[3], &itv[3]);
+    // GetF0CandidateContour (:483-523) + the score normalisation of :562-567
+    const bool usable = cnt[0] > 2 && cnt[1] > 2 && cnt[2] > 2 && cnt[3] > 2;
+    if (usable) for (int q = 0; q < 4; ++q) Interp1Vec(loc[q], itv[q], t, L, &yi[q]);
+    for (int i = 0; i < L; ++i) {
+      double f = 0.0, sc = 100000.0;                                                   // kMaximumValue (constantnumbers.h)
+      if (usable) {
+        f = (yi[0][i] + yi[1][i] + yi[2][i] + yi[3][i]) / 4.0;
+        sc = sqrt(((yi[0][i] - f) * (yi[0][i] - f) + (yi[1][i] - f) * (yi[1][i] - f) +
+                   (yi[2][i] - f) * (yi[2][i] - f) + (yi[3][i] - f) * (yi[3][i] - f)) / 3.0);
+        if (f > boundary[b] || f < boundary[b] / 2.0 || f > o->f0_ceil || f < o->f0_floor) { f = 0.0; sc = 100000.0; }
+      }
+      cand[b][i] = f;
+      score[b][i] = sc / (f + kTiny);
+    }
+  }
+  // GetBestF0Contour (:112-126)
+  std::vector<double> best(L);
+  for (int i = 0; i < L; ++i) {
+    double sc = score[0][i];
+    best[i] = cand[0][i];
+    for (int b = 1; b < nb; ++b) if (sc > score[b][i]) { sc = score[b][i]; best[i] = cand[b][i]; }
+  }
+  // FixF0Contour (:264-289): when the contour is too short the reference leaves f0 untouched; zeros here
+  const int vrm = (int)(0.5 + 1000.0 / o->frame_period / o->f0_floor) * 2 + 1;
+  for (int i = 0; i < L; ++i) f0[i] = 0.0;
+  if (L <= vrm) return;
+  std::vector<double> base(L, 0.0), s1(L, 0.0), s2, s3, s4;
+  for (int i = vrm; i < L - vrm; ++i) base[i] = best[i];                              // FixStep1 (:132-151)
+  for (int i = vrm; i < L; ++i)
+    s1[i] = fabs((base[i] - base[i - 1]) / (kTiny + base[i])) < o->allowed_range ? base[i] : 0.0;
+  s2 = s1;                                                                            // FixStep2 (:157-171)
+  const int center = (vrm - 1) / 2;
+  for (int i = center; i < L - center; ++i)
+    for (int j = -center; j <= center; ++j)
+      if (s1[i + j] == 0) { s2[i] = 0.0; break; }
+  std::vector<int> rise, fall;                                                        // GetNumberOfVoicedSections (:176-187)
+  for (int i = 1; i < L; ++i) {
+    if (s2[i] == 0 && s2[i - 1] != 0) fall.push_back(i - 1);
+    else if (s2[i - 1] == 0 && s2[i] != 0) rise.push_back(i);
+  }
+  s3 = s2;                                                                            // FixStep3 (:222-238): extend forwards
+  for (size_t q = 0; q < fall.size(); ++q) {
+    const int limit = q + 1 == fall.size() ? L - 1 : fall[q + 1];
+    for (int j = fall[q]; j < limit; ++j) {
+      s3[j + 1] = DioSelect(s3[j], s3[j - 1], cand, j + 1, o->allowed_range);
+      if (s3[j + 1] == 0) break;
+    }
+  }
+  s4 = s3;                                                                            // FixStep4 (:244-260): extend backwards
+  for (int q = (int)rise.size() - 1; q >= 0; --q) {
+    const int limit = q == 0 ? 1 : rise[q - 1];
+    for (int j = rise[q]; j > limit; --j) {
+      s4[j - 1] = DioSelect(s4[j], s4[j + 1], cand, j - 1, o->allowed_range);
+      if (s4[j - 1] == 0) break;
+    }
+  }
+  for (int i = 0; i < L; ++i) f0[i] = s4[i];
+}
+
 }  // extern "C"
+
+// test hook: the restated decimate() on its own (matlabfunctions.cpp:178-204)
+extern "C" int OracleDecimate(const double *x, int n, int r, double *y) {
+  std::vector<double> out;
+  Decimate(x, n, r, &out);
+  for (size_t i = 0; i < out.size(); ++i) y[i] = out[i];
+  return (int)out.size();
+}

@@ -39,11 +39,13 @@ class RefWorld:
         L.GetFFTSizeForCheapTrick.restype = C.c_int
         L.GetF0FloorForCheapTrick.restype = C.c_double
         L.GetF0FloorForCheapTrick.argtypes = [C.c_int, C.c_int]
-        self.has_f0 = hasattr(L, "Dio") and hasattr(L, "Harvest")  # the CPU restatement has no Dio/Harvest
-        if self.has_f0:
+        self.has_dio, self.has_harvest = hasattr(L, "Dio"), hasattr(L, "Harvest")  # the restatement has no Harvest
+        self.has_f0 = self.has_dio and self.has_harvest
+        if self.has_dio:
             L.Dio.argtypes = [_P, C.c_int, C.c_int, C.POINTER(DioOption), _P, _P]
-            L.Harvest.argtypes = [_P, C.c_int, C.c_int, C.POINTER(HarvestOption), _P, _P]
             L.Dio.restype = None
+        if self.has_harvest:
+            L.Harvest.argtypes = [_P, C.c_int, C.c_int, C.POINTER(HarvestOption), _P, _P]
             L.Harvest.restype = None
         L.StoneMask.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]
         L.CheapTrick.argtypes = [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.POINTER(CheapTrickOption), _P]

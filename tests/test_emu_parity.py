@@ -2,6 +2,9 @@
 (tests/emu) against the golden vectors and the compiled reference.  This is not the product
 path (that is tests/test_gpu_parity.py, -m gpu); it exists so that arithmetic mistakes are caught
 in the GPU-less build container."""
+import os
+import subprocess
+
 import numpy as np
 import pytest
 
@@ -101,3 +104,26 @@ def test_emu_ingest(emu, ref, golden, tmp_path):
 
 def test_emu_analyze_coded_host(emu, golden):
     pc.check_analyze_coded(emu, golden)
+
+
+def test_emu_host_pipeline_chunking(emu, golden):
+    pc.check_host_pipeline_chunking(emu, golden)
+
+
+def test_emu_dio_agrees_with_port(emu):
+    """Two independent time-domain implementations of Dio (the kernel sources and oracle/world_oracle.cpp)
+    agree to rounding, also where both sit 1e-9 from the reference's FFT-based filtering (decimation)."""
+    from refworld import RefWorld, ORACLE_LIB, rel_err
+    from synth import synth_batch
+    subprocess.check_call(["make", "-s", "-C", os.path.join(pc.os.path.dirname(pc.os.path.dirname(pc.os.path.abspath(pc.__file__))), "oracle"),
+                           "libworld_oracle.so"])
+    port = RefWorld(ORACLE_LIB)
+    for fs, n, seed, speed in ((16000, 16000, 71, 1), (44100, 22050, 72, 11), (48000, 24000, 73, 4)):
+        x = synth_batch([seed], fs, n).numpy()
+        po = port.dio_option(); po.speed = speed
+        eo = emu.dio_option(); eo.speed = speed
+        tp, fp = port.dio(x[0], fs, po)
+        te, fe, fl = emu.dio(x, fs, eo)
+        emu.synchronize()
+        assert np.array_equal(te[0], tp)
+        assert rel_err(fe[0], fp).max() < 1e-12

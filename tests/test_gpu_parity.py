@@ -177,3 +177,9 @@ def test_gpu_legacy_codec(gpu_world, ref, golden):
     pc.assert_close_signed(cap, golden["coded_ap"], "legacy CodeAperiodicity")
     pc.assert_close(dsp[::4], golden["decoded_sp_rows"], "legacy DecodeSpectralEnvelope")
     pc.assert_close(dap[::4], golden["decoded_ap_rows"], "legacy DecodeAperiodicity")
+
+
+def test_gpu_host_pipeline_chunking(gpu_world, golden):
+    from world_b200 import api
+    pc.check_host_pipeline_chunking(gpu_world, golden, api.F0_DIO_STONEMASK)
+    pc.check_host_pipeline_chunking(gpu_world, golden, api.F0_HARVEST)

@@ -371,3 +371,35 @@ def check_analyze_coded(world, golden, f0_method=0):
     xd = rows.astype(np.float64) / 32768.0
     t2, f02, csp2, cap2, _ = world.analyze_coded_host(xd, 0, fs, opt, dims, x_lengths=lens)
     assert np.array_equal(csp2, csp) and np.array_equal(cap2, cap) and np.array_equal(f02, f0)
+
+
+def check_host_pipeline_chunking(world, golden, f0_method=0):
+    """analyze_host / analyze_coded_host with tiny outer / sub chunks (several outer chunks, ring slots
+    reused, ragged last chunks) must give exactly what one big chunk gives."""
+    pcm16 = np.ascontiguousarray(golden["pcm"])
+    fs, dims = int(golden["fs"]), 24
+    n, keep = 7, 6000
+    rows = np.zeros((n, keep), dtype=np.int16)
+    lens = [keep - 311 * u for u in range(n)]
+    for u in range(n):
+        rows[u, :lens[u]] = pcm16[2000 + 97 * u: 2000 + 97 * u + lens[u]]
+    xd = rows.astype(np.float64) / 32768.0
+    opt = world.analysis_option(fs, f0_method)
+    saved = {k: os.environ.get(k) for k in ("WB_HOST_SUB", "WB_HOST_CHUNK")}
+    try:
+        os.environ.pop("WB_HOST_SUB", None); os.environ.pop("WB_HOST_CHUNK", None)
+        want_raw = world.analyze_host(xd, fs, opt, x_lengths=lens)
+        want_cod = world.analyze_coded_host(rows, 16, fs, opt, dims, x_lengths=lens)
+        for sub, outer in ((1, 2), (2, 4), (3, 3)):
+            os.environ["WB_HOST_SUB"], os.environ["WB_HOST_CHUNK"] = str(sub), str(outer)
+            got_raw = world.analyze_host(xd, fs, opt, x_lengths=lens)
+            got_cod = world.analyze_coded_host(rows, 16, fs, opt, dims, x_lengths=lens)
+            for a, b in zip(got_raw[:4] + got_cod[:4], want_raw[:4] + want_cod[:4]):
+                assert np.array_equal(a, b), (sub, outer)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert (want_raw[1] > 0).any() and np.isfinite(want_raw[2]).all()

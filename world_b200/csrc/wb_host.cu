@@ -38,6 +38,14 @@ namespace {
 // One pipeline for both host entry points.  nbit == 0: x holds doubles; otherwise little-endian PCM that
 // is widened on the device (row f3).  dims == 0: the full spectrogram / aperiodicity rows go back to the
 // host; dims > 0: they stay on the device and only their coded rows (row f2) are downloaded.
+//
+// Two granularities.  The F0 stage runs on OUTER chunks (default 256 utterances): its per-utterance
+// kernels (contour tracking, smoothing, decimation) are latency bound -- one launch costs the same
+// for 96 or 500 utterances -- so few large launches beat many small ones.  CheapTrick / D4C (/ codec) run
+// on SUB-chunks (default 64 utterances) whose rows start their trip over PCIe as soon as they exist: the
+// un-overlapped tail is one sub-chunk.  Result buffers form a ring two outer chunks deep, so downloads
+// may lag behind the frame kernels and catch up under the next outer chunk's F0 stage.  Streams: s_in
+// (uploads), the context's stream (all kernels), s_out (downloads); events order buffer reuse.
 int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_stride, const int *x_lengths, int fs,
                      const WorldB200AnalysisOption *opt, int dims, double *time_axis, double *f0, int f0_stride,
                      double *out_sp, double *out_ap) {
@@ -48,15 +56,29 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
   const size_t sp_row = dims ? (size_t)dims : (size_t)bins, ap_row = dims ? (size_t)n_ap : (size_t)bins;
   const double frame_period =
       opt->f0_method == WORLD_B200_F0_HARVEST ? opt->harvest.frame_period : opt->dio.frame_period;
-  // chunk so that two sets of device buffers (double buffering) stay within ~1/3 of the budget
-  const size_t per_utt = (size_t)x_stride * (8 + (nbit ? in_bytes : 0)) +
-                         (size_t)f0_stride * (16 + 2 * (size_t)bins * 8 + (dims ? (sp_row + ap_row) * 8 : 0));
-  int chunk = (int)dmax(1.0, dmin((double)n_utts, (double)(ctx->scratch_budget / 3) / (double)(2 * per_utt)));
-  // small chunks keep the un-overlapped tail (download of the last chunk) short; 96 utterances still
-  // fill the GPU (the per-utterance kernels see 96 CTAs, the frame kernels ~200 k)
-  int cap = 96;
-  if (const char *e = getenv("WB_HOST_CHUNK")) cap = atoi(e) > 0 ? atoi(e) : cap;
-  if (chunk > cap) chunk = cap;
+  const bool want_sp = out_sp != nullptr, want_ap = out_ap != nullptr && (!dims || n_ap > 0);
+  if (n_utts == 0) return 0;
+
+  int sub = 64, outer = 256;
+  if (const char *e = getenv("WB_HOST_SUB")) sub = atoi(e) > 0 ? atoi(e) : sub;
+  if (const char *e = getenv("WB_HOST_CHUNK")) outer = atoi(e) > 0 ? atoi(e) : outer;
+  sub = imin(sub, n_utts);
+  // a third of the scratch budget for this pipeline's own buffers: two outer sets + the result ring
+  const size_t third = ctx->scratch_budget / 3;
+  const size_t per_outer = (size_t)x_stride * (in_bytes + (nbit ? 8 : 0)) + (size_t)f0_stride * 16;
+  const size_t per_sub_out = (size_t)f0_stride * ((want_sp ? sp_row : 0) + (want_ap ? ap_row : 0)) * 8;
+  const size_t per_sub_raw = (size_t)f0_stride * ((want_sp ? bins : 0) + (want_ap ? bins : 0)) * 8;
+  outer = imin(outer, (int)dmax((double)sub, (double)(third / 3) / (double)(2 * per_outer)));
+  outer = imax(sub, outer / sub * sub);
+  outer = imin(outer, (n_utts + sub - 1) / sub * sub);
+  const int subs_per_outer = outer / sub;
+  const double ring_budget = (double)third - (double)imin(n_utts, outer) * 2.0 * (double)per_outer -
+                             (dims ? (double)sub * (double)per_sub_raw : 0.0);
+  int ring = 2 * subs_per_outer;
+  if (per_sub_out > 0)
+    ring = imax(2, imin(ring, (int)dmax(0.0, ring_budget / ((double)sub * (double)per_sub_out))));
+  ring = imin(ring, (n_utts + sub - 1) / sub);
+  if (ring < 1) ring = 1;
 
 #ifndef WB_EMU
   cudaStream_t s_compute = ctx->stream, s_in = nullptr, s_out = nullptr;
@@ -65,45 +87,57 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
     ctx->last_error = "cudaStreamCreate failed";
     return WORLD_B200_ECUDA;
   }
-  cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
+  cudaEvent_t ev_in[2], ev_cdone[2], ev_f0[2], ev_tf[2];
   for (int i = 0; i < 2; ++i) {
     cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_cdone[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_f0[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_tf[i], cudaEventDisableTiming);
+  }
+  std::vector<cudaEvent_t> ev_sub_done(ring), ev_sub_out(ring);
+  for (int i = 0; i < ring; ++i) {
+    cudaEventCreateWithFlags(&ev_sub_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_sub_out[i], cudaEventDisableTiming);
   }
 #endif
-  DevBuf din[2], dx[2], dt[2], df[2], dsp[2], dap[2], dcs[2], dca[2];
+  DevBuf din[2], dx[2], dt[2], df[2];
+  const int raw_slots = dims ? 1 : ring;   // coded mode: the full rows are consumed on the same stream
+  std::vector<DevBuf> dsp(raw_slots), dap(raw_slots), dcs(dims ? ring : 0), dca(dims ? ring : 0);
   int rc = 0;
-  for (int i = 0; i < 2 && !rc; ++i) {
-    rc = ensure(ctx, &din[i], (size_t)chunk * x_stride * in_bytes);
-    if (!rc && nbit) rc = ensure(ctx, &dx[i], (size_t)chunk * x_stride * 8);
-    if (!rc) rc = ensure(ctx, &dt[i], (size_t)chunk * f0_stride * 8);
-    if (!rc) rc = ensure(ctx, &df[i], (size_t)chunk * f0_stride * 8);
-    if (!rc && out_sp) rc = ensure(ctx, &dsp[i], (size_t)chunk * f0_stride * bins * 8);
-    if (!rc && out_ap) rc = ensure(ctx, &dap[i], (size_t)chunk * f0_stride * bins * 8);
-    if (!rc && dims && out_sp) rc = ensure(ctx, &dcs[i], (size_t)chunk * f0_stride * sp_row * 8);
-    if (!rc && dims && out_ap && n_ap > 0) rc = ensure(ctx, &dca[i], (size_t)chunk * f0_stride * ap_row * 8);
+  const int n_outer_bufs = n_utts > outer ? 2 : 1;
+  for (int i = 0; i < n_outer_bufs && !rc; ++i) {
+    rc = ensure(ctx, &din[i], (size_t)outer * x_stride * in_bytes);
+    if (!rc && nbit) rc = ensure(ctx, &dx[i], (size_t)outer * x_stride * 8);
+    if (!rc) rc = ensure(ctx, &dt[i], (size_t)outer * f0_stride * 8);
+    if (!rc) rc = ensure(ctx, &df[i], (size_t)outer * f0_stride * 8);
   }
-  std::vector<int> flen(n_utts > 0 ? n_utts : 1);
+  for (int i = 0; i < raw_slots && !rc; ++i) {
+    if (want_sp) rc = ensure(ctx, &dsp[i], (size_t)sub * f0_stride * bins * 8);
+    if (!rc && want_ap) rc = ensure(ctx, &dap[i], (size_t)sub * f0_stride * bins * 8);
+  }
+  for (int i = 0; i < (dims ? ring : 0) && !rc; ++i) {
+    if (want_sp) rc = ensure(ctx, &dcs[i], (size_t)sub * f0_stride * sp_row * 8);
+    if (!rc && want_ap) rc = ensure(ctx, &dca[i], (size_t)sub * f0_stride * ap_row * 8);
+  }
+  std::vector<int> flen(n_utts);
   for (int i = 0; i < n_utts && !rc; ++i) {
     flen[i] = world_b200_frames(fs, x_lengths ? x_lengths[i] : x_stride, frame_period);
     if (flen[i] > f0_stride) { ctx->last_error = "f0_stride too small"; rc = WORLD_B200_EINVAL; }
   }
-  int it = 0;
-  for (int u0 = 0; u0 < n_utts && !rc; u0 += chunk, ++it) {
-    const int n = imin(chunk, n_utts - u0);
+  int it = 0, g = 0;   // outer chunk counter, global sub-chunk counter
+  for (int u0 = 0; u0 < n_utts && !rc; u0 += outer, ++it) {
+    const int n = imin(outer, n_utts - u0);
     const int s = it & 1;
     const int *xl = x_lengths ? x_lengths + u0 : nullptr;
     const int *fl = flen.data() + u0;
     const size_t fsz = (size_t)n * f0_stride;
     const unsigned char *src = (const unsigned char *)x + (size_t)u0 * x_stride * in_bytes;
 #ifndef WB_EMU
-    // buffers of slot s are free once the download issued two iterations ago has finished
-    if (it >= 2) cudaStreamWaitEvent(s_in, ev_out[s], 0);
+    if (it >= 2) cudaStreamWaitEvent(s_in, ev_cdone[s], 0);   // kernels of outer chunk it-2 read din[s] / dx[s]
     cudaMemcpyAsync(din[s].p, src, (size_t)n * x_stride * in_bytes, cudaMemcpyHostToDevice, s_in);
     cudaEventRecord(ev_in[s], s_in);
     cudaStreamWaitEvent(s_compute, ev_in[s], 0);
-    if (it >= 2) cudaStreamWaitEvent(s_compute, ev_out[s], 0);
+    if (it >= 2) cudaStreamWaitEvent(s_compute, ev_tf[s], 0);  // time_axis / f0 of it-2 are on the host
 #else
     memcpy(din[s].p, src, (size_t)n * x_stride * in_bytes);
 #endif
@@ -111,15 +145,6 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
     if (rc) break;
     dev_memset(ctx, dt[s].p, 0, fsz * 8);
     dev_memset(ctx, df[s].p, 0, fsz * 8);
-    // whole padded rows are downloaded: frames beyond an utterance's length read as zero on the host
-    bool ragged = false;
-    for (int i = 0; i < n; ++i) ragged = ragged || fl[i] != f0_stride;
-    if (ragged) {
-      if (!dims && out_sp) dev_memset(ctx, dsp[s].p, 0, fsz * bins * 8);
-      if (!dims && out_ap) dev_memset(ctx, dap[s].p, 0, fsz * bins * 8);
-      if (dims && out_sp) dev_memset(ctx, dcs[s].p, 0, fsz * sp_row * 8);
-      if (dims && out_ap && n_ap > 0) dev_memset(ctx, dca[s].p, 0, fsz * ap_row * 8);
-    }
     const double *xd = (const double *)(nbit ? dx[s].p : din[s].p);
     double *td = (double *)dt[s].p, *fd = (double *)df[s].p;
     if (opt->f0_method == WORLD_B200_F0_HARVEST) {
@@ -128,43 +153,74 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
       rc = world_b200_dio_batch(h, xd, n, x_stride, xl, fs, &opt->dio, td, fd, f0_stride);
       if (!rc) rc = world_b200_stonemask_batch(h, xd, n, x_stride, xl, fs, td, fd, fl, f0_stride, fd);
     }
-    if (!rc && out_sp)
-      rc = world_b200_cheaptrick_batch(h, xd, n, x_stride, xl, fs, td, fd, fl, f0_stride, &opt->cheaptrick,
-                                       (double *)dsp[s].p);
-    if (!rc && out_ap)
-      rc = world_b200_d4c_batch(h, xd, n, x_stride, xl, fs, td, fd, fl, f0_stride, opt->cheaptrick.fft_size,
-                                &opt->d4c, (double *)dap[s].p);
-    if (!rc && dims && out_sp)
-      rc = world_b200_code_spectral_envelope_batch(h, (const double *)dsp[s].p, n, fl, f0_stride, fs,
-                                                   opt->cheaptrick.fft_size, dims, (double *)dcs[s].p);
-    if (!rc && dims && out_ap && n_ap > 0)
-      rc = world_b200_code_aperiodicity_batch(h, (const double *)dap[s].p, n, fl, f0_stride, fs,
-                                              opt->cheaptrick.fft_size, (double *)dca[s].p);
     if (rc) break;
-    const void *sp_src = dims ? dcs[s].p : dsp[s].p, *ap_src = dims ? dca[s].p : dap[s].p;
-    const bool get_ap = out_ap && (!dims || n_ap > 0);
 #ifndef WB_EMU
-    cudaEventRecord(ev_done[s], s_compute);
-    cudaStreamWaitEvent(s_out, ev_done[s], 0);
+    cudaEventRecord(ev_f0[s], s_compute);
+    cudaStreamWaitEvent(s_out, ev_f0[s], 0);
     if (time_axis) cudaMemcpyAsync(time_axis + (size_t)u0 * f0_stride, td, fsz * 8, cudaMemcpyDeviceToHost, s_out);
     if (f0) cudaMemcpyAsync(f0 + (size_t)u0 * f0_stride, fd, fsz * 8, cudaMemcpyDeviceToHost, s_out);
-    if (out_sp)
-      cudaMemcpyAsync(out_sp + (size_t)u0 * f0_stride * sp_row, sp_src, fsz * sp_row * 8, cudaMemcpyDeviceToHost, s_out);
-    if (get_ap)
-      cudaMemcpyAsync(out_ap + (size_t)u0 * f0_stride * ap_row, ap_src, fsz * ap_row * 8, cudaMemcpyDeviceToHost, s_out);
-    cudaEventRecord(ev_out[s], s_out);
+    cudaEventRecord(ev_tf[s], s_out);
 #else
     if (time_axis) memcpy(time_axis + (size_t)u0 * f0_stride, td, fsz * 8);
     if (f0) memcpy(f0 + (size_t)u0 * f0_stride, fd, fsz * 8);
-    if (out_sp) memcpy(out_sp + (size_t)u0 * f0_stride * sp_row, sp_src, fsz * sp_row * 8);
-    if (get_ap) memcpy(out_ap + (size_t)u0 * f0_stride * ap_row, ap_src, fsz * ap_row * 8);
+#endif
+    for (int v0 = 0; v0 < n && !rc && (want_sp || want_ap); v0 += sub, ++g) {
+      const int m = imin(sub, n - v0);
+      const int slot = g % ring, rslot = dims ? 0 : slot;
+      const int *sxl = xl ? xl + v0 : nullptr;
+      const int *sfl = fl + v0;
+      const size_t ssz = (size_t)m * f0_stride;
+      const double *sx = xd + (size_t)v0 * x_stride, *st = td + (size_t)v0 * f0_stride, *sf = fd + (size_t)v0 * f0_stride;
+#ifndef WB_EMU
+      if (g >= ring) cudaStreamWaitEvent(s_compute, ev_sub_out[slot], 0);   // the slot's previous rows are on the host
+#endif
+      // whole padded rows are downloaded: frames beyond an utterance's length read as zero on the host
+      bool ragged = false;
+      for (int i = 0; i < m; ++i) ragged = ragged || sfl[i] != f0_stride;
+      if (ragged) {
+        if (!dims && want_sp) dev_memset(ctx, dsp[rslot].p, 0, ssz * bins * 8);
+        if (!dims && want_ap) dev_memset(ctx, dap[rslot].p, 0, ssz * bins * 8);
+        if (dims && want_sp) dev_memset(ctx, dcs[slot].p, 0, ssz * sp_row * 8);
+        if (dims && want_ap) dev_memset(ctx, dca[slot].p, 0, ssz * ap_row * 8);
+      }
+      if (want_sp)
+        rc = world_b200_cheaptrick_batch(h, sx, m, x_stride, sxl, fs, st, sf, sfl, f0_stride, &opt->cheaptrick,
+                                         (double *)dsp[rslot].p);
+      if (!rc && want_ap)
+        rc = world_b200_d4c_batch(h, sx, m, x_stride, sxl, fs, st, sf, sfl, f0_stride, opt->cheaptrick.fft_size,
+                                  &opt->d4c, (double *)dap[rslot].p);
+      if (!rc && dims && want_sp)
+        rc = world_b200_code_spectral_envelope_batch(h, (const double *)dsp[0].p, m, sfl, f0_stride, fs,
+                                                     opt->cheaptrick.fft_size, dims, (double *)dcs[slot].p);
+      if (!rc && dims && want_ap)
+        rc = world_b200_code_aperiodicity_batch(h, (const double *)dap[0].p, m, sfl, f0_stride, fs,
+                                                opt->cheaptrick.fft_size, (double *)dca[slot].p);
+      if (rc) break;
+      const void *sp_src = dims ? dcs[slot].p : dsp[rslot].p, *ap_src = dims ? dca[slot].p : dap[rslot].p;
+      const size_t row0 = (size_t)(u0 + v0) * f0_stride;
+#ifndef WB_EMU
+      cudaEventRecord(ev_sub_done[slot], s_compute);
+      cudaStreamWaitEvent(s_out, ev_sub_done[slot], 0);
+      if (want_sp) cudaMemcpyAsync(out_sp + row0 * sp_row, sp_src, ssz * sp_row * 8, cudaMemcpyDeviceToHost, s_out);
+      if (want_ap) cudaMemcpyAsync(out_ap + row0 * ap_row, ap_src, ssz * ap_row * 8, cudaMemcpyDeviceToHost, s_out);
+      cudaEventRecord(ev_sub_out[slot], s_out);
+#else
+      if (want_sp) memcpy(out_sp + row0 * sp_row, sp_src, ssz * sp_row * 8);
+      if (want_ap) memcpy(out_ap + row0 * ap_row, ap_src, ssz * ap_row * 8);
+#endif
+    }
+#ifndef WB_EMU
+    cudaEventRecord(ev_cdone[s], s_compute);
 #endif
   }
 #ifndef WB_EMU
   cudaStreamSynchronize(s_in);
   cudaStreamSynchronize(s_compute);
   cudaStreamSynchronize(s_out);
-  for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_done[i]); cudaEventDestroy(ev_out[i]); }
+  for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_cdone[i]); cudaEventDestroy(ev_f0[i]); cudaEventDestroy(ev_tf[i]);
+  }
+  for (int i = 0; i < ring; ++i) { cudaEventDestroy(ev_sub_done[i]); cudaEventDestroy(ev_sub_out[i]); }
   cudaStreamDestroy(s_in);
   cudaStreamDestroy(s_out);
   if (!rc) {
@@ -172,10 +228,11 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
     if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); rc = WORLD_B200_ECUDA; }
   }
 #endif
-  for (int i = 0; i < 2; ++i) {
-    dev_free(din[i].p); dev_free(dx[i].p); dev_free(dt[i].p); dev_free(df[i].p);
-    dev_free(dsp[i].p); dev_free(dap[i].p); dev_free(dcs[i].p); dev_free(dca[i].p);
-  }
+  for (int i = 0; i < 2; ++i) { dev_free(din[i].p); dev_free(dx[i].p); dev_free(dt[i].p); dev_free(df[i].p); }
+  for (auto &b : dsp) dev_free(b.p);
+  for (auto &b : dap) dev_free(b.p);
+  for (auto &b : dcs) dev_free(b.p);
+  for (auto &b : dca) dev_free(b.p);
   if (!rc) rc = world_b200_synchronize(h);
   return rc;
 }
