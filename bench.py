@@ -259,7 +259,7 @@ def main():
     reserve = torch.empty(int(a.reserve_gb * (1 << 30)), dtype=torch.uint8, device=dev) if a.reserve_gb > 0 else None
     # scratch budget follows what is left after the (possibly gathered) outputs are resident
     free_now, _ = torch.cuda.mem_get_info(dev)
-    budget = int(min(24 << 30, max(2 << 30, free_now * 0.45)))
+    budget = int(min(96 << 30, max(2 << 30, free_now * 0.45)))
     w.set_scratch_budget(budget)
 
     # Two contexts on two streams: the F0 estimator of slice s+1 (FP64 bound) runs concurrently with

@@ -53,7 +53,8 @@ void world_b200_destroy(WorldB200 *ctx);
 /* cuda_stream is a cudaStream_t; NULL selects the default stream. */
 int world_b200_set_stream(WorldB200 *ctx, void *cuda_stream);
 /* Upper bound (bytes) of internal scratch one stage call may hold; batches are processed in
- * utterance chunks that fit it.  Default 24 GiB. */
+ * utterance chunks that fit it.  Default: a third of the memory free at creation, clamped to
+ * [4, 64] GiB. */
 int world_b200_set_scratch_budget(WorldB200 *ctx, unsigned long long bytes);
 int world_b200_synchronize(WorldB200 *ctx);
 const char *world_b200_last_error(const WorldB200 *ctx);

@@ -231,6 +231,15 @@ int world_b200_create(int device, WorldB200 **out) {
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return WORLD_B200_ECUDA; }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->c.sm_count = prop.multiProcessorCount;
+  // default scratch budget: a third of what is free now, between 4 and 64 GiB (a B200 has 180 GB; the
+  // larger the passes, the fewer launches of the latency-bound per-utterance kernels)
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+    size_t want = free_b / 3;
+    if (want > ((size_t)64 << 30)) want = (size_t)64 << 30;
+    if (want < ((size_t)4 << 30)) want = (size_t)4 << 30;
+    h->c.scratch_budget = want;
+  }
 #endif
   int rc = ctx_init_tables(&h->c);
   if (rc) {

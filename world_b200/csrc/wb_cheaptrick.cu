@@ -170,7 +170,7 @@ int cheaptrick_run(Ctx *ctx, const Batch &b, double q1, int fft_size, double *sp
   const size_t draw_stride_full = max_per_frame * (size_t)b.max_f_len;
   // utterances per chunk so that the draw scratch fits the budget
   const size_t per_utt_bytes = draw_stride_full * 4 + (size_t)b.f_stride * 8 + 64;
-  int chunk = (int)imin(b.n, (int)dmax(1.0, (double)ctx->scratch_budget / (double)per_utt_bytes));
+  int chunk = balanced_chunk(b.n, (int)dmin(1e9, (double)ctx->scratch_budget / (double)per_utt_bytes));
   const size_t smem = (size_t)(2 * (fft_size + 2) + WB_RED_DOUBLES) * sizeof(double);
 #ifndef WB_EMU
   static size_t smem_set = 0;

@@ -374,7 +374,7 @@ int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *ap
   const size_t max_b = 3 * (size_t)(2 * round_half_away(4.0 * fs / 47.0 / 2.0) + 1);
   const size_t draw_stride_full = (max_a + max_b) * (size_t)b.max_f_len;
   const size_t per_utt_bytes = draw_stride_full * 4 + (size_t)b.f_stride * 24 + 64;
-  int chunk = (int)imin(imin(b.n, 65535), (int)dmax(1.0, (double)ctx->scratch_budget / (double)per_utt_bytes));
+  int chunk = balanced_chunk(imin(b.n, 65535), (int)dmin(65535.0, (double)ctx->scratch_budget / (double)per_utt_bytes));
   int body_threads = 128, lt_threads = 128;  // r1d sweep: 128-thread CTAs (4 per SM) beat 256 by 18 %
   if (const char *e = getenv("WB_D4C_THREADS")) body_threads = atoi(e);
   if (const char *e = getenv("WB_LT_THREADS")) lt_threads = atoi(e);

@@ -207,7 +207,7 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
   const size_t tmp_stride = ratio != 1 ? (size_t)b.max_x_len + 32 : 0;
   const size_t per_utt = y_stride * 16 + edge_stride * 8 + (size_t)nb * fstr * 16 +
                          (size_t)fstr * (4 * 8 + 2 * 4) + tmp_stride * 16 + 256;
-  int chunk = (int)imin(imin(b.n, 65535), (int)dmax(1.0, (double)ctx->scratch_budget / (double)per_utt));
+  int chunk = balanced_chunk(imin(b.n, 65535), (int)dmin(65535.0, (double)ctx->scratch_budget / (double)per_utt));
 #ifndef WB_EMU
 #endif
   for (int u0 = 0; u0 < b.n; u0 += chunk) {

@@ -729,7 +729,7 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
                          (size_t)l1_stride * (WB_HV_BASE * 8 + 4) + (size_t)l1_stride * max_cand * 8 * 4 +
                          (size_t)l1_stride * (5 * 8 + 6 * 4 + 8) + mc_stride * 8 + pad_stride * (8 + 4) + (size_t)sec_slots * seg_cap * 8 +
                          tmp_stride * 16 + 1024;
-  int chunk = (int)imin(imin(b.n, 65535), (int)dmax(1.0, (double)ctx->scratch_budget / (double)per_utt));
+  int chunk = balanced_chunk(imin(b.n, 65535), (int)dmin(65535.0, (double)ctx->scratch_budget / (double)per_utt));
 #ifndef WB_EMU
   cudaFuncSetAttribute(harvest_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_refine);
 #endif

@@ -33,6 +33,14 @@ struct Ctx {
 // memory helpers (wb_api.cu / emu)
 int ctx_init_tables(Ctx *ctx);
 unsigned char *arena_block(Ctx *ctx, size_t bytes);  // nullptr + last_error on failure
+// Utterances per pass when `fit` fit the scratch budget: as few passes as possible, evenly sized
+// (per-utterance kernels cost one launch latency per pass whatever its size).
+inline int balanced_chunk(int n, int fit) {
+  if (fit < 1) fit = 1;
+  if (n <= fit) return n > 0 ? n : 1;
+  const int passes = (n + fit - 1) / fit;
+  return (n + passes - 1) / passes;
+}
 struct ArenaPlan {                                   // lay out 256-byte aligned sub-blocks
   size_t total = 0;
   size_t add(size_t bytes) { const size_t off = total; total += (bytes + 255) & ~(size_t)255; return off; }

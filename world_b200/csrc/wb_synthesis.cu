@@ -330,7 +330,7 @@ extern "C" int world_b200_synthesis_batch(WorldB200 *h, const double *f0, const 
   const size_t draw_stride = (size_t)max_y + 8;
   const size_t per_utt = (size_t)y_stride * 16 + (size_t)pulse_cap * (4 + 8 + 8) + (size_t)pulse_cap * fft_size * 8 +
                          draw_stride * 4 + 4096;
-  int chunk = (int)imin(imin(n_utts, 65535), (int)dmax(1.0, (double)ctx->scratch_budget / (double)per_utt));
+  int chunk = balanced_chunk(imin(n_utts, 65535), (int)dmin(65535.0, (double)ctx->scratch_budget / (double)per_utt));
   const int half = fft_size / 2;
   const size_t smem = (size_t)(2 * fft_size + 2 * (half + 2) + (fft_size + 2) + 2 * (half + 1) + fft_size + WB_RED_DOUBLES) * 8;
 #ifndef WB_EMU
