@@ -41,8 +41,9 @@ def main():
         w.analyze_coded_host(ph, 16, fs, ao, 60, time_axis=th, f0=fh, coded_sp=csh, coded_ap=cah, f0_stride=L)
 
     raw(); coded()
-    for outer, sub in ((256, 64), (512, 64), (1024, 64), (256, 32), (256, 128), (128, 64), (96, 96)):
+    for outer, sub in ((256, 64), (256, 128), (512, 128), (1024, 128), (96, 96)):
         os.environ["WB_HOST_CHUNK"], os.environ["WB_HOST_SUB"] = str(outer), str(sub)
+        w.trim()
         res = []
         for fn in (raw, coded):
             fn()
@@ -51,6 +52,12 @@ def main():
                 t0 = time.perf_counter(); fn(); ts.append((time.perf_counter() - t0) * 1e3)
             res.append(ts)
         print(f"outer {outer:5d} sub {sub:4d}  raw ms {res[0][0]:8.1f} {res[0][1]:8.1f}   coded ms {res[1][0]:8.1f} {res[1][1]:8.1f}", flush=True)
+    # one traced call each at the defaults
+    os.environ.pop("WB_HOST_CHUNK"); os.environ.pop("WB_HOST_SUB")
+    w.trim(); raw(); coded()
+    os.environ["WB_HOST_TRACE"] = "1"
+    sys.stderr.write("---- trace raw\n"); sys.stderr.flush(); raw()
+    sys.stderr.write("---- trace coded\n"); sys.stderr.flush(); coded()
 
 
 if __name__ == "__main__":

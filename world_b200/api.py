@@ -55,6 +55,7 @@ ABI = {
     "world_b200_set_stream": (C.c_int, [_P, _P]),
     "world_b200_set_scratch_budget": (C.c_int, [_P, C.c_ulonglong]),
     "world_b200_synchronize": (C.c_int, [_P]),
+    "world_b200_trim": (C.c_int, [_P]),
     "world_b200_last_error": (C.c_char_p, [_P]),
     "world_b200_launch_count": (C.c_ulonglong, [_P]),
     "world_b200_frames": (C.c_int, [C.c_int, C.c_int, C.c_double]),
@@ -193,6 +194,10 @@ class World:
 
     def synchronize(self):
         self._check(self.lib.world_b200_synchronize(self._h))
+
+    def trim(self):
+        """give back the device memory cached between calls"""
+        self._check(self.lib.world_b200_trim(self._h))
 
     def launch_count(self) -> int:
         return int(self.lib.world_b200_launch_count(self._h))

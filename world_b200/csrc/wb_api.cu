@@ -4,6 +4,7 @@
 #include "wb_internal.h"
 #include "../../include/world_b200.h"
 #include <stdio.h>
+#include <string.h>
 #include <vector>
 
 struct WorldB200 {
@@ -68,9 +69,43 @@ int dev_sync(Ctx *ctx) {
   return 0;
 }
 
+#ifndef WB_EMU
+// Region of `bytes` in the pinned staging ring (nullptr: too large, or no ring -- caller copies directly).
+static unsigned char *staging_take(Ctx *ctx, size_t bytes) {
+  Staging &st = ctx->staging;
+  if (!st.base) {
+    const size_t half = (size_t)8 << 20;
+    if (cudaHostAlloc((void **)&st.base, 2 * half, cudaHostAllocDefault) != cudaSuccess) { st.base = nullptr; cudaGetLastError(); return nullptr; }
+    st.half_bytes = half;
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      st.left_event[i] = e;
+    }
+  }
+  const size_t need = (bytes + 63) & ~(size_t)63;
+  if (need > st.half_bytes) return nullptr;
+  if (st.used + need > st.half_bytes) {
+    // leave this half: everything copied out of it so far is ordered before this event
+    cudaEventRecord((cudaEvent_t)st.left_event[st.half], ctx->stream);
+    st.pending[st.half] = true;
+    st.half ^= 1;
+    st.used = 0;
+    if (st.pending[st.half]) { cudaEventSynchronize((cudaEvent_t)st.left_event[st.half]); st.pending[st.half] = false; }
+  }
+  unsigned char *p = st.base + (size_t)st.half * st.half_bytes + st.used;
+  st.used += need;
+  return p;
+}
+#endif
+
 int dev_memcpy_h2d(Ctx *ctx, void *dst, const void *src, size_t bytes) {
   if (bytes == 0) return 0;
 #ifndef WB_EMU
+  if (unsigned char *stage = staging_take(ctx, bytes)) {
+    memcpy(stage, src, bytes);
+    src = stage;
+  }
   WB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream), "memcpy h2d");
 #else
   (void)ctx; memcpy(dst, src, bytes);
@@ -121,6 +156,41 @@ void dev_free(void *p) {
 #else
   free(p);
 #endif
+}
+
+void pool_trim(Ctx *ctx) {
+  std::vector<PoolBuf> keep;
+  for (auto &b : ctx->pool) {
+    if (b.busy) keep.push_back(b);
+    else dev_free(b.p);
+  }
+  ctx->pool.swap(keep);
+}
+
+void *pool_acquire(Ctx *ctx, size_t bytes) {
+  if (bytes == 0) bytes = 256;
+  int best = -1;
+  for (int i = 0; i < (int)ctx->pool.size(); ++i) {
+    const PoolBuf &b = ctx->pool[i];
+    if (b.busy || b.cap < bytes || b.cap > bytes + bytes / 2 + ((size_t)1 << 20)) continue;
+    if (best < 0 || b.cap < ctx->pool[best].cap) best = i;
+  }
+  if (best >= 0) { ctx->pool[best].busy = true; return ctx->pool[best].p; }
+  void *p = dev_malloc(ctx, bytes);
+  if (!p) {           // make room: drop what is idle and try once more
+    pool_trim(ctx);
+    p = dev_malloc(ctx, bytes);
+    if (!p) return nullptr;
+  }
+  ctx->pool.push_back(PoolBuf{p, bytes, true});
+  return p;
+}
+
+void pool_release(Ctx *ctx, void *p) {
+  if (!p) return;
+  for (auto &b : ctx->pool)
+    if (b.p == p) { b.busy = false; return; }
+  dev_free(p);
 }
 
 // One block of `bytes` device scratch, valid until the next arena_block() call on this
@@ -259,13 +329,34 @@ void world_b200_destroy(WorldB200 *h) {
   dev_free(h->c.status_dev);
   dev_free(h->c.arena.base);
   dev_free(h->lens_dev);
+  for (auto &b : h->c.pool) dev_free(b.p);
+#ifndef WB_EMU
+  if (h->c.staging.base) {
+    cudaFreeHost(h->c.staging.base);
+    for (int i = 0; i < 2; ++i) cudaEventDestroy((cudaEvent_t)h->c.staging.left_event[i]);
+  }
+#endif
   delete h;
 }
 
 int world_b200_set_stream(WorldB200 *h, void *stream) {
   if (!h) return WORLD_B200_EINVAL;
-  h->c.stream = (wb_stream_t)stream;
+  if (h->c.stream != (wb_stream_t)stream) {
+    // scratch arena and staging ring are reused in stream order: drain the old stream before switching
+    int rc = dev_sync(&h->c);
+    if (rc) return rc;
+    h->c.stream = (wb_stream_t)stream;
+  }
   return 0;
+}
+
+int world_b200_trim(WorldB200 *h) {
+  if (!h) return WORLD_B200_EINVAL;
+  int rc = dev_sync(&h->c);
+  pool_trim(&h->c);
+  dev_free(h->c.arena.base);
+  h->c.arena = Arena();
+  return rc;
 }
 
 int world_b200_set_scratch_budget(WorldB200 *h, unsigned long long bytes) {

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <vector>
 #include <mutex>
+#include <chrono>
 
 using namespace wb;
 
@@ -21,10 +22,10 @@ struct DevBuf {
   size_t cap = 0;
 };
 
-int ensure(Ctx *ctx, DevBuf *b, size_t bytes) {
+int ensure(Ctx *ctx, DevBuf *b, size_t bytes) {   // pooled: kept by the context between calls
   if (bytes <= b->cap) return 0;
-  dev_free(b->p);
-  b->p = dev_malloc(ctx, bytes);
+  pool_release(ctx, b->p);
+  b->p = pool_acquire(ctx, bytes);
   b->cap = b->p ? bytes : 0;
   return b->p ? 0 : WORLD_B200_ENOMEM;
 }
@@ -100,6 +101,27 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
     cudaEventCreateWithFlags(&ev_sub_out[i], cudaEventDisableTiming);
   }
 #endif
+  // WB_HOST_TRACE=1: timeline of this call on stderr (timing events on the three streams + host clock)
+  const bool trace = getenv("WB_HOST_TRACE") != nullptr;
+  struct Mark { const char *what; int idx; double host_ms; void *ev; };
+  std::vector<Mark> marks;
+  const auto t_host0 = std::chrono::steady_clock::now();
+  auto mark = [&](const char *what, int idx, void *stream) {
+    if (!trace) return;
+    Mark m{what, idx, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count(), nullptr};
+#ifndef WB_EMU
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, (cudaStream_t)stream);
+    m.ev = e;
+#else
+    (void)stream;
+#endif
+    marks.push_back(m);
+  };
+#ifndef WB_EMU
+  mark("start", 0, s_compute);
+#endif
   DevBuf din[2], dx[2], dt[2], df[2];
   const int raw_slots = dims ? 1 : ring;   // coded mode: the full rows are consumed on the same stream
   std::vector<DevBuf> dsp(raw_slots), dap(raw_slots), dcs(dims ? ring : 0), dca(dims ? ring : 0);
@@ -136,8 +158,10 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
     if (it >= 2) cudaStreamWaitEvent(s_in, ev_cdone[s], 0);   // kernels of outer chunk it-2 read din[s] / dx[s]
     cudaMemcpyAsync(din[s].p, src, (size_t)n * x_stride * in_bytes, cudaMemcpyHostToDevice, s_in);
     cudaEventRecord(ev_in[s], s_in);
+    mark("h2d_done", it, s_in);
     cudaStreamWaitEvent(s_compute, ev_in[s], 0);
     if (it >= 2) cudaStreamWaitEvent(s_compute, ev_tf[s], 0);  // time_axis / f0 of it-2 are on the host
+    mark("f0_begin", it, s_compute);
 #else
     memcpy(din[s].p, src, (size_t)n * x_stride * in_bytes);
 #endif
@@ -156,6 +180,7 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
     if (rc) break;
 #ifndef WB_EMU
     cudaEventRecord(ev_f0[s], s_compute);
+    mark("f0_end", it, s_compute);
     cudaStreamWaitEvent(s_out, ev_f0[s], 0);
     if (time_axis) cudaMemcpyAsync(time_axis + (size_t)u0 * f0_stride, td, fsz * 8, cudaMemcpyDeviceToHost, s_out);
     if (f0) cudaMemcpyAsync(f0 + (size_t)u0 * f0_stride, fd, fsz * 8, cudaMemcpyDeviceToHost, s_out);
@@ -200,10 +225,12 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
       const size_t row0 = (size_t)(u0 + v0) * f0_stride;
 #ifndef WB_EMU
       cudaEventRecord(ev_sub_done[slot], s_compute);
+      mark("sub_end", g, s_compute);
       cudaStreamWaitEvent(s_out, ev_sub_done[slot], 0);
       if (want_sp) cudaMemcpyAsync(out_sp + row0 * sp_row, sp_src, ssz * sp_row * 8, cudaMemcpyDeviceToHost, s_out);
       if (want_ap) cudaMemcpyAsync(out_ap + row0 * ap_row, ap_src, ssz * ap_row * 8, cudaMemcpyDeviceToHost, s_out);
       cudaEventRecord(ev_sub_out[slot], s_out);
+      mark("d2h_end", g, s_out);
 #else
       if (want_sp) memcpy(out_sp + row0 * sp_row, sp_src, ssz * sp_row * 8);
       if (want_ap) memcpy(out_ap + row0 * ap_row, ap_src, ssz * ap_row * 8);
@@ -214,9 +241,21 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
 #endif
   }
 #ifndef WB_EMU
+  const double issued_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
   cudaStreamSynchronize(s_in);
   cudaStreamSynchronize(s_compute);
   cudaStreamSynchronize(s_out);
+  if (trace && !marks.empty()) {
+    const double done_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+    fprintf(stderr, "[wb trace] outer %d sub %d ring %d n %d: all work issued at %.1f ms, finished at %.1f ms (host clock)\n",
+            outer, sub, ring, n_utts, issued_ms, done_ms);
+    for (size_t i = 1; i < marks.size(); ++i) {
+      float gpu_ms = 0.f;
+      cudaEventElapsedTime(&gpu_ms, (cudaEvent_t)marks[0].ev, (cudaEvent_t)marks[i].ev);
+      fprintf(stderr, "[wb trace] %-9s %3d  issued %8.1f  gpu %8.1f\n", marks[i].what, marks[i].idx, marks[i].host_ms, gpu_ms);
+    }
+    for (auto &m : marks) cudaEventDestroy((cudaEvent_t)m.ev);
+  }
   for (int i = 0; i < 2; ++i) {
     cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_cdone[i]); cudaEventDestroy(ev_f0[i]); cudaEventDestroy(ev_tf[i]);
   }
@@ -228,11 +267,11 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
     if (e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); rc = WORLD_B200_ECUDA; }
   }
 #endif
-  for (int i = 0; i < 2; ++i) { dev_free(din[i].p); dev_free(dx[i].p); dev_free(dt[i].p); dev_free(df[i].p); }
-  for (auto &b : dsp) dev_free(b.p);
-  for (auto &b : dap) dev_free(b.p);
-  for (auto &b : dcs) dev_free(b.p);
-  for (auto &b : dca) dev_free(b.p);
+  for (int i = 0; i < 2; ++i) { pool_release(ctx, din[i].p); pool_release(ctx, dx[i].p); pool_release(ctx, dt[i].p); pool_release(ctx, df[i].p); }
+  for (auto &b : dsp) pool_release(ctx, b.p);
+  for (auto &b : dap) pool_release(ctx, b.p);
+  for (auto &b : dcs) pool_release(ctx, b.p);
+  for (auto &b : dca) pool_release(ctx, b.p);
   if (!rc) rc = world_b200_synchronize(h);
   return rc;
 }

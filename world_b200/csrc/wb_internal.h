@@ -4,6 +4,7 @@
 #include "wb_block.cuh"
 #include "wb_fft.cuh"
 #include <string>
+#include <vector>
 
 #define WB_RNG_CHUNK 128   // draws produced by one rng_fill thread
 #define WB_RNG_NJ 24       // jump tables J_k = T^(12*128*2^k): reach 2^31 draws per utterance
@@ -18,12 +19,31 @@ struct Arena {
   size_t capacity = 0, used = 0;
 };
 
+// Pinned staging ring for the small host tables every stage call uploads (lengths, filter taps, index
+// tables).  cudaMemcpyAsync from PAGEABLE memory first waits for the stream to drain, which would
+// serialise host and device at every stage call; copies out of this ring are truly asynchronous, so the
+// host keeps running ahead of the GPU.  Two halves; a half is reused only after the event recorded when
+// it was left has completed.
+struct Staging {
+  unsigned char *base = nullptr;
+  size_t half_bytes = 0, used = 0;
+  int half = 0;
+  void *left_event[2] = {nullptr, nullptr};   // cudaEvent_t
+  bool pending[2] = {false, false};
+};
+
+// Device buffers of the host pipelines, kept between calls (cudaMalloc / cudaFree of tens of GB per call
+// cost more than the uploads they serve); world_b200_trim() gives them back.
+struct PoolBuf { void *p; size_t cap; bool busy; };
+
 struct Ctx {
   int device = 0;
   wb_stream_t stream = 0;
   double2 *twiddle = nullptr;        // [WB_TW_N/2] exp(-j 2 pi k / WB_TW_N)
   uint32_t *rng_jump = nullptr;      // [WB_RNG_NJ][32][16] uint4
   Arena arena;
+  Staging staging;
+  std::vector<PoolBuf> pool;
   size_t scratch_budget = (size_t)24 << 30;  // bytes of scratch a stage may use per chunk
   int sm_count = 148;
   int *status_dev = nullptr;         // sticky device-side error word
@@ -46,6 +66,9 @@ struct ArenaPlan {                                   // lay out 256-byte aligned
   size_t add(size_t bytes) { const size_t off = total; total += (bytes + 255) & ~(size_t)255; return off; }
 };
 
+void *pool_acquire(Ctx *ctx, size_t bytes);   // cached device buffer >= bytes (nullptr + last_error on failure)
+void pool_release(Ctx *ctx, void *p);
+void pool_trim(Ctx *ctx);                     // frees every idle pooled buffer
 void *dev_malloc(Ctx *ctx, size_t bytes);
 void dev_free(void *p);
 int dev_memcpy_h2d(Ctx *ctx, void *dst, const void *src, size_t bytes);
