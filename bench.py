@@ -384,7 +384,7 @@ def main():
         e2e = {"value": world * Ue * L * ke / dt, "unit": "frames/s",
                "h2d_bytes_per_step": int(Ue * n * 8), "d2h_bytes_per_step": int(2 * Ue * L * bins * 8 + 2 * Ue * L * 8),
                "utts_per_gpu": Ue, "steps": ke, "ms_per_step_rank0": e2e_steps_ms,
-               "note": "world_b200_analyze_host: pinned host buffers in/out, upload/compute/download pipelined over chunks"}
+               "note": "world_b200_analyze_host: pinned host buffers in/out; F0 stage on 512-utterance chunks, CheapTrick+D4C on 128-utterance sub-chunks whose rows are downloaded while the next ones are computed"}
         # the e2e result must be the same numbers the device-resident path produced
         same = bool(torch.equal(fh, f0_last[:Ue].cpu()))
         e2e["matches_device_path"] = same

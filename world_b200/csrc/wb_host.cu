@@ -40,10 +40,10 @@ namespace {
 // is widened on the device (row f3).  dims == 0: the full spectrogram / aperiodicity rows go back to the
 // host; dims > 0: they stay on the device and only their coded rows (row f2) are downloaded.
 //
-// Two granularities.  The F0 stage runs on OUTER chunks (default 256 utterances): its per-utterance
+// Two granularities.  The F0 stage runs on OUTER chunks (default 512 utterances): its per-utterance
 // kernels (contour tracking, smoothing, decimation) are latency bound -- one launch costs the same
 // for 96 or 500 utterances -- so few large launches beat many small ones.  CheapTrick / D4C (/ codec) run
-// on SUB-chunks (default 64 utterances) whose rows start their trip over PCIe as soon as they exist: the
+// on SUB-chunks (default 128 utterances) whose rows start their trip over PCIe as soon as they exist: the
 // un-overlapped tail is one sub-chunk.  Result buffers form a ring two outer chunks deep, so downloads
 // may lag behind the frame kernels and catch up under the next outer chunk's F0 stage.  Streams: s_in
 // (uploads), the context's stream (all kernels), s_out (downloads); events order buffer reuse.
@@ -60,7 +60,7 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
   const bool want_sp = out_sp != nullptr, want_ap = out_ap != nullptr && (!dims || n_ap > 0);
   if (n_utts == 0) return 0;
 
-  int sub = 64, outer = 256;
+  int sub = 128, outer = 512;
   if (const char *e = getenv("WB_HOST_SUB")) sub = atoi(e) > 0 ? atoi(e) : sub;
   if (const char *e = getenv("WB_HOST_CHUNK")) outer = atoi(e) > 0 ? atoi(e) : outer;
   sub = imin(sub, n_utts);
