@@ -360,6 +360,9 @@ def main():
         # free the device-resident outputs of the first phase: analyze_host brings its own buffers
         del sp, ap, sp_all, ap_all
         torch.cuda.empty_cache()
+        # the (possibly gathered) outputs are gone: let the pipeline size its chunks for what is free now
+        free_e2e, _ = torch.cuda.mem_get_info(dev)
+        w.set_scratch_budget(int(min(96 << 30, max(2 << 30, free_e2e * 0.45))))
         ao = w.analysis_option(fs, F0_HARVEST if a.f0 == "harvest" else F0_DIO_STONEMASK)
         w.lib.world_b200_set_stream(w._h, None)
 
