@@ -35,7 +35,8 @@ def test_headers_declare_the_reference_api():
                      "CodeSpectralEnvelope", "DecodeSpectralEnvelope", "world_b200_code_spectral_envelope_batch",
                      "world_b200_code_aperiodicity_batch", "world_b200_decode_spectral_envelope_batch",
                      "world_b200_decode_aperiodicity_batch", "world_b200_pcm_to_double_batch", "world_b200_wav_parse",
-                     "world_b200_analyze_coded_host"]:
+                     "world_b200_analyze_coded_host", "wavread", "wavwrite", "WriteF0", "ReadSpectralEnvelope",
+                     "world_b200_write_rows", "world_b200_trim"]:
         assert required in names
 
 

@@ -100,6 +100,19 @@ ABI = {
     "world_b200_pcm_to_double_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _IP, _P]),
     "world_b200_analyze_coded_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _IP, C.c_int,
                                                 C.POINTER(AnalysisOption), C.c_int, _P, _P, C.c_int, _P, _P]),
+    # host-only file glue (tools/audioio.h, tools/parameterio.h)
+    "wavwrite": (None, [_P, C.c_int, C.c_int, C.c_int, C.c_char_p]),
+    "GetAudioLength": (C.c_int, [C.c_char_p]),
+    "wavread": (None, [C.c_char_p, _IP, _IP, _P]),
+    "WriteF0": (None, [C.c_char_p, C.c_int, C.c_double, _P, _P, C.c_int]),
+    "ReadF0": (C.c_int, [C.c_char_p, _P, _P]),
+    "GetHeaderInformation": (C.c_double, [C.c_char_p, C.c_char_p]),
+    "WriteSpectralEnvelope": (None, [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _P]),
+    "ReadSpectralEnvelope": (C.c_int, [C.c_char_p, _P]),
+    "WriteAperiodicity": (None, [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _P]),
+    "ReadAperiodicity": (C.c_int, [C.c_char_p, _P]),
+    "world_b200_write_rows": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _P]),
+    "world_b200_read_rows": (C.c_int, [C.c_char_p, C.c_char_p, _P, C.c_int]),
     "GetNumberOfAperiodicities": (C.c_int, [C.c_int]),
     "CodeAperiodicity": (None, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "DecodeAperiodicity": (None, [_P, C.c_int, C.c_int, C.c_int, _P]),
