@@ -14,8 +14,9 @@
 // Restated here: randn, interp1Q, interp1, DCCorrection, LinearSmoothing, NuttallWindow, the FFT
 // conventions, StoneMask, CheapTrick, D4C, the option / sizing helpers, and (rows f2 / f3 of SURVEY.md 8)
 // the codec of codec.cpp and the PCM sample conversion of tools/audioio.cpp; Dio (with decimate) as
-// direct time-domain filtering instead of the reference's FFT convolutions.
-// NOT restated (checked against oracle/_ref only): Harvest, Synthesis.
+// direct time-domain filtering instead of the reference's FFT convolutions; Harvest likewise (band-pass
+// FIRs in the time domain, the instantaneous-frequency refinement with full FFTs like the reference).
+// NOT restated (checked against oracle/_ref only): Synthesis.
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -59,11 +60,18 @@ void RealFFT(const std::vector<double> &x, std::vector<double> *re, std::vector<
     j ^= bit;
     if (i < j) std::swap(ar[i], ar[j]);
   }
+  static std::vector<double> tw_r, tw_i;     // exp(-j 2 pi k / n) for the largest n seen (single-threaded use)
+  static int tw_n = 0;
+  if (tw_n < n) {
+    tw_n = n;
+    tw_r.resize(n / 2); tw_i.resize(n / 2);
+    for (int k = 0; k < n / 2; ++k) { tw_r[k] = cos(-2.0 * kPi * k / n); tw_i[k] = sin(-2.0 * kPi * k / n); }
+  }
   for (int len = 2; len <= n; len <<= 1) {
-    const double ang = -2.0 * kPi / len;
+    const int stride = tw_n / len;
     for (int i = 0; i < n; i += len)
       for (int k = 0; k < len / 2; ++k) {
-        const double wr = cos(ang * k), wi = sin(ang * k);
+        const double wr = tw_r[k * stride], wi = tw_i[k * stride];
         const int a = i + k, b = i + k + len / 2;
         const double tr = ar[b] * wr - ai[b] * wi, ti = ar[b] * wi + ai[b] * wr;
         ar[b] = ar[a] - tr; ai[b] = ai[a] - ti;
@@ -638,6 +646,332 @@ void Dio(const double *x, int x_length, int fs, const DioOption *o, double *t, d
     }
   }
   for (int i = 0; i < L; ++i) f0[i] = s4[i];
+}
+
+// ---- Harvest (harvest.cpp).  Everything on the 1 ms grid, then subsampled (:1237-1251).
+typedef struct { double f0_floor, f0_ceil, frame_period; } HarvestOption;            // harvest.h:16-20
+void InitializeHarvestOption(HarvestOption *o) { o->f0_ceil = 800.0; o->f0_floor = 71.0; o->frame_period = 5; }  // harvest.cpp:1257-1263
+
+namespace {
+typedef std::vector<std::vector<double> > Rows;
+
+// SelectBestF0 (:636-650): the LAST candidate among those with the smallest relative error <= allowed
+double HvSelect(double ref, const std::vector<double> &cand, int n, double allowed, double *err) {
+  double best = 0.0;
+  *err = allowed;
+  for (int i = 0; i < n; ++i) {
+    const double e = fabs(ref - cand[i]) / ref;
+    if (e > *err) continue;
+    best = cand[i];
+    *err = e;
+  }
+  return best;
+}
+
+// GetBoundaryList (:727-743): alternating rise / fall positions, falls shifted back by one
+int HvBoundaries(const std::vector<double> &f0, std::vector<int> *list) {
+  const int n = (int)f0.size();
+  list->clear();
+  int prev = 0;
+  for (int i = 1; i < n; ++i) {
+    const int v = (i == n - 1) ? 0 : (f0[i] > 0 ? 1 : 0);
+    if (v != prev) list->push_back(i - (int)list->size() % 2);
+    prev = v;
+  }
+  return (int)list->size();
+}
+
+// GetRefinedF0 (:589-617) with GetMeanF0 (:540-583) and FixF0 (:498-535): two windowed FFTs per candidate
+void HvRefine(const std::vector<double> &y, double fs, double t, double f, double f0_floor, double f0_ceil,
+              double *out_f, double *out_score) {
+  *out_f = 0.0; *out_score = 0.0;
+  if (f <= 0.0) return;
+  const int n = (int)y.size();
+  const int h = (int)(1.5 * fs / f + 1.0), len = 2 * h + 1;
+  const double win_time = (2.0 * h + 1.0) / fs;
+  const int fft_size = (int)pow(2.0, 2.0 + (int)(log(h * 2.0 + 1.0) / kLog2));
+  const int basic = RoundHalfAway((t + (-h) / fs) * fs + 0.001);                       // GetBaseIndex (:434-441)
+  std::vector<double> w(len), dw(len), a(fft_size, 0.0), b(fft_size, 0.0), ar, ai, br, bi;
+  for (int i = 0; i < len; ++i) {                                                      // GetMainWindow (:446-456)
+    const double tau = (basic + i - 1.0) / fs - t;
+    w[i] = 0.42 + 0.5 * cos(2.0 * kPi * tau / win_time) + 0.08 * cos(4.0 * kPi * tau / win_time);
+  }
+  dw[0] = -w[1] / 2.0;                                                                  // GetDiffWindow (:462-468)
+  for (int i = 1; i < len - 1; ++i) dw[i] = -(w[i + 1] - w[i - 1]) / 2.0;
+  dw[len - 1] = w[len - 2] / 2.0;
+  for (int i = 0; i < len; ++i) {                                                      // GetSpectra (:474-496)
+    const double v = y[std::max(0, std::min(n - 1, basic + i - 1))];
+    a[i] = v * w[i];
+    b[i] = v * dw[i];
+  }
+  RealFFT(a, &ar, &ai);
+  RealFFT(b, &br, &bi);
+  const int H = std::min((int)(fs / 2.0 / f), 6);
+  double num = 0.0, den = 0.0, score = 0.0;
+  for (int m = 0; m < H; ++m) {                                                        // FixF0
+    const int k = RoundHalfAway(f * fft_size / fs * (m + 1));
+    const double pw = ar[k] * ar[k] + ai[k] * ai[k];
+    const double ni = ar[k] * bi[k] - ai[k] * br[k];
+    const double inst = pw == 0.0 ? 0.0 : (double)k * fs / fft_size + ni / pw * fs / 2.0 / kPi;
+    const double amp = sqrt(pw);
+    num += amp * inst;
+    den += amp * (m + 1.0);
+    score += fabs((inst / (m + 1.0) - f) / f);
+  }
+  double rf = num / (den + kTiny), rs = 1.0 / (score / H + kTiny);
+  if (rf < f0_floor || rf > f0_ceil || rs < 2.5) { rf = 0.0; rs = 0.0; }
+  *out_f = rf; *out_score = rs;
+}
+
+// ExtendF0 (:806-836): follow the candidates frame by frame from `origin` in direction `shift`
+int HvExtendOne(int origin, int last, int shift, const Rows &cand, int n, double allowed, std::vector<double> *f0) {
+  double cur = (*f0)[origin];
+  int reached = origin, misses = 0;
+  const int distance = abs(last - origin);
+  for (int i = 0; i <= distance; ++i) {
+    const int at = origin + shift * i + shift;
+    double e;
+    (*f0)[at] = HvSelect(cur, cand[at], n, allowed, &e);
+    if ((*f0)[at] == 0.0) {
+      ++misses;
+    } else {
+      cur = (*f0)[at];
+      misses = 0;
+      reached = at;
+    }
+    if (misses == 4) break;
+  }
+  return reached;
+}
+
+double HvScoreOf(double f0, const std::vector<double> &cand, const std::vector<double> &score, int n) {   // SearchScore (:905-911)
+  double s = 0.0;
+  for (int i = 0; i < n; ++i)
+    if (f0 == cand[i] && s < score[i]) s = score[i];
+  return s;
+}
+
+// FixStep3 (:967-996) = GetMultiChannelF0 + Extend (+ ExtendSub) + MergeF0, quirks included: the running mean of
+// ExtendSub is never reset, MergeF0 starts from channel 0 (not the earliest) and reuses boundary slots 0 / 1
+void HvStep3(const std::vector<double> &in, const Rows &cand, const Rows &score, int n, double allowed, std::vector<double> *out) {
+  const int L = (int)in.size();
+  *out = in;
+  std::vector<int> bl;
+  const int nsec = HvBoundaries(in, &bl) / 2;
+  Rows ch(nsec, std::vector<double>(L, 0.0));
+  for (int i = 0; i < nsec; ++i)
+    for (int j = bl[2 * i]; j <= bl[2 * i + 1]; ++j) ch[i][j] = in[j];
+  for (int i = 0; i < nsec; ++i) {                                                     // Extend (:874-889)
+    bl[2 * i + 1] = HvExtendOne(bl[2 * i + 1], std::min(L - 2, bl[2 * i + 1] + 100), 1, cand, n, allowed, &ch[i]);
+    bl[2 * i] = HvExtendOne(bl[2 * i], std::max(1, bl[2 * i] - 100), -1, cand, n, allowed, &ch[i]);
+  }
+  int kept = 0;                                                                        // ExtendSub (:853-869)
+  double mean = 0.0;
+  for (int i = 0; i < nsec; ++i) {
+    const int st = bl[2 * i], ed = bl[2 * i + 1];
+    for (int j = st; j < ed; ++j) mean += ch[i][j];
+    mean /= ed - st;
+    if (2200.0 / mean < ed - st) {
+      std::swap(ch[kept], ch[i]);
+      std::swap(bl[2 * kept], bl[2 * i]);
+      std::swap(bl[2 * kept + 1], bl[2 * i + 1]);
+      ++kept;
+    }
+  }
+  if (kept == 0) return;
+  std::vector<int> order(kept);                                                        // MakeSortedOrder (:891-903)
+  for (int i = 0; i < kept; ++i) order[i] = i;
+  for (int i = 1; i < kept; ++i)             // as written there: position i is the comparison partner throughout,
+    for (int j = i - 1; j >= 0; --j) {       // so this is not a full insertion sort when an element must move far
+      if (bl[order[j] * 2] > bl[order[i] * 2]) std::swap(order[i], order[j]);
+      else break;
+    }
+  std::vector<double> &m = *out;                                                       // MergeF0 (:938-963)
+  m = ch[0];
+  for (int i = 1; i < kept; ++i) {
+    const int st2 = bl[order[i] * 2], ed2 = bl[order[i] * 2 + 1];
+    const std::vector<double> &f2 = ch[order[i]];
+    if (st2 - bl[1] > 0) {
+      for (int j = st2; j <= ed2; ++j) m[j] = f2[j];
+      bl[0] = st2; bl[1] = ed2;
+    } else {                                                                           // MergeF0Sub (:916-933)
+      const int st1 = bl[0], ed1 = bl[1];
+      if (st1 <= st2 && ed1 >= ed2) { bl[1] = ed1; continue; }
+      double s1 = 0.0, s2 = 0.0;
+      for (int j = st2; j <= ed1; ++j) {
+        s1 += HvScoreOf(m[j], cand[j], score[j], n);
+        s2 += HvScoreOf(f2[j], cand[j], score[j], n);
+      }
+      if (s1 > s2) for (int j = ed1; j <= ed2; ++j) m[j] = f2[j];
+      else for (int j = st2; j <= ed2; ++j) m[j] = f2[j];
+      bl[1] = ed2;
+    }
+  }
+}
+
+void HvBody(const double *x, int x_length, int fs, double f0_floor, double f0_ceil, int ratio, std::vector<double> *f0_out) {   // HarvestGeneralBody (:1145-1215)
+  const double ch_per_oct = 40.0, afloor = f0_floor * 0.9, aceil = f0_ceil * 1.1;
+  const int nch = 1 + (int)(log(aceil / afloor) / kLog2 * ch_per_oct);
+  std::vector<double> boundary(nch);
+  for (int i = 0; i < nch; ++i) boundary[i] = afloor * pow(2.0, (i + 1) / ch_per_oct);
+  ratio = std::max(std::min(ratio, 12), 1);
+  const int ylen = (int)ceil((double)x_length / ratio);
+  const double afs = (double)fs / ratio;
+  const int L = GetSamplesForHarvest(fs, x_length, 1.0);
+  std::vector<double> t(L);
+  for (int i = 0; i < L; ++i) t[i] = i * 1 / 1000.0;
+  // GetWaveformAndSpectrum(Sub) (:43-93): decimation of an edge-padded copy, then DC removal
+  std::vector<double> y(ylen, 0.0);
+  if (ratio == 1) {
+    for (int i = 0; i < x_length; ++i) y[i] = x[i];
+  } else {
+    const int lag = (int)(ceil(140.0 / ratio) * ratio);
+    std::vector<double> padded(x_length + 2 * lag), dec;
+    for (int i = 0; i < lag; ++i) padded[i] = x[0];
+    for (int i = 0; i < x_length; ++i) padded[lag + i] = x[i];
+    for (int i = 0; i < lag; ++i) padded[lag + x_length + i] = x[x_length - 1];
+    Decimate(padded.data(), (int)padded.size(), ratio, &dec);
+    for (int i = 0; i < ylen; ++i) y[i] = (lag / ratio + i < (int)dec.size()) ? dec[lag / ratio + i] : 0.0;
+  }
+  double mean = 0.0;
+  for (int i = 0; i < ylen; ++i) mean += y[i];
+  mean /= ylen;
+  for (int i = 0; i < ylen; ++i) y[i] -= mean;
+
+  // raw candidates per channel (:99-147, :162-343): band-pass FIR, four crossing trains, interp1, gate
+  Rows raw(nch, std::vector<double>(L, 0.0));
+  std::vector<double> filt(ylen), work, loc[4], itv[4], yi[4];
+  for (int c = 0; c < nch; ++c) {
+    const int h = RoundHalfAway(afs / boundary[c] * 2.0), M = 2 * h + 1;
+    std::vector<double> bp(M);
+    for (int i = 0; i < M; ++i) {
+      const double u = i / (M - 1.0);
+      bp[i] = (0.355768 - 0.487396 * cos(2.0 * kPi * u) + 0.144232 * cos(4.0 * kPi * u) - 0.012604 * cos(6.0 * kPi * u)) *
+              cos(2 * kPi * boundary[c] * (i - h) / afs);
+    }
+    for (int i = 0; i < ylen; ++i) {                       // delay compensation h + 1 (:137-139)
+      double acc = 0.0;
+      const int k_lo = std::max(0, i + h + 1 - (ylen - 1)), k_hi = std::min(M - 1, i + h + 1);
+      for (int k = k_lo; k <= k_hi; ++k) acc += bp[k] * y[i + h + 1 - k];
+      filt[i] = acc;
+    }
+    int cnt[4];
+    cnt[0] = CrossingIntervals(filt, ylen, afs, &loc[0], &itv[0]);
+    work.assign(filt.begin(), filt.end());
+    for (int i = 0; i < ylen; ++i) work[i] = -work[i];
+    cnt[1] = CrossingIntervals(work, ylen, afs, &loc[1], &itv[1]);
+    for (int i = 0; i + 1 < ylen; ++i) work[i] = work[i] - work[i + 1];
+    cnt[2] = CrossingIntervals(work, ylen - 1, afs, &loc[2], &itv[2]);
+    for (int i = 0; i + 1 < ylen; ++i) work[i] = -work[i];
+    cnt[3] = CrossingIntervals(work, ylen - 1, afs, &loc[3], &itv[3]);
+    if (!(cnt[0] > 2 && cnt[1] > 2 && cnt[2] > 2 && cnt[3] > 2)) continue;
+    for (int q = 0; q < 4; ++q) Interp1Vec(loc[q], itv[q], t.data(), L, &yi[q]);
+    for (int i = 0; i < L; ++i) {
+      const double f = (yi[0][i] + yi[1][i] + yi[2][i] + yi[3][i]) / 4.0;
+      raw[c][i] = (f > boundary[c] * 1.1 || f < boundary[c] * 0.9 || f > f0_ceil || f < f0_floor) ? 0.0 : f;
+    }
+  }
+  // DetectOfficialF0Candidates (:348-412): runs of >= 10 voiced channels -> their mean
+  const int max_cand = RoundHalfAway(nch / 10.0) * 7;
+  Rows cand(L, std::vector<double>(max_cand, 0.0)), score(L, std::vector<double>(max_cand, 0.0));
+  int nc = 0;
+  for (int i = 0; i < L; ++i) {
+    int count = 0, st = 0, prev = 0;
+    for (int c = 1; c < nch; ++c) {
+      const int v = (c == nch - 1) ? 0 : (raw[c][i] > 0 ? 1 : 0);
+      if (v - prev == 1) st = c;
+      if (v - prev == -1 && c - st >= 10) {
+        double sum = 0.0;
+        for (int j = st; j < c; ++j) sum += raw[j][i];
+        cand[i][count++] = sum / (c - st);
+      }
+      prev = v;
+    }
+    nc = std::max(nc, count);
+  }
+  for (int d = 1; d <= 3; ++d)                                                         // OverlapF0Candidates (:417-429)
+    for (int j = 0; j < nc; ++j) {
+      for (int k = d; k < L; ++k) cand[k][j + nc * d] = cand[k - d][j];
+      for (int k = 0; k < L - d; ++k) cand[k][j + nc * (d + 3)] = cand[k + d][j];
+    }
+  const int n = nc * 7;
+  for (int i = 0; i < L; ++i)                                                          // RefineF0Candidates (:622-631)
+    for (int j = 0; j < n; ++j) HvRefine(y, afs, t[i], cand[i][j], f0_floor, f0_ceil, &cand[i][j], &score[i][j]);
+  {                                                                                    // RemoveUnreliableCandidates (:652-688)
+    const Rows before(cand);
+    for (int i = 1; i < L - 1; ++i)
+      for (int j = 0; j < n; ++j) {
+        if (cand[i][j] == 0) continue;
+        double e1, e2;
+        HvSelect(cand[i][j], before[i + 1], n, 1.0, &e1);
+        HvSelect(cand[i][j], before[i - 1], n, 1.0, &e2);
+        if (std::min(e1, e2) > 0.05) { cand[i][j] = 0; score[i][j] = 0; }
+      }
+  }
+  // FixF0Contour (:1035-1053)
+  std::vector<double> base(L, 0.0), s1(L, 0.0), s2, s3, s4;
+  for (int i = 0; i < L; ++i) {                                                        // SearchF0Base (:693-705)
+    double best = 0.0;
+    for (int j = 0; j < n; ++j) if (score[i][j] > best) { base[i] = cand[i][j]; best = score[i][j]; }
+  }
+  for (int i = 2; i < L; ++i) {                                                        // FixStep1 (:710-722), allowed 0.008
+    if (base[i] == 0.0) continue;
+    const double ref = base[i - 1] * 2 - base[i - 2];
+    s1[i] = (fabs((base[i] - ref) / ref) > 0.008 && fabs((base[i] - base[i - 1])) / base[i - 1] > 0.008) ? 0.0 : base[i];
+  }
+  s2 = s1;                                                                             // FixStep2 (:748-762), minimum 6
+  std::vector<int> bl;
+  int nb = HvBoundaries(s1, &bl);
+  for (int i = 0; i < nb / 2; ++i) {
+    if (bl[2 * i + 1] - bl[2 * i] >= 6) continue;
+    for (int j = bl[2 * i]; j <= bl[2 * i + 1]; ++j) s2[j] = 0.0;
+  }
+  HvStep3(s2, cand, score, n, 0.18, &s3);
+  s4 = s3;                                                                             // FixStep4 (:1001-1030), threshold 9
+  nb = HvBoundaries(s3, &bl);
+  for (int i = 0; i < nb / 2 - 1; ++i) {
+    const int gap = bl[(i + 1) * 2] - bl[2 * i + 1] - 1;
+    if (gap >= 9) continue;
+    const double a = s3[bl[2 * i + 1]] + 1, b = s3[bl[(i + 1) * 2]] - 1;
+    const double slope = (b - a) / (gap + 1.0);
+    int count = 1;
+    for (int j = bl[2 * i + 1] + 1; j <= bl[(i + 1) * 2] - 1; ++j) s4[j] = a + slope * count++;
+  }
+  // SmoothF0Contour (:1093-1129): zero-lag 2nd-order Butterworth per voiced section of the padded contour
+  const double fb[2] = {0.0078202080334971724, 0.015640416066994345}, fa[2] = {1.7347257688092754, -0.76600660094326412};
+  const int lag = 300, N = L + 2 * lag;
+  std::vector<double> padded(N, 0.0), xs(N), rev(N), sm(N);
+  for (int i = 0; i < L; ++i) padded[lag + i] = s4[i];
+  f0_out->assign(L, 0.0);
+  nb = HvBoundaries(padded, &bl);
+  for (int i = 0; i < nb / 2; ++i) {
+    const int st = bl[2 * i], ed = bl[2 * i + 1];
+    for (int j = 0; j < N; ++j) xs[j] = padded[std::max(st, std::min(ed, j))];        // FilteringF0 (:1058-1086)
+    double w0 = 0.0, w1 = 0.0;
+    for (int j = 0; j < N; ++j) {
+      const double wt = xs[j] + fa[0] * w0 + fa[1] * w1;
+      rev[N - j - 1] = fb[0] * wt + fb[1] * w0 + fb[0] * w1;
+      w1 = w0; w0 = wt;
+    }
+    w0 = w1 = 0.0;
+    for (int j = 0; j < N; ++j) {
+      const double wt = rev[j] + fa[0] * w0 + fa[1] * w1;
+      sm[N - j - 1] = fb[0] * wt + fb[1] * w0 + fb[0] * w1;
+      w1 = w0; w0 = wt;
+    }
+    for (int j = st; j <= ed; ++j) (*f0_out)[j - lag] = sm[j];
+  }
+}
+}  // namespace
+
+void Harvest(const double *x, int x_length, int fs, const HarvestOption *o, double *t, double *f0) {   // :1223-1255
+  std::vector<double> basic;
+  HvBody(x, x_length, fs, o->f0_floor, o->f0_ceil, RoundHalfAway(fs / 8000.0), &basic);
+  const int L = GetSamplesForHarvest(fs, x_length, o->frame_period);
+  for (int i = 0; i < L; ++i) {
+    t[i] = i * o->frame_period / 1000.0;
+    f0[i] = basic[std::min((int)basic.size() - 1, RoundHalfAway(t[i] * 1000.0))];
+  }
 }
 
 }  // extern "C"

@@ -106,3 +106,26 @@ def test_port_dio_matches_golden_and_reference(port, ref, golden):
             ref.lib.decimate(xs.ctypes.data_as(C.c_void_p), len(xs), speed, y1.ctypes.data_as(C.c_void_p))
             port.lib.OracleDecimate(xs.ctypes.data_as(C.c_void_p), len(xs), speed, y2.ctypes.data_as(C.c_void_p))
             assert np.array_equal(y1, y2)
+
+
+def test_port_harvest_matches_golden_and_reference(port, ref, golden):
+    """The restated Harvest (time-domain band-pass FIRs, own FFT for the refinement) against the goldens and
+    the compiled reference: all frame periods / rates of the parity matrix, no V/UV flip allowed."""
+    assert port.has_harvest
+    x, fs = pc.wav_from_golden(golden)
+    t, f0 = port.harvest(x, fs)
+    assert np.array_equal(t, golden["time_axis"])
+    assert rel_err(f0, golden["f0_harvest"]).max() < 1e-9
+    o = port.harvest_option(); o.f0_floor = 40.0
+    assert rel_err(port.harvest(x, fs, o)[1], golden["f0_harvest_floor40"]).max() < 1e-9
+    from synth import synth_batch
+    for fs2, n, seed, fp in ((16000, 24000, 81, 5.0), (48000, 48000, 82, 1.0), (8000, 12000, 83, 10.0), (22050, 22050, 84, 2.5)):
+        xs = synth_batch([seed], fs2, n).numpy()[0]
+        po = port.harvest_option(); po.frame_period = fp
+        ro = ref.harvest_option(); ro.frame_period = fp
+        tp, fp_ = port.harvest(xs, fs2, po)
+        tr, fr = ref.harvest(xs, fs2, ro)
+        assert np.array_equal(tp, tr)
+        assert not ((fp_ > 0) != (fr > 0)).any()
+        assert rel_err(fp_, fr).max() < 1e-9, (fs2, fp)
+        assert (fr > 0).sum() > 50
