@@ -342,6 +342,24 @@ def main():
     frames_step = world * U * L
     value = frames_step * a.steps / (ms / 1e3)
 
+    # ---- multi-GPU equality: what another rank contributed to the gathered arrays is bit-identical to what
+    # this rank computes for the same utterances on its own GPU (outside the timed region, rank 0 only)
+    gather_check = None
+    if world > 1 and gather and rank == 0:
+        try:
+            r = world - 1
+            xs = synth_batch(range(r * U + 1, r * U + 3), fs, n, device=dev)
+            tt, ff, _ = (w.harvest(xs, fs) if a.f0 == "harvest" else w.dio(xs, fs))
+            if a.f0 != "harvest":
+                ff = w.stonemask(xs, fs, tt, ff)
+            ok = torch.equal(ff, f0_all[r * U:r * U + 2]) and torch.equal(tt, t_all[r * U:r * U + 2])
+            if gather_full:
+                ok = ok and torch.equal(w.cheaptrick(xs, fs, tt, ff, opt), sp_all[r * U:r * U + 2])
+                ok = ok and torch.equal(w.d4c(xs, fs, tt, ff, opt.fft_size), ap_all[r * U:r * U + 2])
+            gather_check = bool(ok)
+        except Exception as e:  # never let the check take the bench line down
+            gather_check = f"error: {e}"
+
     # ---- end to end through the host-pointer ABI (pinned host buffers, copies inside the timed region)
     e2e = None
     if not a.no_e2e:
@@ -503,7 +521,8 @@ def main():
            "config": {"workload": workload_name(a), "fs": fs, "frame_period_ms": 5.0, "frames_per_step": frames_step,
                       "l2_policy": "inputs+outputs per step (>= 18 GB) exceed the 126 MB L2; no flush needed",
                       "multi_gpu": ("utterances sharded over ranks, NCCL all-gather of f0/time_axis" +
-                                    ("/spectrogram/aperiodicity" if gather_full else "")) if world > 1 else "single GPU"},
+                                    ("/spectrogram/aperiodicity" if gather_full else "")) if world > 1 else "single GPU",
+                      "gathered_equals_local_recompute": gather_check},
            "clocks": clocks, "e2e": e2e, "slices": n_slices, "gpu_launches": int(launches), "roofline": roof, "fp64": fp64, "cpu_baseline": cpu,
            "kernels": kernels}
     print(json.dumps(out), flush=True)
