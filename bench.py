@@ -348,7 +348,7 @@ def main():
     if world > 1 and gather and rank == 0:
         try:
             r = world - 1
-            xs = synth_batch(range(r * U + 1, r * U + 3), fs, n, device=dev)
+            xs = synth_batch(range(r * U + 1, r * U + min(U, 64) + 1), fs, n, device=dev)[:2].contiguous()   # same generator call shape as that rank's
             tt, ff, _ = (w.harvest(xs, fs) if a.f0 == "harvest" else w.dio(xs, fs))
             if a.f0 != "harvest":
                 ff = w.stonemask(xs, fs, tt, ff)
