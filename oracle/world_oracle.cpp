@@ -16,7 +16,7 @@
 // the codec of codec.cpp and the PCM sample conversion of tools/audioio.cpp; Dio (with decimate) as
 // direct time-domain filtering instead of the reference's FFT convolutions; Harvest likewise (band-pass
 // FIRs in the time domain, the instantaneous-frequency refinement with full FFTs like the reference).
-// NOT restated (checked against oracle/_ref only): Synthesis.
+// Synthesis (row f1) too: pulse time base, minimum-phase responses, noise responses, overlap-add.
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -971,6 +971,166 @@ void Harvest(const double *x, int x_length, int fs, const HarvestOption *o, doub
   for (int i = 0; i < L; ++i) {
     t[i] = i * o->frame_period / 1000.0;
     f0[i] = basic[std::min((int)basic.size() - 1, RoundHalfAway(t[i] * 1000.0))];
+  }
+}
+
+// ---- Synthesis (synthesis.cpp:339-399).  Transform conventions of fft.cpp written out as plain sums over a
+// textbook complex FFT: c2c FORWARD(a) = FFT(conj a) (:61-71), c2r(X) = X0.re + (-1)^n X_{N/2}.re +
+// 2 sum_k Re(X_k e^{+j 2 pi k n / N}) (:26-35).
+namespace {
+// in-place complex FFT, sum a[n] exp(-j 2 pi k n / N)
+void ComplexFFT(std::vector<double> *re, std::vector<double> *im) {
+  std::vector<double> &ar = *re, &ai = *im;
+  const int n = (int)ar.size();
+  for (int i = 1, j = 0; i < n; ++i) {
+    int bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) { std::swap(ar[i], ar[j]); std::swap(ai[i], ai[j]); }
+  }
+  for (int len = 2; len <= n; len <<= 1)
+    for (int i = 0; i < n; i += len)
+      for (int k = 0; k < len / 2; ++k) {
+        const double wr = cos(-2.0 * kPi * k / len), wi = sin(-2.0 * kPi * k / len);
+        const int a = i + k, b = i + k + len / 2;
+        const double tr = ar[b] * wr - ai[b] * wi, ti = ar[b] * wi + ai[b] * wr;
+        ar[b] = ar[a] - tr; ai[b] = ai[a] - ti;
+        ar[a] += tr; ai[a] += ti;
+      }
+}
+
+// c2r of a half spectrum (N/2+1 bins) -> N real samples, unnormalised
+void HalfToReal(const std::vector<double> &xr, const std::vector<double> &xi, int N, std::vector<double> *out) {
+  std::vector<double> re(N), im(N);
+  for (int k = 0; k <= N / 2; ++k) { re[k] = xr[k]; im[k] = -xi[k]; }     // conj: turns e^{+j} into the forward kernel
+  im[0] = 0.0; im[N / 2] = 0.0;
+  for (int k = N / 2 + 1; k < N; ++k) { re[k] = xr[N - k]; im[k] = xi[N - k]; }
+  ComplexFFT(&re, &im);
+  *out = re;
+}
+
+// GetMinimumPhaseSpectrum (common.cpp:192-226): log spectrum (N/2+1) -> minimum-phase spectrum (N/2+1)
+void MinimumPhase(const std::vector<double> &log_spec, int N, std::vector<double> *mr, std::vector<double> *mi) {
+  std::vector<double> full(N), cr, ci;
+  for (int i = 0; i <= N / 2; ++i) full[i] = log_spec[i];
+  for (int i = N / 2 + 1; i < N; ++i) full[i] = full[N - i];
+  RealFFT(full, &cr, &ci);
+  std::vector<double> re(N, 0.0), im(N, 0.0);
+  re[0] = cr[0]; im[0] = -ci[0];
+  for (int i = 1; i < N / 2; ++i) { re[i] = cr[i] * 2.0; im[i] = ci[i] * -2.0; }
+  re[N / 2] = cr[N / 2]; im[N / 2] = -ci[N / 2];
+  for (int i = 0; i < N; ++i) im[i] = -im[i];                               // FORWARD = FFT(conj a)
+  ComplexFFT(&re, &im);
+  mr->resize(N / 2 + 1); mi->resize(N / 2 + 1);
+  for (int i = 0; i <= N / 2; ++i) {
+    const double e = exp(re[i] / N);
+    (*mr)[i] = e * cos(im[i] / N);
+    (*mi)[i] = e * sin(im[i] / N);
+  }
+}
+
+double SafeAp(double a) { return std::max(0.001, std::min(0.999999999999, a)); }     // common.h GetSafeAperiodicity
+}  // namespace
+
+void Synthesis(const double *f0, int f0_length, const double *const *sp, const double *const *ap, int fft_size,
+               double frame_period_ms, int fs, int y_length, double *y) {
+  const int N = fft_size, half = N / 2;
+  const double fp = frame_period_ms / 1000.0;
+  const double lowest_f0 = fs / fft_size + 1.0;                                        // integer division, as there (:362)
+  for (int i = 0; i < y_length; ++i) y[i] = 0.0;
+  // GetTimeBase (:283-315): interpolate f0 / vuv to the sample grid, accumulate phase, find the wraps
+  std::vector<double> ct(f0_length + 1), cf(f0_length + 1), cv(f0_length + 1), vuv(y_length), wrap(y_length);
+  for (int i = 0; i < f0_length; ++i) {
+    ct[i] = i * fp;
+    cf[i] = f0[i] < lowest_f0 ? 0.0 : f0[i];
+    cv[i] = cf[i] == 0.0 ? 0.0 : 1.0;
+  }
+  ct[f0_length] = f0_length * fp;
+  cf[f0_length] = cf[f0_length - 1] * 2 - cf[f0_length - 2];
+  cv[f0_length] = cv[f0_length - 1] * 2 - cv[f0_length - 2];
+  double total = 0.0;
+  for (int i = 0; i < y_length; ++i) {
+    const double t = i / (double)fs;
+    vuv[i] = Interp1At(ct, cv, t) > 0.5 ? 1.0 : 0.0;
+    const double fi = vuv[i] == 0.0 ? 500.0 : Interp1At(ct, cf, t);                     // kDefaultF0
+    total = i == 0 ? 2.0 * kPi * fi / fs : total + 2.0 * kPi * fi / fs;
+    wrap[i] = fmod(total, 2.0 * kPi);
+  }
+  std::vector<int> pidx;
+  std::vector<double> pshift;
+  for (int i = 0; i + 1 < y_length; ++i)
+    if (fabs(wrap[i + 1] - wrap[i]) > kPi) {
+      const double y1 = wrap[i] - 2.0 * kPi, y2 = wrap[i + 1];
+      pidx.push_back(i);
+      pshift.push_back(-y1 / (y2 - y1) / fs);
+    }
+  std::vector<double> dcr(N);                                                           // GetDCRemover (:319-333)
+  {
+    double dc = 0.0;
+    for (int i = 0; i < half; ++i) {
+      dcr[i] = 0.5 - 0.5 * cos(2.0 * kPi * (i + 1.0) / (1.0 + N));
+      dcr[N - i - 1] = dcr[i];
+      dc += dcr[i] * 2.0;
+    }
+    for (int i = 0; i < half; ++i) { dcr[i] /= dc; dcr[N - i - 1] = dcr[i]; }
+  }
+  Rng rng;
+  const int np = (int)pidx.size();
+  std::vector<double> env(half + 1), ratio(half + 1), lg(half + 1), mr, mi, xr(half + 1), xi(half + 1), wave, per(N), aper(N), noise(N), nr, ni;
+  for (int p = 0; p < np; ++p) {
+    const int noise_size = pidx[std::min(np - 1, p + 1)] - pidx[p];
+    const double cur_vuv = vuv[pidx[p]], cur_t = pidx[p] / (double)fs;
+    // GetSpectralEnvelope / GetAperiodicRatio (:140-179)
+    const int fl = std::min(f0_length - 1, (int)floor(cur_t / fp)), ce = std::min(f0_length - 1, (int)ceil(cur_t / fp));
+    const double w = cur_t / fp - fl;
+    for (int k = 0; k <= half; ++k) {
+      if (fl == ce) {
+        env[k] = fabs(sp[fl][k]);
+        ratio[k] = pow(SafeAp(ap[fl][k]), 2.0);
+      } else {
+        env[k] = (1.0 - w) * fabs(sp[fl][k]) + w * fabs(sp[ce][k]);
+        ratio[k] = pow((1.0 - w) * SafeAp(ap[fl][k]) + w * SafeAp(ap[ce][k]), 2.0);
+      }
+    }
+    // GetPeriodicResponse (:110-138)
+    if (cur_vuv <= 0.5 || ratio[0] > 0.999) {
+      std::fill(per.begin(), per.end(), 0.0);
+    } else {
+      for (int k = 0; k <= half; ++k) lg[k] = log(env[k] * (1.0 - ratio[k]) + kTiny) / 2.0;
+      MinimumPhase(lg, N, &mr, &mi);
+      const double coef = 2.0 * kPi * pshift[p] * fs / N;
+      for (int k = 0; k <= half; ++k) {                                                 // fractional delay (:95-106)
+        const double c = cos(coef * k), sn = sqrt(1.0 - c * c);
+        xr[k] = mr[k] * c + mi[k] * sn;
+        xi[k] = mi[k] * c - mr[k] * sn;
+      }
+      HalfToReal(xr, xi, N, &wave);
+      for (int i = 0; i < half; ++i) { per[i] = wave[i + half]; per[i + half] = wave[i]; }   // fftshift
+      double dc = 0.0;                                                                  // RemoveDCComponent (:73-82)
+      for (int i = half; i < N; ++i) dc += per[i];
+      for (int i = 0; i < half; ++i) per[i] = -dc * dcr[i];
+      for (int i = half; i < N; ++i) per[i] -= dc * dcr[i];
+    }
+    // GetAperiodicResponse (:36-69) with GetNoiseSpectrum (:18-31)
+    double avg = 0.0;
+    std::fill(noise.begin(), noise.end(), 0.0);
+    for (int i = 0; i < noise_size; ++i) { noise[i] = rng.Next(); avg += noise[i]; }
+    avg /= noise_size;
+    for (int i = 0; i < noise_size; ++i) noise[i] -= avg;
+    RealFFT(noise, &nr, &ni);
+    for (int k = 0; k <= half; ++k) lg[k] = (cur_vuv != 0.0 ? log(env[k] * ratio[k]) : log(env[k])) / 2.0;
+    MinimumPhase(lg, N, &mr, &mi);
+    for (int k = 0; k <= half; ++k) {
+      xr[k] = mr[k] * nr[k] - mi[k] * ni[k];
+      xi[k] = mr[k] * ni[k] + mi[k] * nr[k];
+    }
+    HalfToReal(xr, xi, N, &wave);
+    for (int i = 0; i < half; ++i) { aper[i] = wave[i + half]; aper[i + half] = wave[i]; }
+    // GetOneFrameSegment's mix (:203-207) and the overlap-add of :383-390
+    const double sq = sqrt((double)noise_size);
+    const int offset = pidx[p] - half + 1;
+    for (int j = std::max(0, -offset); j < std::min(N, y_length - offset); ++j)
+      y[j + offset] += (per[j] * sq + aper[j]) / N;
   }
 }
 

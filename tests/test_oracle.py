@@ -129,3 +129,16 @@ def test_port_harvest_matches_golden_and_reference(port, ref, golden):
         assert not ((fp_ > 0) != (fr > 0)).any()
         assert rel_err(fp_, fr).max() < 1e-9, (fs2, fp)
         assert (fr > 0).sum() > 50
+
+
+def test_port_synthesis_matches_reference(port, ref, golden):
+    """Row f1: restated Synthesis (own FFTs, transform conventions written out) against the reference."""
+    x, fs = pc.wav_from_golden(golden)
+    fft = int(golden["fft_size"])
+    sp = np.ascontiguousarray(golden["sp"]); ap = np.ascontiguousarray(golden["ap"])
+    for key, fp, n in (("f0_stonemask", 5.0, len(x)), ("f0_dio_floor40", 5.0, len(x) + 3000), ("f0_stonemask", 4.0, len(x) // 2)):
+        f0 = np.ascontiguousarray(golden[key])
+        yp = port.synthesis(f0, sp, ap, fft, fp, fs, n)
+        yr = ref.synthesis(f0, sp, ap, fft, fp, fs, n)
+        assert np.abs(yr).max() > 0.1
+        assert np.abs(yp - yr).max() <= 1e-12 * np.abs(yr).max()
