@@ -147,6 +147,9 @@ WB_DEV double select_kth_largest(const double *a, int n, int kth, double *red) {
   const int tid = WB_TID, nth = WB_NTH;
   unsigned long long pat = 0ull;
   int round = 0;
+  // `red` is the scratch the block reductions read without a trailing barrier: a warp still summing the
+  // previous block_sum's partials must not see round 0's counts (found by compute-sanitizer racecheck)
+  WB_SYNC();
   for (int bit = 62; bit >= 0; bit -= 2, ++round) {
     const bool two = bit >= 1;
     const unsigned long long hi_bit = 1ull << bit, lo_bit = two ? (1ull << (bit - 1)) : 0ull;
