@@ -127,3 +127,7 @@ def test_emu_dio_agrees_with_port(emu):
         emu.synchronize()
         assert np.array_equal(te[0], tp)
         assert rel_err(fe[0], fp).max() < 1e-12
+
+
+def test_emu_event_dense_and_degenerate_bands(emu, ref):
+    pc.check_event_dense_and_degenerate_bands(emu, ref)

@@ -183,3 +183,7 @@ def test_gpu_host_pipeline_chunking(gpu_world, golden):
     from world_b200 import api
     pc.check_host_pipeline_chunking(gpu_world, golden, api.F0_DIO_STONEMASK)
     pc.check_host_pipeline_chunking(gpu_world, golden, api.F0_HARVEST)
+
+
+def test_gpu_event_dense_and_degenerate_bands(gpu_world, ref):
+    pc.check_event_dense_and_degenerate_bands(gpu_world, ref)

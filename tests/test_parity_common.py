@@ -403,3 +403,43 @@ def check_host_pipeline_chunking(world, golden, f0_method=0):
             else:
                 os.environ[k] = v
     assert (want_raw[1] > 0).any() and np.isfinite(want_raw[2]).all()
+
+
+def check_event_dense_and_degenerate_bands(world, ref):
+    """Found by tools/fuzz_emu_parity.py: (1) a loud tone gives every Harvest band far more zero crossings than
+    its centre frequency suggests -- the per-band event lists wrap (history rings) instead of overflowing;
+    (2) DIO bands above the decimated Nyquist have a zero-length window in the reference and contribute no
+    candidate instead of being an error."""
+    fs = 22050
+    n = 19000
+    t = np.arange(n) / fs
+    rng = np.random.default_rng(3)
+    x = np.ascontiguousarray(0.3 * np.sin(2 * np.pi * 523.0 * t) + 1e-4 * rng.normal(size=n))
+    o = world.harvest_option(); o.frame_period = 1.0
+    ro = ref.harvest_option(); ro.frame_period = 1.0
+    # WB_EDGE_CAP_MIN shrinks the rings to the 2.5 x band frequency estimate (150 entries for the 40 Hz band
+    # here, against ~450 crossings of the leaking tone), so this short signal wraps them several times
+    saved = os.environ.get("WB_EDGE_CAP_MIN")
+    os.environ["WB_EDGE_CAP_MIN"] = "64"
+    try:
+        tt, f0, fl = world.harvest(make(world, x[None]), fs, o)
+        world.synchronize()
+    finally:
+        if saved is None:
+            os.environ.pop("WB_EDGE_CAP_MIN", None)
+        else:
+            os.environ["WB_EDGE_CAP_MIN"] = saved
+    tr, fr = ref.harvest(x, fs, ro)
+    assert np.array_equal(to_np(tt)[0], tr)
+    assert not ((to_np(f0)[0] > 0) != (fr > 0)).any()      # (the reference calls a bare sinusoid unvoiced)
+    assert_close(to_np(f0)[0], fr, "Harvest on a loud tone (event rings wrap)")
+    fs = 8000
+    from synth import synth_batch
+    x = synth_batch([91], fs, 4000).numpy()
+    o = world.dio_option(); o.speed = 12; o.f0_ceil = 1000.0
+    ro = ref.dio_option(); ro.speed = 12; ro.f0_ceil = 1000.0
+    tt, f0, fl = world.dio(make(world, x), fs, o)
+    world.synchronize()
+    tr, fr = ref.dio(x[0], fs, ro)
+    assert np.array_equal(to_np(tt)[0], tr)
+    assert not ((to_np(f0)[0] > 0) != (fr > 0)).any()

@@ -9,21 +9,26 @@
 // expressions (and the host libm), so frame counts, band lists and taps are bit-identical.
 #include "wb_internal.h"
 #include "wb_f0common.cuh"
+#include <stdlib.h>
 #include <vector>
 
 namespace wb {
 
 // Event-list capacity per band and train: crossings of a signal band-limited around/below
 // `boundary` cannot be denser than ~boundary per second for long; 2.5x margin, hard bound
-// ylen/2+2 (a negative-going crossing needs two samples).  Overflow raises status bit 4.
+// ylen/2+2 (a negative-going crossing needs two samples).  The lists are history rings: more events
+// than this wrap around; only a look-back beyond the last `cap` events raises status bit 4.
 static void plan_edge_caps(const std::vector<double> &boundary, double afs, int max_ylen,
                            std::vector<int> *cap, std::vector<long long> *off, size_t *stride) {
   const int nb = (int)boundary.size();
   cap->resize(nb); off->resize(nb);
   long long run = 0;
+  long long floor_cap = 2048;
+  if (const char *e = getenv("WB_EDGE_CAP_MIN")) floor_cap = atoll(e) > 0 ? atoll(e) : floor_cap;   // test hook: force wraps
   for (int i = 0; i < nb; ++i) {
     const long long hard = (long long)max_ylen / 2 + 2;
-    const long long soft = (long long)(2.5 * boundary[i] * max_ylen / afs) + 64;
+    long long soft = (long long)(2.5 * boundary[i] * max_ylen / afs) + 64;
+    if (soft < floor_cap) soft = floor_cap;   // a tile can append up to 1025 events per train; the rings look back 256
     (*cap)[i] = (int)(soft < hard ? soft : hard);
     (*off)[i] = run;
     run += 4LL * (*cap)[i];
@@ -179,8 +184,15 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
   int max_taps = 0;
   for (int i = 0; i < nb; ++i) {
     const int ha = round_half_away(afs / boundary[i] / 2.0);
+    if (ha < 1) {
+      // band above afs / 2 (heavy decimation): the reference's window has zero length, its filtered signal
+      // is identically zero, so the band yields no events -- the same through an all-zero filter
+      tap_off[i] = (int)taps.size(); ntaps[i] = 8; shift[i] = 0;
+      for (int j = 0; j < 16; ++j) taps.push_back(0.0);
+      if (8 > max_taps) max_taps = 8;
+      continue;
+    }
     const int len = ha * 4;
-    if (len < 2) { ctx->last_error = "Dio: band filter too short (f0_ceil too high for fs)"; return 3; }
     tap_off[i] = (int)taps.size(); ntaps[i] = len; shift[i] = ha * 2;
     std::vector<double> w(len);
     for (int j = 0; j < len; ++j) {

@@ -54,15 +54,20 @@ WB_KERNEL(256, 3) fir_plain_kernel(FirParams p) {
 #endif
 #define WB_FCHUNK 256  // frames finalised per round (= WB_SWEEP_THREADS)
 struct Trains {
-  const double *g[4];   // global edge lists
-  double *er, *xr, *yr; // shared rings [4][WB_RING]: edges, interval locations, interval values
-  int efrom[4];         // edge ring holds indices >= efrom
+  const double *g[4];   // global edge lists: history rings of `cap` entries (index modulo cap)
+  double *xr, *yr;      // shared rings [4][WB_RING]: interval locations, interval values
+  int cap;
   int ifrom[4];         // interval rings hold indices >= ifrom
   double afs;
 };
+// Edges are read back from global memory (L2): an edge ring in shared memory cost a CTA per SM.  A signal
+// with far more crossings than the band frequency suggests (a loud out-of-band tone) wraps the ring; only a
+// look-back beyond the last `cap` events -- one train silent for that long while another keeps firing --
+// cannot be served; the sweep loop detects that case (status bit 4) before such a read can happen.
 WB_DEV double edge_at(const Trains &T, int q, int i) {
-  (void)T.efrom; (void)T.er;   // edges are read back from global memory (L2): an edge ring cost a CTA per SM
-  return T.g[q][i];
+  int s = i;
+  while (s >= T.cap) s -= T.cap;   // wraps are rare and few: cheaper in registers than a division
+  return T.g[q][s];
 }
 WB_DEV double loc_at(const Trains &T, int q, int j) {
   return j >= T.ifrom[q] ? T.xr[q * WB_RING + (j & (WB_RING - 1))] : (edge_at(T, q, j) + edge_at(T, q, j + 1)) / 2.0 / T.afs;
@@ -198,8 +203,8 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   for (int j = ntaps + tid; j < ntaps + 8; j += nth) hrev[j] = 0.0;
   if (tid == 0) { st[0] = 0.0; st[1] = 0.0; }
   Trains tr;
-  tr.er = nullptr; tr.xr = ring; tr.yr = ring + 4 * WB_RING; tr.afs = p.afs;
-  for (int q = 0; q < 4; ++q) { tr.g[q] = edges + (size_t)q * cap; tr.efrom[q] = 0; tr.ifrom[q] = 0; }
+  tr.xr = ring; tr.yr = ring + 4 * WB_RING; tr.afs = p.afs; tr.cap = cap;
+  for (int q = 0; q < 4; ++q) { tr.g[q] = edges + (size_t)q * cap; tr.ifrom[q] = 0; }
   int ni[4] = {0, 0, 0, 0};   // intervals known so far per train (= max(0, events - 1))
   int tot[4] = {0, 0, 0, 0};  // running event counts per train (identical in every thread)
   int lo_j[4] = {0, 0, 0, 0}; // per train: intervals below this index lie before every unfinished frame
@@ -270,11 +275,8 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
     }
     WB_SYNC();
     const unsigned long long tile_total = scan_packed(cnt, G, 0ull, cnt + G + 4);  // <= 2048 each: fits 16 bit
-    int tcount[4], keep[4];  // events of this tile; after it the ring holds event indices >= keep[q]
-    for (int q = 0; q < 4; ++q) {
-      tcount[q] = (int)((tile_total >> (16 * q)) & 0xffffull);
-      keep[q] = imax(0, tot[q] + tcount[q] - WB_RING);
-    }
+    int tcount[4];  // events of this tile
+    for (int q = 0; q < 4; ++q) tcount[q] = (int)((tile_total >> (16 * q)) & 0xffffull);
     for (int g = tid; g < G; g += nth) {
       const unsigned long long o = cnt[g];
       int off[4] = {(int)(o & 0xffffull), (int)((o >> 16) & 0xffffull), (int)((o >> 32) & 0xffffull), (int)((o >> 48) & 0xffffull)};
@@ -303,13 +305,17 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
           const double d0 = bb - a, d1 = st[pad8(pos + 2)] - bb;
           v = (double)(n0 - 2 + pos + 1) - d0 / (d1 - d0);
         }
-        const int o = tot[q] + e;
-        if (o < cap) edges[(size_t)q * cap + o] = v;
+        int o = tot[q] + e;
+        while (o >= cap) o -= cap;
+        edges[(size_t)q * cap + o] = v;
       }
     }
     tot[0] += (int)(tile_total & 0xffffull); tot[1] += (int)((tile_total >> 16) & 0xffffull);
     tot[2] += (int)((tile_total >> 32) & 0xffffull); tot[3] += (int)((tile_total >> 48) & 0xffffull);
-    for (int q = 0; q < 4; ++q) tr.efrom[q] = keep[q];
+    // unfinished frames still need the intervals from lo_j - 1 on: their edges must not have been overwritten
+    if (tid == 0)
+      for (int q = 0; q < 4; ++q)
+        if (tot[q] - cap > imax(0, lo_j[q] - 1)) atomicOr_status(p.status, 4);
 #ifndef WB_EMU
     __threadfence_block();
 #endif
@@ -319,7 +325,6 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
     // ---- new intervals of this tile -> location / value rings
     bool can = true;
     for (int q = 0; q < 4; ++q) {
-      if (tot[q] > cap) { can = false; continue; }
       const int n_new = imax(0, tot[q] - 1);
       const int from = imax(0, n_new - WB_RING);
       for (int j = imax(ni[q], from) + tid; j < n_new; j += nth) {
@@ -349,7 +354,6 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   // ---- frames after the last complete interval (interp1 extrapolates from the last two samples)
   bool ok = true;
   for (int q = 0; q < 4; ++q) {
-    if (tot[q] > cap) { if (tid == 0) atomicOr_status(p.status, 4); ok = false; }
     const int n_int = tot[q] < 2 ? 0 : tot[q] - 1;  // ZeroCrossingEngine returns count-1 (0 if count<2)
     if (n_int - 2 <= 0) ok = false;                 // CheckEvent(n - 2), dio.cpp:475-484
   }

@@ -13,21 +13,26 @@
 // FixF0 reads (same linear functional).
 #include "wb_internal.h"
 #include "wb_f0common.cuh"
+#include <stdlib.h>
 #include <vector>
 
 namespace wb {
 
 // Event-list capacity per band and train: crossings of a signal band-limited around/below
 // `boundary` cannot be denser than ~boundary per second for long; 2.5x margin, hard bound
-// ylen/2+2 (a negative-going crossing needs two samples).  Overflow raises status bit 4.
+// ylen/2+2 (a negative-going crossing needs two samples).  The lists are history rings: more events
+// than this wrap around; only a look-back beyond the last `cap` events raises status bit 4.
 static void plan_edge_caps(const std::vector<double> &boundary, double afs, int max_ylen,
                            std::vector<int> *cap, std::vector<long long> *off, size_t *stride) {
   const int nb = (int)boundary.size();
   cap->resize(nb); off->resize(nb);
   long long run = 0;
+  long long floor_cap = 2048;
+  if (const char *e = getenv("WB_EDGE_CAP_MIN")) floor_cap = atoll(e) > 0 ? atoll(e) : floor_cap;   // test hook: force wraps
   for (int i = 0; i < nb; ++i) {
     const long long hard = (long long)max_ylen / 2 + 2;
-    const long long soft = (long long)(2.5 * boundary[i] * max_ylen / afs) + 64;
+    long long soft = (long long)(2.5 * boundary[i] * max_ylen / afs) + 64;
+    if (soft < floor_cap) soft = floor_cap;   // a tile can append up to 1025 events per train; the rings look back 256
     (*cap)[i] = (int)(soft < hard ? soft : hard);
     (*off)[i] = run;
     run += 4LL * (*cap)[i];
