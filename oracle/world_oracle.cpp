@@ -548,7 +548,9 @@ void Dio(const double *x, int x_length, int fs, const DioOption *o, double *t, d
   double mean = 0.0;
   for (int i = 0; i < ylen; ++i) mean += y[i];
   mean /= ylen;
-  for (int i = 0; i < ylen; ++i) y[i] -= mean;
+  double dust = 0.0;
+  for (int i = 0; i < ylen; ++i) { y[i] -= mean; dust = std::max(dust, fabs(y[i])); }
+  dust *= 1e-16;
   // DesignLowCutFilter (:40-53): delta minus a unit-sum Hann bump of 2c+1 points, centred on lag 0
   const int c = RoundHalfAway(afs / 50.0), N = 2 * c + 1;
   std::vector<double> lc(N);
@@ -577,6 +579,10 @@ void Dio(const double *x, int x_length, int fs, const DioOption *o, double *t, d
     for (int i = 0; i < ylen; ++i) {
       double acc = 0.0;
       for (int k = 0; k < M; ++k) { const int m = i + 2 * h - k; if (m >= -c && m < ylen + c) acc += w[k] * s[m + c]; }
+      // Model of the reference's FFT rounding noise (not part of its algorithm, but it decides the outcome in
+      // digital silence): what is numerically nothing here -- below 1e-16 of the signal peak -- carries random
+      // signs there and yields dense incoherent crossings; alternate the sign instead of keeping one sign.
+      if (fabs(acc) < dust) acc = (i & 1) ? -1e-300 : 1e-300;
       filt[i] = acc;
     }
     // GetFourZeroCrossingIntervals (:410-444): crossings of s, -s, and of the two signs of the difference

@@ -131,3 +131,7 @@ def test_emu_dio_agrees_with_port(emu):
 
 def test_emu_event_dense_and_degenerate_bands(emu, ref):
     pc.check_event_dense_and_degenerate_bands(emu, ref)
+
+
+def test_emu_zero_tail_f0(emu, ref):
+    pc.check_zero_tail_f0(emu, ref)

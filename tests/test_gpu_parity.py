@@ -187,3 +187,7 @@ def test_gpu_host_pipeline_chunking(gpu_world, golden):
 
 def test_gpu_event_dense_and_degenerate_bands(gpu_world, ref):
     pc.check_event_dense_and_degenerate_bands(gpu_world, ref)
+
+
+def test_gpu_zero_tail_f0(gpu_world, ref):
+    pc.check_zero_tail_f0(gpu_world, ref)

@@ -443,3 +443,23 @@ def check_event_dense_and_degenerate_bands(world, ref):
     tr, fr = ref.dio(x[0], fs, ro)
     assert np.array_equal(to_np(tt)[0], tr)
     assert not ((to_np(f0)[0] > 0) != (fr > 0)).any()
+
+
+def check_zero_tail_f0(world, ref):
+    """utterances that end in 0.5 s of exact zeros.  The F0 estimators must call the tail unvoiced like
+    the reference does (its FFT rounding noise produces dense incoherent zero crossings there; DIO models that,
+    see band_sweep_kernel) -- no V/UV flip, values within the tolerance."""
+    from synth import synth_batch
+    for fs, n, zt, seeds in ((16000, 24000, 8000, [1, 4]), (16000, 40000, 8000, [6]), (22050, 33075, 11025, [5])):
+        x = synth_batch(seeds, fs, n, zero_tail=zt).numpy()
+        xb = make(world, x)
+        td, fd, fl = world.dio(xb, fs)
+        th, fh, _ = world.harvest(xb, fs)
+        world.synchronize()
+        for u in range(len(seeds)):
+            for name, t, f, (tr, fr) in (("dio", td, fd, ref.dio(x[u], fs)), ("harvest", th, fh, ref.harvest(x[u], fs))):
+                got = to_np(f)[u, :fl[u]]
+                assert np.array_equal(to_np(t)[u, :fl[u]], tr)
+                assert not ((got > 0) != (fr > 0)).any(), f"{name}: V/UV flips in the zero tail (fs {fs}, seed {seeds[u]})"
+                assert_close(got, fr, f"{name} f0 with a zero tail (fs {fs}, seed {seeds[u]})")
+                assert not fr[-int(0.4 * zt / fs * 200):].any()

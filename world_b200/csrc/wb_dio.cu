@@ -41,6 +41,7 @@ struct DioPrepParams {
   int ratio;
   double *y; size_t y_stride; int y_origin;   // mean-removed signal, zero padded
   int *y_len;                                  // out: 1 + x_len / ratio
+  double *zero_floor;                          // out: 1e-16 * max |y - mean| (see band_sweep_kernel)
 };
 
 WB_KERNEL(256, 2) dio_prep_kernel(DioPrepParams p) {
@@ -60,8 +61,14 @@ WB_KERNEL(256, 2) dio_prep_kernel(DioPrepParams p) {
   double s = 0.0;
   for (int i = tid; i < ylen; i += nth) s += y[i];
   const double mean = block_sum(s, red) / ylen;
-  for (int i = tid; i < ylen; i += nth) y[i] = y[i] - mean;
-  if (tid == 0) p.y_len[u] = ylen;
+  double amax = 0.0;
+  for (int i = tid; i < ylen; i += nth) {
+    const double v = y[i] - mean;
+    y[i] = v;
+    amax = fmax(amax, fabs(v));
+  }
+  amax = block_max(amax, red);
+  if (tid == 0) { p.y_len[u] = ylen; p.zero_floor[u] = amax * 1e-16; }
 }
 
 struct DioContourParams {
@@ -226,7 +233,7 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     const int n = imin(chunk, b.n - u0);
     ArenaPlan plan;
     const size_t o_y = plan.add((size_t)n * y_stride * 8), o_ylc = plan.add((size_t)n * y_stride * 8);
-    const size_t o_ylen = plan.add((size_t)n * 4);
+    const size_t o_ylen = plan.add((size_t)n * 4), o_zf = plan.add((size_t)n * 8);
     const size_t o_edges = plan.add((size_t)n * edge_stride * 8);
     const size_t o_ecap = plan.add(nb * 4), o_eoff = plan.add(nb * 8);
     const size_t o_cand = plan.add((size_t)n * nb * fstr * 8), o_score = plan.add((size_t)n * nb * fstr * 8);
@@ -253,6 +260,7 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     DioPrepParams pp;
     pp.x = b.x + (size_t)u0 * b.x_stride; pp.x_len = b.x_len + u0; pp.x_stride = b.x_stride; pp.ratio = ratio;
     pp.y = y; pp.y_stride = y_stride; pp.y_origin = padl; pp.y_len = ylen;
+    pp.zero_floor = (double *)(blk + o_zf);
     if (ratio != 1) {
       DecimateParams dp;
       dp.x = pp.x; dp.x_len = pp.x_len; dp.x_stride = pp.x_stride; dp.ratio = ratio; dp.lag = 0;
@@ -279,6 +287,7 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     sp.edge_cap = (const int *)(blk + o_ecap); sp.edge_off = (const long long *)(blk + o_eoff);
     sp.n_frames = b.f_len + u0; sp.frame_stride = fstr; sp.frame_period = opt.frame_period;
     sp.mode = 0; sp.f0_floor = opt.f0_floor; sp.f0_ceil = opt.f0_ceil;
+    sp.zero_floor = (const double *)(blk + o_zf);
     sp.cand = (double *)(blk + o_cand); sp.score = (double *)(blk + o_score);
     sp.max_taps = max_taps; sp.status = ctx->status_dev;
     launch_band_sweep(ctx, sp, (unsigned)n);

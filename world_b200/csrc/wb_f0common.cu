@@ -238,8 +238,19 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
           win[jj] = sp[jj];
         }
       }
+      // DIO only.  Where the filtered signal is numerically nothing (digital silence longer than the filters:
+      // what is left is the rounding residue of the mean removal, ~1e-19, one sign for seconds), the reference
+      // still sees its whole-utterance FFT's rounding noise (~1e-17 of the signal scale) and finds a zero
+      // crossing every few samples; those dense, incoherent events are what makes its candidates fall out of
+      // range there.  Without them interp1 extrapolates the last real interval as a slowly falling "voiced"
+      // ramp.  Stand-in for that noise: values below 1e-16 of the utterance's peak alternate in sign.
+      const double zf = p.zero_floor ? __ldg(p.zero_floor + u) : -1.0;
 #pragma unroll
-      for (int r = 0; r < R; ++r) st[pad8(2 + base + r)] = acc[r];
+      for (int r = 0; r < R; ++r) {
+        double v = acc[r];
+        if (fabs(v) < zf) v = (r & 1) ? -1e-300 : 1e-300;
+        st[pad8(2 + base + r)] = v;
+      }
     }
     WB_SYNC();
     if (p.debug_skip >= 2) { WB_SYNC(); continue; }

@@ -84,6 +84,7 @@ struct SweepParams {
   const int *edge_cap; const long long *edge_off;
   const int *n_frames; int frame_stride; double frame_period;  // frame grid: t_i = i*frame_period/1000
   int mode;                                              // 0 = DIO (candidate + score), 1 = Harvest
+  const double *zero_floor;                              // [n] or nullptr: |filtered| below this is rounding dust (DIO)
   double f0_floor, f0_ceil;
   double *cand; double *score;                           // [(u*nb+b)][frame_stride]
   int max_taps;
