@@ -93,7 +93,7 @@ def main():
                 # the reference's whole-utterance FFT filtering decided (exact-zero stretches, Nyquist-bin quirk)
                 fpo = (port.dio(x, fs, ro) if method == "dio" else port.harvest(x, fs, ro))[1]
                 e_port = rel_err(f0[0], fpo).max() if not ((f0[0] > 0) != (fpo > 0)).any() else float("inf")
-                assert e_port <= 1e-7, f"f0 mismatch, {flips} V/UV flips, and {e_port:.1e} from the time-domain oracle"
+                assert e_port <= TOL, f"f0 mismatch, {flips} V/UV flips, and {e_port:.1e} from the time-domain oracle"
                 refnoise += 1
                 raise RuntimeError(f"REFERENCE-NOISE case: {e_f0:.1e} from the reference ({flips} flips), {e_port:.1e} from the time-domain oracle")
             # spectral stages on the reference's f0, non-default CheapTrick / D4C options now and then
