@@ -8,9 +8,11 @@
 // The reference filters with whole-utterance FFTs (2^17..2^21 points) - far beyond shared
 // memory.  Its filters are short FIRs (<= ~1000 taps), its FFT size is chosen so that the
 // circular convolution never wraps (dio.cpp:592-594, harvest.cpp:1164-1165), and the spectral
-// mirroring quirk is inert, so the filtered signal IS the linear
-// convolution; it is evaluated directly, register-tiled, FP64 FMA bound.  Filter taps are
-// computed on the host with the same libm expressions as the reference and uploaded.
+// mirroring quirk is inert (not for DIO decimated to <= 2 kHz), so
+// the filtered signal IS the linear convolution; it is evaluated directly, register-tiled, FP64
+// FMA bound.  Filter taps are computed on the host with the same libm expressions as the
+// reference and uploaded.  Where the signal is numerically silent the reference's FFT noise
+// decides what it sees; DIO models that (zero_floor, see band_sweep_kernel).
 #pragma once
 #include "wb_platform.cuh"
 #include "wb_block.cuh"
