@@ -135,3 +135,33 @@ def test_emu_event_dense_and_degenerate_bands(emu, ref):
 
 def test_emu_zero_tail_f0(emu, ref):
     pc.check_zero_tail_f0(emu, ref)
+
+
+def test_emu_harvest_chain_refinement(emu, ref):
+    """Experimental refinement kernel (WB_REFINE_CHAIN=1): one template per base candidate
+    shared by its seven overlapped frames.  Its lane layout and shuffles run through the lane-generic macros
+    on the host (32 emulated lanes).  Same tolerance, no V/UV flip."""
+    from refworld import rel_err
+    from synth import synth_batch
+    saved = os.environ.get("WB_REFINE_CHAIN")
+    os.environ["WB_REFINE_CHAIN"] = "1"
+    try:
+        for fs, n, seeds, fp in ((16000, 16000, [1, 2], 5.0), (48000, 24000, [3], 1.0), (8000, 8000, [6], 2.5)):
+            x = synth_batch(seeds, fs, n).numpy()
+            lens = [n - 1234 * u for u in range(len(seeds))]
+            o = emu.harvest_option(); o.frame_period = fp
+            ro = ref.harvest_option(); ro.frame_period = fp
+            t, f, fl = emu.harvest(x, fs, o, x_lengths=lens)
+            emu.synchronize()
+            for u in range(len(seeds)):
+                tr, fr = ref.harvest(x[u, :lens[u]], fs, ro)
+                got = f[u, :fl[u]]
+                assert np.array_equal(t[u, :fl[u]], tr)
+                assert not ((got > 0) != (fr > 0)).any()
+                assert rel_err(got, fr).max() <= pc.TOL
+                assert (fr > 0).sum() > 50
+    finally:
+        if saved is None:
+            os.environ.pop("WB_REFINE_CHAIN", None)
+        else:
+            os.environ["WB_REFINE_CHAIN"] = saved

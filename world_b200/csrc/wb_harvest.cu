@@ -334,6 +334,184 @@ WB_KERNEL(32 * WB_HV_WARPS, 6) harvest_refine_kernel(HvRefineParams p) {
   }
 }
 
+// ------------------------------------------------------------------ K-HVr, chain variant (experimental)
+// DESIGN.md 9 item 2.  When one 1 ms frame is a whole number S of decimated samples (8000 Hz: S = 8), the
+// seven overlapped refinements of a base candidate (frames k-3 .. k+3) share one window and one set of
+// twiddles: GetBaseIndex gives basic = S k' - h, so the window argument (basic + i - 1) / afs - t_k' is
+// (i - h - 1) / afs for every frame.  One warp per SOURCE frame k loops over its base candidates; per sample
+// it builds the template once (w e^{-j theta}, dw e^{-j theta}) and feeds 7 x 4 accumulators from the seven
+// S-shifted samples.  Outputs go to slot j of frame k, slot j + nc g of frame k + g and slot j + nc (g + 3) of
+// frame k - g (the inverse of hv_slot_candidate); every other slot keeps the zero the driver memset.
+// Selected with WB_REFINE_CHAIN=1; not measured on a GPU yet, therefore not the default.
+//
+// Lane-generic source: WB_FOR_LANES runs the lane body for lane = threadIdx.x & 31 on the GPU and for all 32
+// lanes in turn in the host emulation, so the lane layout and the shuffles are checked on the CPU too.
+#ifdef WB_EMU
+#define WB_CL 32
+#define WB_FOR_LANES(l) for (int l = 0; l < 32; ++l)
+#else
+#define WB_CL 1
+#define WB_FOR_LANES(l) for (int l = (int)(threadIdx.x & 31), wb_once_ = 1; wb_once_; wb_once_ = 0)
+#endif
+#define WB_LI(l) ((WB_CL == 1) ? 0 : (l))
+
+// v[lane][i] += v[lane ^ o][i] for every lane
+template <int N>
+WB_DEV void lanes_xor_add(double (&v)[WB_CL][N], int o) {
+#ifdef WB_EMU
+  double t[32][N];
+  for (int l = 0; l < 32; ++l)
+    for (int i = 0; i < N; ++i) t[l][i] = v[l][i];
+  for (int l = 0; l < 32; ++l)
+    for (int i = 0; i < N; ++i) v[l][i] = t[l][i] + t[l ^ o][i];
+#else
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[0][i] += __shfl_xor_sync(0xffffffffu, v[0][i], o);
+#endif
+}
+
+// value held by lane `src`, to every lane
+WB_DEV double lanes_get(const double (&v)[WB_CL], int src) {
+#ifdef WB_EMU
+  return v[src];
+#else
+  return __shfl_sync(0xffffffffu, v[0], src);
+#endif
+}
+
+struct HvChainParams {
+  HvRefineParams r;
+  int frame_samples;   // S
+};
+
+WB_KERNEL(32 * WB_HV_WARPS, 4) harvest_refine_chain_kernel(HvChainParams cp) {
+  WB_DYN_SMEM(double, smem);
+  const HvRefineParams &p = cp.r;
+#ifdef WB_EMU
+  const int warp = 0, nwarps = 1;
+#else
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#endif
+  const int u = blockIdx.y;
+  const int L1 = p.l1[u];
+  const int k = blockIdx.x * nwarps + warp;   // source frame
+  if (k >= L1) return;
+  const int S = cp.frame_samples;
+  const int nc = p.nc[u];
+  const int seg_max = p.nwin_max + 6 * S + 8;
+  double *wbuf = smem + (size_t)warp * (2 * p.nwin_max + seg_max), *dbuf = wbuf + p.nwin_max, *xs = dbuf + p.nwin_max;
+  const double *y = p.y + (size_t)u * p.y_stride + p.y_origin;
+  const int y_len = p.y_len[u];
+  const double afs = p.afs;
+  const double *base = p.base + ((size_t)u * p.l1_stride + k) * WB_HV_BASE;
+  for (int j = 0; j < nc && j < WB_HV_BASE; ++j) {
+    const double f = base[j];
+    if (!(f > 0.0)) continue;
+    const int h = static_cast<int>(1.5 * afs / f + 1.0);
+    const int nwin = 2 * h + 1;
+    int lg = 0;
+    while ((2 << lg) <= nwin) ++lg;
+    const int lg_nfft = lg + 2, nfft = 1 << lg_nfft;
+    const double T = (2.0 * h + 1.0) / afs;
+    const int H = imin(static_cast<int>(afs / 2.0 / f), 6);
+    const int shift = WB_TW_LOG2 - lg_nfft;
+    const int basic0 = S * (k - 3) - h;     // basic index of frame k - 3; frame k + g - 3 starts S g samples later
+    const int nseg = nwin + 6 * S;
+    const double inv_afs = 1.0 / afs, w_scale = 2.0 * kPi / T;
+    WB_FOR_LANES(l) {
+      for (int i = l; i < nseg; i += 32) xs[i] = y[imax(0, imin(y_len - 1, basic0 + i - 1))];
+      for (int i = l; i < nwin; i += 32) {
+        const double tau = (i - h - 1.0) * inv_afs;
+        const double c1 = hv_cos_small(w_scale * tau);
+        wbuf[i] = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
+      }
+    }
+#ifndef WB_EMU
+    __syncwarp();
+#endif
+    WB_FOR_LANES(l) {
+      for (int i = l; i < nwin; i += 32) {
+        double dw;
+        if (i == 0) dw = -wbuf[1] / 2.0;
+        else if (i == nwin - 1) dw = wbuf[nwin - 2] / 2.0;
+        else dw = -(wbuf[i + 1] - wbuf[i - 1]) / 2.0;
+        dbuf[i] = dw;
+      }
+    }
+#ifndef WB_EMU
+    __syncwarp();
+#endif
+    // acc[.][4 g + {0,1,2,3}] = {main re, main im, diff re, diff im} of frame k + g - 3
+    double acc[WB_CL][28];
+    WB_FOR_LANES(l) {
+      const int m = l & 7, c0 = l >> 3;
+      double *a = acc[WB_LI(l)];
+#pragma unroll
+      for (int q = 0; q < 28; ++q) a[q] = 0.0;
+      if (m < H) {
+        const int bin = round_half_away(f * nfft / afs * (m + 1));
+        const double2 rot = hv_tw(p.tw, ((bin * 4) & (nfft - 1)) << shift);
+        double2 w = hv_tw(p.tw, ((bin * c0) & (nfft - 1)) << shift);
+        for (int i = c0; i < nwin; i += 4) {
+          const double wv = wbuf[i], dv = dbuf[i];
+          const double P = wv * w.x, Q = wv * w.y, R = dv * w.x, Sd = dv * w.y;
+#pragma unroll
+          for (int g = 0; g < 7; ++g) {
+            const double xv = xs[i + S * g];
+            a[4 * g + 0] = fma(xv, P, a[4 * g + 0]);
+            a[4 * g + 1] = fma(xv, Q, a[4 * g + 1]);
+            a[4 * g + 2] = fma(xv, R, a[4 * g + 2]);
+            a[4 * g + 3] = fma(xv, Sd, a[4 * g + 3]);
+          }
+          const double nx = fma(w.x, rot.x, -(w.y * rot.y));
+          const double ny = fma(w.x, rot.y, w.y * rot.x);
+          w.x = nx; w.y = ny;
+        }
+      }
+    }
+    lanes_xor_add(acc, 8);
+    lanes_xor_add(acc, 16);
+    for (int g = 0; g < 7; ++g) {
+      const int kk = k + g - 3;
+      if (kk < 0 || kk >= L1) continue;       // uniform over the warp
+      double t_num[WB_CL], t_den[WB_CL], t_sc[WB_CL];
+      WB_FOR_LANES(l) {
+        const int m = l & 7;
+        const double *a = acc[WB_LI(l)];
+        const double mr = a[4 * g], mi = a[4 * g + 1], dr = a[4 * g + 2], di = a[4 * g + 3];
+        const int bin = round_half_away(f * nfft / afs * (m + 1));
+        const double num = mr * di - mi * dr;
+        const double pw = mr * mr + mi * mi;
+        const double inst = pw == 0.0 ? 0.0 : static_cast<double>(bin) * afs / nfft + num / pw * afs / 2.0 / kPi;
+        const double amp = sqrt(pw);
+        t_num[WB_LI(l)] = amp * inst;
+        t_den[WB_LI(l)] = amp * (m + 1.0);
+        t_sc[WB_LI(l)] = fabs((inst / (m + 1.0) - f) / f);
+      }
+      double numerator = 0.0, denominator = 0.0, score = 0.0;   // harmonic order, like FixF0 (harvest.cpp:521-527)
+      for (int mm = 0; mm < H; ++mm) {
+        numerator += lanes_get(t_num, mm);
+        denominator += lanes_get(t_den, mm);
+        score += lanes_get(t_sc, mm);
+      }
+      double rf = numerator / (denominator + kTiny);
+      double rs = 1.0 / (score / H + kTiny);
+      if (rf < p.f0_floor || rf > p.f0_ceil || rs < 2.5) { rf = 0.0; rs = 0.0; }
+      const int d = g - 3;
+      const int slot = d == 0 ? j : (d > 0 ? j + nc * d : j + nc * (3 - d));
+      WB_FOR_LANES(l) {
+        if (l == 0) {
+          p.cand[((size_t)u * p.l1_stride + kk) * p.max_cand + slot] = rf;
+          p.score[((size_t)u * p.l1_stride + kk) * p.max_cand + slot] = rs;
+        }
+      }
+    }
+#ifndef WB_EMU
+    __syncwarp();
+#endif
+  }
+}
+
 // ------------------------------------------------------------------ RemoveUnreliableCandidates
 struct HvRemoveParams {
   const double *cand_in; const double *score_in; double *cand; double *score;
@@ -815,7 +993,22 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
 #else
     const unsigned refine_blocks = (unsigned)((l1_stride + WB_HV_WARPS - 1) / WB_HV_WARPS);
 #endif
-    WB_LAUNCH_COOP(harvest_refine_kernel, dim3(refine_blocks, (unsigned)n), 32 * WB_HV_WARPS, smem_refine, ctx->stream, rp);
+    const int frame_samples = static_cast<int>(afs / 1000.0);
+    if (getenv("WB_REFINE_CHAIN") && frame_samples >= 1 && frame_samples * 1000.0 == afs) {
+      // experimental: slots without an in-range source frame keep these zeros
+      rc = dev_memset(ctx, rp.cand, 0, (size_t)n * l1_stride * max_cand * 8);
+      if (!rc) rc = dev_memset(ctx, rp.score, 0, (size_t)n * l1_stride * max_cand * 8);
+      if (rc) return rc;
+      HvChainParams chp;
+      chp.r = rp; chp.frame_samples = frame_samples;
+      const size_t smem_chain = (size_t)WB_HV_WARPS * (3 * (size_t)nwin_max + 6 * frame_samples + 8) * 8;
+#ifndef WB_EMU
+      cudaFuncSetAttribute(harvest_refine_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain);
+#endif
+      WB_LAUNCH_COOP(harvest_refine_chain_kernel, dim3(refine_blocks, (unsigned)n), 32 * WB_HV_WARPS, smem_chain, ctx->stream, chp);
+    } else {
+      WB_LAUNCH_COOP(harvest_refine_kernel, dim3(refine_blocks, (unsigned)n), 32 * WB_HV_WARPS, smem_refine, ctx->stream, rp);
+    }
 
     HvRemoveParams mp;
     mp.cand_in = rp.cand; mp.score_in = rp.score; mp.cand = (double *)(blk + o_c2); mp.score = (double *)(blk + o_s2);
