@@ -54,7 +54,8 @@ def emu():
     from world_b200.api import World
     path = os.path.join(ROOT, "tests", "emu", "libworld_b200_emu.so")
     subprocess.check_call([os.path.join(ROOT, "tests", "emu", "build.sh")], stdout=subprocess.DEVNULL)
-    return World(lib_path=path, array_module="numpy")
+    # WB_EMU_LIB: an instrumented build of the same sources (e.g. -fsanitize=address, see tests/emu/README)
+    return World(lib_path=os.environ.get("WB_EMU_LIB", path), array_module="numpy")
 
 
 @pytest.fixture(scope="session")

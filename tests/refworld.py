@@ -160,6 +160,9 @@ class RefWorld:
     def wavread(self, path):
         """the reference's own wavread (tools/audioio.cpp:217-252); only in oracle/_ref"""
         self.lib.GetAudioLength.restype = C.c_int
+        self.lib.GetAudioLength.argtypes = [C.c_char_p]
+        self.lib.wavread.restype = None
+        self.lib.wavread.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), _P]
         n = self.lib.GetAudioLength(path.encode())
         x = np.zeros(max(n, 1)); fs = C.c_int(); nbit = C.c_int()
         self.lib.wavread(path.encode(), C.byref(fs), C.byref(nbit), x.ctypes.data)

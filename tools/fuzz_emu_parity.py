@@ -44,7 +44,7 @@ def main():
     rng = np.random.default_rng(seed)
     ref = RefWorld()
     port = RefWorld(ORACLE_LIB)   # the time-domain restatement: arbiter when the reference's FFT noise decides
-    emu = World(lib_path=os.path.join(ROOT, "tests", "emu", "libworld_b200_emu.so"), array_module="numpy")
+    emu = World(lib_path=os.environ.get("WB_EMU_LIB", os.path.join(ROOT, "tests", "emu", "libworld_b200_emu.so")), array_module="numpy")
     bad = 0
     refnoise = 0
     for case in range(n_cases):

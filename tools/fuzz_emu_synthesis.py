@@ -20,7 +20,7 @@ def main():
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     rng = np.random.default_rng(seed)
     ref = RefWorld()
-    emu = World(lib_path=os.path.join(ROOT, "tests", "emu", "libworld_b200_emu.so"), array_module="numpy")
+    emu = World(lib_path=os.environ.get("WB_EMU_LIB", os.path.join(ROOT, "tests", "emu", "libworld_b200_emu.so")), array_module="numpy")
     bad = 0
     for case in range(n_cases):
         fs = int(rng.choice([16000, 22050, 44100, 48000]))
