@@ -113,7 +113,7 @@ namespace wb { extern unsigned long long g_launches; }
     }                                                                  \
   })
 
-struct double2 { double x, y; };
+struct alignas(16) double2 { double x, y; };   // CUDA's double2 is 16-byte aligned: keep UBSan's alignment check meaningful
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 struct uint4 { unsigned x, y, z, w; };
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
