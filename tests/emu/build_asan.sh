@@ -4,7 +4,7 @@
 #   sh tests/emu/build_asan.sh /tmp/asan
 #   ASAN_OPTIONS=detect_leaks=0 LD_PRELOAD=$(g++ -print-file-name=libasan.so) \
 #     WB_EMU_LIB=/tmp/asan/libworld_b200_emu_asan.so python -m pytest tests/test_emu_parity.py -q
-# (the fuzz tools under tools/ honour WB_EMU_LIB as well)
+# (the fuzzers under tests/fuzz/ honour WB_EMU_LIB as well)
 set -e
 OUT=${1:-/tmp/asan}
 cd "$(dirname "$0")"

@@ -2,7 +2,7 @@
 # GPU experiment for DESIGN.md 9 item 2 (run on the B200 box from the repo root):
 #   1. parity of the chain refinement kernel against the compiled reference on the GPU,
 #   2. bench with the default kernel and with WB_REFINE_CHAIN=1 (device-resident part only).
-# Usage: gpurun --timeout 500 -- 'sh tools/exp_refine_chain.sh > gpurun_out/exp_refine_chain.txt 2>&1'
+# Usage: gpurun --timeout 500 -- 'sh tests/fuzz/exp_refine_chain.sh > gpurun_out/exp_refine_chain.txt 2>&1'
 set -x
 python - <<'PY'
 import os, sys

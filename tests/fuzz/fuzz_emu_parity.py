@@ -1,12 +1,12 @@
 """Randomised parity sweep of the kernel sources (host emulation) against the compiled reference (CPU only).
-Usage: python tools/fuzz_emu_parity.py [n_cases] [seed]   -- prints one line per case, exits non-zero on a mismatch."""
+Usage: python tests/fuzz/fuzz_emu_parity.py [n_cases] [seed]   -- prints one line per case, exits non-zero on a mismatch."""
 import os
 import sys
 import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from refworld import RefWorld, ORACLE_LIB, rel_err  # noqa: E402

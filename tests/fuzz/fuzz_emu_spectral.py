@@ -1,13 +1,13 @@
 """Randomised parity sweep of StoneMask / CheapTrick / D4C (kernel sources on the host vs the compiled
 reference) with adversarial f0 contours: values below the floors, near fs/2, jumps, zeros, time axes with
-non-default frame periods, ragged batches.  CPU only.  Usage: python tools/fuzz_emu_spectral.py [n_cases] [seed]"""
+non-default frame periods, ragged batches.  CPU only.  Usage: python tests/fuzz/fuzz_emu_spectral.py [n_cases] [seed]"""
 import os
 import sys
 import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from refworld import RefWorld, rel_err  # noqa: E402

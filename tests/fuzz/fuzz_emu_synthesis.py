@@ -1,13 +1,13 @@
 """Randomised parity sweep of batched Synthesis (kernel sources on the host vs the compiled reference): random
 rates, frame periods, output lengths, f0 contours (incl. unvoiced stretches, values below the synthesis floor),
-envelopes from the reference's own analysis.  CPU only.  Usage: python tools/fuzz_emu_synthesis.py [n_cases] [seed]"""
+envelopes from the reference's own analysis.  CPU only.  Usage: python tests/fuzz/fuzz_emu_synthesis.py [n_cases] [seed]"""
 import os
 import sys
 import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from refworld import RefWorld  # noqa: E402

@@ -406,7 +406,7 @@ def check_host_pipeline_chunking(world, golden, f0_method=0):
 
 
 def check_event_dense_and_degenerate_bands(world, ref):
-    """Found by tools/fuzz_emu_parity.py: (1) a loud tone gives every Harvest band far more zero crossings than
+    """Found by tests/fuzz/fuzz_emu_parity.py: (1) a loud tone gives every Harvest band far more zero crossings than
     its centre frequency suggests -- the per-band event lists wrap (history rings) instead of overflowing;
     (2) DIO bands above the decimated Nyquist have a zero-length window in the reference and contribute no
     candidate instead of being an error."""
