@@ -379,6 +379,14 @@ WB_DEV double lanes_get(const double (&v)[WB_CL], int src) {
 #endif
 }
 
+// element `src` of a per-lane value, read by every lane at once (src may differ per lane); on the host the
+// array must have been filled by an earlier WB_FOR_LANES block
+#ifdef WB_EMU
+#define WB_LANE_READ(arr, src) (arr[(src)])
+#else
+#define WB_LANE_READ(arr, src) __shfl_sync(0xffffffffu, arr[0], (src))
+#endif
+
 struct HvChainParams {
   HvRefineParams r;
   int frame_samples;   // S
@@ -471,14 +479,18 @@ WB_KERNEL(32 * WB_HV_WARPS, 4) harvest_refine_chain_kernel(HvChainParams cp) {
     }
     lanes_xor_add(acc, 8);
     lanes_xor_add(acc, 16);
-    for (int g = 0; g < 7; ++g) {
-      const int kk = k + g - 3;
-      if (kk < 0 || kk >= L1) continue;       // uniform over the warp
+    // FixF0 (harvest.cpp:498-535) for the seven frames, spread over the four sample-class groups: the 8-lane
+    // group c0 = lane >> 3 takes frames g = c0 and c0 + 4 (harmonic m = lane & 7 as before), so two rounds
+    // instead of seven; the harmonic sums run in index order inside each group, lane 8 c0 writes the result.
+    for (int round = 0; round < 2; ++round) {
       double t_num[WB_CL], t_den[WB_CL], t_sc[WB_CL];
       WB_FOR_LANES(l) {
-        const int m = l & 7;
+        const int m = l & 7, g = (l >> 3) + 4 * round;
         const double *a = acc[WB_LI(l)];
-        const double mr = a[4 * g], mi = a[4 * g + 1], dr = a[4 * g + 2], di = a[4 * g + 3];
+        double mr = 0.0, mi = 0.0, dr = 0.0, di = 0.0;
+#pragma unroll
+        for (int gg = 0; gg < 7; ++gg)      // register array: select by comparison, not by a runtime index
+          if (gg == g) { mr = a[4 * gg]; mi = a[4 * gg + 1]; dr = a[4 * gg + 2]; di = a[4 * gg + 3]; }
         const int bin = round_half_away(f * nfft / afs * (m + 1));
         const double num = mr * di - mi * dr;
         const double pw = mr * mr + mi * mi;
@@ -488,19 +500,21 @@ WB_KERNEL(32 * WB_HV_WARPS, 4) harvest_refine_chain_kernel(HvChainParams cp) {
         t_den[WB_LI(l)] = amp * (m + 1.0);
         t_sc[WB_LI(l)] = fabs((inst / (m + 1.0) - f) / f);
       }
-      double numerator = 0.0, denominator = 0.0, score = 0.0;   // harmonic order, like FixF0 (harvest.cpp:521-527)
-      for (int mm = 0; mm < H; ++mm) {
-        numerator += lanes_get(t_num, mm);
-        denominator += lanes_get(t_den, mm);
-        score += lanes_get(t_sc, mm);
-      }
-      double rf = numerator / (denominator + kTiny);
-      double rs = 1.0 / (score / H + kTiny);
-      if (rf < p.f0_floor || rf > p.f0_ceil || rs < 2.5) { rf = 0.0; rs = 0.0; }
-      const int d = g - 3;
-      const int slot = d == 0 ? j : (d > 0 ? j + nc * d : j + nc * (3 - d));
       WB_FOR_LANES(l) {
-        if (l == 0) {
+        const int g = (l >> 3) + 4 * round, kk = k + g - 3;
+        double numerator = 0.0, denominator = 0.0, score = 0.0;   // harmonic order, like FixF0 (harvest.cpp:521-527)
+        for (int mm = 0; mm < H; ++mm) {
+          const int src = (l & 24) | mm;
+          numerator += WB_LANE_READ(t_num, src);
+          denominator += WB_LANE_READ(t_den, src);
+          score += WB_LANE_READ(t_sc, src);
+        }
+        if ((l & 7) == 0 && g < 7 && kk >= 0 && kk < L1) {
+          double rf = numerator / (denominator + kTiny);
+          double rs = 1.0 / (score / H + kTiny);
+          if (rf < p.f0_floor || rf > p.f0_ceil || rs < 2.5) { rf = 0.0; rs = 0.0; }
+          const int d = g - 3;
+          const int slot = d == 0 ? j : (d > 0 ? j + nc * d : j + nc * (3 - d));
           p.cand[((size_t)u * p.l1_stride + kk) * p.max_cand + slot] = rf;
           p.score[((size_t)u * p.l1_stride + kk) * p.max_cand + slot] = rs;
         }
