@@ -64,7 +64,9 @@ def test_no_gpu_means_loud_failure():
 
 def test_headers_are_c99(tmp_path):
     src = tmp_path / "c99.c"
-    src.write_text('#include "world_b200.h"\nint main(void){DioOption o; InitializeDioOption(&o); return (int)o.speed;}\n')
+    src.write_text('#include "world_b200.h"\n#include "world/matlabfunctions.h"\n#include "tools/audioio.h"\n'
+                   '#include "tools/parameterio.h"\n'
+                   'int main(void){DioOption o; RandnState r; InitializeDioOption(&o); randn_reseed(&r); return (int)o.speed;}\n')
     subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-I", INC, str(src)])
 
 

@@ -113,6 +113,17 @@ ABI = {
     "ReadAperiodicity": (C.c_int, [C.c_char_p, _P]),
     "world_b200_write_rows": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _P]),
     "world_b200_read_rows": (C.c_int, [C.c_char_p, C.c_char_p, _P, C.c_int]),
+    # public MATLAB-style helpers (world/matlabfunctions.h), host only
+    "fftshift": (None, [_P, C.c_int, _P]),
+    "histc": (None, [_P, C.c_int, _P, C.c_int, _P]),
+    "interp1": (None, [_P, _P, C.c_int, _P, C.c_int, _P]),
+    "decimate": (None, [_P, C.c_int, C.c_int, _P]),
+    "matlab_round": (C.c_int, [C.c_double]),
+    "diff": (None, [_P, C.c_int, _P]),
+    "interp1Q": (None, [C.c_double, C.c_double, _P, C.c_int, _P, C.c_int, _P]),
+    "randn": (C.c_double, [_P]),
+    "randn_reseed": (None, [_P]),
+    "matlab_std": (C.c_double, [_P, C.c_int]),
     "GetNumberOfAperiodicities": (C.c_int, [C.c_int]),
     "CodeAperiodicity": (None, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "DecodeAperiodicity": (None, [_P, C.c_int, C.c_int, C.c_int, _P]),

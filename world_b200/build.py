@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
-SOURCES = ["wb_api.cu", "wb_host.cu", "wb_rng.cu", "wb_cheaptrick.cu", "wb_d4c.cu", "wb_stonemask.cu", "wb_synthesis.cu", "wb_codec.cu", "wb_fileio.cu",
+SOURCES = ["wb_api.cu", "wb_host.cu", "wb_rng.cu", "wb_cheaptrick.cu", "wb_d4c.cu", "wb_stonemask.cu", "wb_synthesis.cu", "wb_codec.cu", "wb_fileio.cu", "wb_matlab.cu",
            "wb_f0common.cu", "wb_dio.cu", "wb_harvest.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: values that feed int casts / comparisons must round like the reference's x86-64 -O1
