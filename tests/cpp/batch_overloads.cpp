@@ -72,6 +72,20 @@ int main() {
     for (size_t i = 0; i < s1.size(); ++i) bad += (s1[i] != sp[u][i]) + (a1[i] != ap[u][i]);
     for (int i = 0; i < lens[u]; ++i) bad += (y1[i] != y[u][i]);
   }
+  // Harvest: batched overload against the single-utterance entry point
+  {
+    HarvestOption hopt; InitializeHarvestOption(&hopt);
+    std::vector<std::vector<double>> th(n_utts), fh(n_utts);
+    double *thp[3], *fhp[3];
+    for (int u = 0; u < n_utts; ++u) { th[u].resize(fl[u]); fh[u].resize(fl[u]); thp[u] = th[u].data(); fhp[u] = fh[u].data(); }
+    rc = Harvest(xs, lens, n_utts, fs, &hopt, thp, fhp);
+    if (rc) { std::printf("FAIL: batched Harvest returned %d\n", rc); return 1; }
+    for (int u = 0; u < n_utts; ++u) {
+      std::vector<double> t1(fl[u]), f1(fl[u]);
+      Harvest(xs[u], lens[u], fs, &hopt, t1.data(), f1.data());
+      for (int i = 0; i < fl[u]; ++i) bad += (t1[i] != th[u][i]) + (f1[i] != fh[u][i]);
+    }
+  }
   if (bad || voiced == 0) { std::printf("FAIL: %d mismatching values, %d voiced frames\n", bad, voiced); return 1; }
   std::printf("OK: batched overloads == single-utterance API on %d utterances (%d voiced frames)\n", n_utts, voiced);
   return 0;
