@@ -116,11 +116,3 @@ def test_cpp_batched_overloads_compile_and_fail_loudly_without_gpu(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode != 0
     assert "no CPU path" in r.stderr
-
-
-@pytest.mark.gpu
-def test_gpu_cpp_batched_overloads_equal_single_utterance_api(tmp_path):
-    exe = build_cpp_overload_program(tmp_path / "batch_overloads")
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.startswith("OK")

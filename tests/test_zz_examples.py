@@ -10,6 +10,7 @@ import wave
 import numpy as np
 import pytest
 
+import test_abi
 import test_parity_common as pc
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -101,3 +102,11 @@ def test_gpu_reference_examples_run_on_this_library(examples, golden, tmp_path):
         ra, rb = np.frombuffer(ba[skip:], dtype="<f8"), np.frombuffer(bb[skip:], dtype="<f8")
         assert ra.size % width == 0 and ra.size > 0
         pc.assert_close(rb, ra, f"analysis example, .{ext} stream")
+
+
+@pytest.mark.gpu
+def test_gpu_cpp_batched_overloads_equal_single_utterance_api(tmp_path):
+    exe = test_abi.build_cpp_overload_program(tmp_path / "batch_overloads")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("OK")
