@@ -566,6 +566,15 @@ void Dio(const double *x, int x_length, int fs, const DioOption *o, double *t, d
     s[n + c] = acc;
   }
 
+  // bins N/2 - 1 and N/2 of the low-cut filtered spectrum, N = the reference's fft_size (dio.cpp:590-592)
+  const int NF = (int)pow(2.0, (int)(log((double)(ylen + RoundHalfAway(afs / 50.0) * 2 + 1 + 4 * (int)(1.0 + afs / boundary[0] / 2.0))) / kLog2) + 1.0);
+  const int N2 = NF / 2;
+  double ys1r = 0.0, ys1i = 0.0, ys2 = 0.0;
+  for (int n = -c; n < ylen + c; ++n) {
+    const double v = s[n + c];
+    ys1r += v * cos(2.0 * kPi * (N2 - 1) * n / NF); ys1i -= v * sin(2.0 * kPi * (N2 - 1) * n / NF);
+    ys2 += v * ((n & 1) ? -1.0 : 1.0);
+  }
   std::vector<std::vector<double> > cand(nb, std::vector<double>(L)), score(nb, std::vector<double>(L));
   std::vector<double> filt(ylen), work, loc[4], itv[4], yi[4];
   for (int b = 0; b < nb; ++b) {
@@ -576,12 +585,27 @@ void Dio(const double *x, int x_length, int fs, const DioOption *o, double *t, d
       const double u = i / (M - 1.0);
       w[i] = 0.355768 - 0.487396 * cos(2.0 * kPi * u) + 0.144232 * cos(4.0 * kPi * u) - 0.012604 * cos(6.0 * kPi * u);
     }
+    // F at bins N/2 - 1 and N/2, and the difference between what the mirroring loop leaves there and the product
+    double f1r = 0.0, f1i = 0.0, f2 = 0.0;
+    for (int k = 0; k < M; ++k) {
+      f1r += w[k] * cos(2.0 * kPi * (N2 - 1) * k / NF); f1i -= w[k] * sin(2.0 * kPi * (N2 - 1) * k / NF);
+      f2 += w[k] * ((k & 1) ? -1.0 : 1.0);
+    }
+    const double p_re = ys1r * f1r - ys1i * f1i, p_im = ys1r * f1i + ys1i * f1r;     // Ys[N/2-1] F[N/2-1]
+    const double dq_re = ys2 * p_re - p_re, dq_im = ys2 * p_im - p_im;             // Q - product at N/2 - 1
+    const double dn = ys2 * p_re - ys2 * f2;                                        // Re Q - product at N/2
     for (int i = 0; i < ylen; ++i) {
       double acc = 0.0;
       for (int k = 0; k < M; ++k) { const int m = i + 2 * h - k; if (m >= -c && m < ylen + c) acc += w[k] * s[m + c]; }
       // Model of the reference's FFT rounding noise (not part of its algorithm, but it decides the outcome in
       // digital silence): what is numerically nothing here -- below 1e-16 of the signal peak -- carries random
       // signs there and yields dense incoherent crossings; alternate the sign instead of keeping one sign.
+      // The reference's spectral "mirroring" loop (dio.cpp:319-328) writes product bin i to slot N - i - 1; for
+      // i = N/2 - 1 and N/2 those slots are N/2 and N/2 - 1, i.e. inside the half c2r reads: both end up as
+      // Q = Ys[N/2] * (Ys[N/2-1] F[N/2-1]).  Inert for long filters (F ~ 0 near Nyquist), visible for the 4..12
+      // tap windows of heavy decimation.  Added here as the time-domain signal it amounts to.
+      acc += (2.0 * (dq_re * cos(2.0 * kPi * (N2 - 1) * (i + 2 * h) / NF) - dq_im * sin(2.0 * kPi * (N2 - 1) * (i + 2 * h) / NF)) +
+              dn * (((i + 2 * h) & 1) ? -1.0 : 1.0)) / NF;
       if (fabs(acc) < dust) acc = (i & 1) ? -1e-300 : 1e-300;
       filt[i] = acc;
     }
