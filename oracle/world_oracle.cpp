@@ -548,9 +548,7 @@ void Dio(const double *x, int x_length, int fs, const DioOption *o, double *t, d
   double mean = 0.0;
   for (int i = 0; i < ylen; ++i) mean += y[i];
   mean /= ylen;
-  double dust = 0.0;
-  for (int i = 0; i < ylen; ++i) { y[i] -= mean; dust = std::max(dust, fabs(y[i])); }
-  dust *= 1e-16;
+  for (int i = 0; i < ylen; ++i) y[i] -= mean;
   // DesignLowCutFilter (:40-53): delta minus a unit-sum Hann bump of 2c+1 points, centred on lag 0
   const int c = RoundHalfAway(afs / 50.0), N = 2 * c + 1;
   std::vector<double> lc(N);
@@ -597,16 +595,15 @@ void Dio(const double *x, int x_length, int fs, const DioOption *o, double *t, d
     for (int i = 0; i < ylen; ++i) {
       double acc = 0.0;
       for (int k = 0; k < M; ++k) { const int m = i + 2 * h - k; if (m >= -c && m < ylen + c) acc += w[k] * s[m + c]; }
-      // Model of the reference's FFT rounding noise (not part of its algorithm, but it decides the outcome in
-      // digital silence): what is numerically nothing here -- below 1e-16 of the signal peak -- carries random
-      // signs there and yields dense incoherent crossings; alternate the sign instead of keeping one sign.
       // The reference's spectral "mirroring" loop (dio.cpp:319-328) writes product bin i to slot N - i - 1; for
       // i = N/2 - 1 and N/2 those slots are N/2 and N/2 - 1, i.e. inside the half c2r reads: both end up as
-      // Q = Ys[N/2] * (Ys[N/2-1] F[N/2-1]).  Inert for long filters (F ~ 0 near Nyquist), visible for the 4..12
-      // tap windows of heavy decimation.  Added here as the time-domain signal it amounts to.
+      // Q = Ys[N/2] * (Ys[N/2-1] F[N/2-1]).  Negligible next to a real signal when the filter is long (F ~ 0 near
+      // Nyquist), visible for the 4..12 tap windows of heavy decimation -- and the ONLY thing left in digital
+      // silence, where this near-Nyquist ripple gives the reference a zero crossing every sample or two (which is
+      // why it calls silence unvoiced instead of extrapolating the last interval).  Added here as the time-domain
+      // signal it amounts to.
       acc += (2.0 * (dq_re * cos(2.0 * kPi * (N2 - 1) * (i + 2 * h) / NF) - dq_im * sin(2.0 * kPi * (N2 - 1) * (i + 2 * h) / NF)) +
               dn * (((i + 2 * h) & 1) ? -1.0 : 1.0)) / NF;
-      if (fabs(acc) < dust) acc = (i & 1) ? -1e-300 : 1e-300;
       filt[i] = acc;
     }
     // GetFourZeroCrossingIntervals (:410-444): crossings of s, -s, and of the two signs of the difference
@@ -868,6 +865,14 @@ void HvBody(const double *x, int x_length, int fs, double f0_floor, double f0_ce
   mean /= ylen;
   for (int i = 0; i < ylen; ++i) y[i] -= mean;
 
+  // bins NF/2 - 1 and NF/2 of the signal's spectrum, NF = the reference's fft_size (:1164-1165)
+  const int NF = (int)pow(2.0, (int)(log((double)(ylen + 5 + 2 * (int)(2.0 * afs / boundary[0]))) / kLog2) + 1.0);
+  const int N2 = NF / 2;
+  double ys1r = 0.0, ys1i = 0.0, ys2 = 0.0;
+  for (int n = 0; n < ylen; ++n) {
+    ys1r += y[n] * cos(2.0 * kPi * (N2 - 1) * n / NF); ys1i -= y[n] * sin(2.0 * kPi * (N2 - 1) * n / NF);
+    ys2 += y[n] * ((n & 1) ? -1.0 : 1.0);
+  }
   // raw candidates per channel (:99-147, :162-343): band-pass FIR, four crossing trains, interp1, gate
   Rows raw(nch, std::vector<double>(L, 0.0));
   std::vector<double> filt(ylen), work, loc[4], itv[4], yi[4];
@@ -879,10 +884,23 @@ void HvBody(const double *x, int x_length, int fs, double f0_floor, double f0_ce
       bp[i] = (0.355768 - 0.487396 * cos(2.0 * kPi * u) + 0.144232 * cos(4.0 * kPi * u) - 0.012604 * cos(6.0 * kPi * u)) *
               cos(2 * kPi * boundary[c] * (i - h) / afs);
     }
+    // the mirroring loop of harvest.cpp:122-135 (same as DIO's, see Dio above): bins NF/2 - 1 and NF/2 of the
+    // product both become Ys[NF/2] * (Ys[NF/2-1] F[NF/2-1]); the resulting ripple is ~1e-20 of the signal for
+    // these long band-pass filters and matters only where the input is digitally silent
+    double f1r = 0.0, f1i = 0.0, f2 = 0.0;
+    for (int k = 0; k < M; ++k) {
+      f1r += bp[k] * cos(2.0 * kPi * (N2 - 1) * k / NF); f1i -= bp[k] * sin(2.0 * kPi * (N2 - 1) * k / NF);
+      f2 += bp[k] * ((k & 1) ? -1.0 : 1.0);
+    }
+    const double p_re = ys1r * f1r - ys1i * f1i, p_im = ys1r * f1i + ys1i * f1r;
+    const double dq_re = ys2 * p_re - p_re, dq_im = ys2 * p_im - p_im, dn = ys2 * p_re - ys2 * f2;
     for (int i = 0; i < ylen; ++i) {                       // delay compensation h + 1 (:137-139)
       double acc = 0.0;
       const int k_lo = std::max(0, i + h + 1 - (ylen - 1)), k_hi = std::min(M - 1, i + h + 1);
       for (int k = k_lo; k <= k_hi; ++k) acc += bp[k] * y[i + h + 1 - k];
+      const int m = i + h + 1;
+      acc += (2.0 * (dq_re * cos(2.0 * kPi * (N2 - 1) * m / NF) - dq_im * sin(2.0 * kPi * (N2 - 1) * m / NF)) +
+              dn * ((m & 1) ? -1.0 : 1.0)) / NF;
       filt[i] = acc;
     }
     int cnt[4];

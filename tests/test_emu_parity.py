@@ -111,8 +111,8 @@ def test_emu_host_pipeline_chunking(emu, golden):
 
 
 def test_emu_dio_agrees_with_port(emu):
-    """Two independent time-domain implementations of Dio (the kernel sources and oracle/world_oracle.cpp)
-    agree to rounding, also where both sit 1e-9 from the reference's FFT-based filtering (decimation)."""
+    """Two independent time-domain implementations of Dio (the kernel sources and oracle/world_oracle.cpp), both
+    with the ripple of the reference's spectral mirroring loop written out, agree to rounding."""
     from refworld import RefWorld, ORACLE_LIB, rel_err
     from synth import synth_batch
     subprocess.check_call(["make", "-s", "-C", os.path.join(pc.os.path.dirname(pc.os.path.dirname(pc.os.path.abspath(pc.__file__))), "oracle"),

@@ -91,14 +91,11 @@ def test_port_dio_matches_golden_and_reference(port, ref, golden):
         tp, fp = port.dio(xs, fs2, po)
         tr, fr = ref.dio(xs, fs2, ro)
         assert np.array_equal(tp, tr)
-        # time-domain filtering here, FFT convolution there: the reference's FFT noise moves the zero
-        # crossings by up to ~2e-9 relative (median 2e-11) in the decimated cases, 1e-13 without decimation.
-        # It is the reference's noise, not the restatement's: the kernel sources compiled for the host, a
-        # second independent time-domain implementation, agree with this one to 5e-15
-        # (tests/test_emu_parity.py::test_emu_dio_agrees_with_port).  Bound: 1e-7, an order below the
-        # 1e-6 parity tolerance.
+        # time-domain filtering here, whole-utterance FFT convolution there -- plus the ripple of the reference's
+        # spectral mirroring loop written out (see Dio in oracle/world_oracle.cpp): without it the decimated
+        # cases sat 2e-9 (here) to 2e-2 (speed 10..12 at 8..16 kHz) from the reference
         r = rel_err(fp, fr)
-        assert r.max() < 1e-7 and np.median(r) < 1e-9, (fs2, speed, r.max())
+        assert r.max() < 1e-9, (fs2, speed, r.max())
         assert (fr > 0).sum() > 20
         y1 = np.zeros(len(xs)); y2 = np.zeros(len(xs))
         if speed > 1:   # the restated decimate() alone is bit-identical to the reference's

@@ -448,6 +448,7 @@ int world_b200_dio_batch(WorldB200 *h, const double *x, int n, int x_stride, con
   b.x = x; b.n = n; b.x_stride = x_stride; b.fs = fs; b.time_axis = time_axis; b.f0 = f0; b.f_stride = f0_stride;
   rc = upload_lengths(h, n, x_stride, x_lengths, f0_stride, fl.data(), &b);
   if (rc) return rc;
+  b.x_len_host = x_lengths;
   DioParams p = {opt->f0_floor, opt->f0_ceil, opt->channels_in_octave, opt->frame_period,
                  opt->allowed_range, opt->speed};
   return dio_run(&h->c, b, p, time_axis, f0);

@@ -27,23 +27,6 @@ WB_DEV double block_sum(double v, double *red) {
 #endif
 }
 
-// maximum over the block (values >= 0)
-WB_DEV double block_max(double v, double *red) {
-#ifdef WB_EMU
-  (void)red;
-  return v;
-#else
-  for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  __syncthreads();
-  if (lane == 0) red[w] = v;
-  __syncthreads();
-  double s = 0.0;
-  for (int i = 0; i < nw; ++i) s = fmax(s, red[i]);
-  return s;
-#endif
-}
-
 // two sums with one pair of barriers
 WB_DEV void block_sum2(double &a, double &b, double *red) {
 #ifdef WB_EMU

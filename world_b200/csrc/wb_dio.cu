@@ -41,7 +41,6 @@ struct DioPrepParams {
   int ratio;
   double *y; size_t y_stride; int y_origin;   // mean-removed signal, zero padded
   int *y_len;                                  // out: 1 + x_len / ratio
-  double *zero_floor;                          // out: 1e-16 * max |y - mean| (see band_sweep_kernel)
 };
 
 WB_KERNEL(256, 2) dio_prep_kernel(DioPrepParams p) {
@@ -61,14 +60,47 @@ WB_KERNEL(256, 2) dio_prep_kernel(DioPrepParams p) {
   double s = 0.0;
   for (int i = tid; i < ylen; i += nth) s += y[i];
   const double mean = block_sum(s, red) / ylen;
-  double amax = 0.0;
-  for (int i = tid; i < ylen; i += nth) {
-    const double v = y[i] - mean;
-    y[i] = v;
-    amax = fmax(amax, fabs(v));
+  for (int i = tid; i < ylen; i += nth) y[i] = y[i] - mean;
+  if (tid == 0) p.y_len[u] = ylen;
+}
+
+// Bins N/2 - 1 and N/2 of the low-cut filtered spectrum, N = the reference's fft_size for this utterance
+// (dio.cpp:590-592, computed on the host).  The reference's spectral "mirroring" loop (dio.cpp:319-328) stores
+// product bin i in slot N - i - 1 as well; for i = N/2 - 1 and N/2 those slots lie inside the half its c2r
+// reads, so both bins end up as Q = Ys[N/2] * (Ys[N/2-1] * F[N/2-1]) instead of Ys[k] F[k].  What that adds to
+// every band's filtered signal is a near-Nyquist ripple: negligible next to a real signal when the band's
+// window is long, visible for the 4..12-tap windows of heavy decimation, and the ONLY thing left in digital
+// silence -- where it gives the reference a zero crossing every sample or two, which is why it calls silence
+// unvoiced instead of extrapolating the last interval.  band_sweep_dio_kernel adds the same ripple.
+//   exp(-j 2 pi (N/2 - 1) n / N) = (-1)^n exp(+j 2 pi n / N);  2 n / N is exact (N is a power of two).
+struct DioNyquistParams {
+  const double *ylc; size_t y_stride; int origin;   // ylc[u*stride + origin + q], time index n = q - c
+  const int *y_len; int c;
+  const int *nfft;                                   // [n] reference FFT size per utterance
+  double *nyq;                                       // out [n][4]: Re Ys[N/2-1], Im Ys[N/2-1], Ys[N/2], N
+};
+
+WB_KERNEL(256, 2) dio_nyquist_kernel(DioNyquistParams p) {
+  WB_SHARED double red[WB_RED_DOUBLES];
+  const int tid = WB_TID, nth = WB_NTH, u = blockIdx.x;
+  const int N = p.nfft[u];
+  const int len = p.y_len[u] + 2 * p.c;
+  const double *s = p.ylc + (size_t)u * p.y_stride + p.origin;
+  double a = 0.0, b = 0.0, d = 0.0;
+  for (int q = tid; q < len; q += nth) {
+    const int n = q - p.c;
+    const double v = (n & 1) ? -s[q] : s[q];
+    const double ang = 2.0 * n / N;
+    a = fma(v, cospi(ang), a);
+    b = fma(v, sinpi(ang), b);
+    d += v;
   }
-  amax = block_max(amax, red);
-  if (tid == 0) { p.y_len[u] = ylen; p.zero_floor[u] = amax * 1e-16; }
+  block_sum2(a, b, red);
+  d = block_sum(d, red);
+  if (tid == 0) {
+    double *o = p.nyq + 4 * (size_t)u;
+    o[0] = a; o[1] = b; o[2] = d; o[3] = static_cast<double>(N);
+  }
 }
 
 struct DioContourParams {
@@ -233,7 +265,7 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     const int n = imin(chunk, b.n - u0);
     ArenaPlan plan;
     const size_t o_y = plan.add((size_t)n * y_stride * 8), o_ylc = plan.add((size_t)n * y_stride * 8);
-    const size_t o_ylen = plan.add((size_t)n * 4), o_zf = plan.add((size_t)n * 8);
+    const size_t o_ylen = plan.add((size_t)n * 4), o_nyq = plan.add((size_t)n * 32), o_nfft = plan.add((size_t)n * 4);
     const size_t o_edges = plan.add((size_t)n * edge_stride * 8);
     const size_t o_ecap = plan.add(nb * 4), o_eoff = plan.add(nb * 8);
     const size_t o_cand = plan.add((size_t)n * nb * fstr * 8), o_score = plan.add((size_t)n * nb * fstr * 8);
@@ -260,7 +292,6 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     DioPrepParams pp;
     pp.x = b.x + (size_t)u0 * b.x_stride; pp.x_len = b.x_len + u0; pp.x_stride = b.x_stride; pp.ratio = ratio;
     pp.y = y; pp.y_stride = y_stride; pp.y_origin = padl; pp.y_len = ylen;
-    pp.zero_floor = (double *)(blk + o_zf);
     if (ratio != 1) {
       DecimateParams dp;
       dp.x = pp.x; dp.x_len = pp.x_len; dp.x_stride = pp.x_stride; dp.ratio = ratio; dp.lag = 0;
@@ -278,6 +309,22 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     const unsigned tiles = (unsigned)((max_ylen + 2 * c + 2047) / 2048);
     launch_fir_plain(ctx, fp, tiles, (unsigned)n);
 
+    // the reference's FFT size per utterance: GetSuitableFFTSize(y_length + 2 c + 1 + 4 int(1 + afs / b0 / 2))
+    // (dio.cpp:590-592, common.cpp:51-54), host libm like there
+    std::vector<int> nfft(n);
+    for (int i = 0; i < n; ++i) {
+      const int xl = b.x_len_host ? b.x_len_host[u0 + i] : b.x_stride;
+      const int yl = 1 + xl / ratio;
+      const int sample = yl + c * 2 + 1 + 4 * static_cast<int>(1.0 + afs / boundary[0] / 2.0);
+      nfft[i] = static_cast<int>(pow(2.0, static_cast<int>(log(static_cast<double>(sample)) / kLog2) + 1.0));
+    }
+    rc = dev_memcpy_h2d(ctx, blk + o_nfft, nfft.data(), (size_t)n * 4);
+    if (rc) return rc;
+    DioNyquistParams np_;
+    np_.ylc = ylc; np_.y_stride = y_stride; np_.origin = padl; np_.y_len = ylen; np_.c = c;
+    np_.nfft = (const int *)(blk + o_nfft); np_.nyq = (double *)(blk + o_nyq);
+    WB_LAUNCH_COOP(dio_nyquist_kernel, dim3((unsigned)n), 256, 0, ctx->stream, np_);
+
     SweepParams sp;
     sp.sig = ylc; sp.sig_stride = y_stride; sp.sig_origin = padl + c; sp.y_len = ylen; sp.n_bands = nb;
     sp.taps_rev = (const double *)(blk + o_taps); sp.tap_off = (const int *)(blk + o_toff);
@@ -287,7 +334,7 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     sp.edge_cap = (const int *)(blk + o_ecap); sp.edge_off = (const long long *)(blk + o_eoff);
     sp.n_frames = b.f_len + u0; sp.frame_stride = fstr; sp.frame_period = opt.frame_period;
     sp.mode = 0; sp.f0_floor = opt.f0_floor; sp.f0_ceil = opt.f0_ceil;
-    sp.zero_floor = (const double *)(blk + o_zf);
+    sp.nyq = (const double *)(blk + o_nyq);
     sp.cand = (double *)(blk + o_cand); sp.score = (double *)(blk + o_score);
     sp.max_taps = max_taps; sp.status = ctx->status_dev;
     launch_band_sweep(ctx, sp, (unsigned)n);

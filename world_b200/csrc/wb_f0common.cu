@@ -179,7 +179,10 @@ WB_DEV void finalize_frames(const SweepParams &p, const Trains &T, int *lo_j, co
   }
 }
 
-WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
+// kDio = 1 adds what DIO needs on top of the shared sweep: the near-Nyquist ripple of the reference's spectral
+// mirroring loop (see dio_nyquist_kernel in wb_dio.cu).  Harvest's instantiation carries none of it.
+template <int kDio>
+WB_DEV void sweep_body(const SweepParams &p) {
   WB_DYN_SMEM(double, smem);
   const int tid = WB_TID, nth = WB_NTH;
   const int b = blockIdx.x, u = blockIdx.y;
@@ -214,6 +217,32 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   double *score = p.score ? p.score + ((size_t)u * p.n_bands + b) * p.frame_stride : nullptr;
   const double bf = p.boundary[b];
   WB_SYNC();
+  // DIO: this band's window at bins N/2 - 1 and N/2, combined with the utterance's spectrum there into the
+  // amplitudes of the ripple  (-1)^m (2 Re(dq e^{-j 2 pi m / N}) + dn) / N  at filtered-signal index m - shift
+  double rip_a = 0.0, rip_b = 0.0, rip_d = 0.0, rot_c = 1.0, rot_s = 0.0, inv_half_n = 0.0;
+  if (kDio) {
+    double *red = reinterpret_cast<double *>(cnt);   // idle until the event phase of the first tile
+    const double *ny = p.nyq + 4 * (size_t)u;
+    const double nf = ny[3];
+    double f1r = 0.0, f1i = 0.0, f2 = 0.0;
+    for (int k = tid; k < ntaps; k += nth) {
+      const double w = hrev[ntaps - 1 - k];
+      const double v = (k & 1) ? -w : w;
+      const double ang = 2.0 * k / nf;
+      f1r = fma(v, cospi(ang), f1r);
+      f1i = fma(v, sinpi(ang), f1i);
+      f2 += v;
+    }
+    block_sum2(f1r, f1i, red);
+    f2 = block_sum(f2, red);
+    const double p_re = ny[0] * f1r - ny[1] * f1i, p_im = ny[0] * f1i + ny[1] * f1r;   // Ys[N/2-1] F[N/2-1]
+    rip_a = 2.0 * (ny[2] * p_re - p_re) / nf;
+    rip_b = 2.0 * (ny[2] * p_im - p_im) / nf;
+    rip_d = (ny[2] * p_re - ny[2] * f2) / nf;
+    rot_c = cospi(2.0 / nf); rot_s = sinpi(2.0 / nf);
+    inv_half_n = 2.0 / nf;
+    WB_SYNC();
+  }
 
   // Tile k produces outputs n0..n0+T-1 into st[2..]; events are detected for positions
   // i = n0-2 .. n0+T-3 (they need s[i], s[i+1], s[i+2]); the last two outputs carry over.
@@ -238,19 +267,20 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
           win[jj] = sp[jj];
         }
       }
-      // DIO only.  Where the filtered signal is numerically nothing (digital silence longer than the filters:
-      // what is left is the rounding residue of the mean removal, ~1e-19, one sign for seconds), the reference
-      // still sees its whole-utterance FFT's rounding noise (~1e-17 of the signal scale) and finds a zero
-      // crossing every few samples; those dense, incoherent events are what makes its candidates fall out of
-      // range there.  Without them interp1 extrapolates the last real interval as a slowly falling "voiced"
-      // ramp.  Stand-in for that noise: values below 1e-16 of the utterance's peak alternate in sign.
-      const double zf = p.zero_floor ? __ldg(p.zero_floor + u) : -1.0;
+      if (kDio) {
+        const int m0 = n0 + base + shift;              // n0 and base are even: the parity of m is that of shift + r
+        double c = cospi(inv_half_n * m0), sn = sinpi(inv_half_n * m0);
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        double v = acc[r];
-        if (fabs(v) < zf) v = (r & 1) ? -1e-300 : 1e-300;
-        st[pad8(2 + base + r)] = v;
+        for (int r = 0; r < R; ++r) {
+          const double ripple = fma(rip_a, c, fma(rip_b, sn, rip_d));
+          acc[r] += ((shift + r) & 1) ? -ripple : ripple;
+          const double c2 = fma(c, rot_c, -(sn * rot_s));
+          sn = fma(sn, rot_c, c * rot_s);
+          c = c2;
+        }
       }
+#pragma unroll
+      for (int r = 0; r < R; ++r) st[pad8(2 + base + r)] = acc[r];
     }
     WB_SYNC();
     if (p.debug_skip >= 2) { WB_SYNC(); continue; }
@@ -378,6 +408,9 @@ WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) {
   }
 }
 
+WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) { sweep_body<0>(p); }       // Harvest
+WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_dio_kernel(SweepParams p) { sweep_body<1>(p); }   // DIO
+
 // extended input of decimate(): 9 mirrored samples on both sides of the edge-padded signal
 WB_DEV double dec_ext(const double *__restrict__ x, int n, int lag, int nx, int i) {
 #define WB_XIN(k) x[imin(n - 1, imax(0, (k) - lag))]
@@ -452,10 +485,17 @@ void launch_band_sweep(Ctx *ctx, const SweepParams &p_in, unsigned n_utts) {
   p.debug_skip = 0;
   if (const char *e = getenv("WB_SWEEP_DEBUG")) p.debug_skip = atoi(e);
   const size_t smem = sweep_smem_bytes(p.max_taps);
+  if (p.mode == 0) {
 #ifndef WB_EMU
-  cudaFuncSetAttribute(band_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(band_sweep_dio_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-  WB_LAUNCH_COOP(band_sweep_kernel, dim3((unsigned)p.n_bands, n_utts), WB_SWEEP_THREADS, smem, ctx->stream, p);
+    WB_LAUNCH_COOP(band_sweep_dio_kernel, dim3((unsigned)p.n_bands, n_utts), WB_SWEEP_THREADS, smem, ctx->stream, p);
+  } else {
+#ifndef WB_EMU
+    cudaFuncSetAttribute(band_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    WB_LAUNCH_COOP(band_sweep_kernel, dim3((unsigned)p.n_bands, n_utts), WB_SWEEP_THREADS, smem, ctx->stream, p);
+  }
 }
 
 }  // namespace wb

@@ -8,11 +8,11 @@
 // The reference filters with whole-utterance FFTs (2^17..2^21 points) - far beyond shared
 // memory.  Its filters are short FIRs (<= ~1000 taps), its FFT size is chosen so that the
 // circular convolution never wraps (dio.cpp:592-594, harvest.cpp:1164-1165), and the spectral
-// mirroring quirk is inert (not for DIO decimated to <= 2 kHz), so
+// mirroring quirk is inert for Harvest's long band-pass filters, so
 // the filtered signal IS the linear convolution; it is evaluated directly, register-tiled, FP64
 // FMA bound.  Filter taps are computed on the host with the same libm expressions as the
-// reference and uploaded.  Where the signal is numerically silent the reference's FFT noise
-// decides what it sees; DIO models that (zero_floor, see band_sweep_kernel).
+// reference and uploaded.  For DIO the ripple the mirroring loop leaves behind IS added (dio_nyquist_kernel,
+// band_sweep_dio_kernel): it decides what the reference sees in digital silence and under heavy decimation.
 #pragma once
 #include "wb_platform.cuh"
 #include "wb_block.cuh"
@@ -86,7 +86,7 @@ struct SweepParams {
   const int *edge_cap; const long long *edge_off;
   const int *n_frames; int frame_stride; double frame_period;  // frame grid: t_i = i*frame_period/1000
   int mode;                                              // 0 = DIO (candidate + score), 1 = Harvest
-  const double *zero_floor;                              // [n] or nullptr: |filtered| below this is rounding dust (DIO)
+  const double *nyq;                                     // DIO: [n][4] from dio_nyquist_kernel (mirroring-loop ripple); Harvest: unused
   double f0_floor, f0_ceil;
   double *cand; double *score;                           // [(u*nb+b)][frame_stride]
   int max_taps;

@@ -986,7 +986,7 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     sp.edge_cap = (const int *)(blk + o_ecap); sp.edge_off = (const long long *)(blk + o_eoff);
     sp.n_frames = l1; sp.frame_stride = l1_stride; sp.frame_period = 1.0;
     sp.mode = 1; sp.f0_floor = opt.f0_floor; sp.f0_ceil = opt.f0_ceil;
-    sp.zero_floor = nullptr;   // Harvest's +-10 % gate and refinement reject the extrapolated values on their own
+    sp.nyq = nullptr;
     sp.cand = (double *)(blk + o_raw); sp.score = nullptr;
     sp.max_taps = max_taps; sp.status = ctx->status_dev;
     launch_band_sweep(ctx, sp, (unsigned)n);

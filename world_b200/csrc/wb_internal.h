@@ -95,6 +95,7 @@ struct Batch {
   int f_stride;
   int max_x_len, max_f_len;  // host-known maxima
   const int *l1_host = nullptr;  // [n] host: frames on the 1 ms grid (Harvest only)
+  const int *x_len_host = nullptr;  // [n] host copy of x_len, or nullptr = every row is full (DIO only)
 };
 
 // stage drivers (each: enqueue on ctx->stream, return 0 / error code)

@@ -119,6 +119,8 @@ struct uint4 { unsigned x, y, z, w; };
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
   uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r;
 }
+static inline double cospi(double x) { return cos(3.1415926535897932384 * x); }   // CUDA math functions used by kernels
+static inline double sinpi(double x) { return sin(3.1415926535897932384 * x); }
 static inline double2 __ldg(const double2 *p) { return *p; }
 static inline uint4 __ldg(const uint4 *p) { return *p; }
 static inline double __ldg(const double *p) { return *p; }
