@@ -45,7 +45,6 @@ def main():
     ref = RefWorld()
     emu = World(lib_path=os.environ.get("WB_EMU_LIB", os.path.join(ROOT, "tests", "emu", "libworld_b200_emu.so")), array_module="numpy")
     bad = 0
-    known = 0
     for case in range(n_cases):
         fs = int(rng.choice([8000, 11025, 16000, 22050, 32000, 44100, 48000]))
         n = int(rng.uniform(0.15, 0.9) * fs)
@@ -87,14 +86,7 @@ def main():
             flips = int(((f0[0] > 0) != (fr > 0)).sum())
             e_f0 = rel_err(f0[0], fr).max() if flips == 0 else float("inf")
             msg.append(f"f0 {e_f0:.1e} voiced {int((fr > 0).sum())}/{len(fr)}")
-            if not (flips == 0 and e_f0 <= TOL):
-                # the one documented deviation: Harvest does not add the ripple of the reference's
-                # spectral mirroring loop (1e-20 of the signal); it only matters where the INPUT is digitally
-                # silent and not decimated, i.e. exact zeros in 8 kHz audio
-                if method == "harvest" and fs == 8000 and kind == "silence_mix":
-                    known += 1
-                    raise RuntimeError(f"KNOWN DEVIATION: {e_f0:.1e} from the reference ({flips} flips), digital silence at 8 kHz")
-                assert False, f"f0 mismatch, {flips} V/UV flips"
+            assert flips == 0 and e_f0 <= TOL, f"f0 mismatch, {flips} V/UV flips"
             # spectral stages on the reference's f0, non-default CheapTrick / D4C options now and then
             if fs >= 16000:
                 co = emu.cheaptrick_option(fs); rco = ref.cheaptrick_option(fs)
@@ -117,14 +109,11 @@ def main():
         except AssertionError as e:
             status = f"MISMATCH {e}"
             bad += 1
-        except RuntimeError as e:
-            status = str(e)
         except Exception as e:   # library errors (EDOMAIN etc.) are reported, not hidden
             status = f"ERROR {type(e).__name__}: {e}"
             bad += 1
         print(f"case {case:3d} fs {fs:5d} n {n:6d} {kind:11s} {method:7s} fp {fp:4.1f}  {'  '.join(msg):60s} {status}  ({time.time() - t0:.1f}s)", flush=True)
-    print(f"{n_cases - bad - known}/{n_cases} cases agree with the reference within {TOL}; {known} known deviations "
-          f"(Harvest, digital silence at 8 kHz); {bad} failures")
+    print(f"{n_cases - bad}/{n_cases} cases agree with the reference within {TOL}; {bad} failures")
     sys.exit(1 if bad else 0)
 
 

@@ -467,6 +467,7 @@ int world_b200_harvest_batch(WorldB200 *h, const double *x, int n, int x_stride,
   std::vector<int> l1(n > 0 ? n : 1);
   for (int i = 0; i < n; ++i) l1[i] = frames_for(fs, x_lengths ? x_lengths[i] : x_stride, 1.0);
   b.l1_host = l1.data();
+  b.x_len_host = x_lengths;
   HarvestParams p = {opt->f0_floor, opt->f0_ceil, opt->frame_period};
   return harvest_run(&h->c, b, p, time_axis, f0);
 }

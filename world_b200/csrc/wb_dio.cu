@@ -64,45 +64,6 @@ WB_KERNEL(256, 2) dio_prep_kernel(DioPrepParams p) {
   if (tid == 0) p.y_len[u] = ylen;
 }
 
-// Bins N/2 - 1 and N/2 of the low-cut filtered spectrum, N = the reference's fft_size for this utterance
-// (dio.cpp:590-592, computed on the host).  The reference's spectral "mirroring" loop (dio.cpp:319-328) stores
-// product bin i in slot N - i - 1 as well; for i = N/2 - 1 and N/2 those slots lie inside the half its c2r
-// reads, so both bins end up as Q = Ys[N/2] * (Ys[N/2-1] * F[N/2-1]) instead of Ys[k] F[k].  What that adds to
-// every band's filtered signal is a near-Nyquist ripple: negligible next to a real signal when the band's
-// window is long, visible for the 4..12-tap windows of heavy decimation, and the ONLY thing left in digital
-// silence -- where it gives the reference a zero crossing every sample or two, which is why it calls silence
-// unvoiced instead of extrapolating the last interval.  band_sweep_dio_kernel adds the same ripple.
-//   exp(-j 2 pi (N/2 - 1) n / N) = (-1)^n exp(+j 2 pi n / N);  2 n / N is exact (N is a power of two).
-struct DioNyquistParams {
-  const double *ylc; size_t y_stride; int origin;   // ylc[u*stride + origin + q], time index n = q - c
-  const int *y_len; int c;
-  const int *nfft;                                   // [n] reference FFT size per utterance
-  double *nyq;                                       // out [n][4]: Re Ys[N/2-1], Im Ys[N/2-1], Ys[N/2], N
-};
-
-WB_KERNEL(256, 2) dio_nyquist_kernel(DioNyquistParams p) {
-  WB_SHARED double red[WB_RED_DOUBLES];
-  const int tid = WB_TID, nth = WB_NTH, u = blockIdx.x;
-  const int N = p.nfft[u];
-  const int len = p.y_len[u] + 2 * p.c;
-  const double *s = p.ylc + (size_t)u * p.y_stride + p.origin;
-  double a = 0.0, b = 0.0, d = 0.0;
-  for (int q = tid; q < len; q += nth) {
-    const int n = q - p.c;
-    const double v = (n & 1) ? -s[q] : s[q];
-    const double ang = 2.0 * n / N;
-    a = fma(v, cospi(ang), a);
-    b = fma(v, sinpi(ang), b);
-    d += v;
-  }
-  block_sum2(a, b, red);
-  d = block_sum(d, red);
-  if (tid == 0) {
-    double *o = p.nyq + 4 * (size_t)u;
-    o[0] = a; o[1] = b; o[2] = d; o[3] = static_cast<double>(N);
-  }
-}
-
 struct DioContourParams {
   const double *cand; const double *score; int n_bands; int frame_stride;
   const int *f_len; double frame_period, f0_floor, allowed_range;
@@ -320,10 +281,10 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     }
     rc = dev_memcpy_h2d(ctx, blk + o_nfft, nfft.data(), (size_t)n * 4);
     if (rc) return rc;
-    DioNyquistParams np_;
-    np_.ylc = ylc; np_.y_stride = y_stride; np_.origin = padl; np_.y_len = ylen; np_.c = c;
+    NyquistParams np_;
+    np_.sig = ylc; np_.stride = y_stride; np_.origin = padl; np_.y_len = ylen; np_.c = c;
     np_.nfft = (const int *)(blk + o_nfft); np_.nyq = (double *)(blk + o_nyq);
-    WB_LAUNCH_COOP(dio_nyquist_kernel, dim3((unsigned)n), 256, 0, ctx->stream, np_);
+    launch_nyquist_bins(ctx, np_, (unsigned)n);
 
     SweepParams sp;
     sp.sig = ylc; sp.sig_stride = y_stride; sp.sig_origin = padl + c; sp.y_len = ylen; sp.n_bands = nb;
@@ -334,7 +295,7 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     sp.edge_cap = (const int *)(blk + o_ecap); sp.edge_off = (const long long *)(blk + o_eoff);
     sp.n_frames = b.f_len + u0; sp.frame_stride = fstr; sp.frame_period = opt.frame_period;
     sp.mode = 0; sp.f0_floor = opt.f0_floor; sp.f0_ceil = opt.f0_ceil;
-    sp.nyq = (const double *)(blk + o_nyq);
+    sp.nyq = (const double *)(blk + o_nyq); sp.ripple = 1;
     sp.cand = (double *)(blk + o_cand); sp.score = (double *)(blk + o_score);
     sp.max_taps = max_taps; sp.status = ctx->status_dev;
     launch_band_sweep(ctx, sp, (unsigned)n);

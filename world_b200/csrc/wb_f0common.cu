@@ -179,9 +179,43 @@ WB_DEV void finalize_frames(const SweepParams &p, const Trains &T, int *lo_j, co
   }
 }
 
-// kDio = 1 adds what DIO needs on top of the shared sweep: the near-Nyquist ripple of the reference's spectral
-// mirroring loop (see dio_nyquist_kernel in wb_dio.cu).  Harvest's instantiation carries none of it.
-template <int kDio>
+// Bins N/2 - 1 and N/2 of the spectrum of the signal the band filters see, N = the reference's fft_size for
+// this utterance (dio.cpp:590-592 / harvest.cpp:1164-1165, computed on the host).  The reference's spectral "mirroring" loop (dio.cpp:319-328, harvest.cpp:122-135) stores
+// product bin i in slot N - i - 1 as well; for i = N/2 - 1 and N/2 those slots lie inside the half its c2r
+// reads, so both bins end up as Q = Ys[N/2] * (Ys[N/2-1] * F[N/2-1]) instead of Ys[k] F[k].  What that adds to
+// every band's filtered signal is a near-Nyquist ripple: negligible next to a real signal when the band's
+// window is long, visible for the 4..12-tap windows of heavy decimation, and the ONLY thing left in digital
+// silence -- where it gives the reference a zero crossing every sample or two, which is why it calls silence
+// unvoiced instead of extrapolating the last interval.  band_sweep_ripple_kernel adds the same ripple (DIO
+// always; Harvest only when its input is not decimated, the one case where exact zeros survive to this point).
+//   exp(-j 2 pi (N/2 - 1) n / N) = (-1)^n exp(+j 2 pi n / N);  2 n / N is exact (N is a power of two).
+WB_KERNEL(256, 2) nyquist_bins_kernel(NyquistParams p) {
+  WB_SHARED double red[WB_RED_DOUBLES];
+  const int tid = WB_TID, nth = WB_NTH, u = blockIdx.x;
+  const int N = p.nfft[u];
+  const int len = p.y_len[u] + 2 * p.c;
+  const double *s = p.sig + (size_t)u * p.stride + p.origin;
+  double a = 0.0, b = 0.0, d = 0.0;
+  for (int q = tid; q < len; q += nth) {
+    const int n = q - p.c;
+    const double v = (n & 1) ? -s[q] : s[q];
+    const double ang = 2.0 * n / N;
+    a = fma(v, cospi(ang), a);
+    b = fma(v, sinpi(ang), b);
+    d += v;
+  }
+  block_sum2(a, b, red);
+  d = block_sum(d, red);
+  if (tid == 0) {
+    double *o = p.nyq + 4 * (size_t)u;
+    o[0] = a; o[1] = b; o[2] = d; o[3] = static_cast<double>(N);
+  }
+}
+
+
+// kRipple = 1 adds the near-Nyquist ripple of the reference's spectral mirroring loop (nyquist_bins_kernel
+// above); the default instantiation carries none of it.
+template <int kRipple>
 WB_DEV void sweep_body(const SweepParams &p) {
   WB_DYN_SMEM(double, smem);
   const int tid = WB_TID, nth = WB_NTH;
@@ -220,7 +254,7 @@ WB_DEV void sweep_body(const SweepParams &p) {
   // DIO: this band's window at bins N/2 - 1 and N/2, combined with the utterance's spectrum there into the
   // amplitudes of the ripple  (-1)^m (2 Re(dq e^{-j 2 pi m / N}) + dn) / N  at filtered-signal index m - shift
   double rip_a = 0.0, rip_b = 0.0, rip_d = 0.0, rot_c = 1.0, rot_s = 0.0, inv_half_n = 0.0;
-  if (kDio) {
+  if (kRipple) {
     double *red = reinterpret_cast<double *>(cnt);   // idle until the event phase of the first tile
     const double *ny = p.nyq + 4 * (size_t)u;
     const double nf = ny[3];
@@ -267,7 +301,7 @@ WB_DEV void sweep_body(const SweepParams &p) {
           win[jj] = sp[jj];
         }
       }
-      if (kDio) {
+      if (kRipple) {
         const int m0 = n0 + base + shift;              // n0 and base are even: the parity of m is that of shift + r
         double c = cospi(inv_half_n * m0), sn = sinpi(inv_half_n * m0);
 #pragma unroll
@@ -408,8 +442,8 @@ WB_DEV void sweep_body(const SweepParams &p) {
   }
 }
 
-WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) { sweep_body<0>(p); }       // Harvest
-WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_dio_kernel(SweepParams p) { sweep_body<1>(p); }   // DIO
+WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) { sweep_body<0>(p); }          // Harvest on decimated input
+WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_ripple_kernel(SweepParams p) { sweep_body<1>(p); }   // DIO; Harvest at ratio 1
 
 // extended input of decimate(): 9 mirrored samples on both sides of the edge-padded signal
 WB_DEV double dec_ext(const double *__restrict__ x, int n, int lag, int nx, int i) {
@@ -480,16 +514,20 @@ void launch_fir_plain(Ctx *ctx, const FirParams &p, unsigned tiles, unsigned n_u
   WB_LAUNCH_COOP(fir_plain_kernel, dim3(tiles, n_utts), 256, smem, ctx->stream, p);
 }
 
+void launch_nyquist_bins(Ctx *ctx, const NyquistParams &p, unsigned n_utts) {
+  WB_LAUNCH_COOP(nyquist_bins_kernel, dim3(n_utts), 256, 0, ctx->stream, p);
+}
+
 void launch_band_sweep(Ctx *ctx, const SweepParams &p_in, unsigned n_utts) {
   SweepParams p = p_in;
   p.debug_skip = 0;
   if (const char *e = getenv("WB_SWEEP_DEBUG")) p.debug_skip = atoi(e);
   const size_t smem = sweep_smem_bytes(p.max_taps);
-  if (p.mode == 0) {
+  if (p.ripple) {
 #ifndef WB_EMU
-    cudaFuncSetAttribute(band_sweep_dio_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(band_sweep_ripple_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-    WB_LAUNCH_COOP(band_sweep_dio_kernel, dim3((unsigned)p.n_bands, n_utts), WB_SWEEP_THREADS, smem, ctx->stream, p);
+    WB_LAUNCH_COOP(band_sweep_ripple_kernel, dim3((unsigned)p.n_bands, n_utts), WB_SWEEP_THREADS, smem, ctx->stream, p);
   } else {
 #ifndef WB_EMU
     cudaFuncSetAttribute(band_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

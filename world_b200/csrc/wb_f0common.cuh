@@ -11,8 +11,9 @@
 // mirroring quirk is inert for Harvest's long band-pass filters, so
 // the filtered signal IS the linear convolution; it is evaluated directly, register-tiled, FP64
 // FMA bound.  Filter taps are computed on the host with the same libm expressions as the
-// reference and uploaded.  For DIO the ripple the mirroring loop leaves behind IS added (dio_nyquist_kernel,
-// band_sweep_dio_kernel): it decides what the reference sees in digital silence and under heavy decimation.
+// reference and uploaded.  Where it matters the ripple the mirroring loop leaves behind IS added
+// (nyquist_bins_kernel, band_sweep_ripple_kernel): DIO always -- it decides what the reference sees in digital
+// silence and under heavy decimation -- and Harvest when its input is not decimated.
 #pragma once
 #include "wb_platform.cuh"
 #include "wb_block.cuh"
@@ -86,7 +87,7 @@ struct SweepParams {
   const int *edge_cap; const long long *edge_off;
   const int *n_frames; int frame_stride; double frame_period;  // frame grid: t_i = i*frame_period/1000
   int mode;                                              // 0 = DIO (candidate + score), 1 = Harvest
-  const double *nyq;                                     // DIO: [n][4] from dio_nyquist_kernel (mirroring-loop ripple); Harvest: unused
+  const double *nyq; int ripple;                         // ripple = 1: [n][4] from nyquist_bins_kernel, band_sweep_ripple_kernel runs
   double f0_floor, f0_ceil;
   double *cand; double *score;                           // [(u*nb+b)][frame_stride]
   int max_taps;
@@ -121,5 +122,14 @@ struct DecimateParams {
 void launch_decimate(Ctx *ctx, const DecimateParams &p, int max_x_len, unsigned n_utts);
 void launch_fir_plain(Ctx *ctx, const FirParams &p, unsigned tiles, unsigned n_utts);
 void launch_band_sweep(Ctx *ctx, const SweepParams &p, unsigned n_utts);
+
+// the two spectrum bins the reference's mirroring loop corrupts (see nyquist_bins_kernel)
+struct NyquistParams {
+  const double *sig; size_t stride; int origin;      // sig[u*stride + origin + q], time index n = q - c
+  const int *y_len; int c;                           // q in [0, y_len[u] + 2 c)
+  const int *nfft;                                   // [n] reference FFT size per utterance
+  double *nyq;                                       // out [n][4]: Re Ys[N/2-1], Im Ys[N/2-1], Ys[N/2], N
+};
+void launch_nyquist_bins(Ctx *ctx, const NyquistParams &p, unsigned n_utts);
 
 }  // namespace wb

@@ -935,6 +935,7 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     ArenaPlan plan;
     const size_t o_y = plan.add((size_t)n * y_stride * 8), o_ylen = plan.add((size_t)n * 4);
     const size_t o_l1 = plan.add((size_t)n * 4), o_nc = plan.add((size_t)n * 4);
+    const size_t o_nyq = plan.add((size_t)n * 32), o_nfft = plan.add((size_t)n * 4);
     const size_t o_edges = plan.add((size_t)n * edge_stride * 8);
     const size_t o_ecap = plan.add(nb * 4), o_eoff = plan.add(nb * 8);
     const size_t o_raw = plan.add((size_t)n * nb * l1_stride * 8);
@@ -986,7 +987,26 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     sp.edge_cap = (const int *)(blk + o_ecap); sp.edge_off = (const long long *)(blk + o_eoff);
     sp.n_frames = l1; sp.frame_stride = l1_stride; sp.frame_period = 1.0;
     sp.mode = 1; sp.f0_floor = opt.f0_floor; sp.f0_ceil = opt.f0_ceil;
-    sp.nyq = nullptr;
+    sp.nyq = nullptr; sp.ripple = 0;
+    if (ratio == 1) {
+      // Input not decimated (fs below 12 kHz): exact zeros in the waveform reach the band filters, and there the
+      // ripple of the reference's mirroring loop (harvest.cpp:122-135; see nyquist_bins_kernel) is all its
+      // filtered signal consists of.  1e-20 of a real signal, so the decimated rates skip it.
+      std::vector<int> nfft(n);
+      for (int i = 0; i < n; ++i) {
+        const int xl = b.x_len_host ? b.x_len_host[u0 + i] : b.x_stride;
+        const int yl = static_cast<int>(ceil(static_cast<double>(xl) / ratio));
+        const int sample = yl + 5 + 2 * static_cast<int>(2.0 * afs / boundary[0]);
+        nfft[i] = static_cast<int>(pow(2.0, static_cast<int>(log(static_cast<double>(sample)) / kLog2) + 1.0));
+      }
+      rc = dev_memcpy_h2d(ctx, blk + o_nfft, nfft.data(), (size_t)n * 4);
+      if (rc) return rc;
+      NyquistParams np_;
+      np_.sig = y; np_.stride = y_stride; np_.origin = padl; np_.y_len = ylen; np_.c = 0;
+      np_.nfft = (const int *)(blk + o_nfft); np_.nyq = (double *)(blk + o_nyq);
+      launch_nyquist_bins(ctx, np_, (unsigned)n);
+      sp.nyq = (const double *)(blk + o_nyq); sp.ripple = 1;
+    }
     sp.cand = (double *)(blk + o_raw); sp.score = nullptr;
     sp.max_taps = max_taps; sp.status = ctx->status_dev;
     launch_band_sweep(ctx, sp, (unsigned)n);
