@@ -448,7 +448,7 @@ def check_event_dense_and_degenerate_bands(world, ref):
 def check_zero_tail_f0(world, ref):
     """utterances that end in 0.5 s of exact zeros.  The F0 estimators must call the tail unvoiced like
     the reference does (the near-Nyquist ripple of its spectral mirroring loop is all that is left there and
-    gives it a zero crossing every sample or two; DIO adds the same ripple, see dio_nyquist_kernel) -- no V/UV
+    gives it a zero crossing every sample or two; the library adds the same ripple, see nyquist_bins_kernel) -- no V/UV
     flip, values within the tolerance."""
     from synth import synth_batch
     for fs, n, zt, seeds in ((16000, 24000, 8000, [1, 4]), (16000, 40000, 8000, [6]), (22050, 33075, 11025, [5])):
