@@ -165,3 +165,7 @@ def test_emu_harvest_chain_refinement(emu, ref):
             os.environ.pop("WB_REFINE_CHAIN", None)
         else:
             os.environ["WB_REFINE_CHAIN"] = saved
+
+
+def test_emu_mirroring_ripple_cases(emu, ref):
+    pc.check_mirroring_ripple_cases(emu, ref)

@@ -191,3 +191,7 @@ def test_gpu_event_dense_and_degenerate_bands(gpu_world, ref):
 
 def test_gpu_zero_tail_f0(gpu_world, ref):
     pc.check_zero_tail_f0(gpu_world, ref)
+
+
+def test_gpu_mirroring_ripple_cases(gpu_world, ref):
+    pc.check_mirroring_ripple_cases(gpu_world, ref)

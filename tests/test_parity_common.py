@@ -464,3 +464,35 @@ def check_zero_tail_f0(world, ref):
                 assert not ((got > 0) != (fr > 0)).any(), f"{name}: V/UV flips in the zero tail (fs {fs}, seed {seeds[u]})"
                 assert_close(got, fr, f"{name} f0 with a zero tail (fs {fs}, seed {seeds[u]})")
                 assert not fr[-int(0.4 * zt / fs * 200):].any()
+
+
+def check_mirroring_ripple_cases(world, ref):
+    """The two situations where the reference's spectral mirroring loop (dio.cpp:319-328, harvest.cpp:122-135)
+    decides its output and the library has to add the same ripple: DIO decimated to <= 2 kHz (4..12-tap band
+    windows), and digital silence reaching Harvest's band filters undecimated (8 kHz input)."""
+    from synth import synth_batch
+    for fs, n, seed, speed, ceil in ((11025, 7502, 9, 10, 800.0), (16000, 12300, 33, 10, 1000.0), (16000, 10435, 23, 12, 400.0),
+                                     (8000, 4280, 35, 12, 800.0), (16000, 13859, 43, 8, 800.0)):
+        x = synth_batch([seed], fs, n).numpy()
+        o = world.dio_option(); o.speed = speed; o.f0_ceil = ceil
+        ro = ref.dio_option(); ro.speed = speed; ro.f0_ceil = ceil
+        t, f0, fl = world.dio(make(world, x), fs, o)
+        world.synchronize()
+        tr, fr = ref.dio(x[0], fs, ro)
+        assert np.array_equal(to_np(t)[0], tr)
+        assert_close(to_np(f0)[0], fr, f"DIO fs {fs} speed {speed}")
+        assert (fr > 0).sum() > 20
+    rng = np.random.default_rng(11)
+    for case in range(4):
+        fs, n = 8000, int(rng.uniform(0.5, 1.0) * 8000)
+        x = synth_batch([int(rng.integers(1, 1 << 30))], fs, n).numpy()
+        a, b = sorted(rng.integers(0, n, size=2))
+        x[0, a:b] = 0.0
+        if case % 2 == 0:
+            x[0, int(0.7 * n):] = 0.0
+        t, f0, fl = world.harvest(make(world, x), fs)
+        world.synchronize()
+        tr, fr = ref.harvest(x[0], fs)
+        got = to_np(f0)[0]
+        assert not ((got > 0) != (fr > 0)).any(), f"Harvest, digital silence at 8 kHz, case {case}: V/UV flips"
+        assert_close(got, fr, f"Harvest, digital silence at 8 kHz, case {case}")

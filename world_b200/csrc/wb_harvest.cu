@@ -22,7 +22,7 @@ namespace wb {
 // `boundary` cannot be denser than ~boundary per second for long; 2.5x margin, hard bound
 // ylen/2+2 (a negative-going crossing needs two samples).  The lists are history rings: more events
 // than this wrap around; only a look-back beyond the last `cap` events raises status bit 4.
-static void plan_edge_caps(const std::vector<double> &boundary, double afs, int max_ylen,
+static void plan_edge_caps(const std::vector<double> &boundary, double afs, int max_ylen, bool full,
                            std::vector<int> *cap, std::vector<long long> *off, size_t *stride) {
   const int nb = (int)boundary.size();
   cap->resize(nb); off->resize(nb);
@@ -33,6 +33,9 @@ static void plan_edge_caps(const std::vector<double> &boundary, double afs, int 
     const long long hard = (long long)max_ylen / 2 + 2;
     long long soft = (long long)(2.5 * boundary[i] * max_ylen / afs) + 64;
     if (soft < floor_cap) soft = floor_cap;   // a tile can append up to 1025 events per train; the rings look back 256
+    // non-decimated input (ripple path): in digital silence the difference trains fire every sample while the
+    // crossing trains are silent, so frames cannot be finalised until the silence ends -- keep every event
+    if (full) soft = hard;
     (*cap)[i] = (int)(soft < hard ? soft : hard);
     (*off)[i] = run;
     run += 4LL * (*cap)[i];
@@ -915,7 +918,7 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
   const int padl = max_taps + 16;
   const size_t y_stride = (size_t)padl + max_ylen + 3 * T + max_taps + 64;
   std::vector<int> ecap; std::vector<long long> eoff; size_t edge_stride = 0;
-  plan_edge_caps(boundary, afs, max_ylen, &ecap, &eoff, &edge_stride);
+  plan_edge_caps(boundary, afs, max_ylen, ratio == 1, &ecap, &eoff, &edge_stride);
   const int lag = static_cast<int>(ceil(140.0 / ratio) * ratio);
   const size_t tmp_stride = ratio != 1 ? (size_t)b.max_x_len + 2 * lag + 32 : 0;
   const size_t pad_stride = (size_t)l1_stride + 600 + 8;
