@@ -29,6 +29,10 @@ static void plan_edge_caps(const std::vector<double> &boundary, double afs, int 
     const long long hard = (long long)max_ylen / 2 + 2;
     long long soft = (long long)(2.5 * boundary[i] * max_ylen / afs) + 64;
     if (soft < floor_cap) soft = floor_cap;   // a tile can append up to 1025 events per train; the rings look back 256
+    // DIO keeps every event: with the mirroring ripple in, digital silence makes the difference trains fire
+    // every sample while the crossing trains may stay silent, so frames cannot be finalised until the silence
+    // ends and the look-back is as long as the silence (few bands, so the full lists are affordable)
+    soft = hard;
     (*cap)[i] = (int)(soft < hard ? soft : hard);
     (*off)[i] = run;
     run += 4LL * (*cap)[i];
