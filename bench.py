@@ -140,6 +140,9 @@ def algorithmic_bytes_per_step(kernel, a, n_utts):
         "d4c_lovetrain_kernel": n_utts * L * (hop + 16),
         # decimated waveform once + the candidate map it produces (152 channels x 1 ms frames)
         "band_sweep_kernel": n_utts * (ylen * 8 + (152 if a.f0 == "harvest" else 7) * (L1 if a.f0 == "harvest" else L) * 8),
+        "band_sweep_ripple_kernel": n_utts * (ylen * 8 + (152 if a.f0 == "harvest" else 7) * (L1 if a.f0 == "harvest" else L) * 8),
+        "nyquist_bins_kernel": n_utts * ylen * 8,
+        "harvest_refine_chain_kernel": n_utts * (ylen * 8 + L1 * 21 * 16),
         # candidate map in, refined candidates + scores out (upper bound 105 slots)
         "harvest_refine_kernel": n_utts * (ylen * 8 + L1 * 21 * 16),
         "harvest_detect_kernel": n_utts * 152 * L1 * 8,
