@@ -169,3 +169,38 @@ def test_emu_harvest_chain_refinement(emu, ref):
 
 def test_emu_mirroring_ripple_cases(emu, ref):
     pc.check_mirroring_ripple_cases(emu, ref)
+
+
+def test_emu_argument_errors(emu):
+    """The batched ABI answers bad arguments with an error code and a message instead of the reference's undefined
+    behaviour; empty batches are fine."""
+    import ctypes as C
+    from world_b200 import api
+    lib, h = emu.lib, emu._h
+    fs = 16000
+    x = np.zeros((2, 800)); t = np.zeros((2, 11)); f0 = np.zeros((2, 11)); sp = np.zeros((2, 11, 513))
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    do = emu.dio_option(); ho = emu.harvest_option(); co = emu.cheaptrick_option(fs); d4 = emu.d4c_option()
+    ok, einval = 0, 3
+    # empty batch
+    assert lib.world_b200_dio_batch(h, P(x), 0, 800, None, fs, C.byref(do), P(t), P(f0), 11) == ok
+    assert lib.world_b200_harvest_batch(h, P(x), 0, 800, None, fs, C.byref(ho), P(t), P(f0), 11) == ok
+    # null pointers, negative counts, bad rates
+    assert lib.world_b200_dio_batch(h, None, 2, 800, None, fs, C.byref(do), P(t), P(f0), 11) == einval
+    assert lib.world_b200_dio_batch(h, P(x), -1, 800, None, fs, C.byref(do), P(t), P(f0), 11) == einval
+    assert lib.world_b200_harvest_batch(h, P(x), 2, 800, None, 0, C.byref(ho), P(t), P(f0), 11) == einval
+    # rows shorter than the frame count / lengths beyond the row
+    assert lib.world_b200_dio_batch(h, P(x), 2, 800, None, fs, C.byref(do), P(t), P(f0), 5) == einval
+    assert b"f0_stride" in lib.world_b200_last_error(h)
+    lens = (C.c_int * 2)(800, 801)
+    assert lib.world_b200_cheaptrick_batch(h, P(x), 2, 800, lens, fs, P(t), P(f0), None, 11, C.byref(co), P(sp)) == einval
+    # fft sizes the on-chip transforms cannot do
+    bad = api.CheapTrickOption(); bad.q1 = -0.15; bad.f0_floor = 71.0; bad.fft_size = 1000
+    assert lib.world_b200_cheaptrick_batch(h, P(x), 2, 800, None, fs, P(t), P(f0), None, 11, C.byref(bad), P(sp)) == einval
+    # (D4C's fft_size only sets the width of the output rows, fft_size / 2 + 1: any value is legal, as in the reference)
+    assert lib.world_b200_d4c_batch(h, P(x), 2, 800, None, fs, P(t), P(f0), None, 11, 1000, C.byref(d4), P(sp)) == ok
+    assert lib.world_b200_code_spectral_envelope_batch(h, P(sp), 2, None, 11, fs, 1000, 40, P(sp)) == einval
+    assert lib.world_b200_code_spectral_envelope_batch(h, P(sp), 2, None, 11, fs, 1024, 400, P(sp)) == einval
+    assert lib.world_b200_pcm_to_double_batch(h, P(x), 12, 2, 800, None, P(x)) == einval
+    assert lib.world_b200_synthesis_batch(h, P(f0), None, 2, 11, P(sp), P(sp), 1000, 5.0, fs, None, 800, P(x)) == einval
+    emu.synchronize()      # none of the rejected calls left the context in an error state
