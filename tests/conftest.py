@@ -21,7 +21,15 @@ def _have_gpu():
         return False
 
 
+# GPU tests that exercise code changed after the last run on a B200 (DIO's ripple path, event rings, drop-in
+# programs) run after the ones that were measured there: with `pytest -x` an early surprise must not hide the rest.
+_RUN_LAST = ("golden_dio", "dio_path", "dio_decimated", "edge_cases", "long_48k", "legacy_api_and_analyze_host",
+             "analyze_coded_host", "host_pipeline_chunking", "event_dense", "zero_tail_f0", "mirroring_ripple",
+             "reference_examples", "cpp_batched")
+
+
 def pytest_collection_modifyitems(config, items):
+    items.sort(key=lambda it: 1 if ("gpu" in it.keywords and any(k in it.name for k in _RUN_LAST)) else 0)
     if _have_gpu():
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
