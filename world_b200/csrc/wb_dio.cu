@@ -299,7 +299,7 @@ int dio_run(Ctx *ctx, const Batch &b, const DioParams &opt, double *time_axis_ou
     sp.edge_cap = (const int *)(blk + o_ecap); sp.edge_off = (const long long *)(blk + o_eoff);
     sp.n_frames = b.f_len + u0; sp.frame_stride = fstr; sp.frame_period = opt.frame_period;
     sp.mode = 0; sp.f0_floor = opt.f0_floor; sp.f0_ceil = opt.f0_ceil;
-    sp.nyq = (const double *)(blk + o_nyq); sp.ripple = 1;
+    sp.nyq = (const double *)(blk + o_nyq); sp.ripple = getenv("WB_NO_RIPPLE") ? 0 : 1;   // A/B switch for experiments
     sp.cand = (double *)(blk + o_cand); sp.score = (double *)(blk + o_score);
     sp.max_taps = max_taps; sp.status = ctx->status_dev;
     launch_band_sweep(ctx, sp, (unsigned)n);

@@ -991,7 +991,7 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     sp.n_frames = l1; sp.frame_stride = l1_stride; sp.frame_period = 1.0;
     sp.mode = 1; sp.f0_floor = opt.f0_floor; sp.f0_ceil = opt.f0_ceil;
     sp.nyq = nullptr; sp.ripple = 0;
-    if (ratio == 1) {
+    if (ratio == 1 && !getenv("WB_NO_RIPPLE")) {
       // Input not decimated (fs below 12 kHz): exact zeros in the waveform reach the band filters, and there the
       // ripple of the reference's mirroring loop (harvest.cpp:122-135; see nyquist_bins_kernel) is all its
       // filtered signal consists of.  1e-20 of a real signal, so the decimated rates skip it.
