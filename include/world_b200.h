@@ -77,6 +77,8 @@ int world_b200_fp64_peak(WorldB200 *ctx, double *tflops);
 /* Test hook: forward real FFT of n = 2^k doubles (4 <= n <= 8192) with the library's shared-memory
  * FFT; out_dev receives n/2+1 interleaved complex values (n + 2 doubles).  DEVICE pointers. */
 int world_b200_rfft_test(WorldB200 *ctx, const double *x_dev, int n, double *out_dev);
+/* same, through the self-sorting padded FFT the frame kernels use since round 2 */
+int world_b200_sfft_test(WorldB200 *ctx, const double *x_dev, int n, double *out_dev);
 
 /* Test hook: first n_draws values of the reference's randn() stream (matlabfunctions.cpp:237-264)
  * as raw 32-bit sums (value = sum / 2^28 - 6) into a DEVICE buffer of n_draws uint32. */

@@ -221,13 +221,14 @@ def check_fft_known_answers(world):
     for lg in range(2, 14):
         n = 1 << lg
         x = rng.standard_normal(n)
-        out = make(world, np.zeros(n + 2))
-        world.rfft_test(make(world, x), out)
-        world.synchronize()
-        got = to_np(out).reshape(-1, 2)
         want = np.fft.rfft(x)
-        err = np.abs(got[:, 0] + 1j * got[:, 1] - want).max() / np.abs(want).max()
-        assert err < 1e-13, f"rfft n={n}: {err:.2e}"
+        for name in ("rfft_test", "sfft_test"):   # in-place DIT (synthesis, codec) / self-sorting padded (frame kernels)
+            out = make(world, np.zeros(n + 2))
+            getattr(world, name)(make(world, x), out)
+            world.synchronize()
+            got = to_np(out).reshape(-1, 2)
+            err = np.abs(got[:, 0] + 1j * got[:, 1] - want).max() / np.abs(want).max()
+            assert err < 1e-13, f"{name} n={n}: {err:.2e}"
 
 
 # ---------------------------------------------------------------- codec (row f2) and ingest (row f3)

@@ -61,6 +61,7 @@ ABI = {
     "world_b200_frames": (C.c_int, [C.c_int, C.c_int, C.c_double]),
     "world_b200_randn_stream": (C.c_int, [_P, C.c_uint, _P]),
     "world_b200_rfft_test": (C.c_int, [_P, _P, C.c_int, _P]),
+    "world_b200_sfft_test": (C.c_int, [_P, _P, C.c_int, _P]),
     "world_b200_fp64_peak": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "world_b200_profile": (C.c_int, [_P, C.c_int]),
     "world_b200_profile_report": (C.c_int, [_P, C.c_char_p, C.c_ulonglong]),
@@ -232,6 +233,11 @@ class World:
     def rfft_test(self, x, out):
         self._use_current_stream()
         self._check(self.lib.world_b200_rfft_test(self._h, _ptr(x), int(x.shape[0]), _ptr(out)))
+        return out
+
+    def sfft_test(self, x, out):
+        self._use_current_stream()
+        self._check(self.lib.world_b200_sfft_test(self._h, _ptr(x), int(x.shape[0]), _ptr(out)))
         return out
 
     def fp64_peak(self) -> float:

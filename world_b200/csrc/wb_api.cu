@@ -560,7 +560,31 @@ WB_KERNEL(128, 1) rfft_test_kernel(const double *x, int n, int lg, double *out, 
   rfft_forward(buf, lg, tw);
   for (int i = WB_TID; i < n + 2; i += WB_NTH) out[i] = buf[i];
 }
+// the Stockham path of the frame kernels (wb_fft.cuh, round 2): packed padded input, ping-pong, fused unpack
+WB_KERNEL(128, 1) sfft_test_kernel(const double *x, int n, int lg, double *out, const double2 *tw) {
+  WB_DYN_SMEM(double, buf);
+  const int slots = WB_FPAD_SLOTS(n >> 1);
+  double2 *a = reinterpret_cast<double2 *>(buf), *b = a + slots;
+  for (int i = WB_TID; i < n; i += WB_NTH) buf[rpad(i)] = x[i];
+  WB_SYNC();
+  const double2 *z = sfft_forward(a, b, lg - 1, tw);
+  rfft_unpack(z, lg, tw, [&](int k, double2 v) { out[2 * k] = v.x; out[2 * k + 1] = v.y; });
+}
 }  // namespace wb
+
+int world_b200_sfft_test(WorldB200 *h, const double *x_dev, int n, double *out_dev) {
+  if (!h || !x_dev || !out_dev) return WORLD_B200_EINVAL;
+  int lg = 0;
+  while ((1 << lg) < n) ++lg;
+  if ((1 << lg) != n || n < 4 || n > WB_TW_N) return WORLD_B200_EINVAL;
+  Ctx *ctx = &h->c;
+  const size_t smem = (size_t)2 * WB_FPAD_SLOTS(n >> 1) * 16;
+#ifndef WB_EMU
+  cudaFuncSetAttribute(sfft_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+  WB_LAUNCH_COOP(sfft_test_kernel, dim3(1), 128, smem, ctx->stream, x_dev, n, lg, out_dev, ctx->twiddle);
+  return dev_check(ctx, "sfft_test");
+}
 
 int world_b200_rfft_test(WorldB200 *h, const double *x_dev, int n, double *out_dev) {
   if (!h || !x_dev || !out_dev) return WORLD_B200_EINVAL;

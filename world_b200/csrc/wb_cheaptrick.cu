@@ -47,15 +47,22 @@ WB_KERNEL_PLAIN ct_count_kernel(const double *__restrict__ f0, const int *__rest
   counts[g] = c;
 }
 
+// Shared memory: two padded complex buffers of fft_size/2 slots (the FFT ping-pongs between them, wb_fft.cuh)
+// + the reduction scratch.  Between transforms the buffer that does not hold FFT input serves as the plain
+// double array of the phase (window, power spectrum, smoothing scratch), so nothing else is needed.
+WB_HD inline size_t ct_smem_bytes(int fft_size) {
+  return (size_t)2 * WB_FPAD_SLOTS(fft_size / 2) * sizeof(double2) + WB_RED_DOUBLES * sizeof(double);
+}
+
 WB_KERNEL(128, 8) ct_frame_kernel(CtParams p) {
-  WB_DYN_SMEM(double, smem);
+  WB_DYN_SMEM(double2, smem2);
   const int tid = WB_TID, nth = WB_NTH;
   const int u = blockIdx.y, i = blockIdx.x;
   if (i >= p.f_len[u]) return;
   const int N = p.fft_size, half = N / 2;
-  double *buf = smem;                 // N + 2
-  double *ext = smem + (N + 2);       // N + 2
-  double *red = ext + (N + 2);        // WB_RED_DOUBLES
+  const int slots = WB_FPAD_SLOTS(half);
+  double2 *A = smem2, *B = smem2 + slots;
+  double *red = reinterpret_cast<double *>(B + slots);   // WB_RED_DOUBLES
 
   const size_t fidx = (size_t)u * p.f_stride + i;
   const double f = ct_effective_f0(p.f0[fidx], p.f0_floor);
@@ -75,84 +82,77 @@ WB_KERNEL(128, 8) ct_frame_kernel(CtParams p) {
   const int origin = round_half_away(t * fs + 0.001);
 
   // ---- F0-adaptive Hanning window, normalised to unit energy (cheaptrick.cpp:97-106)
+  double *za = reinterpret_cast<double *>(A);   // packed FFT input: sample e at rpad(e)
+  double *wv = reinterpret_cast<double *>(B);   // window values
   double sq = 0.0;
-  WB_UNROLL4
   for (int j = tid; j < nwin; j += nth) {
     const double pos = (j - h) / 1.5 / fs;
     const double w = 0.5 * cos(kPi * pos * f) + 0.5;
-    ext[j] = w;
+    wv[j] = w;
     sq += w * w;
   }
   const double norm = sqrt(block_sum(sq, red));
   // ---- windowed waveform + 1e-12 * randn, weighted-mean removal (:126-137)
   double s1 = 0.0, s2 = 0.0;
-  WB_UNROLL4
   for (int j = tid; j < nwin; j += nth) {
-    const double w = ext[j] / norm;
-    ext[j] = w;
+    const double w = wv[j] / norm;
+    wv[j] = w;
     const int idx = imin(x_len - 1, imax(0, origin + j - h));
     const double v = x[idx] * w + randn_value(draw[j]) * kTiny;
-    buf[j] = v;
+    za[rpad(j)] = v;
     s1 += v;
     s2 += w;
   }
   block_sum2(s1, s2, red);
   const double coef = s1 / s2;
-  WB_UNROLL4
-  for (int j = tid; j < N + 2; j += nth) buf[j] = (j < nwin) ? buf[j] - ext[j] * coef : 0.0;
+  for (int j = tid; j < N; j += nth) za[rpad(j)] = (j < nwin) ? za[rpad(j)] - wv[j] * coef : 0.0;
   WB_SYNC();
 
-  // ---- power spectrum (:71-78) into ext[0..half]
-  rfft_forward(buf, p.lg_fft, p.tw);
-  {
-    const double2 *z = reinterpret_cast<const double2 *>(buf);
-    WB_UNROLL4
-    for (int k = tid; k <= half; k += nth) { const double2 c = z[k]; ext[k] = c.x * c.x + c.y * c.y; }
-  }
+  // ---- power spectrum (:71-78): the unpack of the real FFT squares straight into the idle buffer
+  const int lgc = p.lg_fft - 1;
+  double2 *z = sfft_forward(A, B, lgc, p.tw);
+  double2 *o = (z == A) ? B : A;
+  double *pw = reinterpret_cast<double *>(o);
+  rfft_unpack(z, p.lg_fft, p.tw, [&](int k, double2 c) { pw[k] = c.x * c.x + c.y * c.y; });
   WB_SYNC();
-  dc_correction(ext, f, fs, N, buf);
-  if (!linear_smoothing<true>(ext, f * 2.0 / 3.0, fs, N, ext, buf, red)) {
+  dc_correction(pw, f, fs, N, reinterpret_cast<double *>(z));
+  if (!linear_smoothing<true>(pw, f * 2.0 / 3.0, fs, N, pw, reinterpret_cast<double *>(z), red)) {
     if (tid == 0) atomicOr_status(p.status, 2);
     return;
   }
-  // ---- + |randn| * eps (:147-151), log, mirror (:39-42)
-  WB_UNROLL4
-  for (int k = tid; k <= half; k += nth) {
-    const double v = ext[k] + fabs(randn_value(draw[nwin + k])) * kEps;
-    const double l = log(v);
-    buf[k] = l;
-    if (k > 0 && k < half) buf[N - k] = l;
-  }
-  WB_SYNC();
-  rfft_forward(buf, p.lg_fft, p.tw);
-  // ---- liftering in the cepstrum domain (:28-37, 45-49)
+  // ---- + |randn| * eps (:147-151), log, mirrored to an even sequence of N (:39-42) = input of the next FFT
   {
-    const double2 *z = reinterpret_cast<const double2 *>(buf);
-    WB_UNROLL4
+    double *zin = reinterpret_cast<double *>(z);
     for (int k = tid; k <= half; k += nth) {
-      double sl = 1.0, cl = (1.0 - 2.0 * p.q1) + 2.0 * p.q1;
-      if (k > 0) {
-        const double quef = static_cast<double>(k) / fs;
-        sl = sin(kPi * f * quef) / (kPi * f * quef);
-        cl = (1.0 - 2.0 * p.q1) + 2.0 * p.q1 * cos(2.0 * kPi * quef * f);
-      }
-      ext[k] = z[k].x * sl * cl / N;
+      const double v = pw[k] + fabs(randn_value(draw[nwin + k])) * kEps;
+      const double l = log(v);
+      zin[rpad(k)] = l;
+      if (k > 0 && k < half) zin[rpad(N - k)] = l;
     }
   }
   WB_SYNC();
-  WB_UNROLL4
-  for (int k = tid; k <= half; k += nth) {
-    const double v = ext[k];
-    buf[k] = v;
-    if (k > 0 && k < half) buf[N - k] = v;
+  double2 *z2 = sfft_forward(z, o, lgc, p.tw);
+  double2 *o2 = (z2 == A) ? B : A;
+  // ---- liftering in the cepstrum domain (:28-37, 45-49); cos(2a) = 1 - 2 sin(a)^2 saves the cosine
+  {
+    double *zin = reinterpret_cast<double *>(o2);
+    const double q1 = p.q1;
+    rfft_unpack(z2, p.lg_fft, p.tw, [&](int k, double2 c) {
+      double sl = 1.0, cl = (1.0 - 2.0 * q1) + 2.0 * q1;
+      if (k > 0) {
+        const double quef = static_cast<double>(k) / fs;
+        const double sn = sin(kPi * f * quef);
+        sl = sn / (kPi * f * quef);
+        cl = (1.0 - 2.0 * q1) + 2.0 * q1 * (1.0 - 2.0 * sn * sn);
+      }
+      const double v = c.x * sl * cl / N;
+      zin[rpad(k)] = v;
+      if (k > 0 && k < half) zin[rpad(N - k)] = v;
+    });
   }
   WB_SYNC();
-  rfft_forward(buf, p.lg_fft, p.tw);
-  {
-    const double2 *z = reinterpret_cast<const double2 *>(buf);
-    WB_UNROLL4
-    for (int k = tid; k <= half; k += nth) row[k] = exp(z[k].x);
-  }
+  const double2 *z3 = sfft_forward(o2, z2, lgc, p.tw);
+  rfft_unpack(z3, p.lg_fft, p.tw, [&](int k, double2 c) { row[k] = exp(c.x); });
 }
 
 int cheaptrick_run(Ctx *ctx, const Batch &b, double q1, int fft_size, double *spectrogram) {
@@ -170,14 +170,10 @@ int cheaptrick_run(Ctx *ctx, const Batch &b, double q1, int fft_size, double *sp
   const size_t draw_stride_full = max_per_frame * (size_t)b.max_f_len;
   // utterances per chunk so that the draw scratch fits the budget
   const size_t per_utt_bytes = draw_stride_full * 4 + (size_t)b.f_stride * 8 + 64;
-  int chunk = balanced_chunk(b.n, (int)dmin(1e9, (double)ctx->scratch_budget / (double)per_utt_bytes));
-  const size_t smem = (size_t)(2 * (fft_size + 2) + WB_RED_DOUBLES) * sizeof(double);
+  int chunk = balanced_chunk(imin(b.n, 65535), (int)dmin(65535.0, (double)ctx->scratch_budget / (double)per_utt_bytes));
+  const size_t smem = ct_smem_bytes(fft_size);
 #ifndef WB_EMU
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaFuncSetAttribute(ct_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smem_set = smem;
-  }
+  cudaFuncSetAttribute(ct_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
   for (int u0 = 0; u0 < b.n; u0 += chunk) {
     const int n = imin(chunk, b.n - u0);

@@ -48,18 +48,18 @@ WB_KERNEL_PLAIN d4c_count_a_kernel(const double *__restrict__ f0, const int *__r
   counts[g] = c;
 }
 
-// F0-adaptive window + noise + weighted mean removal (d4c.cpp:21-83).  v -> dst_v[0..nwin),
-// window -> dst_w[0..nwin) (strides let callers interleave).  window_type 1 = Hanning,
-// 2 = Blackman.  Ends with a barrier; every thread returns the same nwin.
+// F0-adaptive window + noise + weighted mean removal (d4c.cpp:21-83).  The windowed sample j goes to *pv(j), the
+// window value to *pw(j) (callers choose the layout: packed FFT input, complex slot halves, ...).
+// window_type 1 = Hanning, 2 = Blackman.  Ends with a barrier; every thread returns the same nwin.
+template <class PV, class PW>
 WB_DEV int d4c_windowed(const double *__restrict__ x, int x_len, int fs, double f, double pos,
                         int window_type, double ratio, const unsigned *__restrict__ draw,
-                        double *dst_v, double *dst_w, int stride, double *red) {
+                        PV pv, PW pw, double *red) {
   const int tid = WB_TID, nth = WB_NTH;
   const int h = round_half_away(ratio * fs / f / 2.0);
   const int nwin = 2 * h + 1;
   const int origin = round_half_away(pos * fs + 0.001);
   double s1 = 0.0, s2 = 0.0;
-  WB_UNROLL4
   for (int j = tid; j < nwin; j += nth) {
     const double position = (2.0 * (j - h) / ratio) / fs;
     double w;
@@ -69,16 +69,14 @@ WB_DEV int d4c_windowed(const double *__restrict__ x, int x_len, int fs, double 
       w = 0.42 + 0.5 * cos(kPi * position * f) + 0.08 * cos(kPi * position * f * 2);
     const int idx = imin(x_len - 1, imax(0, origin + j - h));
     const double v = x[idx] * w + randn_value(draw[j]) * 0.000001;  // kSafeGuardD4C
-    dst_v[(size_t)j * stride] = v;
-    dst_w[(size_t)j * stride] = w;
+    *pv(j) = v;
+    *pw(j) = w;
     s1 += v;
     s2 += w;
   }
   block_sum2(s1, s2, red);
   const double coef = s1 / s2;
-  WB_UNROLL4
-  for (int j = tid; j < nwin; j += nth)
-    dst_v[(size_t)j * stride] = dst_v[(size_t)j * stride] - dst_w[(size_t)j * stride] * coef;
+  for (int j = tid; j < nwin; j += nth) *pv(j) = *pv(j) - *pw(j) * coef;
   WB_SYNC();
   return nwin;
 }
@@ -89,7 +87,7 @@ WB_DEV void d4c_fill_row(double *row, int bins) {
 
 // ------------------------------------------------------------------ pass A: LoveTrain
 WB_KERNEL(128, 4) d4c_lovetrain_kernel(D4cParams p) {
-  WB_DYN_SMEM(double, smem);
+  WB_DYN_SMEM(double2, smem2);
   const int tid = WB_TID, nth = WB_NTH;
   const int u = blockIdx.y, i = blockIdx.x;
   if (i >= p.f_len[u]) return;
@@ -103,27 +101,28 @@ WB_KERNEL(128, 4) d4c_lovetrain_kernel(D4cParams p) {
     return;
   }
   const int N = p.lt_fft, half = N / 2;
-  double *buf = smem;            // N + 2
-  double *win = smem + (N + 2);  // N
-  double *red = win + N;
+  const int slots = WB_FPAD_SLOTS(half);
+  double2 *A = smem2, *B = smem2 + slots;         // padded ping-pong pair of N/2 complex slots (wb_fft.cuh)
+  double *red = reinterpret_cast<double *>(B + slots);
+  double *za = reinterpret_cast<double *>(A), *win = reinterpret_cast<double *>(B);
   const double f = dmax(f0, 40.0);
   const double *x = p.x + (size_t)u * p.x_stride;
   const unsigned *draw = p.draws + (size_t)u * p.draw_stride + p.off_a[fidx];
-  const int nwin = d4c_windowed(x, p.x_len[u], p.fs, f, p.time_axis[fidx], 2, 3.0, draw, buf, win, 1, red);
-  WB_UNROLL4
-  for (int j = nwin + tid; j < N + 2; j += nth) buf[j] = 0.0;
+  const int nwin = d4c_windowed(x, p.x_len[u], p.fs, f, p.time_axis[fidx], 2, 3.0, draw,
+                                [&](int j) { return za + rpad(j); }, [&](int j) { return win + j; }, red);
+  for (int j = nwin + tid; j < N; j += nth) za[rpad(j)] = 0.0;
   WB_SYNC();
-  rfft_forward(buf, p.lt_lg, p.tw);
-  // cumulative power b0+1..b1 and b0+1..b2 (d4c.cpp:241-249)
-  const double2 *z = reinterpret_cast<const double2 *>(buf);
+  const double2 *z = sfft_forward(A, B, p.lt_lg - 1, p.tw);
+  // cumulative power b0+1..b1 and b0+1..b2 (d4c.cpp:241-249), summed while the real FFT is unpacked
   double s_lo = 0.0, s_hi = 0.0;
-  const int hi_end = imin(p.b2, half);
-  for (int k = p.b0 + 1 + tid; k <= hi_end; k += nth) {
-    const double2 c = z[k];
-    const double pw = c.x * c.x + c.y * c.y;
-    s_hi += pw;
-    if (k <= p.b1) s_lo += pw;
-  }
+  const int lo = p.b0 + 1, hi_end = imin(p.b2, half), b1 = p.b1;
+  rfft_unpack(z, p.lt_lg, p.tw, [&](int k, double2 c) {
+    if (k >= lo && k <= hi_end) {
+      const double pw = c.x * c.x + c.y * c.y;
+      s_hi += pw;
+      if (k <= b1) s_lo += pw;
+    }
+  });
   block_sum2(s_lo, s_hi, red);
   const double ap0 = s_lo / s_hi;
   const bool sel = ap0 > p.threshold;  // d4c.cpp:386
@@ -155,8 +154,7 @@ WB_DEV double select_kth_largest(const double *a, int n, int kth, double *red) {
     const unsigned long long hi_bit = 1ull << bit, lo_bit = two ? (1ull << (bit - 1)) : 0ull;
     const unsigned long long p01 = pat | lo_bit, p10 = pat | hi_bit, p11 = pat | hi_bit | lo_bit;
     int c01 = 0, c10 = 0, c11 = 0;
-    WB_UNROLL4
-    for (int j = tid; j < n; j += nth) {
+        for (int j = tid; j < n; j += nth) {
       const double v = a[j];
       unsigned long long bits;
 #ifdef WB_EMU
@@ -197,7 +195,154 @@ WB_DEV double select_kth_largest(const double *a, int n, int kth, double *red) {
 }
 
 // ------------------------------------------------------------------ pass B: general body
-WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
+// Shared memory: two padded ping-pong buffers of d_fft complex slots (wb_fft.cuh), the centroid / power rows,
+// reduction scratch.  The centroid transform is one complex FFT of d_fft (v and (n+1) v packed as re / im); the
+// power spectrum and the n_ap band transforms are real FFTs = complex FFTs of d_fft / 2 in the same two buffers.
+// Between transforms the idle buffer is the plain scratch of the smoothers.
+WB_HD inline size_t d4c_body_smem_bytes(int d_fft, int n_ap, int threads) {
+  return (size_t)2 * WB_FPAD_SLOTS(d_fft) * sizeof(double2) +
+         (size_t)(2 * (d_fft / 2 + 1) + WB_RED_DOUBLES + (threads + 1) + (n_ap + 2) + 2) * sizeof(double);
+}
+
+WB_KERNEL(512, 1) d4c_body_kernel(D4cParams p) {
+  WB_DYN_SMEM(double2, smem2);
+  const int tid = WB_TID, nth = WB_NTH;
+  const int u = blockIdx.y, i = blockIdx.x;
+  if (i >= p.f_len[u]) return;
+  const size_t fidx = (size_t)u * p.f_stride + i;
+  if (!p.selected[fidx]) return;
+  const int N = p.d_fft, half = N / 2, fs = p.fs;
+  const int slots = WB_FPAD_SLOTS(N);
+  double2 *A = smem2, *B = smem2 + slots;
+  double *cent = reinterpret_cast<double *>(B + slots);  // half + 1
+  double *pw = cent + (half + 1);          // half + 1
+  double *red = pw + (half + 1);           // WB_RED_DOUBLES
+  double *red_big = red + WB_RED_DOUBLES;  // nth + 1
+  double *coarse = red_big + (nth + 1);    // n_ap + 2
+  double *ad = reinterpret_cast<double *>(A), *bd = reinterpret_cast<double *>(B);
+
+  const double f = dmax(47.0, p.f0[fidx]);
+  const double t = p.time_axis[fidx];
+  const double *x = p.x + (size_t)u * p.x_stride;
+  const int x_len = p.x_len[u];
+  const unsigned *draw = p.draws + (size_t)u * p.draw_stride + p.off_b[fidx];
+
+  // ---- static centroid = centroid(t - 1/4f) + centroid(t + 1/4f)   (d4c.cpp:90-140)
+  for (int pass = 0; pass < 2; ++pass) {
+    const double pos = pass == 0 ? t - 0.25 / f : t + 0.25 / f;
+    // re = windowed sample, im = window (scratch) while the mean is removed
+    const int nwin = d4c_windowed(x, x_len, fs, f, pos, 2, 4.0, draw, [&](int j) { return &A[fpad(j)].x; },
+                                  [&](int j) { return &A[fpad(j)].y; }, red);
+    draw += nwin;
+    double sq = 0.0;
+    for (int j = tid; j < nwin; j += nth) { const double v = A[fpad(j)].x; sq += v * v; }
+    const double rt = sqrt(block_sum(sq, red));
+    for (int j = tid; j < N; j += nth) {
+      if (j < nwin) {
+        const double v = A[fpad(j)].x / rt;
+        A[fpad(j)] = make_double2(v, v * (j + 1.0));
+      } else {
+        A[fpad(j)] = make_double2(0.0, 0.0);
+      }
+    }
+    WB_SYNC();
+    const double2 *z = sfft_forward(A, B, p.d_lg, p.tw);
+    for (int k = tid; k <= half; k += nth) {
+      // two real FFTs from one complex FFT: Z[k] and conj(Z[N-k]) give A[k] (of v) and B[k] (of (n+1) v)
+      const double2 zp = z[fpad(k)], zq = z[fpad((N - k) & (N - 1))];
+      const double ar = 0.5 * (zp.x + zq.x), ai = 0.5 * (zp.y - zq.y);
+      const double br = 0.5 * (zp.y + zq.y), bi = -0.5 * (zp.x - zq.x);
+      const double c = br * ar + ai * bi;
+      cent[k] = pass == 0 ? c : cent[k] + c;
+    }
+    WB_SYNC();
+  }
+  dc_correction(cent, f, fs, N, ad);
+
+  // ---- smoothed power spectrum (d4c.cpp:149-166)
+  {
+    const int nwin = d4c_windowed(x, x_len, fs, f, t, 1, 4.0, draw, [&](int j) { return ad + rpad(j); },
+                                  [&](int j) { return bd + j; }, red);
+    for (int j = nwin + tid; j < N; j += nth) ad[rpad(j)] = 0.0;
+    WB_SYNC();
+    double2 *z = sfft_forward(A, B, p.d_lg - 1, p.tw);
+    rfft_unpack(z, p.d_lg, p.tw, [&](int k, double2 c) { pw[k] = c.x * c.x + c.y * c.y; });
+    WB_SYNC();
+    dc_correction(pw, f, fs, N, ad);
+    if (!linear_smoothing<false>(pw, f, fs, N, pw, ad, red_big)) {
+      if (tid == 0) atomicOr_status(p.status, 2);
+      return;
+    }
+  }
+  // ---- static group delay (d4c.cpp:172-188): g = cent / pw, two smoothers
+  for (int k = tid; k <= half; k += nth) pw[k] = cent[k] / pw[k];
+  WB_SYNC();
+  bool ok = linear_smoothing<false>(pw, f / 2.0, fs, N, pw, ad, red_big);
+  ok = ok && linear_smoothing<false>(pw, f, fs, N, cent, ad, red_big);
+  if (!ok) {
+    if (tid == 0) atomicOr_status(p.status, 2);
+    return;
+  }
+  for (int k = tid; k <= half; k += nth) pw[k] = pw[k] - cent[k];
+  WB_SYNC();
+
+  // ---- coarse aperiodicity per 3 kHz band (d4c.cpp:194-225)
+  const int half_w = p.win_len / 2;
+  for (int b = 0; b < p.n_ap; ++b) {
+    const int center = static_cast<int>(3000.0 * (b + 1) * N / fs);
+    for (int j = tid; j < N; j += nth)
+      ad[rpad(j)] = (j <= half_w * 2) ? pw[center - half_w + j] * __ldg(&p.nuttall[j]) : 0.0;
+    WB_SYNC();
+    const double2 *z = sfft_forward(A, B, p.d_lg - 1, p.tw);
+    double tot = 0.0;
+    rfft_unpack(z, p.d_lg, p.tw, [&](int k, double2 c) {
+      const double v = c.x * c.x + c.y * c.y;
+      cent[k] = v;
+      tot += v;
+    });
+    tot = block_sum(tot, red);  // contains the barrier that publishes cent[]
+    const int n_small = half - p.bd;  // entries in the sorted prefix, index half-bd-1 inclusive
+    const double kth = select_kth_largest(cent, half + 1, p.bd + 1, red);
+    double below = 0.0;
+    int n_below = 0;
+    for (int k = tid; k <= half; k += nth)
+      if (cent[k] < kth) { below += cent[k]; ++n_below; }
+    below = block_sum(below, red);
+    n_below = block_sum_int(n_below, red);
+    const double small = below + (double)(n_small - n_below) * kth;
+    if (tid == 0) {
+      const double c = 10.0 * log10(small / tot);
+      coarse[b + 1] = dmin(0.0, c + (f - 100.0) / 50.0);  // d4c.cpp:314-316
+    }
+    WB_SYNC();
+  }
+  if (tid == 0) { coarse[0] = -60.0; coarse[p.n_ap + 1] = -kTiny; }
+  WB_SYNC();
+
+  // ---- interp1 onto the CheapTrick frequency grid, dB -> amplitude (d4c.cpp:330-338, 372-383)
+  const int bins = p.ct_fft_size / 2 + 1;
+  double *row = p.out + fidx * (size_t)bins;
+  const int nx = p.n_ap + 2;
+  for (int k = tid; k < bins; k += nth) {
+    const double xi = static_cast<double>(k) * fs / p.ct_fft_size;
+    int idx = 0;  // number of axis points <= xi
+    for (int j = 0; j < nx; ++j) {
+      const double xj = (j == nx - 1) ? fs / 2.0 : j * 3000.0;
+      idx += (xj <= xi) ? 1 : 0;
+    }
+    idx = imin(nx - 1, imax(1, idx));
+    const double x0 = (idx - 1) * 3000.0;
+    const double x1 = (idx == nx - 1) ? fs / 2.0 : idx * 3000.0;
+    const double s = (xi - x0) / (x1 - x0);
+    const double y = coarse[idx - 1] + s * (coarse[idx] - coarse[idx - 1]);
+    row[k] = pow(10.0, y / 20.0);
+  }
+}
+
+// ------------------------------------------------------------------ pass B, in-place variant (d_fft > 4096 only)
+// Round-1 kernel on the in-place DIT FFT: kept for sampling rates above 48.1 kHz, where the two padded ping-pong
+// buffers of d_fft complex slots the kernel below wants no longer fit in shared memory.
+WB_KERNEL(256, 2) d4c_body_inplace_kernel(D4cParams p) {
   WB_DYN_SMEM(double, smem);
   const int tid = WB_TID, nth = WB_NTH;
   const int u = blockIdx.y, i = blockIdx.x;
@@ -223,14 +368,13 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
   for (int pass = 0; pass < 2; ++pass) {
     const double pos = pass == 0 ? t - 0.25 / f : t + 0.25 / f;
     // re = windowed sample, im = window (scratch) while the mean is removed
-    const int nwin = d4c_windowed(x, x_len, fs, f, pos, 2, 4.0, draw, zb, zb + 1, 2, red);
+    const int nwin = d4c_windowed(x, x_len, fs, f, pos, 2, 4.0, draw, [&](int j) { return zb + 2 * j; },
+                                  [&](int j) { return zb + 2 * j + 1; }, red);
     draw += nwin;
     double sq = 0.0;
-    WB_UNROLL4
-    for (int j = tid; j < nwin; j += nth) sq += z[j].x * z[j].x;
+        for (int j = tid; j < nwin; j += nth) sq += z[j].x * z[j].x;
     const double rt = sqrt(block_sum(sq, red));
-    WB_UNROLL4
-    for (int j = tid; j < N; j += nth) {
+        for (int j = tid; j < N; j += nth) {
       if (j < nwin) {
         const double v = z[j].x / rt;
         z[j] = make_double2(v, v * (j + 1.0));
@@ -240,8 +384,7 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
     }
     WB_SYNC();
     cfft_forward(z, p.d_lg, p.tw);
-    WB_UNROLL4
-    for (int k = tid; k <= half; k += nth) {
+        for (int k = tid; k <= half; k += nth) {
       double2 A, B;
       split_pair(z, N, k, A, B);
       const double c = B.x * A.x + A.y * B.y;
@@ -253,13 +396,12 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
 
   // ---- smoothed power spectrum (d4c.cpp:149-166)
   {
-    const int nwin = d4c_windowed(x, x_len, fs, f, t, 1, 4.0, draw, zb, zb + N + 2, 1, red);
-    WB_UNROLL4
-    for (int j = nwin + tid; j < N + 2; j += nth) zb[j] = 0.0;
+    const int nwin = d4c_windowed(x, x_len, fs, f, t, 1, 4.0, draw, [&](int j) { return zb + j; },
+                                  [&](int j) { return zb + N + 2 + j; }, red);
+        for (int j = nwin + tid; j < N + 2; j += nth) zb[j] = 0.0;
     WB_SYNC();
     rfft_forward(zb, p.d_lg, p.tw);
-    WB_UNROLL4
-    for (int k = tid; k <= half; k += nth) { const double2 c = z[k]; pw[k] = c.x * c.x + c.y * c.y; }
+        for (int k = tid; k <= half; k += nth) { const double2 c = z[k]; pw[k] = c.x * c.x + c.y * c.y; }
     WB_SYNC();
     dc_correction(pw, f, fs, N, zb);
     if (!linear_smoothing<false>(pw, f, fs, N, pw, zb, red_big)) {
@@ -268,8 +410,7 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
     }
   }
   // ---- static group delay (d4c.cpp:172-188): g = cent / pw, two smoothers
-  WB_UNROLL4
-  for (int k = tid; k <= half; k += nth) pw[k] = cent[k] / pw[k];
+    for (int k = tid; k <= half; k += nth) pw[k] = cent[k] / pw[k];
   WB_SYNC();
   bool ok = linear_smoothing<false>(pw, f / 2.0, fs, N, pw, zb, red_big);
   ok = ok && linear_smoothing<false>(pw, f, fs, N, cent, zb, red_big);
@@ -277,22 +418,19 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
     if (tid == 0) atomicOr_status(p.status, 2);
     return;
   }
-  WB_UNROLL4
-  for (int k = tid; k <= half; k += nth) pw[k] = pw[k] - cent[k];
+    for (int k = tid; k <= half; k += nth) pw[k] = pw[k] - cent[k];
   WB_SYNC();
 
   // ---- coarse aperiodicity per 3 kHz band (d4c.cpp:194-225)
   const int half_w = p.win_len / 2;
   for (int b = 0; b < p.n_ap; ++b) {
     const int center = static_cast<int>(3000.0 * (b + 1) * N / fs);
-    WB_UNROLL4
-    for (int j = tid; j < N + 2; j += nth)
+        for (int j = tid; j < N + 2; j += nth)
       zb[j] = (j <= half_w * 2) ? pw[center - half_w + j] * __ldg(&p.nuttall[j]) : 0.0;
     WB_SYNC();
     rfft_forward(zb, p.d_lg, p.tw);
     double tot = 0.0;
-    WB_UNROLL4
-    for (int k = tid; k <= half; k += nth) {
+        for (int k = tid; k <= half; k += nth) {
       const double2 c = z[k];
       const double v = c.x * c.x + c.y * c.y;
       cent[k] = v;
@@ -303,8 +441,7 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
     const double kth = select_kth_largest(cent, half + 1, p.bd + 1, red);
     double below = 0.0;
     int n_below = 0;
-    WB_UNROLL4
-    for (int k = tid; k <= half; k += nth)
+        for (int k = tid; k <= half; k += nth)
       if (cent[k] < kth) { below += cent[k]; ++n_below; }
     below = block_sum(below, red);
     n_below = block_sum_int(n_below, red);
@@ -322,8 +459,7 @@ WB_KERNEL(256, 2) d4c_body_kernel(D4cParams p) {
   const int bins = p.ct_fft_size / 2 + 1;
   double *row = p.out + fidx * (size_t)bins;
   const int nx = p.n_ap + 2;
-  WB_UNROLL4
-  for (int k = tid; k < bins; k += nth) {
+    for (int k = tid; k < bins; k += nth) {
     const double xi = static_cast<double>(k) * fs / p.ct_fft_size;
     int idx = 0;  // number of axis points <= xi
     for (int j = 0; j < nx; ++j) {
@@ -378,15 +514,19 @@ int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *ap
   const size_t draw_stride_full = (max_a + max_b) * (size_t)b.max_f_len;
   const size_t per_utt_bytes = draw_stride_full * 4 + (size_t)b.f_stride * 24 + 64;
   int chunk = balanced_chunk(imin(b.n, 65535), (int)dmin(65535.0, (double)ctx->scratch_budget / (double)per_utt_bytes));
-  int body_threads = 128, lt_threads = 128;  // r1d sweep: 128-thread CTAs (4 per SM) beat 256 by 18 %
+  // one radix-8 butterfly per thread in the passes of the d_fft complex transform
+  const bool inplace = p.d_fft > 4096;   // two padded buffers of d_fft slots no longer fit: round-1 kernel
+  int body_threads = inplace ? 128 : (p.d_fft >= 4096 ? 512 : 256), lt_threads = 128;
   if (const char *e = getenv("WB_D4C_THREADS")) body_threads = atoi(e);
   if (const char *e = getenv("WB_LT_THREADS")) lt_threads = atoi(e);
-  const size_t smem_lt = (size_t)((p.lt_fft + 2) + p.lt_fft + WB_RED_DOUBLES) * sizeof(double);
-  const size_t smem_body = (size_t)((2 * p.d_fft + 2) + 2 * (p.d_fft / 2 + 1) + WB_RED_DOUBLES +
-                                    (body_threads + 1) + (p.n_ap + 2) + 2) * sizeof(double);
+  const size_t smem_lt = (size_t)2 * WB_FPAD_SLOTS(p.lt_fft / 2) * sizeof(double2) + WB_RED_DOUBLES * sizeof(double);
+  const size_t smem_body = inplace ? (size_t)((2 * p.d_fft + 2) + 2 * (p.d_fft / 2 + 1) + WB_RED_DOUBLES +
+                                              (body_threads + 1) + (p.n_ap + 2) + 2) * sizeof(double)
+                                   : d4c_body_smem_bytes(p.d_fft, p.n_ap, body_threads);
 #ifndef WB_EMU
   cudaFuncSetAttribute(d4c_lovetrain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lt);
-  cudaFuncSetAttribute(d4c_body_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_body);
+  if (inplace) cudaFuncSetAttribute(d4c_body_inplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_body);
+  else cudaFuncSetAttribute(d4c_body_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_body);
 #endif
   int rc = 0;
   for (int u0 = 0; u0 < b.n && rc == 0; u0 += chunk) {
@@ -426,8 +566,12 @@ int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *ap
     scan_counts(ctx, count_b, f_len, b.f_stride, total_a, off_b, total_ab, n);
     // regenerates the pass-A prefix as well (identical values) -- simple, and pass A is ~20 % of the stream
     rng_fill(ctx, total_ab, draws, draw_stride_full, draw_stride_full, n);
-    WB_LAUNCH_COOP(d4c_body_kernel, dim3((unsigned)b.max_f_len, (unsigned)n), body_threads, smem_body,
-                   ctx->stream, p);
+    if (inplace)
+      WB_LAUNCH_COOP(d4c_body_inplace_kernel, dim3((unsigned)b.max_f_len, (unsigned)n), body_threads, smem_body,
+                     ctx->stream, p);
+    else
+      WB_LAUNCH_COOP(d4c_body_kernel, dim3((unsigned)b.max_f_len, (unsigned)n), body_threads, smem_body,
+                     ctx->stream, p);
     rc = dev_check(ctx, "d4c");
   }
   // nuttall_host was copied with an async copy from pageable memory: the runtime stages it

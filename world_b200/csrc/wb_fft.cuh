@@ -165,4 +165,158 @@ WB_DEV void split_pair(const double2 *z, int n, int k, double2 &A, double2 &B) {
   B = make_double2(0.5 * (p.y + q.y), -0.5 * (p.x - q.x));
 }
 
+// =============================================================================================
+// Stockham (self-sorting) FFT, round 2.  The in-place DIT above needs a bit-reversal pass and its first
+// passes walk shared memory with power-of-two strides of double2: 38-50 % of the shared wavefronts of the
+// frame kernels were bank conflicts (profiles/r1l_ncu_*).  The transform below goes natural order in ->
+// natural order out with NO permutation pass, ping-ponging between two buffers (one barrier per pass, any
+// block size, also one emulated thread), and every access is conflict free:
+//   * layout: element i of a buffer lives at fpad(i) = i + (i >> 3) (one spare double2 per 8);
+//   * reads  x[i + r T] (T = n / R): eight consecutive threads read eight consecutive double2;
+//   * writes y[j + m p], j = (i - k) R + k, k = i & (p - 1): for p >= 8 again consecutive; for p = 1, 2, 4 the
+//     stride-R pattern lands on distinct 16-byte bank groups because of the padding.
+// Pass structure (DIT Stockham): p = product of the radices already applied; thread i loads u[r] = x[i + r T],
+// multiplies by w^r, w = exp(-j 2 pi k / (p R)), does an R-point DFT and stores y[j + m p].  The first pass
+// has k = 0, i.e. no twiddles at all, so it is always the radix-8 one.  The radix-8 arithmetic is the
+// register butterfly of fft_pass_radix8 (three DIT stages with twiddles w^4, w^2, w).
+WB_DEV int fpad(int i) { return i + (i >> 3); }
+// double2 slots a padded buffer of n complex values needs
+#define WB_FPAD_SLOTS(n) ((n) + ((n) >> 3) + 1)
+// index, in doubles, of real sample e of a sequence packed two per complex slot (z[e >> 1].{x, y})
+WB_DEV int rpad(int e) { return (fpad(e >> 1) << 1) | (e & 1); }
+
+// x[]: inputs in bit-reversed slot order (x[bitrev3(r)] = u[r]); on return x[m] = sum_r u[r] w^r W_8^{r m}
+template <bool kTw>
+WB_DEV void radix8_butterfly(double2 (&x)[8], double2 c) {
+  const double r = 0.70710678118654752440;
+  double2 y0, y1, y2, y3, y4, y5, y6, y7;
+  if (kTw) {
+    const double2 b = cmul(c, c);
+    const double2 a = cmul(b, b);
+    const double2 t1 = cmul(a, x[1]), t3 = cmul(a, x[3]), t5 = cmul(a, x[5]), t7 = cmul(a, x[7]);
+    y0 = cadd(x[0], t1); y1 = csub(x[0], t1); y2 = cadd(x[2], t3); y3 = csub(x[2], t3);
+    y4 = cadd(x[4], t5); y5 = csub(x[4], t5); y6 = cadd(x[6], t7); y7 = csub(x[6], t7);
+    const double2 u2 = cmul(b, y2), u6 = cmul(b, y6), u3 = mul_mj(cmul(b, y3)), u7 = mul_mj(cmul(b, y7));
+    const double2 w0 = cadd(y0, u2), w2 = csub(y0, u2), w1 = cadd(y1, u3), w3 = csub(y1, u3);
+    const double2 w4 = cadd(y4, u6), w6 = csub(y4, u6), w5 = cadd(y5, u7), w7 = csub(y5, u7);
+    const double2 v4 = cmul(c, w4);
+    const double2 c5 = cmul(c, w5), v5 = make_double2((c5.x + c5.y) * r, (c5.y - c5.x) * r);
+    const double2 v6 = mul_mj(cmul(c, w6));
+    const double2 c7 = cmul(c, w7), v7 = make_double2((c7.y - c7.x) * r, -(c7.x + c7.y) * r);
+    x[0] = cadd(w0, v4); x[4] = csub(w0, v4); x[1] = cadd(w1, v5); x[5] = csub(w1, v5);
+    x[2] = cadd(w2, v6); x[6] = csub(w2, v6); x[3] = cadd(w3, v7); x[7] = csub(w3, v7);
+  } else {
+    y0 = cadd(x[0], x[1]); y1 = csub(x[0], x[1]); y2 = cadd(x[2], x[3]); y3 = csub(x[2], x[3]);
+    y4 = cadd(x[4], x[5]); y5 = csub(x[4], x[5]); y6 = cadd(x[6], x[7]); y7 = csub(x[6], x[7]);
+    const double2 u3 = mul_mj(y3), u7 = mul_mj(y7);
+    const double2 w0 = cadd(y0, y2), w2 = csub(y0, y2), w1 = cadd(y1, u3), w3 = csub(y1, u3);
+    const double2 w4 = cadd(y4, y6), w6 = csub(y4, y6), w5 = cadd(y5, u7), w7 = csub(y5, u7);
+    const double2 v5 = make_double2((w5.x + w5.y) * r, (w5.y - w5.x) * r);
+    const double2 v6 = mul_mj(w6);
+    const double2 v7 = make_double2((w7.y - w7.x) * r, -(w7.x + w7.y) * r);
+    x[0] = cadd(w0, w4); x[4] = csub(w0, w4); x[1] = cadd(w1, v5); x[5] = csub(w1, v5);
+    x[2] = cadd(w2, v6); x[6] = csub(w2, v6); x[3] = cadd(w3, v7); x[7] = csub(w3, v7);
+  }
+}
+
+template <bool kTw>
+WB_DEV void sfft_pass8(const double2 *src, double2 *dst, int n, int lgp, const double2 *__restrict__ tw) {
+  const int tid = WB_TID, nth = WB_NTH;
+  const int T = n >> 3, p = 1 << lgp;
+  for (int i = tid; i < T; i += nth) {
+    const int k = i & (p - 1), j = ((i - k) << 3) + k;
+    double2 x[8];
+    x[0] = src[fpad(i)];         x[4] = src[fpad(i + T)];     x[2] = src[fpad(i + 2 * T)]; x[6] = src[fpad(i + 3 * T)];
+    x[1] = src[fpad(i + 4 * T)]; x[5] = src[fpad(i + 5 * T)]; x[3] = src[fpad(i + 6 * T)]; x[7] = src[fpad(i + 7 * T)];
+    double2 c = make_double2(1.0, 0.0);
+    if (kTw) c = __ldg(&tw[k << (WB_TW_LOG2 - lgp - 3)]);
+    radix8_butterfly<kTw>(x, c);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) dst[fpad(j + m * p)] = x[m];
+  }
+  WB_SYNC();
+}
+
+WB_DEV void sfft_pass4(const double2 *src, double2 *dst, int n, int lgp, const double2 *__restrict__ tw) {
+  const int tid = WB_TID, nth = WB_NTH;
+  const int T = n >> 2, p = 1 << lgp;
+  for (int i = tid; i < T; i += nth) {
+    const int k = i & (p - 1), j = ((i - k) << 2) + k;
+    const double2 u0 = src[fpad(i)], u1 = src[fpad(i + T)], u2 = src[fpad(i + 2 * T)], u3 = src[fpad(i + 3 * T)];
+    const double2 b = __ldg(&tw[k << (WB_TW_LOG2 - lgp - 2)]);
+    const double2 a = cmul(b, b);
+    const double2 t2 = cmul(a, u2), t3 = cmul(a, u3);
+    const double2 y0 = cadd(u0, t2), y1 = csub(u0, t2), y2 = cadd(u1, t3), y3 = csub(u1, t3);
+    const double2 v2 = cmul(b, y2), v3 = mul_mj(cmul(b, y3));
+    dst[fpad(j)] = cadd(y0, v2);         dst[fpad(j + 2 * p)] = csub(y0, v2);
+    dst[fpad(j + p)] = cadd(y1, v3);     dst[fpad(j + 3 * p)] = csub(y1, v3);
+  }
+  WB_SYNC();
+}
+
+WB_DEV void sfft_pass2(const double2 *src, double2 *dst, int n, int lgp, const double2 *__restrict__ tw) {
+  const int tid = WB_TID, nth = WB_NTH;
+  const int T = n >> 1, p = 1 << lgp;
+  for (int i = tid; i < T; i += nth) {
+    const int k = i & (p - 1), j = ((i - k) << 1) + k;
+    const double2 u0 = src[fpad(i)];
+    const double2 v = cmul(__ldg(&tw[k << (WB_TW_LOG2 - lgp - 1)]), src[fpad(i + T)]);
+    dst[fpad(j)] = cadd(u0, v);
+    dst[fpad(j + p)] = csub(u0, v);
+  }
+  WB_SYNC();
+}
+
+// Forward complex FFT of the 2^lg values in padded buffer `a` (natural order); `b` is a second padded buffer of
+// the same size.  Both are clobbered; returns the one that holds the result (natural order, padded).  The caller
+// must have made `a` visible (barrier) before the call; ends with a barrier.
+WB_DEV double2 *sfft_forward(double2 *a, double2 *b, int lg, const double2 *__restrict__ tw) {
+  const int n = 1 << lg;
+  double2 *src = a, *dst = b;
+  int lgp = 0;
+  if (lg >= 3) {
+    sfft_pass8<false>(src, dst, n, 0, tw);
+    double2 *t = src; src = dst; dst = t;
+    lgp = 3;
+    for (; lg - lgp >= 3; lgp += 3) {
+      sfft_pass8<true>(src, dst, n, lgp, tw);
+      t = src; src = dst; dst = t;
+    }
+  }
+  if (lg - lgp == 2) {
+    sfft_pass4(src, dst, n, lgp, tw);
+    double2 *t = src; src = dst; dst = t;
+  } else if (lg - lgp == 1) {
+    sfft_pass2(src, dst, n, lgp, tw);
+    double2 *t = src; src = dst; dst = t;
+  }
+  return src;
+}
+
+// Real FFT on top: the N = 2^lg real samples were packed two per slot (sample e at rpad(e)) and transformed as
+// N/2 complex values by sfft_forward -> z.  Calls f(k, X[k]) once for every k in 0..N/2 (thread t handles k = t
+// and N/2 - t), X = r2c of the real sequence.  No barrier; reads z only.
+template <class F>
+WB_DEV void rfft_unpack(const double2 *z, int lg, const double2 *__restrict__ tw, F f) {
+  const int tid = WB_TID, nth = WB_NTH;
+  const int m = 1 << (lg - 1);
+  const int tws = WB_TW_LOG2 - lg;
+  for (int k = tid; k <= (m >> 1); k += nth) {
+    if (k == 0) {
+      const double2 z0 = z[0];
+      f(0, make_double2(z0.x + z0.y, 0.0));
+      f(m, make_double2(z0.x - z0.y, 0.0));
+    } else {
+      const double2 a = z[fpad(k)], b = z[fpad(m - k)];
+      const double er = 0.5 * (a.x + b.x), ei = 0.5 * (a.y - b.y);
+      const double orr = 0.5 * (a.y + b.y), oi = -0.5 * (a.x - b.x);
+      const double2 w = __ldg(&tw[k << tws]);
+      const double pr = fma(w.x, orr, -(w.y * oi));
+      const double pi = fma(w.x, oi, w.y * orr);
+      f(k, make_double2(er + pr, ei + pi));
+      if (k != m - k) f(m - k, make_double2(er - pr, -(ei - pi)));
+    }
+  }
+}
+
 }  // namespace wb
