@@ -28,7 +28,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "analysis frames/sec (Harvest+CheapTrick+D4C)"
 
 
 def parse():
@@ -48,14 +47,87 @@ def parse():
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--reserve-gb", type=float, default=0.0,
                     help="test hook: hold this much extra device memory (emulates the gathered arrays of a larger world)")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5],
+                    help="BASELINE.json configs[N-1]: 2 = 1024x10s Dio+StoneMask chain, 3 = 1024x10s Harvest chain (default), "
+                         "4 = 256x30s @48 kHz CheapTrick+D4C on a precomputed f0, 5 = 8192x5s Harvest chain sharded over --gpus")
+    ap.add_argument("--stages", default="full", choices=["full", "spectral"],
+                    help="spectral: time CheapTrick+D4C only, on an f0 computed (untimed) by Dio+StoneMask")
+    ap.add_argument("--parity-utts", type=int, default=3, help="extra utterances (middle / last rows of the batch) checked against the reference")
     ap.add_argument("--slices", type=int, default=1,
                     help="utterance slices per step: F0 of slice s+1 overlaps CheapTrick/D4C of slice s on a second stream")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config == 2:
+        a.f0, a.utts, a.seconds, a.fs = "dio", 1024, 10.0, 16000
+    elif a.config == 3:
+        a.f0, a.utts, a.seconds, a.fs = "harvest", 1024, 10.0, 16000
+    elif a.config == 4:
+        a.f0, a.utts, a.seconds, a.fs, a.stages = "dio", 256, 30.0, 48000, "spectral"
+    elif a.config == 5:
+        a.f0, a.utts, a.seconds, a.fs = "harvest", max(1, 8192 // max(1, a.gpus)), 5.0, 16000
+    return a
+
+
+def chain_name(a):
+    if a.stages == "spectral":
+        return "CheapTrick+D4C"
+    return "Harvest+CheapTrick+D4C" if a.f0 == "harvest" else "Dio+StoneMask+CheapTrick+D4C"
 
 
 def workload_name(a):
-    chain = "Harvest+CheapTrick+D4C" if a.f0 == "harvest" else "Dio+StoneMask+CheapTrick+D4C"
-    return f"{a.utts}x{a.seconds:g}s synthetic {a.fs // 1000} kHz batch per GPU, {chain}"
+    tail = " (f0 from Dio+StoneMask, not timed)" if a.stages == "spectral" else ""
+    return f"{a.utts}x{a.seconds:g}s synthetic {a.fs // 1000} kHz batch per GPU, {chain_name(a)}{tail}"
+
+
+def metric_name(a):
+    return f"analysis frames/sec ({chain_name(a)})"
+
+
+def ref_chain(ref, a, xu, keep=False):
+    """The reference's own chain on one utterance (oracle/_ref, stock API).  Returns frames, or all outputs."""
+    import numpy as np
+    xu = np.ascontiguousarray(xu)
+    if a.f0 == "harvest":
+        t, f0 = ref.harvest(xu, a.fs)
+    else:
+        t, f0 = ref.dio(xu, a.fs)
+        f0 = ref.stonemask(xu, a.fs, t, f0)
+    opt = ref.cheaptrick_option(a.fs)
+    sp = ref.cheaptrick(xu, a.fs, t, f0, opt)
+    ap = ref.d4c(xu, a.fs, t, f0, opt.fft_size)
+    return (t, f0, sp, ap) if keep else len(f0)
+
+
+def parity_entry(np, got, want):
+    """got / want: (time_axis, f0, sp, ap) of one utterance.  Relative errors against the reference; entries
+    where the reference is exactly 0 must be exactly 0."""
+    def rel(g, w):
+        den = np.where(w == 0, 1.0, np.abs(w))
+        return np.abs(g - w) / den
+    t, f0, sp, ap = got
+    tr, fr, spr, apr = want
+    flips = int(((f0 > 0) != (fr > 0)).sum())
+    both = (f0 > 0) & (fr > 0)
+    e = {"time_axis_exact": bool(np.array_equal(t, tr)), "frames": int(len(fr)), "vuv_flips": flips,
+         "f0_max_rel": float(rel(f0[both], fr[both]).max()) if both.any() else 0.0}
+    for name, g, w in (("sp", sp, spr), ("ap", ap, apr)):
+        r = rel(g, w)
+        e[name + "_max_rel"] = float(r.max())
+        e[name + "_frac_gt_1e-6"] = float((r > 1e-6).mean())
+    return e
+
+
+def parity_summary(entries, rows, what):
+    if not entries:
+        return None
+    keys = ["f0_max_rel", "sp_max_rel", "ap_max_rel", "sp_frac_gt_1e-6", "ap_frac_gt_1e-6"]
+    out = {"against": what, "rows": rows, "frames": sum(e["frames"] for e in entries),
+           "time_axis_bit_exact": all(e["time_axis_exact"] for e in entries),
+           "vuv_flips": sum(e["vuv_flips"] for e in entries)}
+    for k in keys:
+        out[k] = max(e[k] for e in entries)
+    out["within_1e-6"] = bool(out["time_axis_bit_exact"] and out["vuv_flips"] == 0 and
+                              max(out["f0_max_rel"], out["sp_max_rel"], out["ap_max_rel"]) <= 1e-6)
+    return out
 
 
 class ClockSampler:
@@ -157,49 +229,93 @@ def algorithmic_bytes_per_step(kernel, a, n_utts):
     return table.get(kernel)
 
 
+_REF = None
+
+
+def _ref_worker_init(cores_list, counter):
+    """One process per host core, pinned: the reference news / frees an FFT plan ~182 k times per utterance
+    (harvest.cpp:545-546); threads of one process serialise on the glibc arena, processes do not."""
+    global _REF
+    with counter.get_lock():
+        idx = counter.value
+        counter.value += 1
+    try:
+        os.sched_setaffinity(0, {cores_list[idx % len(cores_list)]})
+    except Exception:
+        pass
+    import torch
+    torch.set_num_threads(1)
+    from refworld import RefWorld, REF_LIB, ORACLE_LIB
+    _REF = RefWorld(REF_LIB if os.path.exists(REF_LIB) else ORACLE_LIB)
+
+
+_REF_X = {}
+
+
+def _ref_worker_run(args):
+    a, seed = args
+    x = _REF_X[seed]     # generated by the parent before the fork: resident, shared copy-on-write
+    t0 = time.perf_counter()
+    if a.stages == "spectral":
+        t, f0 = _REF.dio(x, a.fs)
+        f0 = _REF.stonemask(x, a.fs, t, f0)
+        t0 = time.perf_counter()     # the f0 stage is not part of this workload
+        opt = _REF.cheaptrick_option(a.fs)
+        _REF.cheaptrick(x, a.fs, t, f0, opt)
+        _REF.d4c(x, a.fs, t, f0, opt.fft_size)
+        frames = len(f0)
+    else:
+        frames = ref_chain(_REF, a, x)
+    return frames, time.perf_counter() - t0
+
+
 def run_reference(a, rank, world):
-    """--impl reference: the unmodified reference (oracle/_ref) on all host cores, rank 0 only."""
+    """--impl reference: the unmodified reference (oracle/_ref) on all host cores, rank 0 only.  One pinned worker
+    process per core; a step = one utterance of the named workload per core (a bounded sample of the batch)."""
     if rank != 0:
         return
-    import numpy as np
-    import torch
-    from concurrent.futures import ThreadPoolExecutor
-    from refworld import RefWorld, REF_LIB
+    import multiprocessing as mp
+    from refworld import REF_LIB
+    try:
+        cores_list = sorted(os.sched_getaffinity(0))
+    except Exception:
+        cores_list = list(range(os.cpu_count() or 1))
+    cores = len(cores_list)
+    per_step = cores
     from synth import synth_batch
-    cores = os.cpu_count() or 1
-    ref = RefWorld(REF_LIB)
     n = int(a.fs * a.seconds)
-    per_step = cores  # one utterance per core per step: a bounded sample of the named batch
-    x = synth_batch(range(1, per_step + 1), a.fs, n, device="cpu").numpy()
-    L = frames_of(a.fs, n)
-
-    def one(u):
-        xu = np.ascontiguousarray(x[u])
-        if a.f0 == "harvest":
-            t, f0 = ref.harvest(xu, a.fs)
-        else:
-            t, f0 = ref.dio(xu, a.fs)
-            f0 = ref.stonemask(xu, a.fs, t, f0)
-        opt = ref.cheaptrick_option(a.fs)
-        ref.cheaptrick(xu, a.fs, t, f0, opt)
-        ref.d4c(xu, a.fs, t, f0, opt.fft_size)
-        return len(f0)
-
-    with ThreadPoolExecutor(max_workers=cores) as ex:
+    for s0 in range(1, per_step + 1, 16):
+        seeds = list(range(s0, min(per_step, s0 + 15) + 1))
+        xs = synth_batch(seeds, a.fs, n, device="cpu").numpy()
+        for j, sd in enumerate(seeds):
+            _REF_X[sd] = xs[j].copy()
+    ctx = mp.get_context("fork")
+    counter = ctx.Value("i", 0)
+    with ctx.Pool(cores, initializer=_ref_worker_init, initargs=(cores_list, counter)) as pool:
+        jobs = [(a, s) for s in range(1, per_step + 1)]
         for _ in range(max(1, min(a.warmup, 1))):
-            list(ex.map(one, range(per_step)))
+            pool.map(_ref_worker_run, jobs, chunksize=1)
         t0 = time.perf_counter()
-        frames = 0
+        frames, busy = 0, 0.0
         for _ in range(a.steps):
-            frames += sum(ex.map(one, range(per_step)))
+            res = pool.map(_ref_worker_run, jobs, chunksize=1)
+            frames += sum(r[0] for r in res)
+            busy += sum(r[1] for r in res)
         dt = time.perf_counter() - t0
+        # single-core figure on an otherwise idle box: the denominator of the parallel efficiency
+        f1, t_in = pool.apply(_ref_worker_run, ((a, 1),))
+        single = f1 / t_in
     value = frames / dt
-    sample = f"{per_step} utterances x {a.seconds:g} s per step ({cores} threads, one utterance each), {a.steps} steps"
-    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": a.gpus,
+    sample = (f"{per_step} utterances x {a.seconds:g} s per step (one pinned process per core, {cores} cores, one utterance each), "
+              f"{a.steps} steps; in-worker time {busy / a.steps:.1f} core-s per step")
+    out = {"impl": "reference", "metric": metric_name(a), "value": value, "unit": "frames/s", "n_gpus": a.gpus,
            "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(a), "fs": a.fs, "frame_period_ms": 5.0},
-           "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
+           "config": {"workload": workload_name(a), "fs": a.fs, "frame_period_ms": 5.0,
+                      "sample_per_step": f"{per_step} utterances of the named batch"},
+           "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores,
+                            "kind": "reference" if os.path.exists(REF_LIB) else "port", "sample": sample,
+                            "single_core_value": single, "parallel_efficiency": value / (cores * single)},
            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -277,12 +393,25 @@ def main():
         w2.set_scratch_budget(budget // 2)
         w.set_scratch_budget(budget // 2)
 
+    spectral = a.stages == "spectral"
+    if spectral:   # config 4: the f0 contour is an input of the timed region
+        t_fix = torch.empty((U, L), dtype=torch.float64, device=dev)
+        f0_fix = torch.empty((U, L), dtype=torch.float64, device=dev)
+        for u0 in range(0, U, 64):
+            u1 = min(U, u0 + 64)
+            tt, ff, _ = w.dio(x[u0:u1], fs)
+            f0_fix[u0:u1] = w.stonemask(x[u0:u1], fs, tt, ff)
+            t_fix[u0:u1] = tt
+        w.synchronize()
+
     def step():
         main = torch.cuda.current_stream(dev)
         for si in range(n_slices):
             b0, b1 = bounds[si], bounds[si + 1]
             xs = x[b0:b1]
-            if a.f0 == "harvest":
+            if spectral:
+                t, f0 = t_fix[b0:b1], f0_fix[b0:b1]
+            elif a.f0 == "harvest":
                 t, f0, fl = w.harvest(xs, fs)
             else:
                 t, f0, fl = w.dio(xs, fs)
@@ -350,18 +479,34 @@ def main():
     gather_check = None
     if world > 1 and gather and rank == 0:
         try:
-            r = world - 1
-            xs = synth_batch(range(r * U + 1, r * U + min(U, 64) + 1), fs, n, device=dev)[:2].contiguous()   # same generator call shape as that rank's
-            tt, ff, _ = (w.harvest(xs, fs) if a.f0 == "harvest" else w.dio(xs, fs))
-            if a.f0 != "harvest":
-                ff = w.stonemask(xs, fs, tt, ff)
-            ok = torch.equal(ff, f0_all[r * U:r * U + 2]) and torch.equal(tt, t_all[r * U:r * U + 2])
-            if gather_full:
-                ok = ok and torch.equal(w.cheaptrick(xs, fs, tt, ff, opt), sp_all[r * U:r * U + 2])
-                ok = ok and torch.equal(w.d4c(xs, fs, tt, ff, opt.fft_size), ap_all[r * U:r * U + 2])
-            gather_check = bool(ok)
+            ok, checked = True, []
+            for r in range(1, world):     # the first utterance of EVERY other rank's shard
+                xs = synth_batch(range(r * U + 1, r * U + min(U, 64) + 1), fs, n, device=dev)[:1].contiguous()   # same generator call shape as that rank's
+                tt, ff, _ = (w.harvest(xs, fs) if a.f0 == "harvest" else w.dio(xs, fs))
+                if a.f0 != "harvest":
+                    ff = w.stonemask(xs, fs, tt, ff)
+                ok = ok and torch.equal(ff, f0_all[r * U:r * U + 1]) and torch.equal(tt, t_all[r * U:r * U + 1])
+                if gather_full:
+                    ok = ok and torch.equal(w.cheaptrick(xs, fs, tt, ff, opt), sp_all[r * U:r * U + 1])
+                    ok = ok and torch.equal(w.d4c(xs, fs, tt, ff, opt.fft_size), ap_all[r * U:r * U + 1])
+                checked.append(r * U)
+            gather_check = {"bit_identical": bool(ok), "rows": checked}
         except Exception as e:  # never let the check take the bench line down
             gather_check = f"error: {e}"
+
+    # ---- rows of the TIMED batch kept for the parity report (compared with the reference's own chain below)
+    k_cpu = 0 if a.no_cpu else max(1, min(a.cpu_utts if world == 1 else 1, U))
+    par_rows = list(range(k_cpu))
+    for r in ([U // 2 - 1, U // 2, U - 1][:max(0, a.parity_utts)] if not a.no_cpu else []):
+        if 0 <= r < U and r not in par_rows:
+            par_rows.append(r)
+    par_dev = {}
+    if rank == 0:
+        tsrc, fsrc = (t_fix, f0_fix) if spectral else (t_loc, f0_loc)
+        for r in par_rows:
+            par_dev[r] = (tsrc[r].cpu().numpy(), fsrc[r].cpu().numpy(), sp[r].cpu().numpy(), ap[r].cpu().numpy())
+        par_x = {r: x[r].cpu().numpy() for r in par_rows}
+    par_e2e = {}
 
     # ---- end to end through the host-pointer ABI (pinned host buffers, copies inside the timed region)
     e2e = None
@@ -385,10 +530,31 @@ def main():
         free_e2e, _ = torch.cuda.mem_get_info(dev)
         w.set_scratch_budget(int(min(96 << 30, max(2 << 30, free_e2e * 0.45))))
         ao = w.analysis_option(fs, F0_HARVEST if a.f0 == "harvest" else F0_DIO_STONEMASK)
-        w.lib.world_b200_set_stream(w._h, None)
+        if spectral:
+            th.copy_(t_fix[:Ue]); fh.copy_(f0_fix[:Ue])
+            sub = 32     # utterances per upload / compute / download round
+            xd = torch.empty((sub, n), dtype=torch.float64, device=dev)
+            td = torch.empty((sub, L), dtype=torch.float64, device=dev)
+            fd = torch.empty((sub, L), dtype=torch.float64, device=dev)
+            spd = torch.empty((sub, L, bins), dtype=torch.float64, device=dev)
+            apd = torch.empty((sub, L, bins), dtype=torch.float64, device=dev)
 
-        def e2e_step():
-            w.analyze_host(xh, fs, ao, time_axis=th, f0=fh, spectrogram=sph, aperiodicity=aph, f0_stride=L)
+            def e2e_step():   # host waveform + host f0 in, host spectrogram + aperiodicity out, batched C ABI in between
+                for u0 in range(0, Ue, sub):
+                    m = min(sub, Ue - u0)
+                    xd[:m].copy_(xh[u0:u0 + m], non_blocking=True)
+                    td[:m].copy_(th[u0:u0 + m], non_blocking=True)
+                    fd[:m].copy_(fh[u0:u0 + m], non_blocking=True)
+                    w.cheaptrick(xd[:m], fs, td[:m], fd[:m], opt, out=spd[:m])
+                    w.d4c(xd[:m], fs, td[:m], fd[:m], opt.fft_size, out=apd[:m])
+                    sph[u0:u0 + m].copy_(spd[:m], non_blocking=True)
+                    aph[u0:u0 + m].copy_(apd[:m], non_blocking=True)
+                torch.cuda.synchronize()
+        else:
+            w.lib.world_b200_set_stream(w._h, None)
+
+            def e2e_step():
+                w.analyze_host(xh, fs, ao, time_axis=th, f0=fh, spectrogram=sph, aperiodicity=aph, f0_stride=L)
 
         e2e_step()
         barrier()
@@ -408,13 +574,22 @@ def main():
         e2e = {"value": world * Ue * L * ke / dt, "unit": "frames/s",
                "h2d_bytes_per_step": int(Ue * n * 8), "d2h_bytes_per_step": int(2 * Ue * L * bins * 8 + 2 * Ue * L * 8),
                "utts_per_gpu": Ue, "steps": ke, "ms_per_step_rank0": e2e_steps_ms,
-               "note": "world_b200_analyze_host: pinned host buffers in/out; F0 stage on 512-utterance chunks, CheapTrick+D4C on 128-utterance sub-chunks whose rows are downloaded while the next ones are computed"}
+               "note": ("world_b200_cheaptrick_batch + world_b200_d4c_batch on 32-utterance rounds: pinned host waveform / f0 up, pinned host rows down"
+                        if spectral else
+                        "world_b200_analyze_host: pinned host buffers in/out; F0 stage on 512-utterance chunks, CheapTrick+D4C on 128-utterance sub-chunks whose rows are downloaded while the next ones are computed")}
+        if spectral:
+            e2e["h2d_bytes_per_step"] = int(Ue * n * 8 + 2 * Ue * L * 8)
+            e2e["d2h_bytes_per_step"] = int(2 * Ue * L * bins * 8)
         # the e2e result must be the same numbers the device-resident path produced
         same = bool(torch.equal(fh, f0_last[:Ue].cpu()))
         e2e["matches_device_path"] = same
+        if rank == 0:
+            for r in par_rows:
+                if r < Ue:
+                    par_e2e[r] = (th[r].numpy().copy(), fh[r].numpy().copy(), sph[r].numpy().copy(), aph[r].numpy().copy())
         # the same chain with the ingest (int16 PCM in) and the codec (60 mel-cepstral dimensions + band
         # aperiodicities out) fused in on the device -- SURVEY.md 8 rows f2/f3: what crosses PCIe shrinks
-        if not a.no_coded:
+        if not a.no_coded and not spectral:
             try:
                 dims = 60
                 n_ap = max(1, w.number_of_aperiodicities(fs))
@@ -494,43 +669,53 @@ def main():
     except Exception as e:  # never let the extra figure break the bench line
         fp64 = {"error": str(e)[:100]}
 
-    # ---- CPU baseline: the compiled reference, one thread, bounded sample of the same batch
-    cpu = None
-    if not a.no_cpu and world == 1:
+    # ---- CPU baseline: the compiled reference, one thread, bounded sample of the same batch; its OUTPUTS are the
+    # parity check of the timed batch (rows 0..k-1 plus the middle / last rows: real chunk boundaries and ring sizes)
+    cpu, parity = None, None
+    if not a.no_cpu:
         from refworld import RefWorld, REF_LIB, ORACLE_LIB
         kind, lib = ("reference", REF_LIB) if os.path.exists(REF_LIB) else ("port", ORACLE_LIB)
         ref = RefWorld(lib)
-        k = max(1, min(a.cpu_utts, U))
-        xs = x[:k].cpu().numpy()
+        want = {}
         t0 = time.perf_counter()
         fr = 0
-        for u in range(k):
-            xu = np.ascontiguousarray(xs[u])
-            if a.f0 == "harvest":
-                t, f0 = ref.harvest(xu, fs)
+        dt = None
+        for j, r in enumerate(par_rows):
+            if j == k_cpu:
+                dt = time.perf_counter() - t0
+            if spectral:   # the f0 stage is not part of this workload: the reference runs on the same contour
+                tr_, fr_ = par_dev[r][0], par_dev[r][1]
+                xu = np.ascontiguousarray(par_x[r])
+                o = ref.cheaptrick_option(fs)
+                want[r] = (tr_, fr_, ref.cheaptrick(xu, fs, tr_, fr_, o), ref.d4c(xu, fs, tr_, fr_, o.fft_size))
             else:
-                t, f0 = ref.dio(xu, fs)
-                f0 = ref.stonemask(xu, fs, t, f0)
-            o = ref.cheaptrick_option(fs)
-            ref.cheaptrick(xu, fs, t, f0, o)
-            ref.d4c(xu, fs, t, f0, o.fft_size)
-            fr += len(f0)
-        dt = time.perf_counter() - t0
-        cpu = {"value": fr / dt, "unit": "frames/s", "cores": 1, "kind": kind,
-               "sample": f"utterances 1..{k} of the batch ({k} x {a.seconds:g} s), single thread, {dt:.1f} s",
-               "host_cores_available": os.cpu_count()}
+                want[r] = ref_chain(ref, a, par_x[r], keep=True)
+            if j < k_cpu:
+                fr += len(want[r][1])
+        if dt is None:
+            dt = time.perf_counter() - t0
+        if world == 1:
+            cpu = {"value": fr / dt, "unit": "frames/s", "cores": 1, "kind": kind,
+                   "sample": f"utterances 1..{k_cpu} of the batch ({k_cpu} x {a.seconds:g} s), single thread, {dt:.1f} s",
+                   "host_cores_available": os.cpu_count()}
+        what = ("the reference's own chain (oracle/_ref: its f0 -> its CheapTrick / D4C) on the same waveforms" if not spectral
+                else "oracle/_ref CheapTrick / D4C on the same waveforms and f0 contour")
+        parity = {"device_resident": parity_summary([parity_entry(np, par_dev[r], want[r]) for r in par_rows], par_rows, what),
+                  "e2e_host_arrays": parity_summary([parity_entry(np, par_e2e[r], want[r]) for r in par_rows if r in par_e2e],
+                                                    [r for r in par_rows if r in par_e2e], what),
+                  "tolerance": "1e-6 relative (north_star); time_axis bit exact; no V/UV flip"}
 
-    out = {"metric": METRIC if a.f0 == "harvest" else "analysis frames/sec (Dio+StoneMask+CheapTrick+D4C)",
+    out = {"metric": metric_name(a),
            "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(a), "fs": fs, "frame_period_ms": 5.0, "frames_per_step": frames_step,
+           "config": {"workload": workload_name(a), "baseline_config": a.config or None, "fs": fs, "frame_period_ms": 5.0, "frames_per_step": frames_step,
                       "l2_policy": "inputs+outputs per step (>= 18 GB) exceed the 126 MB L2; no flush needed",
                       "multi_gpu": ("utterances sharded over ranks, NCCL all-gather of f0/time_axis" +
                                     ("/spectrogram/aperiodicity" if gather_full else "")) if world > 1 else "single GPU",
                       "gathered_equals_local_recompute": gather_check},
            "clocks": clocks, "e2e": e2e, "slices": n_slices, "gpu_launches": int(launches), "roofline": roof, "fp64": fp64, "cpu_baseline": cpu,
-           "kernels": kernels}
+           "parity": parity, "kernels": kernels}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

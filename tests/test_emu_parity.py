@@ -137,14 +137,15 @@ def test_emu_zero_tail_f0(emu, ref):
     pc.check_zero_tail_f0(emu, ref)
 
 
-def test_emu_harvest_chain_refinement(emu, ref):
-    """Experimental refinement kernel (WB_REFINE_CHAIN=1): one template per base candidate
-    shared by its seven overlapped frames.  Its lane layout and shuffles run through the lane-generic macros
-    on the host (32 emulated lanes).  Same tolerance, no V/UV flip."""
+def test_emu_harvest_per_frame_refinement(emu, ref):
+    """The per-frame refinement kernel (WB_NO_REFINE_CHAIN=1): the default since round 2 is the chain kernel
+    (one template per base candidate shared by its seven overlapped frames) wherever a 1 ms frame is a whole
+    number of decimated samples; the per-frame kernel still serves the other rates (22.05 / 44.1 kHz) and must
+    give the same contour everywhere.  Same tolerance, no V/UV flip."""
     from refworld import rel_err
     from synth import synth_batch
-    saved = os.environ.get("WB_REFINE_CHAIN")
-    os.environ["WB_REFINE_CHAIN"] = "1"
+    saved = os.environ.get("WB_NO_REFINE_CHAIN")
+    os.environ["WB_NO_REFINE_CHAIN"] = "1"
     try:
         for fs, n, seeds, fp in ((16000, 16000, [1, 2], 5.0), (48000, 24000, [3], 1.0), (8000, 8000, [6], 2.5)):
             x = synth_batch(seeds, fs, n).numpy()
@@ -162,9 +163,9 @@ def test_emu_harvest_chain_refinement(emu, ref):
                 assert (fr > 0).sum() > 50
     finally:
         if saved is None:
-            os.environ.pop("WB_REFINE_CHAIN", None)
+            os.environ.pop("WB_NO_REFINE_CHAIN", None)
         else:
-            os.environ["WB_REFINE_CHAIN"] = saved
+            os.environ["WB_NO_REFINE_CHAIN"] = saved
 
 
 def test_emu_mirroring_ripple_cases(emu, ref):

@@ -133,10 +133,19 @@ int dev_memset(Ctx *ctx, void *dst, int value, size_t bytes) {
   return 0;
 }
 
+void pool_trim(Ctx *ctx);
+
 void *dev_malloc(Ctx *ctx, size_t bytes) {
   void *p = nullptr;
 #ifndef WB_EMU
   cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess && ctx && !ctx->pool.empty()) {
+    // idle pipeline buffers can hold tens of GB: give them back and try once more before reporting ENOMEM
+    cudaGetLastError();
+    cudaStreamSynchronize(ctx->stream);
+    pool_trim(ctx);
+    e = cudaMalloc(&p, bytes);
+  }
   if (e != cudaSuccess) {
     cuda_fail(ctx, e, "cudaMalloc");
     cudaGetLastError();
@@ -176,12 +185,8 @@ void *pool_acquire(Ctx *ctx, size_t bytes) {
     if (best < 0 || b.cap < ctx->pool[best].cap) best = i;
   }
   if (best >= 0) { ctx->pool[best].busy = true; return ctx->pool[best].p; }
-  void *p = dev_malloc(ctx, bytes);
-  if (!p) {           // make room: drop what is idle and try once more
-    pool_trim(ctx);
-    p = dev_malloc(ctx, bytes);
-    if (!p) return nullptr;
-  }
+  void *p = dev_malloc(ctx, bytes);   // trims the idle pooled buffers itself when the device is full
+  if (!p) return nullptr;
   ctx->pool.push_back(PoolBuf{p, bytes, true});
   return p;
 }
@@ -323,6 +328,7 @@ int world_b200_create(int device, WorldB200 **out) {
 
 void world_b200_destroy(WorldB200 *h) {
   if (!h) return;
+  DeviceGuard guard_(&h->c);
   dev_sync(&h->c);
   dev_free(h->c.twiddle);
   dev_free(h->c.rng_jump);
@@ -341,6 +347,7 @@ void world_b200_destroy(WorldB200 *h) {
 
 int world_b200_set_stream(WorldB200 *h, void *stream) {
   if (!h) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   if (h->c.stream != (wb_stream_t)stream) {
     // scratch arena and staging ring are reused in stream order: drain the old stream before switching
     int rc = dev_sync(&h->c);
@@ -352,6 +359,7 @@ int world_b200_set_stream(WorldB200 *h, void *stream) {
 
 int world_b200_trim(WorldB200 *h) {
   if (!h) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   int rc = dev_sync(&h->c);
   pool_trim(&h->c);
   dev_free(h->c.arena.base);
@@ -361,12 +369,14 @@ int world_b200_trim(WorldB200 *h) {
 
 int world_b200_set_scratch_budget(WorldB200 *h, unsigned long long bytes) {
   if (!h || bytes < ((unsigned long long)64 << 20)) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   h->c.scratch_budget = (size_t)bytes;
   return 0;
 }
 
 int world_b200_synchronize(WorldB200 *h) {
   if (!h) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   int rc = dev_sync(&h->c);
   if (rc) return rc;
   int status = 0;
@@ -395,6 +405,7 @@ int world_b200_cheaptrick_batch(WorldB200 *h, const double *x, int n, int x_stri
                                 int fs, const double *time_axis, const double *f0, const int *f0_lengths,
                                 int f0_stride, const CheapTrickOption *opt, double *spectrogram) {
   if (!h || !x || !time_axis || !f0 || !opt || !spectrogram || n < 0 || fs <= 0) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   Batch b;
   b.x = x; b.n = n; b.x_stride = x_stride; b.fs = fs; b.time_axis = time_axis; b.f0 = f0; b.f_stride = f0_stride;
   int rc = upload_lengths(h, n, x_stride, x_lengths, f0_stride, f0_lengths, &b);
@@ -406,6 +417,7 @@ int world_b200_d4c_batch(WorldB200 *h, const double *x, int n, int x_stride, con
                          const double *time_axis, const double *f0, const int *f0_lengths, int f0_stride,
                          int fft_size, const D4COption *opt, double *aperiodicity) {
   if (!h || !x || !time_axis || !f0 || !opt || !aperiodicity || n < 0 || fs <= 0) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   Batch b;
   b.x = x; b.n = n; b.x_stride = x_stride; b.fs = fs; b.time_axis = time_axis; b.f0 = f0; b.f_stride = f0_stride;
   int rc = upload_lengths(h, n, x_stride, x_lengths, f0_stride, f0_lengths, &b);
@@ -417,6 +429,7 @@ int world_b200_stonemask_batch(WorldB200 *h, const double *x, int n, int x_strid
                                int fs, const double *time_axis, const double *f0, const int *f0_lengths,
                                int f0_stride, double *refined_f0) {
   if (!h || !x || !time_axis || !f0 || !refined_f0 || n < 0 || fs <= 0) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   Batch b;
   b.x = x; b.n = n; b.x_stride = x_stride; b.fs = fs; b.time_axis = time_axis; b.f0 = f0; b.f_stride = f0_stride;
   int rc = upload_lengths(h, n, x_stride, x_lengths, f0_stride, f0_lengths, &b);
@@ -441,6 +454,7 @@ static int f0_lengths_from_x(int n, int x_stride, const int *x_lengths, int fs, 
 int world_b200_dio_batch(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths, int fs,
                          const DioOption *opt, double *time_axis, double *f0, int f0_stride) {
   if (!h || !x || !time_axis || !f0 || !opt || n < 0 || fs <= 0) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   std::vector<int> fl;
   int rc = f0_lengths_from_x(n, x_stride, x_lengths, fs, opt->frame_period, f0_stride, &fl, &h->c.last_error);
   if (rc) return rc;
@@ -457,6 +471,7 @@ int world_b200_dio_batch(WorldB200 *h, const double *x, int n, int x_stride, con
 int world_b200_harvest_batch(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths,
                              int fs, const HarvestOption *opt, double *time_axis, double *f0, int f0_stride) {
   if (!h || !x || !time_axis || !f0 || !opt || n < 0 || fs <= 0) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   std::vector<int> fl;
   int rc = f0_lengths_from_x(n, x_stride, x_lengths, fs, opt->frame_period, f0_stride, &fl, &h->c.last_error);
   if (rc) return rc;
@@ -476,12 +491,14 @@ int world_b200_harvest_batch(WorldB200 *h, const double *x, int n, int x_stride,
 // (CUDA events recorded on the context's stream around every launch; report() synchronises).
 int world_b200_profile(WorldB200 *h, int enable) {
   if (!h) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   wb::g_prof_on = enable ? 1 : 0;
   return 0;
 }
 
 int world_b200_profile_report(WorldB200 *h, char *buf, unsigned long long cap) {
   if (!h || !buf || cap < 3) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   std::string out = "{";
 #ifndef WB_EMU
   int rc = dev_sync(&h->c);
@@ -525,6 +542,7 @@ __global__ void fp64_peak_kernel(double *out, int iters) {
 
 int world_b200_fp64_peak(WorldB200 *h, double *tflops) {
   if (!h || !tflops) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   *tflops = 0.0;
 #ifndef WB_EMU
   Ctx *ctx = &h->c;
@@ -574,6 +592,7 @@ WB_KERNEL(128, 1) sfft_test_kernel(const double *x, int n, int lg, double *out, 
 
 int world_b200_sfft_test(WorldB200 *h, const double *x_dev, int n, double *out_dev) {
   if (!h || !x_dev || !out_dev) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   int lg = 0;
   while ((1 << lg) < n) ++lg;
   if ((1 << lg) != n || n < 4 || n > WB_TW_N) return WORLD_B200_EINVAL;
@@ -588,6 +607,7 @@ int world_b200_sfft_test(WorldB200 *h, const double *x_dev, int n, double *out_d
 
 int world_b200_rfft_test(WorldB200 *h, const double *x_dev, int n, double *out_dev) {
   if (!h || !x_dev || !out_dev) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   int lg = 0;
   while ((1 << lg) < n) ++lg;
   if ((1 << lg) != n || n < 4 || n > WB_TW_N) return WORLD_B200_EINVAL;
@@ -604,6 +624,7 @@ int world_b200_rfft_test(WorldB200 *h, const double *x_dev, int n, double *out_d
 // sums (value = sum / 2^28 - 6), written to a device buffer of n_draws uint32.
 int world_b200_randn_stream(WorldB200 *h, unsigned n_draws, unsigned *out_dev) {
   if (!h || !out_dev) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
   Ctx *ctx = &h->c;
   unsigned char *blk = arena_block(ctx, 256);
   if (!blk) return WORLD_B200_ENOMEM;

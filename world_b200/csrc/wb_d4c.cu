@@ -30,6 +30,7 @@ struct D4cParams {
   const unsigned *draws; size_t draw_stride;
   const unsigned *off_a; unsigned *count_b; const unsigned *off_b;
   unsigned char *selected;  // [n][f_stride]
+  int *slow_list; int *slow_count;   // frames whose window does not fit the fast body kernel (long windows, f0 near the floor)
   double *out;
   const double2 *tw;
   int *status;
@@ -195,16 +196,23 @@ WB_DEV double select_kth_largest(const double *a, int n, int kth, double *red) {
 }
 
 // ------------------------------------------------------------------ pass B: general body
-// Shared memory: two padded ping-pong buffers of d_fft complex slots (wb_fft.cuh), the centroid / power rows,
-// reduction scratch.  The centroid transform is one complex FFT of d_fft (v and (n+1) v packed as re / im); the
-// power spectrum and the n_ap band transforms are real FFTs = complex FFTs of d_fft / 2 in the same two buffers.
-// Between transforms the idle buffer is the plain scratch of the smoothers.
+// One CTA of d_fft / 16 threads per selected frame.  Shared memory: ONE padded buffer of d_fft / 2 complex slots
+// (in-place self-sorting FFT, wb_fft.cuh: one radix-8 butterfly per thread and pass), the centroid row, the power
+// row, reduction scratch -- 36.5 KB at 16 kHz, six CTAs per SM.  Every transform is a complex FFT of d_fft / 2:
+//   * power spectrum and the n_ap band spectra: real FFTs, two samples per slot, unpacked on the fly;
+//   * centroid: the reference's two real FFTs of v and (n+1) v = one complex FFT of d_fft of z = v + j (n+1) v, done
+//     here as its two decimation-in-frequency halves -- even bins from z[n] + z[n + d_fft/2], odd bins from
+//     (z[n] - z[n + d_fft/2]) W^n -- one after the other in the same buffer (bins k and d_fft - k, which the
+//     split of the two real spectra pairs up, have the same parity).  The windowed signal waits in the power row.
+// Frames whose window is longer than that row (f0 within ~30 % of the 47 Hz floor) go to slow_list and are done
+// by d4c_body_slow_kernel (the round-1 body on the in-place DIT FFT, any window length).
 WB_HD inline size_t d4c_body_smem_bytes(int d_fft, int n_ap, int threads) {
-  return (size_t)2 * WB_FPAD_SLOTS(d_fft) * sizeof(double2) +
+  return (size_t)WB_FPAD_SLOTS(d_fft / 2) * sizeof(double2) +
          (size_t)(2 * (d_fft / 2 + 1) + WB_RED_DOUBLES + (threads + 1) + (n_ap + 2) + 2) * sizeof(double);
 }
 
-WB_KERNEL(512, 1) d4c_body_kernel(D4cParams p) {
+template <int kOcc>   // CTAs of 128 threads per SM the register budget is cut for (A/B: WB_D4C_OCC)
+WB_DEV void d4c_body_frame(const D4cParams &p) {
   WB_DYN_SMEM(double2, smem2);
   const int tid = WB_TID, nth = WB_NTH;
   const int u = blockIdx.y, i = blockIdx.x;
@@ -212,64 +220,82 @@ WB_KERNEL(512, 1) d4c_body_kernel(D4cParams p) {
   const size_t fidx = (size_t)u * p.f_stride + i;
   if (!p.selected[fidx]) return;
   const int N = p.d_fft, half = N / 2, fs = p.fs;
-  const int slots = WB_FPAD_SLOTS(N);
-  double2 *A = smem2, *B = smem2 + slots;
-  double *cent = reinterpret_cast<double *>(B + slots);  // half + 1
-  double *pw = cent + (half + 1);          // half + 1
+  const int slots = WB_FPAD_SLOTS(half);
+  double2 *P = smem2;
+  double *pd = reinterpret_cast<double *>(P);            // the same buffer as 2 * slots plain doubles
+  double *cent = reinterpret_cast<double *>(P + slots);  // half + 1
+  double *pw = cent + (half + 1);          // half + 1; holds the windowed signal during the centroid transforms
   double *red = pw + (half + 1);           // WB_RED_DOUBLES
   double *red_big = red + WB_RED_DOUBLES;  // nth + 1
   double *coarse = red_big + (nth + 1);    // n_ap + 2
-  double *ad = reinterpret_cast<double *>(A), *bd = reinterpret_cast<double *>(B);
+  double *wv = pd + slots;                 // window values (second half of the buffer), <= half + 1 of them
 
   const double f = dmax(47.0, p.f0[fidx]);
   const double t = p.time_axis[fidx];
+  {
+    const int nwin4 = 2 * round_half_away(4.0 * fs / f / 2.0) + 1;   // both ratio-4 windows (d4c_windowed)
+    if (nwin4 > half + 1) {
+      if (tid == 0) {
+#ifdef WB_EMU
+        const int at = (*p.slow_count)++;
+#else
+        const int at = atomicAdd(p.slow_count, 1);
+#endif
+        p.slow_list[at] = (int)(u * p.f_stride + i);
+      }
+      return;
+    }
+  }
   const double *x = p.x + (size_t)u * p.x_stride;
   const int x_len = p.x_len[u];
   const unsigned *draw = p.draws + (size_t)u * p.draw_stride + p.off_b[fidx];
+  const int lgh = p.d_lg - 1;              // log2(half)
+  const int tw_shift = WB_TW_LOG2 - p.d_lg;
 
   // ---- static centroid = centroid(t - 1/4f) + centroid(t + 1/4f)   (d4c.cpp:90-140)
   for (int pass = 0; pass < 2; ++pass) {
     const double pos = pass == 0 ? t - 0.25 / f : t + 0.25 / f;
-    // re = windowed sample, im = window (scratch) while the mean is removed
-    const int nwin = d4c_windowed(x, x_len, fs, f, pos, 2, 4.0, draw, [&](int j) { return &A[fpad(j)].x; },
-                                  [&](int j) { return &A[fpad(j)].y; }, red);
+    const int nwin = d4c_windowed(x, x_len, fs, f, pos, 2, 4.0, draw, [&](int j) { return pw + j; },
+                                  [&](int j) { return wv + j; }, red);
     draw += nwin;
     double sq = 0.0;
-    for (int j = tid; j < nwin; j += nth) { const double v = A[fpad(j)].x; sq += v * v; }
+    for (int j = tid; j < nwin; j += nth) { const double v = pw[j]; sq += v * v; }
     const double rt = sqrt(block_sum(sq, red));
-    for (int j = tid; j < N; j += nth) {
-      if (j < nwin) {
-        const double v = A[fpad(j)].x / rt;
-        A[fpad(j)] = make_double2(v, v * (j + 1.0));
-      } else {
-        A[fpad(j)] = make_double2(0.0, 0.0);
+    for (int part = 0; part < 2; ++part) {
+      // input of the half transform: z[n] = v[n] / rt * (1 + j (n + 1)), n < nwin
+      for (int n = tid; n < half; n += nth) {
+        double2 z0 = make_double2(0.0, 0.0), z1 = make_double2(0.0, 0.0);
+        if (n < nwin) { const double v = pw[n] / rt; z0 = make_double2(v, v * (n + 1.0)); }
+        if (n + half < nwin) { const double v = pw[n + half] / rt; z1 = make_double2(v, v * (n + half + 1.0)); }
+        P[fpad(n)] = part == 0 ? cadd(z0, z1) : cmul(__ldg(&p.tw[n << tw_shift]), csub(z0, z1));
       }
+      WB_SYNC();
+      sfft_forward_inplace(P, lgh, p.tw);
+      // bins k = 2 m + part; partner N - k = 2 (half - m - part) + part.  A = spectrum of v, B = of (n+1) v
+      for (int m = tid; 2 * m + part <= half; m += nth) {
+        const double2 zp = P[fpad(m)], zq = P[fpad((half - m - part) & (half - 1))];
+        const double ar = 0.5 * (zp.x + zq.x), ai = 0.5 * (zp.y - zq.y);
+        const double br = 0.5 * (zp.y + zq.y), bi = -0.5 * (zp.x - zq.x);
+        const double c = br * ar + ai * bi;
+        const int k = 2 * m + part;
+        cent[k] = pass == 0 ? c : cent[k] + c;
+      }
+      WB_SYNC();
     }
-    WB_SYNC();
-    const double2 *z = sfft_forward(A, B, p.d_lg, p.tw);
-    for (int k = tid; k <= half; k += nth) {
-      // two real FFTs from one complex FFT: Z[k] and conj(Z[N-k]) give A[k] (of v) and B[k] (of (n+1) v)
-      const double2 zp = z[fpad(k)], zq = z[fpad((N - k) & (N - 1))];
-      const double ar = 0.5 * (zp.x + zq.x), ai = 0.5 * (zp.y - zq.y);
-      const double br = 0.5 * (zp.y + zq.y), bi = -0.5 * (zp.x - zq.x);
-      const double c = br * ar + ai * bi;
-      cent[k] = pass == 0 ? c : cent[k] + c;
-    }
-    WB_SYNC();
   }
-  dc_correction(cent, f, fs, N, ad);
+  dc_correction(cent, f, fs, N, pd);
 
   // ---- smoothed power spectrum (d4c.cpp:149-166)
   {
-    const int nwin = d4c_windowed(x, x_len, fs, f, t, 1, 4.0, draw, [&](int j) { return ad + rpad(j); },
-                                  [&](int j) { return bd + j; }, red);
-    for (int j = nwin + tid; j < N; j += nth) ad[rpad(j)] = 0.0;
+    const int nwin = d4c_windowed(x, x_len, fs, f, t, 1, 4.0, draw, [&](int j) { return pd + rpad(j); },
+                                  [&](int j) { return pw + j; }, red);
+    for (int j = nwin + tid; j < N; j += nth) pd[rpad(j)] = 0.0;
     WB_SYNC();
-    double2 *z = sfft_forward(A, B, p.d_lg - 1, p.tw);
-    rfft_unpack(z, p.d_lg, p.tw, [&](int k, double2 c) { pw[k] = c.x * c.x + c.y * c.y; });
+    sfft_forward_inplace(P, lgh, p.tw);
+    rfft_unpack(P, p.d_lg, p.tw, [&](int k, double2 c) { pw[k] = c.x * c.x + c.y * c.y; });
     WB_SYNC();
-    dc_correction(pw, f, fs, N, ad);
-    if (!linear_smoothing<false>(pw, f, fs, N, pw, ad, red_big)) {
+    dc_correction(pw, f, fs, N, pd);
+    if (!linear_smoothing<false>(pw, f, fs, N, pw, pd, red_big)) {
       if (tid == 0) atomicOr_status(p.status, 2);
       return;
     }
@@ -277,8 +303,8 @@ WB_KERNEL(512, 1) d4c_body_kernel(D4cParams p) {
   // ---- static group delay (d4c.cpp:172-188): g = cent / pw, two smoothers
   for (int k = tid; k <= half; k += nth) pw[k] = cent[k] / pw[k];
   WB_SYNC();
-  bool ok = linear_smoothing<false>(pw, f / 2.0, fs, N, pw, ad, red_big);
-  ok = ok && linear_smoothing<false>(pw, f, fs, N, cent, ad, red_big);
+  bool ok = linear_smoothing<false>(pw, f / 2.0, fs, N, pw, pd, red_big);
+  ok = ok && linear_smoothing<false>(pw, f, fs, N, cent, pd, red_big);
   if (!ok) {
     if (tid == 0) atomicOr_status(p.status, 2);
     return;
@@ -291,11 +317,11 @@ WB_KERNEL(512, 1) d4c_body_kernel(D4cParams p) {
   for (int b = 0; b < p.n_ap; ++b) {
     const int center = static_cast<int>(3000.0 * (b + 1) * N / fs);
     for (int j = tid; j < N; j += nth)
-      ad[rpad(j)] = (j <= half_w * 2) ? pw[center - half_w + j] * __ldg(&p.nuttall[j]) : 0.0;
+      pd[rpad(j)] = (j <= half_w * 2) ? pw[center - half_w + j] * __ldg(&p.nuttall[j]) : 0.0;
     WB_SYNC();
-    const double2 *z = sfft_forward(A, B, p.d_lg - 1, p.tw);
+    sfft_forward_inplace(P, lgh, p.tw);
     double tot = 0.0;
-    rfft_unpack(z, p.d_lg, p.tw, [&](int k, double2 c) {
+    rfft_unpack(P, p.d_lg, p.tw, [&](int k, double2 c) {
       const double v = c.x * c.x + c.y * c.y;
       cent[k] = v;
       tot += v;
@@ -339,16 +365,19 @@ WB_KERNEL(512, 1) d4c_body_kernel(D4cParams p) {
   }
 }
 
-// ------------------------------------------------------------------ pass B, in-place variant (d_fft > 4096 only)
-// Round-1 kernel on the in-place DIT FFT: kept for sampling rates above 48.1 kHz, where the two padded ping-pong
-// buffers of d_fft complex slots the kernel below wants no longer fit in shared memory.
-WB_KERNEL(256, 2) d4c_body_inplace_kernel(D4cParams p) {
-  WB_DYN_SMEM(double, smem);
+#ifndef WB_EMU
+__global__ void __launch_bounds__(256, 3) d4c_body_kernel(D4cParams p) { d4c_body_frame<6>(p); }      // 80 registers
+__global__ void __launch_bounds__(256, 2) d4c_body_kernel_r128(D4cParams p) { d4c_body_frame<4>(p); } // 128 registers
+#else
+void d4c_body_kernel(D4cParams p) { d4c_body_frame<6>(p); }
+#endif
+
+// ------------------------------------------------------------------ pass B, any window length (round-1 body, in-place DIT FFT)
+// Persistent kernel over slow_list (frames the fast kernel handed over); with d_fft > 4096 (fs above 48.1 kHz: the
+// fast kernel's thread count would exceed a CTA) the driver puts every selected frame on the list instead.
+WB_DEV void d4c_body_slow_frame(const D4cParams &p, int u, int i, double *smem) {
   const int tid = WB_TID, nth = WB_NTH;
-  const int u = blockIdx.y, i = blockIdx.x;
-  if (i >= p.f_len[u]) return;
   const size_t fidx = (size_t)u * p.f_stride + i;
-  if (!p.selected[fidx]) return;
   const int N = p.d_fft, half = N / 2, fs = p.fs;
   double *zb = smem;                       // 2N (+2): complex FFT buffer / smoothing scratch
   double *cent = zb + 2 * N + 2;           // half + 1
@@ -475,6 +504,30 @@ WB_KERNEL(256, 2) d4c_body_inplace_kernel(D4cParams p) {
   }
 }
 
+WB_KERNEL(256, 2) d4c_body_slow_kernel(D4cParams p) {
+  WB_DYN_SMEM(double, smem);
+  const int count = *p.slow_count;
+  for (int at = blockIdx.x; at < count; at += gridDim.x) {
+    const int g = p.slow_list[at];
+    d4c_body_slow_frame(p, g / p.f_stride, g % p.f_stride, smem);
+    WB_SYNC();   // the next frame reuses the shared buffers
+  }
+}
+
+// d_fft > 4096: every selected frame goes through the list
+WB_KERNEL_PLAIN d4c_list_all_kernel(D4cParams p, int n_utts) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)n_utts * p.f_stride) return;
+  const int u = (int)(g / p.f_stride), i = (int)(g % p.f_stride);
+  if (i >= p.f_len[u] || !p.selected[g]) return;
+#ifdef WB_EMU
+  const int at = (*p.slow_count)++;
+#else
+  const int at = atomicAdd(p.slow_count, 1);
+#endif
+  p.slow_list[at] = (int)g;
+}
+
 int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *aperiodicity) {
   if (b.n <= 0 || b.max_f_len <= 0) return 0;
   const int fs = b.fs;
@@ -512,21 +565,22 @@ int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *ap
   const size_t max_a = (size_t)(2 * round_half_away(3.0 * fs / 40.0 / 2.0) + 1);
   const size_t max_b = 3 * (size_t)(2 * round_half_away(4.0 * fs / 47.0 / 2.0) + 1);
   const size_t draw_stride_full = (max_a + max_b) * (size_t)b.max_f_len;
-  const size_t per_utt_bytes = draw_stride_full * 4 + (size_t)b.f_stride * 24 + 64;
+  const size_t per_utt_bytes = draw_stride_full * 4 + (size_t)b.f_stride * 28 + 64;
   int chunk = balanced_chunk(imin(b.n, 65535), (int)dmin(65535.0, (double)ctx->scratch_budget / (double)per_utt_bytes));
-  // one radix-8 butterfly per thread in the passes of the d_fft complex transform
-  const bool inplace = p.d_fft > 4096;   // two padded buffers of d_fft slots no longer fit: round-1 kernel
-  int body_threads = inplace ? 128 : (p.d_fft >= 4096 ? 512 : 256), lt_threads = 128;
-  if (const char *e = getenv("WB_D4C_THREADS")) body_threads = atoi(e);
+  // fast body kernel: one radix-8 butterfly per thread in the passes of the d_fft / 2 complex transforms
+  const bool all_slow = p.d_fft > 4096;   // d_fft / 16 threads would exceed the kernel's launch bounds
+  int body_threads = imax(32, p.d_fft / 16), lt_threads = 128, slow_threads = 128;
   if (const char *e = getenv("WB_LT_THREADS")) lt_threads = atoi(e);
   const size_t smem_lt = (size_t)2 * WB_FPAD_SLOTS(p.lt_fft / 2) * sizeof(double2) + WB_RED_DOUBLES * sizeof(double);
-  const size_t smem_body = inplace ? (size_t)((2 * p.d_fft + 2) + 2 * (p.d_fft / 2 + 1) + WB_RED_DOUBLES +
-                                              (body_threads + 1) + (p.n_ap + 2) + 2) * sizeof(double)
-                                   : d4c_body_smem_bytes(p.d_fft, p.n_ap, body_threads);
+  const size_t smem_body = d4c_body_smem_bytes(p.d_fft, p.n_ap, body_threads);
+  const size_t smem_slow = (size_t)((2 * p.d_fft + 2) + 2 * (p.d_fft / 2 + 1) + WB_RED_DOUBLES +
+                                    (slow_threads + 1) + (p.n_ap + 2) + 2) * sizeof(double);
 #ifndef WB_EMU
   cudaFuncSetAttribute(d4c_lovetrain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lt);
-  if (inplace) cudaFuncSetAttribute(d4c_body_inplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_body);
-  else cudaFuncSetAttribute(d4c_body_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_body);
+  cudaFuncSetAttribute(d4c_body_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_body);
+  cudaFuncSetAttribute(d4c_body_kernel_r128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_body);
+  const bool fat_regs = getenv("WB_D4C_FAT") != nullptr;
+  cudaFuncSetAttribute(d4c_body_slow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_slow);
 #endif
   int rc = 0;
   for (int u0 = 0; u0 < b.n && rc == 0; u0 += chunk) {
@@ -537,6 +591,7 @@ int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *ap
     const size_t o_cb = plan.add(slots * 4), o_ob = plan.add(slots * 4);
     const size_t o_ta = plan.add((size_t)n * 4), o_tab = plan.add((size_t)n * 4);
     const size_t o_sel = plan.add(slots), o_nut = plan.add((size_t)p.win_len * 8);
+    const size_t o_slow = plan.add(slots * 4), o_nslow = plan.add(4);
     const size_t o_draws = plan.add((size_t)n * draw_stride_full * 4);
     unsigned char *blk = arena_block(ctx, plan.total);
     if (!blk) { rc = 2; break; }
@@ -556,6 +611,8 @@ int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *ap
     p.off_a = off_a; p.count_b = count_b; p.off_b = off_b; p.selected = selected;
     p.out = aperiodicity + (size_t)u0 * b.f_stride * bins;
     p.tw = ctx->twiddle; p.status = ctx->status_dev;
+    p.slow_list = (int *)(blk + o_slow); p.slow_count = (int *)(blk + o_nslow);
+    dev_memset(ctx, p.slow_count, 0, 4);
 
     WB_LAUNCH_FLAT(d4c_count_a_kernel, dim3((unsigned)((slots + 255) / 256)), 256, 0, ctx->stream, f0,
                    f_len, b.f_stride, n, fs, count_a);
@@ -566,12 +623,21 @@ int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *ap
     scan_counts(ctx, count_b, f_len, b.f_stride, total_a, off_b, total_ab, n);
     // regenerates the pass-A prefix as well (identical values) -- simple, and pass A is ~20 % of the stream
     rng_fill(ctx, total_ab, draws, draw_stride_full, draw_stride_full, n);
-    if (inplace)
-      WB_LAUNCH_COOP(d4c_body_inplace_kernel, dim3((unsigned)b.max_f_len, (unsigned)n), body_threads, smem_body,
-                     ctx->stream, p);
+    if (all_slow)
+      WB_LAUNCH_FLAT(d4c_list_all_kernel, dim3((unsigned)((slots + 255) / 256)), 256, 0, ctx->stream, p, n);
     else
+    {
+#ifndef WB_EMU
+      if (fat_regs)
+        WB_LAUNCH_COOP(d4c_body_kernel_r128, dim3((unsigned)b.max_f_len, (unsigned)n), body_threads, smem_body,
+                       ctx->stream, p);
+      else
+#endif
       WB_LAUNCH_COOP(d4c_body_kernel, dim3((unsigned)b.max_f_len, (unsigned)n), body_threads, smem_body,
                      ctx->stream, p);
+    }
+    // long windows (f0 near the floor): persistent CTAs over the list the fast kernel filled, usually empty
+    WB_LAUNCH_COOP(d4c_body_slow_kernel, dim3((unsigned)(2 * ctx->sm_count)), slow_threads, smem_slow, ctx->stream, p);
     rc = dev_check(ctx, "d4c");
   }
   // nuttall_host was copied with an async copy from pageable memory: the runtime stages it

@@ -293,6 +293,91 @@ WB_DEV double2 *sfft_forward(double2 *a, double2 *b, int lg, const double2 *__re
   return src;
 }
 
+// Same transform in ONE padded buffer: every thread keeps the (at most) eight values it owns in a pass in
+// registers -- load, barrier, butterflies + store, barrier.  Two barriers per pass instead of one, half the shared
+// memory (more CTAs per SM for the barrier-heavy frame kernels).  Needs 2^lg <= 8 * blockDim.x.  Natural order in,
+// natural order out, result in `a`; the caller must have made `a` visible; ends with a barrier.
+WB_DEV void sfft_forward_inplace(double2 *a, int lg, const double2 *__restrict__ tw) {
+#ifdef WB_EMU
+  // one emulated thread: run the ping-pong passes against a scratch buffer (same arithmetic), copy back
+  static double2 tmp[WB_FPAD_SLOTS(WB_TW_N)];
+  double2 *r = sfft_forward(a, tmp, lg, tw);
+  if (r != a) for (int i = 0; i < WB_FPAD_SLOTS(1 << lg); ++i) a[i] = r[i];
+#else
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int n = 1 << lg;
+  int lgp = 0;
+  if (lg >= 3) {
+    const int T = n >> 3;
+    for (; lg - lgp >= 3; lgp += 3) {
+      const int p = 1 << lgp, i = tid;
+      double2 x[8];
+      if (i < T) {
+        x[0] = a[fpad(i)];         x[4] = a[fpad(i + T)];     x[2] = a[fpad(i + 2 * T)]; x[6] = a[fpad(i + 3 * T)];
+        x[1] = a[fpad(i + 4 * T)]; x[5] = a[fpad(i + 5 * T)]; x[3] = a[fpad(i + 6 * T)]; x[7] = a[fpad(i + 7 * T)];
+      }
+      __syncthreads();
+      if (i < T) {
+        const int k = i & (p - 1), j = ((i - k) << 3) + k;
+        if (lgp == 0) {
+          radix8_butterfly<false>(x, make_double2(1.0, 0.0));
+        } else {
+          radix8_butterfly<true>(x, __ldg(&tw[k << (WB_TW_LOG2 - lgp - 3)]));
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) a[fpad(j + m * p)] = x[m];
+      }
+      __syncthreads();
+    }
+  }
+  if (lg - lgp == 2) {
+    const int T = n >> 2, p = 1 << lgp;
+    double2 u[2][4];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = tid + q * nth;
+      if (i < T) { u[q][0] = a[fpad(i)]; u[q][1] = a[fpad(i + T)]; u[q][2] = a[fpad(i + 2 * T)]; u[q][3] = a[fpad(i + 3 * T)]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = tid + q * nth;
+      if (i < T) {
+        const int k = i & (p - 1), j = ((i - k) << 2) + k;
+        const double2 b = __ldg(&tw[k << (WB_TW_LOG2 - lgp - 2)]);
+        const double2 aa = cmul(b, b);
+        const double2 t2 = cmul(aa, u[q][2]), t3 = cmul(aa, u[q][3]);
+        const double2 y0 = cadd(u[q][0], t2), y1 = csub(u[q][0], t2), y2 = cadd(u[q][1], t3), y3 = csub(u[q][1], t3);
+        const double2 v2 = cmul(b, y2), v3 = mul_mj(cmul(b, y3));
+        a[fpad(j)] = cadd(y0, v2);     a[fpad(j + 2 * p)] = csub(y0, v2);
+        a[fpad(j + p)] = cadd(y1, v3); a[fpad(j + 3 * p)] = csub(y1, v3);
+      }
+    }
+    __syncthreads();
+  } else if (lg - lgp == 1) {
+    const int T = n >> 1, p = 1 << lgp;
+    double2 u[4][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = tid + q * nth;
+      if (i < T) { u[q][0] = a[fpad(i)]; u[q][1] = a[fpad(i + T)]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = tid + q * nth;
+      if (i < T) {
+        const int k = i & (p - 1), j = ((i - k) << 1) + k;
+        const double2 v = cmul(__ldg(&tw[k << (WB_TW_LOG2 - lgp - 1)]), u[q][1]);
+        a[fpad(j)] = cadd(u[q][0], v);
+        a[fpad(j + p)] = csub(u[q][0], v);
+      }
+    }
+    __syncthreads();
+  }
+#endif
+}
+
 // Real FFT on top: the N = 2^lg real samples were packed two per slot (sample e at rpad(e)) and transformed as
 // N/2 complex values by sfft_forward -> z.  Calls f(k, X[k]) once for every k in 0..N/2 (thread t handles k = t
 // and N/2 - t), X = r2c of the real sequence.  No barrier; reads z only.

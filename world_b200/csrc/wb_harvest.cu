@@ -337,7 +337,7 @@ WB_KERNEL(32 * WB_HV_WARPS, 6) harvest_refine_kernel(HvRefineParams p) {
   }
 }
 
-// ------------------------------------------------------------------ K-HVr, chain variant (experimental)
+// ------------------------------------------------------------------ K-HVr, chain variant (the default where it applies)
 // DESIGN.md 9 item 2.  When one 1 ms frame is a whole number S of decimated samples (8000 Hz: S = 8), the
 // seven overlapped refinements of a base candidate (frames k-3 .. k+3) share one window and one set of
 // twiddles: GetBaseIndex gives basic = S k' - h, so the window argument (basic + i - 1) / afs - t_k' is
@@ -345,7 +345,8 @@ WB_KERNEL(32 * WB_HV_WARPS, 6) harvest_refine_kernel(HvRefineParams p) {
 // it builds the template once (w e^{-j theta}, dw e^{-j theta}) and feeds 7 x 4 accumulators from the seven
 // S-shifted samples.  Outputs go to slot j of frame k, slot j + nc g of frame k + g and slot j + nc (g + 3) of
 // frame k - g (the inverse of hv_slot_candidate); every other slot keeps the zero the driver memset.
-// Selected with WB_REFINE_CHAIN=1; not measured on a GPU yet, therefore not the default.
+// Default since round 2 wherever S is integral (profiles/r2b: 379.5 -> 152.1 ms per 1024 x 10 s, f0 within 2e-14 of
+// the reference with no V/UV flip on the GPU); WB_NO_REFINE_CHAIN=1 selects the per-frame kernel for A/B runs.
 //
 // Lane-generic source: WB_FOR_LANES runs the lane body for lane = threadIdx.x & 31 on the GPU and for all 32
 // lanes in turn in the host emulation, so the lane layout and the shuffles are checked on the CPU too.
@@ -1031,8 +1032,8 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     const unsigned refine_blocks = (unsigned)((l1_stride + WB_HV_WARPS - 1) / WB_HV_WARPS);
 #endif
     const int frame_samples = static_cast<int>(afs / 1000.0);
-    if (getenv("WB_REFINE_CHAIN") && frame_samples >= 1 && frame_samples * 1000.0 == afs) {
-      // experimental: slots without an in-range source frame keep these zeros
+    if (!getenv("WB_NO_REFINE_CHAIN") && frame_samples >= 1 && frame_samples * 1000.0 == afs) {
+      // slots without an in-range source frame keep these zeros
       rc = dev_memset(ctx, rp.cand, 0, (size_t)n * l1_stride * max_cand * 8);
       if (!rc) rc = dev_memset(ctx, rp.score, 0, (size_t)n * l1_stride * max_cand * 8);
       if (rc) return rc;

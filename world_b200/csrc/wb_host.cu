@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
+#include <memory>
 #include <mutex>
 #include <chrono>
 
@@ -283,6 +284,7 @@ extern "C" int world_b200_analyze_host(WorldB200 *h, const double *x, int n_utts
                                        double *time_axis, double *f0, int f0_stride, double *spectrogram,
                                        double *aperiodicity) {
   if (!h || !x || !opt || n_utts < 0 || fs <= 0 || x_stride <= 0 || f0_stride <= 0) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(reinterpret_cast<const Ctx *>(h));  // Ctx is the first member of WorldB200
   return analyze_pipeline(h, x, 0, n_utts, x_stride, x_lengths, fs, opt, 0, time_axis, f0, f0_stride, spectrogram,
                           aperiodicity);
 }
@@ -292,6 +294,7 @@ extern "C" int world_b200_analyze_coded_host(WorldB200 *h, const void *x, int nb
                                              int number_of_dimensions, double *time_axis, double *f0, int f0_stride,
                                              double *coded_spectral_envelope, double *coded_aperiodicity) {
   if (!h || !x || !opt || n_utts < 0 || fs <= 0 || x_stride <= 0 || f0_stride <= 0) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(reinterpret_cast<const Ctx *>(h));  // Ctx is the first member of WorldB200
   if (nbit != 0 && nbit != 8 && nbit != 16 && nbit != 24 && nbit != 32) return WORLD_B200_EINVAL;
   if (number_of_dimensions < 1 || number_of_dimensions > opt->cheaptrick.fft_size / 4 + 1) {
     ctx_of(h)->last_error = "analyze_coded_host: number_of_dimensions must be in [1, fft_size/4 + 1]";
@@ -319,7 +322,17 @@ WorldB200 *legacy_ctx() {
 }
 
 void report(WorldB200 *h, const char *fn, int rc) {
-  if (rc) fprintf(stderr, "world_b200: %s failed (%d): %s\n", fn, rc, world_b200_last_error(h));
+  if (rc) fprintf(stderr, "world_b200: %s failed (%d): %s\n", fn, rc, h ? world_b200_last_error(h) : "no CUDA context");
+}
+
+// The reference's void API cannot report an error: when a legacy call fails the caller's outputs are set to
+// defined values (f0 / time axis 0 = "unvoiced", aperiodicity 1 - 1e-12 = the reference's default row,
+// d4c.cpp:323-328, spectral envelope 1e-12, waveform 0) instead of being left uninitialised.
+void fill(double *p, size_t n, double v) {
+  if (p) for (size_t i = 0; i < n; ++i) p[i] = v;
+}
+void fill_rows(double **rows, int n_rows, int width, double v) {
+  if (rows) for (int i = 0; i < n_rows; ++i) fill(rows[i], (size_t)width, v);
 }
 
 // stage(x dev, t dev, f0 dev) helpers share the upload of x / time / f0
@@ -327,10 +340,12 @@ struct Legacy1 {
   WorldB200 *h; Ctx *ctx;
   double *x = nullptr, *t = nullptr, *f = nullptr;
   int rc = 0;
+  std::unique_ptr<DeviceGuard> guard;   // the legacy context's device is current while this object lives
   Legacy1(const double *xh, int x_length, const double *th, const double *fh, int f0_length) {
     h = legacy_ctx();
     ctx = h ? ctx_of(h) : nullptr;
     if (!h) { rc = WORLD_B200_ECUDA; return; }
+    guard.reset(new DeviceGuard(ctx));
     x = (double *)dev_malloc(ctx, (size_t)x_length * 8);
     t = (double *)dev_malloc(ctx, (size_t)imax(1, f0_length) * 8);
     f = (double *)dev_malloc(ctx, (size_t)imax(1, f0_length) * 8);
@@ -356,7 +371,8 @@ void Dio(const double *x, int x_length, int fs, const DioOption *option, double 
   if (!rc) rc = dev_memcpy_d2h(d.ctx, temporal_positions, d.t, (size_t)L * 8);
   if (!rc) rc = dev_memcpy_d2h(d.ctx, f0, d.f, (size_t)L * 8);
   if (!rc) rc = world_b200_synchronize(d.h);
-  if (d.h) report(d.h, "Dio", rc);
+  if (rc) { fill(temporal_positions, (size_t)L, 0.0); fill(f0, (size_t)L, 0.0); }
+  report(d.h, "Dio", rc);
 }
 
 void Harvest(const double *x, int x_length, int fs, const HarvestOption *option, double *temporal_positions,
@@ -369,7 +385,8 @@ void Harvest(const double *x, int x_length, int fs, const HarvestOption *option,
   if (!rc) rc = dev_memcpy_d2h(d.ctx, temporal_positions, d.t, (size_t)L * 8);
   if (!rc) rc = dev_memcpy_d2h(d.ctx, f0, d.f, (size_t)L * 8);
   if (!rc) rc = world_b200_synchronize(d.h);
-  if (d.h) report(d.h, "Harvest", rc);
+  if (rc) { fill(temporal_positions, (size_t)L, 0.0); fill(f0, (size_t)L, 0.0); }
+  report(d.h, "Harvest", rc);
 }
 
 void StoneMask(const double *x, int x_length, int fs, const double *temporal_positions, const double *f0,
@@ -380,16 +397,20 @@ void StoneMask(const double *x, int x_length, int fs, const double *temporal_pos
   if (!rc) rc = world_b200_stonemask_batch(d.h, d.x, 1, x_length, nullptr, fs, d.t, d.f, nullptr, f0_length, d.f);
   if (!rc) rc = dev_memcpy_d2h(d.ctx, refined_f0, d.f, (size_t)f0_length * 8);
   if (!rc) rc = world_b200_synchronize(d.h);
-  if (d.h) report(d.h, "StoneMask", rc);
+  if (rc) fill(refined_f0, (size_t)f0_length, 0.0);
+  report(d.h, "StoneMask", rc);
 }
 
-static void rows_out(Legacy1 &d, const char *name, int rc, double *dev_rows, int f0_length, int bins, double **rows) {
+static void rows_out(Legacy1 &d, const char *name, int rc, double *dev_rows, int f0_length, int bins, double **rows,
+                     double fail_value) {
   std::vector<double> flat((size_t)f0_length * bins);
   if (!rc) rc = dev_memcpy_d2h(d.ctx, flat.data(), dev_rows, flat.size() * 8);
   if (!rc) rc = world_b200_synchronize(d.h);
   if (!rc)
     for (int i = 0; i < f0_length; ++i) memcpy(rows[i], flat.data() + (size_t)i * bins, (size_t)bins * 8);
-  if (d.h) report(d.h, name, rc);
+  else
+    fill_rows(rows, f0_length, bins, fail_value);
+  report(d.h, name, rc);
 }
 
 void CheapTrick(const double *x, int x_length, int fs, const double *temporal_positions, const double *f0,
@@ -400,7 +421,7 @@ void CheapTrick(const double *x, int x_length, int fs, const double *temporal_po
   double *rows = d.rc ? nullptr : (double *)dev_malloc(d.ctx, (size_t)imax(1, f0_length) * bins * 8);
   int rc = d.rc ? d.rc : (rows ? 0 : WORLD_B200_ENOMEM);
   if (!rc) rc = world_b200_cheaptrick_batch(d.h, d.x, 1, x_length, nullptr, fs, d.t, d.f, nullptr, f0_length, option, rows);
-  rows_out(d, "CheapTrick", rc, rows, f0_length, bins, spectrogram);
+  rows_out(d, "CheapTrick", rc, rows, f0_length, bins, spectrogram, kTiny);
   dev_free(rows);
 }
 
@@ -412,7 +433,7 @@ void D4C(const double *x, int x_length, int fs, const double *temporal_positions
   double *rows = d.rc ? nullptr : (double *)dev_malloc(d.ctx, (size_t)imax(1, f0_length) * bins * 8);
   int rc = d.rc ? d.rc : (rows ? 0 : WORLD_B200_ENOMEM);
   if (!rc) rc = world_b200_d4c_batch(d.h, d.x, 1, x_length, nullptr, fs, d.t, d.f, nullptr, f0_length, fft_size, option, rows);
-  rows_out(d, "D4C", rc, rows, f0_length, bins, aperiodicity);
+  rows_out(d, "D4C", rc, rows, f0_length, bins, aperiodicity, 1.0 - kTiny);
   dev_free(rows);
 }
 
@@ -420,7 +441,8 @@ void Synthesis(const double *f0, int f0_length, const double *const *spectrogram
                int fft_size, double frame_period, int fs, int y_length, double *y) {
   std::lock_guard<std::mutex> lock(g_legacy_mutex);
   WorldB200 *h = legacy_ctx();
-  if (!h) return;
+  if (!h) { fill(y, (size_t)imax(0, y_length), 0.0); report(h, "Synthesis", WORLD_B200_ECUDA); return; }
+  DeviceGuard guard_(reinterpret_cast<const Ctx *>(h));  // Ctx is the first member of WorldB200
   Ctx *ctx = ctx_of(h);
   const int bins = fft_size / 2 + 1;
   std::vector<double> flat((size_t)f0_length * bins);
@@ -439,6 +461,7 @@ void Synthesis(const double *f0, int f0_length, const double *const *spectrogram
                                            nullptr, y_length, d_y);
   if (!rc) rc = dev_memcpy_d2h(ctx, y, d_y, (size_t)y_length * 8);
   if (!rc) rc = world_b200_synchronize(h);
+  if (rc) fill(y, (size_t)imax(0, y_length), 0.0);
   report(h, "Synthesis", rc);
   dev_free(d_f0); dev_free(d_sp); dev_free(d_ap); dev_free(d_y);
 }
@@ -448,7 +471,9 @@ static void codec_rows(const char *name, const double *const *in_rows, int f0_le
                        double **out_rows, int (*run)(WorldB200 *, const double *, double *, void *), void *arg) {
   std::lock_guard<std::mutex> lock(g_legacy_mutex);
   WorldB200 *h = legacy_ctx();
-  if (!h || f0_length <= 0 || out_w <= 0) return;
+  if (f0_length <= 0 || out_w <= 0) return;
+  if (!h) { fill_rows(out_rows, f0_length, out_w, 0.0); report(h, name, WORLD_B200_ECUDA); return; }
+  DeviceGuard guard_(reinterpret_cast<const Ctx *>(h));  // Ctx is the first member of WorldB200
   Ctx *ctx = ctx_of(h);
   std::vector<double> flat_in((size_t)f0_length * imax(1, in_w)), flat_out((size_t)f0_length * out_w);
   for (int i = 0; i < f0_length && in_w > 0; ++i) memcpy(flat_in.data() + (size_t)i * in_w, in_rows[i], (size_t)in_w * 8);
@@ -460,6 +485,8 @@ static void codec_rows(const char *name, const double *const *in_rows, int f0_le
   if (!rc) rc = world_b200_synchronize(h);
   if (!rc)
     for (int i = 0; i < f0_length; ++i) memcpy(out_rows[i], flat_out.data() + (size_t)i * out_w, (size_t)out_w * 8);
+  else
+    fill_rows(out_rows, f0_length, out_w, 0.0);
   report(h, name, rc);
   dev_free(d_in); dev_free(d_out);
 }

@@ -50,6 +50,24 @@ struct Ctx {
   std::string last_error;
 };
 
+// The CUDA current device is per thread; every extern "C" entry point that touches a context makes the
+// context's device current for its own duration (a call from another thread, or a second context on another GPU
+// of the same process, would otherwise allocate and launch on the caller's device) and restores the caller's.
+struct DeviceGuard {
+#ifndef WB_EMU
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const Ctx *c) {
+    if (c && cudaGetDevice(&prev) == cudaSuccess && prev != c->device) switched = cudaSetDevice(c->device) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+#else
+  explicit DeviceGuard(const Ctx *) {}
+#endif
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 // memory helpers (wb_api.cu / emu)
 int ctx_init_tables(Ctx *ctx);
 unsigned char *arena_block(Ctx *ctx, size_t bytes);  // nullptr + last_error on failure

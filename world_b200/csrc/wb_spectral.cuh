@@ -24,6 +24,10 @@ WB_DEV double interp1q_at(double x0, double dx, const double *y, int ny, double 
 // DCCorrection(in -> in, in place).  `tmp` needs upper_limit doubles.  Ends with a barrier.
 WB_DEV void dc_correction(double *spec, double f0, int fs, int fft_size, double *tmp) {
   const int tid = WB_TID, nth = WB_NTH;
+  // f0 is caller supplied: at or above fs/2 (or non-finite) the reference indexes past its arrays.  Here such a
+  // value is clamped two bins below the Nyquist bin -- every index stays inside the fft_size/2 + 1 values of
+  // `spec`; the row is meaningless either way, but there is no fault.  No effect on any f0 the reference accepts.
+  f0 = dmin(dmax(f0, 0.0), (0.5 - 2.0 / fft_size) * fs);
   const int upper_limit = 2 + static_cast<int>(f0 * fft_size / fs);
   const int n_rep = upper_limit - 1;
   const double dx = -static_cast<double>(fs) / fft_size;

@@ -295,6 +295,7 @@ extern "C" int world_b200_synthesis_batch(WorldB200 *h, const double *f0, const 
                                           int y_stride, double *y) {
   if (!h || !f0 || !spectrogram || !aperiodicity || !y || n_utts < 0 || fs <= 0 || frame_period <= 0)
     return WORLD_B200_EINVAL;
+  DeviceGuard guard_(reinterpret_cast<const Ctx *>(h));  // Ctx is the first member of WorldB200
   Ctx *ctx = reinterpret_cast<Ctx *>(h);
   int lg = 0;
   while ((1 << lg) < fft_size) ++lg;
