@@ -160,6 +160,17 @@ typedef struct {
 
 void world_b200_default_analysis_option(int fs, int f0_method, WorldB200AnalysisOption *option);
 
+/* The whole chain on DEVICE arrays (layouts as above; x_lengths HOST or NULL): {Dio+StoneMask | Harvest} ->
+ * CheapTrick -> D4C.  The batch is cut into utterance slices that alternate between two internal streams, so the
+ * latency-bound per-utterance kernels of one slice run under the FP64-bound kernels of the other.  The work is
+ * ordered after what is already on the context's stream, and that stream waits for it: like the *_batch stages the
+ * call does not synchronise the host.  spectrogram / aperiodicity may be NULL to stop after the F0 stage / after
+ * CheapTrick.  Each internal stream may use half the scratch budget. */
+int world_b200_analyze_batch(WorldB200 *ctx, const double *x, int n_utts, int x_stride,
+                             const int *x_lengths, int fs, const WorldB200AnalysisOption *option,
+                             double *time_axis, double *f0, int f0_stride, double *spectrogram,
+                             double *aperiodicity);
+
 /* {Dio+StoneMask | Harvest} -> CheapTrick -> D4C for n_utts host waveforms; outputs are host
  * arrays laid out as described above.  Input upload, compute and result download are pipelined
  * over utterance chunks.  Any output pointer may be NULL to skip its download.  Whole padded rows

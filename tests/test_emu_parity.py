@@ -106,6 +106,10 @@ def test_emu_analyze_coded_host(emu, golden):
     pc.check_analyze_coded(emu, golden)
 
 
+def test_emu_analyze_batch(emu, golden):
+    pc.check_analyze_batch(emu, golden)
+
+
 def test_emu_host_pipeline_chunking(emu, golden):
     pc.check_host_pipeline_chunking(emu, golden)
 

@@ -179,6 +179,10 @@ def test_gpu_legacy_codec(gpu_world, ref, golden):
     pc.assert_close(dap[::4], golden["decoded_ap_rows"], "legacy DecodeAperiodicity")
 
 
+def test_gpu_analyze_batch_lanes(gpu_world, golden):
+    pc.check_analyze_batch(gpu_world, golden)
+
+
 def test_gpu_host_pipeline_chunking(gpu_world, golden):
     from world_b200 import api
     pc.check_host_pipeline_chunking(gpu_world, golden, api.F0_DIO_STONEMASK)

@@ -406,6 +406,47 @@ def check_host_pipeline_chunking(world, golden, f0_method=0):
     assert (want_raw[1] > 0).any() and np.isfinite(want_raw[2]).all()
 
 
+def check_analyze_batch(world, golden):
+    """world_b200_analyze_batch (whole chain, device arrays, utterance slices on two internal streams) must give
+    exactly what the separate stage calls give, for both F0 front ends and for every slice count."""
+    pcm16 = np.ascontiguousarray(golden["pcm"])
+    fs = int(golden["fs"])
+    n, keep = 5, 7000
+    x = np.zeros((n, keep))
+    lens = [keep - 403 * u for u in range(n)]
+    for u in range(n):
+        x[u, :lens[u]] = pcm16[1500 + 211 * u: 1500 + 211 * u + lens[u]].astype(np.float64) / 32768.0
+    xd = make(world, x)
+    saved = os.environ.get("WB_LANE_SLICES")
+    try:
+        for method in (0, 1):
+            opt = world.analysis_option(fs, method)
+            if method == 1:
+                t, f0, fl = world.harvest(xd, fs, opt.harvest, x_lengths=lens)
+            else:
+                t, f0, fl = world.dio(xd, fs, opt.dio, x_lengths=lens)
+                f0 = world.stonemask(xd, fs, t, f0, x_lengths=lens, f0_lengths=fl)
+            sp = world.cheaptrick(xd, fs, t, f0, opt.cheaptrick, x_lengths=lens, f0_lengths=fl)
+            ap = world.d4c(xd, fs, t, f0, opt.cheaptrick.fft_size, x_lengths=lens, f0_lengths=fl)
+            world.synchronize()
+            want = [to_np(a).copy() for a in (t, f0, sp, ap)]
+            for slices in (1, 2, 4, 5):
+                os.environ["WB_LANE_SLICES"] = str(slices)
+                got = world.analyze_batch(xd, fs, opt, x_lengths=lens)
+                world.synchronize()
+                assert got[4] == fl
+                for g, w_ in zip(got[:4], want):
+                    g = to_np(g)
+                    for u in range(n):   # rows beyond an utterance's frames are never written by either path
+                        assert np.array_equal(g[u, :fl[u]], w_[u, :fl[u]]), (method, slices, u)
+            assert (want[1] > 0).any()
+    finally:
+        if saved is None:
+            os.environ.pop("WB_LANE_SLICES", None)
+        else:
+            os.environ["WB_LANE_SLICES"] = saved
+
+
 def check_event_dense_and_degenerate_bands(world, ref):
     """Found by tests/fuzz/fuzz_emu_parity.py: (1) a loud tone gives every Harvest band far more zero crossings than
     its centre frequency suggests -- the per-band event lists wrap (history rings) instead of overflowing;

@@ -77,6 +77,8 @@ ABI = {
     "world_b200_default_analysis_option": (None, [C.c_int, C.c_int, C.POINTER(AnalysisOption)]),
     "world_b200_analyze_host": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, C.POINTER(AnalysisOption),
                                           _P, _P, C.c_int, _P, _P]),
+    "world_b200_analyze_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, C.POINTER(AnalysisOption),
+                                           _P, _P, C.c_int, _P, _P]),
     # legacy single-utterance API (host pointers)
     "Dio": (None, [_P, C.c_int, C.c_int, C.POINTER(DioOption), _P, _P]),
     "Harvest": (None, [_P, C.c_int, C.c_int, C.POINTER(HarvestOption), _P, _P]),
@@ -370,6 +372,28 @@ class World:
         o = AnalysisOption()
         self.lib.world_b200_default_analysis_option(fs, f0_method, C.byref(o))
         return o
+
+    def analyze_batch(self, x, fs, option: AnalysisOption, x_lengths=None, time_axis=None, f0=None,
+                      spectrogram=None, aperiodicity=None):
+        """Whole chain on DEVICE arrays in one call (two internal streams); returns (t, f0, sp, ap, frame counts)."""
+        n, stride = x.shape
+        frame_period = option.dio.frame_period if option.f0_method == F0_DIO_STONEMASK else option.harvest.frame_period
+        f_stride, fl = self._f0_stride(fs, x, x_lengths, frame_period)
+        bins = option.cheaptrick.fft_size // 2 + 1
+        if time_axis is None:
+            time_axis = self._zeros(x, (n, f_stride))
+        if f0 is None:
+            f0 = self._zeros(x, (n, f_stride))
+        if spectrogram is None:
+            spectrogram = self._zeros(x, (n, f_stride, bins))
+        if aperiodicity is None:
+            aperiodicity = self._zeros(x, (n, f_stride, bins))
+        xl, keep = _int_array(x_lengths, n)
+        self._use_current_stream()
+        self._check(self.lib.world_b200_analyze_batch(self._h, _ptr(x), n, stride, xl, fs, C.byref(option),
+                                                      _ptr(time_axis), _ptr(f0), time_axis.shape[1],
+                                                      _ptr(spectrogram), _ptr(aperiodicity)))
+        return time_axis, f0, spectrogram, aperiodicity, fl
 
     def analyze_host(self, x_host, fs, option: AnalysisOption, x_lengths=None, time_axis=None, f0=None,
                      spectrogram=None, aperiodicity=None, f0_stride=None):

@@ -5,12 +5,18 @@
 #include "../../include/world_b200.h"
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <vector>
 
 struct WorldB200 {
   wb::Ctx c;
   int *lens_dev = nullptr;
   size_t lens_cap = 0;
+  // world_b200_analyze_batch: two sibling contexts ("lanes"), each with its own stream, scratch arena and staging
+  // ring, created on first use; fork / join events order them against this context's stream
+  WorldB200 *lane[2] = {nullptr, nullptr};
+  void *lane_stream[2] = {nullptr, nullptr};   // cudaStream_t
+  void *ev_fork = nullptr, *ev_join[2] = {nullptr, nullptr};   // cudaEvent_t
 };
 
 namespace wb {
@@ -330,6 +336,16 @@ void world_b200_destroy(WorldB200 *h) {
   if (!h) return;
   DeviceGuard guard_(&h->c);
   dev_sync(&h->c);
+  for (int l = 0; l < 2; ++l) {
+    if (h->lane[l]) world_b200_destroy(h->lane[l]);
+#ifndef WB_EMU
+    if (h->lane_stream[l]) cudaStreamDestroy((cudaStream_t)h->lane_stream[l]);
+    if (h->ev_join[l]) cudaEventDestroy((cudaEvent_t)h->ev_join[l]);
+#endif
+  }
+#ifndef WB_EMU
+  if (h->ev_fork) cudaEventDestroy((cudaEvent_t)h->ev_fork);
+#endif
   dev_free(h->c.twiddle);
   dev_free(h->c.rng_jump);
   dev_free(h->c.status_dev);
@@ -361,6 +377,8 @@ int world_b200_trim(WorldB200 *h) {
   if (!h) return WORLD_B200_EINVAL;
   DeviceGuard guard_(&h->c);
   int rc = dev_sync(&h->c);
+  for (int l = 0; l < 2; ++l)
+    if (h->lane[l]) world_b200_trim(h->lane[l]);
   pool_trim(&h->c);
   dev_free(h->c.arena.base);
   h->c.arena = Arena();
@@ -379,6 +397,11 @@ int world_b200_synchronize(WorldB200 *h) {
   DeviceGuard guard_(&h->c);
   int rc = dev_sync(&h->c);
   if (rc) return rc;
+  for (int l = 0; l < 2; ++l)
+    if (h->lane[l]) {   // frames that hit an undefined case inside world_b200_analyze_batch set the lane's status word
+      rc = world_b200_synchronize(h->lane[l]);
+      if (rc) { h->c.last_error = h->lane[l]->c.last_error; return rc; }
+    }
   int status = 0;
   rc = dev_memcpy_d2h(&h->c, &status, h->c.status_dev, sizeof(int));
   if (!rc) rc = dev_sync(&h->c);
@@ -485,6 +508,89 @@ int world_b200_harvest_batch(WorldB200 *h, const double *x, int n, int x_stride,
   b.x_len_host = x_lengths;
   HarvestParams p = {opt->f0_floor, opt->f0_ceil, opt->frame_period};
   return harvest_run(&h->c, b, p, time_axis, f0);
+}
+
+// The whole chain on device arrays, cut into utterance slices that alternate between two lanes (sibling contexts
+// on their own non-blocking streams).  Per slice the stages run in order on the lane's stream; the two lanes run
+// concurrently, so the latency-bound per-utterance kernels of one slice (contour tracking, candidate clean-up, the
+// draw stream, decimation) execute under the FP64-bound kernels of the other.  Ordered after the work already on the
+// context's stream; that stream waits for both lanes before the function returns (no host synchronisation).
+int world_b200_analyze_batch(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths, int fs,
+                             const WorldB200AnalysisOption *opt, double *time_axis, double *f0, int f0_stride,
+                             double *spectrogram, double *aperiodicity) {
+  if (!h || !x || !opt || !time_axis || !f0 || n < 0 || fs <= 0 || x_stride <= 0 || f0_stride <= 0) return WORLD_B200_EINVAL;
+  if ((spectrogram || aperiodicity) && opt->cheaptrick.fft_size < 16) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
+  if (n == 0) return 0;
+  const int bins = opt->cheaptrick.fft_size / 2 + 1;
+  const double frame_period = opt->f0_method == WORLD_B200_F0_HARVEST ? opt->harvest.frame_period : opt->dio.frame_period;
+  int n_slices = 4;
+  if (const char *e = getenv("WB_LANE_SLICES")) n_slices = atoi(e);
+  n_slices = imax(1, imin(n_slices, n));
+  WorldB200 *lanes[2] = {h, h};
+#ifndef WB_EMU
+  if (n_slices > 1) {
+    for (int l = 0; l < 2; ++l) {
+      if (!h->lane[l]) {
+        int rc = world_b200_create(h->c.device, &h->lane[l]);
+        if (rc) { h->c.last_error = "analyze_batch: cannot create a lane context"; return rc; }
+        cudaStream_t st;
+        cudaEvent_t ev;
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+          h->c.last_error = "analyze_batch: cannot create a lane stream";
+          return WORLD_B200_ECUDA;
+        }
+        h->lane_stream[l] = st; h->ev_join[l] = ev;
+        h->lane[l]->c.stream = st;
+      }
+      h->lane[l]->c.scratch_budget = h->c.scratch_budget / 2;
+      lanes[l] = h->lane[l];
+    }
+    if (!h->ev_fork) {
+      cudaEvent_t ev;
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return WORLD_B200_ECUDA;
+      h->ev_fork = ev;
+    }
+    cudaEventRecord((cudaEvent_t)h->ev_fork, h->c.stream);
+    for (int l = 0; l < 2; ++l) cudaStreamWaitEvent((cudaStream_t)h->lane_stream[l], (cudaEvent_t)h->ev_fork, 0);
+  }
+#else
+  n_slices = imin(n_slices, 2);   // one emulated stream: the slicing itself is still exercised
+#endif
+  int rc = 0;
+  std::vector<int> fl(n);
+  for (int i = 0; i < n; ++i) fl[i] = frames_for(fs, x_lengths ? x_lengths[i] : x_stride, frame_period);
+  for (int s = 0; s < n_slices && !rc; ++s) {
+    const int u0 = (int)((long long)n * s / n_slices), u1 = (int)((long long)n * (s + 1) / n_slices);
+    const int m = u1 - u0;
+    if (m <= 0) continue;
+    WorldB200 *L = lanes[s & 1];
+    const double *xs = x + (size_t)u0 * x_stride;
+    const int *xl = x_lengths ? x_lengths + u0 : nullptr;
+    double *ts = time_axis + (size_t)u0 * f0_stride, *fs_ = f0 + (size_t)u0 * f0_stride;
+    if (opt->f0_method == WORLD_B200_F0_HARVEST) {
+      rc = world_b200_harvest_batch(L, xs, m, x_stride, xl, fs, &opt->harvest, ts, fs_, f0_stride);
+    } else {
+      rc = world_b200_dio_batch(L, xs, m, x_stride, xl, fs, &opt->dio, ts, fs_, f0_stride);
+      if (!rc) rc = world_b200_stonemask_batch(L, xs, m, x_stride, xl, fs, ts, fs_, fl.data() + u0, f0_stride, fs_);
+    }
+    if (!rc && spectrogram)
+      rc = world_b200_cheaptrick_batch(L, xs, m, x_stride, xl, fs, ts, fs_, fl.data() + u0, f0_stride, &opt->cheaptrick,
+                                       spectrogram + (size_t)u0 * f0_stride * bins);
+    if (!rc && aperiodicity)
+      rc = world_b200_d4c_batch(L, xs, m, x_stride, xl, fs, ts, fs_, fl.data() + u0, f0_stride, opt->cheaptrick.fft_size,
+                                &opt->d4c, aperiodicity + (size_t)u0 * f0_stride * bins);
+    if (rc && L != h) h->c.last_error = L->c.last_error;
+  }
+#ifndef WB_EMU
+  if (lanes[0] != h)
+    for (int l = 0; l < 2; ++l) {   // join even after an error: the caller's stream must not run ahead of the lanes
+      cudaEventRecord((cudaEvent_t)h->ev_join[l], (cudaStream_t)h->lane_stream[l]);
+      cudaStreamWaitEvent(h->c.stream, (cudaEvent_t)h->ev_join[l], 0);
+    }
+#endif
+  return rc;
 }
 
 // Per-kernel timing: enable, run, then fetch a JSON object {"kernel": {"launches": n, "ms": t}, ...}

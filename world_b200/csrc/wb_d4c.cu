@@ -195,6 +195,70 @@ WB_DEV double select_kth_largest(const double *a, int n, int kth, double *red) {
   return r;
 }
 
+// The same order statistic through a short candidate list (GPU only; round 1's bisection -- 32 rounds over all n
+// values with a barrier each -- was a quarter of the body kernel's instructions, profiles/r2c_ncu_d4c_body_kernel.txt):
+//   1. every thread takes the maximum of the values it owns (a[tid], a[tid + nth], ...);
+//   2. L = the kth largest of those nth maxima is a lower bound of the answer (the kth largest maxima are kth
+//      distinct elements >= L), and for spectra -- no long runs of equal values -- only a few more than kth elements
+//      reach it;
+//   3. the elements >= L are collected (shared-memory counter) and ranked against each other exactly.
+// Comparisons run on the IEEE bit patterns (a total order on the non-negative values, ties broken by index), so the
+// value returned is the one the bisection returns.  Returns false to every thread -- nothing useful in *out -- when
+// kth > nth or more than WB_SEL_CAP elements reach L; the caller then falls back to the bisection.
+// scratch: nth + WB_SEL_CAP + 4 64-bit words of shared memory.  Contains barriers.
+#define WB_SEL_CAP 256
+WB_DEV bool select_kth_largest_fast(const double *a, int n, int kth, unsigned long long *scratch, double *out) {
+#ifdef WB_EMU
+  (void)a; (void)n; (void)kth; (void)scratch; (void)out;
+  return false;   // one emulated thread: the bisection is the reference semantics anyway
+#else
+  const int tid = threadIdx.x, nth = blockDim.x;
+  if (kth < 1 || kth > nth || kth > n) return false;
+  unsigned long long *cand = scratch + nth + 4;
+  unsigned *counter = reinterpret_cast<unsigned *>(scratch + nth + 1);
+  unsigned long long mx = 0ull;
+  for (int j = tid; j < n; j += nth) {
+    const unsigned long long k = (unsigned long long)__double_as_longlong(a[j]);
+    mx = k > mx ? k : mx;
+  }
+  scratch[tid] = mx;
+  if (tid == 0) *counter = 0u;
+  __syncthreads();
+  {
+    int r = 0;
+    for (int t = 0; t < nth; ++t) {
+      const unsigned long long kt = scratch[t];
+      r += (kt > mx || (kt == mx && t < tid)) ? 1 : 0;
+    }
+    if (r == kth - 1) scratch[nth] = mx;
+  }
+  __syncthreads();
+  const unsigned long long L = scratch[nth];
+  for (int j = tid; j < n; j += nth) {
+    const unsigned long long k = (unsigned long long)__double_as_longlong(a[j]);
+    if (k >= L) {
+      const unsigned at = atomicAdd(counter, 1u);
+      if (at < WB_SEL_CAP) cand[at] = k;
+    }
+  }
+  __syncthreads();
+  const int c = (int)*counter;
+  if (c > WB_SEL_CAP) return false;
+  for (int i = tid; i < c; i += nth) {
+    const unsigned long long ki = cand[i];
+    int r = 0;
+    for (int t = 0; t < c; ++t) {
+      const unsigned long long kt = cand[t];
+      r += (kt > ki || (kt == ki && t < i)) ? 1 : 0;
+    }
+    if (r == kth - 1) scratch[nth + 2] = ki;
+  }
+  __syncthreads();
+  *out = __longlong_as_double((long long)scratch[nth + 2]);
+  return true;
+#endif
+}
+
 // ------------------------------------------------------------------ pass B: general body
 // One CTA of d_fft / 16 threads per selected frame.  Shared memory: ONE padded buffer of d_fft / 2 complex slots
 // (in-place self-sorting FFT, wb_fft.cuh: one radix-8 butterfly per thread and pass), the centroid row, the power
@@ -328,7 +392,10 @@ WB_DEV void d4c_body_frame(const D4cParams &p) {
     });
     tot = block_sum(tot, red);  // contains the barrier that publishes cent[]
     const int n_small = half - p.bd;  // entries in the sorted prefix, index half-bd-1 inclusive
-    const double kth = select_kth_largest(cent, half + 1, p.bd + 1, red);
+    double kth;
+    // the FFT buffer is idle: candidate scratch (nth + WB_SEL_CAP + 4 words <= 2 * slots)
+    if (!select_kth_largest_fast(cent, half + 1, p.bd + 1, reinterpret_cast<unsigned long long *>(pd), &kth))
+      kth = select_kth_largest(cent, half + 1, p.bd + 1, red);
     double below = 0.0;
     int n_below = 0;
     for (int k = tid; k <= half; k += nth)

@@ -547,8 +547,19 @@ WB_DEV double hv_min_rel_error(double reference, const double *row, int n) {
   return e > 1.0 ? 1.0 : e;
 }
 
-WB_KERNEL_PLAIN harvest_remove_kernel(HvRemoveParams p) {
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per 1 ms frame, lanes over the frame's candidate slots (round 1 ran one THREAD per frame: rows of 105
+// doubles read with an 840-byte stride between threads; 40 ms per 1024 x 10 s).  Neighbour rows are read by all
+// lanes at the same address (broadcast).  SearchF0Base keeps the FIRST slot with the highest score: the warp
+// arg-max breaks ties towards the lower slot index.
+#define WB_RM_WARPS 8
+WB_KERNEL(32 * WB_RM_WARPS, 4) harvest_remove_kernel(HvRemoveParams p) {
+#ifdef WB_EMU
+  const int warp = 0, nwarps = 1;
+#else
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#endif
+  const int lane = WB_LANE;
+  const long long g = (long long)blockIdx.x * nwarps + warp;
   if (g >= (long long)p.n_utts * p.l1_stride) return;
   const int u = (int)(g / p.l1_stride), i = (int)(g % p.l1_stride);
   const int L1 = p.l1[u];
@@ -557,18 +568,28 @@ WB_KERNEL_PLAIN harvest_remove_kernel(HvRemoveParams p) {
   const double *row = p.cand_in + (size_t)g * p.max_cand;
   double *oc = p.cand + (size_t)g * p.max_cand, *os = p.score + (size_t)g * p.max_cand;
   const double *srow = p.score_in + (size_t)g * p.max_cand;
+  const bool interior = i >= 1 && i < L1 - 1;
   double best = 0.0, best_score = 0.0;  // SearchF0Base (harvest.cpp:693-705) on the cleaned candidates
-  for (int j = 0; j < n; ++j) {
+  int best_j = 0x7fffffff;
+  for (int j = lane; j < n; j += WB_LANES) {
     double c = row[j], s = srow[j];
-    if (i >= 1 && i < L1 - 1 && c != 0) {
+    if (interior && c != 0) {
       const double e1 = hv_min_rel_error(c, row + p.max_cand, n);
       const double e2 = hv_min_rel_error(c, row - p.max_cand, n);
       if (dmin(e1, e2) > 0.05) { c = 0.0; s = 0.0; }
     }
     oc[j] = c; os[j] = s;
-    if (s > best_score) { best = c; best_score = s; }
+    if (s > best_score) { best = c; best_score = s; best_j = j; }
   }
-  p.f0_base[(size_t)u * 5 * p.l1_stride + i] = best;
+#ifndef WB_EMU
+  for (int o = 16; o; o >>= 1) {
+    const double s2 = __shfl_xor_sync(0xffffffffu, best_score, o);
+    const double c2 = __shfl_xor_sync(0xffffffffu, best, o);
+    const int j2 = __shfl_xor_sync(0xffffffffu, best_j, o);
+    if (s2 > best_score || (s2 == best_score && j2 < best_j)) { best_score = s2; best = c2; best_j = j2; }
+  }
+#endif
+  if (lane == 0) p.f0_base[(size_t)u * 5 * p.l1_stride + i] = best;
 }
 
 // ------------------------------------------------------------------ K-HVc
@@ -1052,7 +1073,12 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     mp.cand_in = rp.cand; mp.score_in = rp.score; mp.cand = (double *)(blk + o_c2); mp.score = (double *)(blk + o_s2);
     mp.nc = nc; mp.l1 = l1; mp.l1_stride = l1_stride; mp.max_cand = max_cand; mp.n_utts = n;
     mp.f0_base = (double *)(blk + o_work);
-    WB_LAUNCH_FLAT(harvest_remove_kernel, dim3((unsigned)((slots + 127) / 128)), 128, 0, ctx->stream, mp);
+#ifdef WB_EMU
+    const unsigned remove_blocks = (unsigned)slots;
+#else
+    const unsigned remove_blocks = (unsigned)((slots + WB_RM_WARPS - 1) / WB_RM_WARPS);
+#endif
+    WB_LAUNCH_COOP(harvest_remove_kernel, dim3(remove_blocks), 32 * WB_RM_WARPS, 0, ctx->stream, mp);
 
     HvContourParams cp;
     cp.cand = mp.cand; cp.score = mp.score; cp.nc = nc; cp.l1 = l1; cp.l1_stride = l1_stride; cp.max_cand = max_cand;
