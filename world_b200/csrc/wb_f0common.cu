@@ -216,10 +216,9 @@ WB_KERNEL(256, 2) nyquist_bins_kernel(NyquistParams p) {
 // kRipple = 1 adds the near-Nyquist ripple of the reference's spectral mirroring loop (nyquist_bins_kernel
 // above); the default instantiation carries none of it.
 template <int kRipple>
-WB_DEV void sweep_body(const SweepParams &p) {
+WB_DEV void sweep_body(const SweepParams &p, const int b, const int u) {
   WB_DYN_SMEM(double, smem);
   const int tid = WB_TID, nth = WB_NTH;
-  const int b = blockIdx.x, u = blockIdx.y;
   const int T = WB_SWEEP_T, R = WB_SWEEP_R, G = T / R;
   const int ntaps = p.ntaps[b], shift = p.shift[b];
   const int seg_len = T + ntaps - 1;
@@ -442,8 +441,325 @@ WB_DEV void sweep_body(const SweepParams &p) {
   }
 }
 
-WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) { sweep_body<0>(p); }          // Harvest on decimated input
-WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_ripple_kernel(SweepParams p) { sweep_body<1>(p); }   // DIO; Harvest at ratio 1
+WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_kernel(SweepParams p) { sweep_body<0>(p, blockIdx.x, blockIdx.y); }          // Harvest on decimated input
+WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_ripple_kernel(SweepParams p) { sweep_body<1>(p, blockIdx.x, blockIdx.y); }   // DIO; Harvest at ratio 1
+// the same streaming sweep over a device list of (utterance, band) pairs: bands whose complete edge lists did not fit
+// (band_fir_events_kernel), i.e. far more zero crossings than the band frequency allows for -- usually none
+WB_KERNEL(WB_SWEEP_THREADS, 3) band_sweep_list_kernel(SweepParams p) {
+  const int n = *p.redo_count;
+  for (int at = blockIdx.x; at < n; at += gridDim.x) {
+    const int pair = p.redo_list[at];
+    sweep_body<0>(p, pair % p.n_bands, pair / p.n_bands);
+    WB_SYNC();
+  }
+}
+
+// =============================================================================================
+// Round 2: the Harvest sweep on decimated input as two kernels.
+//
+// band_sweep_kernel does everything for one (utterance, band) in one streaming pass: FIR tile, event detection,
+// compaction, interval rings, frame finalisation -- fourteen block barriers per tile and a round trip of the fine
+// edges through global memory; the FIR ran at 45 % of the FP64 pipe (profiles/r2c_ncu_band_sweep_kernel.txt).
+// Split:
+//   band_fir_events_kernel  FIR (the same register tile, the same FMA order: bit-identical filtered samples) +
+//                           the four event trains of every tile, fine edges appended to COMPLETE per-train lists
+//                           in global memory (written once, never read back here).  Three block barriers per tile.
+//                           The input segment of the next tile arrives by TMA (cp.async.bulk + mbarrier) while the
+//                           current one is filtered: nine outputs per thread make consecutive threads 9 doubles
+//                           apart -- conflict free without padding, so the segment is one contiguous bulk copy.
+//   band_interp_kernel      edge lists -> intervals -> interp1 onto the frame grid, 256 frames per round; interval
+//                           counts per frame by a fill (every interval owns the frames between its first frame and
+//                           the next interval's), no search, no scan.
+// A band whose lists overflow their capacity (far more crossings than its frequency allows for: a loud out-of-band
+// tone) is left to the streaming kernel, whose history rings wrap instead (band_sweep_list_kernel).
+#ifndef WB_EMU
+WB_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+WB_DEV void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+WB_DEV void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D TMA: `bytes` (multiple of 16) from global (16-byte aligned) to shared (16-byte aligned); completes on `bar`
+WB_DEV void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+WB_DEV void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+
+// event flags of position pos (relative to n0 - 2) from three consecutive filtered samples: bit q = train q
+WB_DEV unsigned fe_flags(double a, double bb, double cc, int i, int ylen) {
+  unsigned m = 0u;
+  const double d0 = bb - a, d1 = cc - bb;
+  if (i >= 0 && i + 1 <= ylen - 1) {
+    if (0.0 < a && bb <= 0.0) m |= 1u;
+    if (a < 0.0 && 0.0 <= bb) m |= 2u;
+  }
+  if (i >= 0 && i + 1 <= ylen - 2) {
+    if (0.0 < d0 && d1 <= 0.0) m |= 4u;
+    if (d0 < 0.0 && 0.0 <= d1) m |= 8u;
+  }
+  return m;
+}
+
+WB_KERNEL(WB_SWEEP_THREADS, 3) band_fir_events_kernel(SweepParams p) {
+  WB_DYN_SMEM(double, smem);
+  const int tid = WB_TID, nth = WB_NTH;
+  const int b = blockIdx.x, u = blockIdx.y;
+  const int T = WB_FE_T, R = WB_FE_R, G = WB_FE_T / WB_FE_R;
+  const int ntaps = p.ntaps[b], shift = p.shift[b];
+  const int nt9 = ((ntaps + R - 1) / R) * R;     // taps in whole register rounds; hrev is zero beyond ntaps
+  const int segd = fe_seg_doubles(p.max_taps);
+  double *segbuf[2] = {smem, smem + segd};
+  const int hcap = ((p.max_taps + R - 1) / R) * R + R;
+  double *hrev = smem + 2 * segd;                // hcap
+  double *st = hrev + hcap;                      // [0..1] carry, [2..T+2) this tile
+  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(st + (T + 8));   // G packed counters + 33 warp totals
+  unsigned long long *bars = cnt + G + 40;       // two mbarriers
+  const int ylen = p.y_len[u];
+  const size_t abs0 = (size_t)u * p.sig_stride + p.sig_origin;   // index of s(0) in p.sig
+  double *edges = p.edges + (size_t)u * p.edge_stride + (size_t)p.edge_off[b];
+  const int cap = p.edge_cap[b];
+  for (int j = tid; j < nt9 + R; j += nth) hrev[j] = j < ntaps ? __ldg(&p.taps_rev[p.tap_off[b] + j]) : 0.0;
+  if (tid == 0) { st[0] = 0.0; st[1] = 0.0; }
+  int tot[4] = {0, 0, 0, 0};   // events so far per train (identical in every thread)
+  const int n_tiles = (ylen + 2 + T - 1) / T;
+  // segment of tile t: seg[i] = s(n0 + shift - ntaps + 1 + i), i < T + nt9 (beyond the filter span the taps are zero;
+  // the signal buffer is zero padded, so whatever lies there is finite)
+  const int seg_count = (T + nt9 + 2) & ~1;
+#ifndef WB_EMU
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0 && n_tiles > 0) {
+    const size_t a = abs0 + (size_t)(shift - ntaps + 1);
+    mbar_expect_tx(&bars[0], (unsigned)seg_count * 8u);
+    tma_load_1d(segbuf[0], p.sig + (a & ~(size_t)1), (unsigned)seg_count * 8u, &bars[0]);
+  }
+#else
+  WB_SYNC();
+#endif
+  for (int t = 0; t < n_tiles; ++t) {
+    const int n0 = t * T;
+    const size_t a0 = abs0 + (size_t)(n0 + shift - ntaps + 1);
+#ifndef WB_EMU
+    // every thread has left tile t-1 (barrier at its end), whose FIR was the last reader of the other buffer
+    if (tid == 0 && t + 1 < n_tiles) {
+      const size_t a1 = a0 + (size_t)T;
+      mbar_expect_tx(&bars[(t + 1) & 1], (unsigned)seg_count * 8u);
+      tma_load_1d(segbuf[(t + 1) & 1], p.sig + (a1 & ~(size_t)1), (unsigned)seg_count * 8u, &bars[(t + 1) & 1]);
+    }
+    mbar_wait(&bars[t & 1], (unsigned)((t >> 1) & 1));
+    const double *seg = segbuf[t & 1] + (a0 & 1);
+#else
+    for (int i = tid; i < seg_count; i += nth) segbuf[0][i] = p.sig[a0 + i];
+    const double *seg = segbuf[0];
+#endif
+    for (int g = tid; g < G; g += nth) {
+      const int base = R * g;
+      double acc[WB_FE_R], win[WB_FE_R];
+      const double *sp = seg + base + R;
+      const double *hp = hrev;
+#pragma unroll
+      for (int r = 0; r < R; ++r) { acc[r] = 0.0; win[r] = seg[base + r]; }
+      for (int j0 = 0; j0 < ntaps; j0 += R, sp += R, hp += R) {
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj) {
+          const double hj = hp[jj];
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = fma(hj, win[(r + jj) % WB_FE_R], acc[r]);
+          win[jj] = sp[jj];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) st[2 + base + r] = acc[r];
+    }
+    WB_SYNC();
+    // ---- events at positions i = n0 - 2 + pos, pos = R g + r (they need s[i], s[i+1], s[i+2])
+    for (int g = tid; g < G; g += nth) {
+      unsigned long long c = 0ull;
+      const int base = R * g;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const unsigned m = fe_flags(st[base + r], st[base + r + 1], st[base + r + 2], n0 - 2 + base + r, ylen);
+        c += (unsigned long long)(m & 1u) + ((unsigned long long)((m >> 1) & 1u) << 16) +
+             ((unsigned long long)((m >> 2) & 1u) << 32) + ((unsigned long long)((m >> 3) & 1u) << 48);
+      }
+      cnt[g] = c;
+    }
+    WB_SYNC();
+    const unsigned long long tile_total = scan_packed(cnt, G, 0ull, cnt + G + 4);
+    // ---- fine edges straight from the detecting thread (one division per event), appended in position order
+    for (int g = tid; g < G; g += nth) {
+      const unsigned long long o = cnt[g];
+      int off[4] = {(int)(o & 0xffffull), (int)((o >> 16) & 0xffffull), (int)((o >> 32) & 0xffffull), (int)((o >> 48) & 0xffffull)};
+      const int base = R * g;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int pos = base + r;
+        const double a = st[pos], bb = st[pos + 1], cc = st[pos + 2];
+        unsigned m = fe_flags(a, bb, cc, n0 - 2 + pos, ylen);
+        while (m) {
+#ifdef WB_EMU
+          const int q = __builtin_ctz(m);
+#else
+          const int q = __ffs((int)m) - 1;
+#endif
+          m &= m - 1u;
+          double v;
+          if (q < 2) {
+            v = (double)(n0 - 2 + pos + 1) - a / (bb - a);
+          } else {
+            const double d0 = bb - a, d1 = cc - bb;
+            v = (double)(n0 - 2 + pos + 1) - d0 / (d1 - d0);
+          }
+          const int at = tot[q] + off[q];
+          ++off[q];
+          if (at < cap) edges[(size_t)q * cap + at] = v;
+        }
+      }
+    }
+    tot[0] += (int)(tile_total & 0xffffull); tot[1] += (int)((tile_total >> 16) & 0xffffull);
+    tot[2] += (int)((tile_total >> 32) & 0xffffull); tot[3] += (int)((tile_total >> 48) & 0xffffull);
+    // positions 0 and 1 of the next tile read st[0], st[1]: only thread 0 (group 0) reads them, so it can move the
+    // carry as soon as its own events are out
+    if (tid == 0) { st[0] = st[T]; st[1] = st[T + 1]; }
+    WB_SYNC();
+  }
+  if (tid == 0) {
+    int *ec = p.ev_count + ((size_t)u * p.n_bands + b) * 4;
+    bool over = false;
+    for (int q = 0; q < 4; ++q) { ec[q] = tot[q]; over = over || tot[q] > cap; }
+    if (over) {
+      ec[0] = -1;
+#ifdef WB_EMU
+      const int at = (*p.redo_count)++;
+#else
+      const int at = atomicAdd(p.redo_count, 1);
+#endif
+      p.redo_list[at] = u * p.n_bands + b;
+    }
+  }
+}
+
+// ---- edge lists -> candidates
+#define WB_IP_F 256     // frames per round
+#define WB_IP_W 256     // intervals per train and window
+struct IpTrain {        // one train of one band: complete edge list in global memory
+  const double *e; int n_int; double afs;
+};
+WB_DEV double ip_loc(const IpTrain &T, int j) { return (T.e[j] + T.e[j + 1]) / 2.0 / T.afs; }     // dio.cpp:357-393
+WB_DEV double ip_val(const IpTrain &T, int j) { return T.afs / (T.e[j + 1] - T.e[j]); }
+
+WB_KERNEL(256, 4) band_interp_kernel(SweepParams p) {
+  WB_SHARED double xw[4][WB_IP_W + 4], yw[4][WB_IP_W + 4];
+  WB_SHARED int mw[4][WB_IP_W + 4];
+  WB_SHARED int cnt[4][WB_IP_F];
+  WB_SHARED int used[4];
+  const int tid = WB_TID, nth = WB_NTH;
+  const int b = blockIdx.x, u = blockIdx.y;
+  const int *ec = p.ev_count + ((size_t)u * p.n_bands + b) * 4;
+  if (ec[0] < 0) return;   // lists overflowed: the streaming kernel redoes this band
+  const int nf = p.n_frames[u];
+  double *cand = p.cand + ((size_t)u * p.n_bands + b) * p.frame_stride;
+  double *score = p.score ? p.score + ((size_t)u * p.n_bands + b) * p.frame_stride : nullptr;
+  const double bf = p.boundary[b];
+  const int cap = p.edge_cap[b];
+  const double *edges = p.edges + (size_t)u * p.edge_stride + (size_t)p.edge_off[b];
+  IpTrain tr[4];
+  bool ok = true;
+  for (int q = 0; q < 4; ++q) {
+    tr[q].e = edges + (size_t)q * cap; tr[q].afs = p.afs;
+    tr[q].n_int = ec[q] < 2 ? 0 : ec[q] - 1;        // ZeroCrossingEngine returns count-1 (0 if count<2)
+    if (tr[q].n_int - 2 <= 0) ok = false;           // CheckEvent(n - 2), dio.cpp:475-484
+  }
+  if (!ok) {
+    for (int i = tid; i < nf; i += nth) {
+      cand[i] = 0.0;
+      if (score) score[i] = 100000.0 / (0.0 + kTiny);
+    }
+    return;
+  }
+  int cursor[4] = {0, 0, 0, 0};   // intervals whose first frame lies before the current round (identical in every thread)
+  for (int c0 = 0; c0 < nf; c0 += WB_IP_F) {
+    const int c1 = imin(nf, c0 + WB_IP_F);
+    int wbase[4] = {0, 0, 0, 0}, wlen[4] = {0, 0, 0, 0};
+    bool more = true;
+    for (int q = 0; q < 4; ++q)
+      for (int i = tid; i < WB_IP_F; i += nth) cnt[q][i] = cursor[q];
+    for (int iter = 0; more; ++iter) {
+      // window of train q: intervals cursor-2 .. cursor+W (two before the cursor serve the frames no new interval reaches)
+      for (int q = 0; q < 4; ++q) {
+        wbase[q] = imax(0, cursor[q] - 2);
+        wlen[q] = imin(tr[q].n_int - wbase[q], WB_IP_W + 3);
+        for (int k = tid; k < wlen[q]; k += nth) {
+          const double x = ip_loc(tr[q], wbase[q] + k);
+          xw[q][k] = x; yw[q][k] = ip_val(tr[q], wbase[q] + k);
+          mw[q][k] = first_frame_at_or_after(x, p.frame_period);
+        }
+      }
+      if (tid < 4) used[tid] = 0;
+      WB_SYNC();
+      // interval j (first frame m_j < c1) owns the frames [m_j, m_{j+1}): their count of intervals <= t is j + 1
+      for (int q = 0; q < 4; ++q) {
+        const int k0 = cursor[q] - wbase[q];
+        const int kend = imin(wlen[q], k0 + WB_IP_W);           // intervals examined in this window
+        for (int k = k0 + tid; k < kend; k += nth) {
+          const int m = mw[q][k];
+          if (m >= c1) continue;
+          const int m_next = (k + 1 < wlen[q]) ? mw[q][k + 1] : 0x7fffffff;   // beyond the window only when the list ends
+          for (int i = imax(m, c0); i < imin(m_next, c1); ++i) cnt[q][i - c0] = wbase[q] + k + 1;
+          if (k + 1 == kend || mw[q][k + 1] >= c1) used[q] = k + 1 - k0;      // the last interval consumed by this round
+        }
+      }
+      WB_SYNC();
+      more = false;
+      for (int q = 0; q < 4; ++q) {
+        const int k0 = cursor[q] - wbase[q];
+        const int examined = imin(wlen[q], k0 + WB_IP_W) - k0;
+        const int un = used[q];
+        cursor[q] += un;
+        if (un == examined && examined == WB_IP_W && cursor[q] < tr[q].n_int) more = true;   // window exhausted inside the round
+      }
+      WB_SYNC();   // `used` and the windows are rewritten by the next iteration
+    }
+    // shared memory holds the windows of the LAST iteration (wbase / wlen); anything outside comes from the lists
+    for (int i = c0 + tid; i < c1; i += nth) {
+      const double t = i * p.frame_period / 1000.0;
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = imin(tr[q].n_int - 1, imax(1, cnt[q][i - c0]));   // interp1's segment (matlabfunctions.cpp:157-176)
+        double x0, x1, y0, y1;
+        const int w0 = k - 1 - wbase[q];
+        if (w0 >= 0 && w0 + 1 < wlen[q]) {
+          x0 = xw[q][w0]; x1 = xw[q][w0 + 1]; y0 = yw[q][w0]; y1 = yw[q][w0 + 1];
+        } else {
+          x0 = ip_loc(tr[q], k - 1); x1 = ip_loc(tr[q], k);
+          y0 = ip_val(tr[q], k - 1); y1 = ip_val(tr[q], k);
+        }
+        const double s = (t - x0) / (x1 - x0);
+        v[q] = y0 + s * (y1 - y0);
+      }
+      sweep_store_candidate(p, v[0], v[1], v[2], v[3], i, bf, cand, score);
+    }
+    WB_SYNC();
+  }
+}
 
 // extended input of decimate(): 9 mirrored samples on both sides of the edge-padded signal
 WB_DEV double dec_ext(const double *__restrict__ x, int n, int lag, int nx, int i) {
@@ -534,6 +850,20 @@ void launch_band_sweep(Ctx *ctx, const SweepParams &p_in, unsigned n_utts) {
 #endif
     WB_LAUNCH_COOP(band_sweep_kernel, dim3((unsigned)p.n_bands, n_utts), WB_SWEEP_THREADS, smem, ctx->stream, p);
   }
+}
+
+void launch_band_sweep_split(Ctx *ctx, const SweepParams &p_in, unsigned n_utts) {
+  SweepParams p = p_in;
+  p.debug_skip = 0;
+  const size_t smem_fe = fe_smem_bytes(p.max_taps), smem_sw = sweep_smem_bytes(p.max_taps);
+#ifndef WB_EMU
+  cudaFuncSetAttribute(band_fir_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fe);
+  cudaFuncSetAttribute(band_sweep_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sw);
+#endif
+  WB_LAUNCH_COOP(band_fir_events_kernel, dim3((unsigned)p.n_bands, n_utts), WB_SWEEP_THREADS, smem_fe, ctx->stream, p);
+  WB_LAUNCH_COOP(band_interp_kernel, dim3((unsigned)p.n_bands, n_utts), 256, 0, ctx->stream, p);
+  // bands whose edge lists overflowed (usually none): the streaming kernel with its history rings, over the list
+  WB_LAUNCH_COOP(band_sweep_list_kernel, dim3((unsigned)(3 * ctx->sm_count)), WB_SWEEP_THREADS, smem_sw, ctx->stream, p);
 }
 
 }  // namespace wb

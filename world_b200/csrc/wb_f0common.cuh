@@ -93,7 +93,22 @@ struct SweepParams {
   int max_taps;
   int *status;
   int debug_skip;   // experiments only: 1 = no candidate phase, 2 = no event phase either
+  // round 2, Harvest on decimated input: the sweep is split into band_fir_events_kernel (FIR + the four event trains,
+  // complete edge lists to global memory) and band_interp_kernel (edge lists -> candidates on the frame grid).
+  int *ev_count;          // [n][n_bands][4] events per train; ev_count[..][0] = -1 marks a band whose lists overflowed
+  int *redo_list; int *redo_count;   // (utterance * n_bands + band) pairs for the streaming kernel (history rings)
 };
+
+// outputs per tile of band_fir_events_kernel: 9 per thread, so that consecutive threads walk shared memory with a
+// stride of 9 doubles -- conflict free WITHOUT padding, which lets the input segment arrive as one TMA bulk copy
+#define WB_FE_R 9
+#define WB_FE_T (WB_FE_R * WB_SWEEP_THREADS)
+WB_HD inline int fe_seg_doubles(int max_taps) {   // one input segment: tile + filter span + slack, even
+  return (WB_FE_T + ((max_taps + WB_FE_R - 1) / WB_FE_R) * WB_FE_R + WB_FE_R + 8) & ~1;
+}
+WB_HD inline size_t fe_smem_bytes(int max_taps) {
+  return (size_t)(2 * fe_seg_doubles(max_taps) + (((max_taps + WB_FE_R - 1) / WB_FE_R) * WB_FE_R + WB_FE_R) + (WB_FE_T + 8) + 48) * 8;
+}
 
 WB_HD inline size_t sweep_smem_bytes(int max_taps) {
   const int seg = WB_SWEEP_T + max_taps + 16;
@@ -122,6 +137,8 @@ struct DecimateParams {
 void launch_decimate(Ctx *ctx, const DecimateParams &p, int max_x_len, unsigned n_utts);
 void launch_fir_plain(Ctx *ctx, const FirParams &p, unsigned tiles, unsigned n_utts);
 void launch_band_sweep(Ctx *ctx, const SweepParams &p, unsigned n_utts);
+// Harvest, decimated input: FIR + events, interpolation, then the streaming kernel for the bands whose lists overflowed
+void launch_band_sweep_split(Ctx *ctx, const SweepParams &p, unsigned n_utts);
 
 // the two spectrum bins the reference's mirroring loop corrupts (see nyquist_bins_kernel)
 struct NyquistParams {

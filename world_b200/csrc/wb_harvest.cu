@@ -950,7 +950,7 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
   const size_t per_utt = y_stride * 8 + edge_stride * 8 + (size_t)nb * l1_stride * 8 +
                          (size_t)l1_stride * (WB_HV_BASE * 8 + 4) + (size_t)l1_stride * max_cand * 8 * 4 +
                          (size_t)l1_stride * (5 * 8 + 6 * 4 + 8) + mc_stride * 8 + pad_stride * (8 + 4) + (size_t)sec_slots * seg_cap * 8 +
-                         tmp_stride * 16 + 1024;
+                         tmp_stride * 16 + (size_t)nb * 20 + 1024;
   int chunk = balanced_chunk(imin(b.n, 65535), (int)dmin(65535.0, (double)ctx->scratch_budget / (double)per_utt));
 #ifndef WB_EMU
   cudaFuncSetAttribute(harvest_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_refine);
@@ -963,6 +963,7 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     const size_t o_nyq = plan.add((size_t)n * 32), o_nfft = plan.add((size_t)n * 4);
     const size_t o_edges = plan.add((size_t)n * edge_stride * 8);
     const size_t o_ecap = plan.add(nb * 4), o_eoff = plan.add(nb * 8);
+    const size_t o_evc = plan.add((size_t)n * nb * 16), o_redo = plan.add((size_t)n * nb * 4), o_nredo = plan.add(4);
     const size_t o_raw = plan.add((size_t)n * nb * l1_stride * 8);
     const size_t o_base = plan.add((size_t)n * l1_stride * WB_HV_BASE * 8), o_bcnt = plan.add((size_t)n * l1_stride * 4);
     const size_t o_c1 = plan.add((size_t)n * l1_stride * max_cand * 8), o_s1 = plan.add((size_t)n * l1_stride * max_cand * 8);
@@ -1034,7 +1035,15 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     }
     sp.cand = (double *)(blk + o_raw); sp.score = nullptr;
     sp.max_taps = max_taps; sp.status = ctx->status_dev;
-    launch_band_sweep(ctx, sp, (unsigned)n);
+    sp.ev_count = (int *)(blk + o_evc); sp.redo_list = (int *)(blk + o_redo); sp.redo_count = (int *)(blk + o_nredo);
+    if (!sp.ripple && !getenv("WB_SWEEP_STREAMING") && fe_smem_bytes(max_taps) <= 200 * 1024) {
+      // decimated input (every rate from 12 kHz up): FIR + events, then interpolation (wb_f0common.cu)
+      rc = dev_memset(ctx, sp.redo_count, 0, 4);
+      if (rc) return rc;
+      launch_band_sweep_split(ctx, sp, (unsigned)n);
+    } else {
+      launch_band_sweep(ctx, sp, (unsigned)n);
+    }
 
     const long long slots = (long long)n * l1_stride;
     HvDetectParams dp;
