@@ -355,6 +355,21 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     w = World(device=local)
+    if world > 1:
+        # the library's own NCCL communicator (C ABI, include/world_b200.h): torch.distributed only carries the 128-byte id
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(w.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            w.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     fs, n = a.fs, int(a.fs * a.seconds)
     U = a.utts
     L = frames_of(fs, n)
@@ -389,8 +404,9 @@ def main():
     w2 = World(device=local) if n_slices > 1 else w
     side = torch.cuda.Stream(device=dev) if n_slices > 1 else None
     bounds = [U * i // n_slices for i in range(n_slices + 1)]
-    t_loc = torch.zeros((U, L), dtype=torch.float64, device=dev)
-    f0_loc = torch.zeros((U, L), dtype=torch.float64, device=dev)
+    # this rank's f0 / time axis rows live inside the gathered arrays (in-place all-gather)
+    t_loc = t_all[rank * U:(rank + 1) * U] if gather else torch.zeros((U, L), dtype=torch.float64, device=dev)
+    f0_loc = f0_all[rank * U:(rank + 1) * U] if gather else torch.zeros((U, L), dtype=torch.float64, device=dev)
     if w2 is not w:
         w2.set_scratch_budget(budget // 2)
         w.set_scratch_budget(budget // 2)
@@ -411,7 +427,11 @@ def main():
 
     def step():
         main = torch.cuda.current_stream(dev)
-        if use_lanes:   # the whole chain in one C-ABI call: utterance slices on two internal streams
+        if use_lanes and gather_full:
+            # multi-GPU: the same call with the FULL arrays; every finished slice is broadcast to the other ranks by the
+            # library's NCCL communicator while the next slice is computed
+            w.analyze_batch_allgather(x, fs, ao_dev, t_all, f0_all, sp_all, ap_all)
+        elif use_lanes:   # the whole chain in one C-ABI call: utterance slices on two internal streams
             w.analyze_batch(x, fs, ao_dev, time_axis=t_loc, f0=f0_loc, spectrogram=sp, aperiodicity=ap)
         for si in range(0 if use_lanes else n_slices):
             b0, b1 = bounds[si], bounds[si + 1]
@@ -438,12 +458,12 @@ def main():
         if side is not None:
             main.wait_stream(side)
         t, f0 = t_loc, f0_loc
-        if gather:
-            dist.all_gather_into_tensor(f0_all, f0)
-            dist.all_gather_into_tensor(t_all, t)
+        if gather and not (use_lanes and gather_full):   # in-place all-gathers through the C ABI (wb_multi.cu)
+            w.allgather_rows(f0_all, U)
+            w.allgather_rows(t_all, U)
             if gather_full:
-                dist.all_gather_into_tensor(sp_all, sp)
-                dist.all_gather_into_tensor(ap_all, ap)
+                w.allgather_rows(sp_all, U)
+                w.allgather_rows(ap_all, U)
         return f0
 
     def barrier():
@@ -719,8 +739,8 @@ def main():
            "dtype": "f64", "data": "synthetic",
            "config": {"workload": workload_name(a), "baseline_config": a.config or None, "fs": fs, "frame_period_ms": 5.0, "frames_per_step": frames_step,
                       "l2_policy": "inputs+outputs per step (>= 18 GB) exceed the 126 MB L2; no flush needed",
-                      "multi_gpu": ("utterances sharded over ranks, NCCL all-gather of f0/time_axis" +
-                                    ("/spectrogram/aperiodicity" if gather_full else "")) if world > 1 else "single GPU",
+                      "multi_gpu": ("utterances sharded over ranks; the library's own NCCL communicator (C ABI) reassembles f0/time_axis" +
+                                    ("/spectrogram/aperiodicity, slice by slice under the compute" if gather_full else "")) if world > 1 else "single GPU",
                       "gathered_equals_local_recompute": gather_check},
            "clocks": clocks, "e2e": e2e, "slices": n_slices,
            "device_resident_api": ("world_b200_analyze_batch (utterance slices on two internal streams; per-kernel times below overlap, "

@@ -171,6 +171,29 @@ int world_b200_analyze_batch(WorldB200 *ctx, const double *x, int n_utts, int x_
                              double *time_axis, double *f0, int f0_stride, double *spectrogram,
                              double *aperiodicity);
 
+/* ---- multi-GPU: one context per GPU (one process or thread each), utterances sharded over ranks --------------
+ * There is no exchange inside the analysis; the one collective reassembles the output arrays on every rank
+ * (north_star; reference loops src/harvest.cpp:1223-1255, cheaptrick.cpp:200-229, d4c.cpp:342-403 are per utterance).
+ * NCCL is bound at run time (dlopen of libnccl.so.2) -- single-GPU users never load it.  Rank 0 creates the id and
+ * the CALLER hands its 128 bytes to the other ranks (MPI, torch.distributed, a socket, a file ...). */
+int world_b200_comm_unique_id(unsigned char *id, int id_bytes /* >= 128 */);
+int world_b200_comm_init(WorldB200 *ctx, int n_ranks, int rank, const unsigned char *id, int id_bytes);
+int world_b200_comm_destroy(WorldB200 *ctx);
+/* In-place all-gather: `full` is [n_ranks][rows_per_rank][row_elems] doubles (DEVICE) with this rank's block already
+ * in place.  Ordered after the work on the context's stream; that stream waits for the result. */
+int world_b200_allgather_rows(WorldB200 *ctx, double *full, unsigned long long row_elems,
+                              unsigned long long rows_per_rank);
+/* world_b200_analyze_batch on this rank's n_utts utterances (every rank passes the same n_utts, strides and options),
+ * with the four outputs given as the FULL arrays of n_ranks * n_utts utterances: the rank computes into its own
+ * block and each finished utterance slice is sent to all other ranks (grouped ncclBroadcast on a communication
+ * stream) while the next slice is computed -- the transfer hides under the compute.  On return the work is
+ * enqueued; after the context's stream (world_b200_synchronize) every rank holds the complete arrays, bit-identical
+ * to a single-GPU run. */
+int world_b200_analyze_batch_allgather(WorldB200 *ctx, const double *x, int n_utts, int x_stride,
+                                       const int *x_lengths, int fs, const WorldB200AnalysisOption *option,
+                                       double *time_axis_full, double *f0_full, int f0_stride,
+                                       double *spectrogram_full, double *aperiodicity_full);
+
 /* {Dio+StoneMask | Harvest} -> CheapTrick -> D4C for n_utts host waveforms; outputs are host
  * arrays laid out as described above.  Input upload, compute and result download are pipelined
  * over utterance chunks.  Any output pointer may be NULL to skip its download.  Whole padded rows

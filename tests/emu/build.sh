@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")"
 SRC=../../world_b200/csrc
 OUT=libworld_b200_emu.so
-FILES="$SRC/wb_api.cu $SRC/wb_rng.cu $SRC/wb_cheaptrick.cu $SRC/wb_d4c.cu $SRC/wb_stonemask.cu $SRC/wb_synthesis.cu $SRC/wb_codec.cu $SRC/wb_fileio.cu $SRC/wb_matlab.cu $SRC/wb_f0common.cu $SRC/wb_dio.cu $SRC/wb_harvest.cu $SRC/wb_host.cu"
+FILES="$SRC/wb_api.cu $SRC/wb_rng.cu $SRC/wb_cheaptrick.cu $SRC/wb_d4c.cu $SRC/wb_stonemask.cu $SRC/wb_synthesis.cu $SRC/wb_codec.cu $SRC/wb_fileio.cu $SRC/wb_matlab.cu $SRC/wb_f0common.cu $SRC/wb_dio.cu $SRC/wb_harvest.cu $SRC/wb_host.cu $SRC/wb_multi.cu"
 OBJS=""
 for f in $FILES; do
   o="_$(basename $f .cu).o"

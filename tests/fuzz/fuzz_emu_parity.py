@@ -1,4 +1,5 @@
-"""Randomised parity sweep of the kernel sources (host emulation) against the compiled reference (CPU only).
+"""Randomised parity sweep against the compiled reference: the kernel sources as host emulation (default, CPU only)
+or the CUDA library on cuda:0 (WB_FUZZ_GPU=1; tests/test_fuzz.py runs a short sweep of each under pytest).
 Usage: python tests/fuzz/fuzz_emu_parity.py [n_cases] [seed]   -- prints one line per case, exits non-zero on a mismatch."""
 import os
 import sys
@@ -12,6 +13,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from refworld import RefWorld, rel_err  # noqa: E402
 from world_b200.api import World  # noqa: E402
 from synth import synth_batch  # noqa: E402
+from test_parity_common import make, to_np  # noqa: E402
 
 TOL = 1e-6
 
@@ -38,12 +40,23 @@ def make_signal(rng, fs, n):
     return kind, np.ascontiguousarray(x)
 
 
+def open_world():
+    if os.environ.get("WB_FUZZ_GPU"):
+        import torch
+        torch.cuda.set_device(0)
+        return World(device=0)
+    return World(lib_path=os.environ.get("WB_EMU_LIB", os.path.join(ROOT, "tests", "emu", "libworld_b200_emu.so")), array_module="numpy")
+
+
 def main():
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    bad = run(open_world(), RefWorld(), n_cases, seed)
+    sys.exit(1 if bad else 0)
+
+
+def run(emu, ref, n_cases, seed, out=print):
     rng = np.random.default_rng(seed)
-    ref = RefWorld()
-    emu = World(lib_path=os.environ.get("WB_EMU_LIB", os.path.join(ROOT, "tests", "emu", "libworld_b200_emu.so")), array_module="numpy")
     bad = 0
     for case in range(n_cases):
         fs = int(rng.choice([8000, 11025, 16000, 22050, 32000, 44100, 48000]))
@@ -63,12 +76,13 @@ def main():
                     q.f0_ceil = [800.0, 400.0, 1000.0][(case // 3) % 3]
                     q.channels_in_octave = [2.0, 4.0, 1.0][(case // 2) % 3]
                     q.allowed_range = [0.1, 0.2][case % 2]
-                t, f0, fl = emu.dio(x[None], fs, o)
+                xd = make(emu, x[None])
+                t, f0, fl = emu.dio(xd, fs, o)
                 emu.synchronize()
                 tr, fr = ref.dio(x, fs, ro)
                 # same input to both (the reference's DIO f0): StoneMask rounds f0 * fft / fs * k to a bin, so
                 # inputs that differ in the last digits can legitimately land on different bins
-                f0s = emu.stonemask(x[None], fs, tr[None], np.ascontiguousarray(fr)[None]); emu.synchronize()
+                f0s = to_np(emu.stonemask(xd, fs, make(emu, tr[None]), make(emu, np.ascontiguousarray(fr)[None]))); emu.synchronize()
                 frs = ref.stonemask(x, fs, tr, fr)
                 e_sm = rel_err(f0s[0], frs).max()
                 msg.append(f"stonemask {e_sm:.1e}")
@@ -79,9 +93,11 @@ def main():
                     q.frame_period = fp
                     q.f0_floor = [71.0, 40.0, 100.0][case % 3]
                     q.f0_ceil = [800.0, 500.0, 1100.0][(case // 3) % 3]
-                t, f0, fl = emu.harvest(x[None], fs, o)
+                xd = make(emu, x[None])
+                t, f0, fl = emu.harvest(xd, fs, o)
                 emu.synchronize()
                 tr, fr = ref.harvest(x, fs, ro)
+            t, f0 = to_np(t), to_np(f0)
             assert fl[0] == len(tr) and np.array_equal(t[0], tr), "time axis"
             flips = int(((f0[0] > 0) != (fr > 0)).sum())
             e_f0 = rel_err(f0[0], fr).max() if flips == 0 else float("inf")
@@ -98,9 +114,10 @@ def main():
                 if case % 5 == 2:
                     do.threshold = rdo.threshold = 0.5
                 frc = np.ascontiguousarray(fr)
-                sp = emu.cheaptrick(x[None], fs, tr[None], frc[None], co)
-                ap = emu.d4c(x[None], fs, tr[None], frc[None], co.fft_size, do)
+                sp = emu.cheaptrick(xd, fs, make(emu, tr[None]), make(emu, frc[None]), co)
+                ap = emu.d4c(xd, fs, make(emu, tr[None]), make(emu, frc[None]), co.fft_size, do)
                 emu.synchronize()
+                sp, ap = to_np(sp), to_np(ap)
                 e_sp = rel_err(sp[0], ref.cheaptrick(x, fs, tr, frc, rco)).max()
                 e_ap = rel_err(ap[0], ref.d4c(x, fs, tr, frc, rco.fft_size, rdo)).max()
                 msg.append(f"sp {e_sp:.1e} ap {e_ap:.1e}")
@@ -112,9 +129,9 @@ def main():
         except Exception as e:   # library errors (EDOMAIN etc.) are reported, not hidden
             status = f"ERROR {type(e).__name__}: {e}"
             bad += 1
-        print(f"case {case:3d} fs {fs:5d} n {n:6d} {kind:11s} {method:7s} fp {fp:4.1f}  {'  '.join(msg):60s} {status}  ({time.time() - t0:.1f}s)", flush=True)
-    print(f"{n_cases - bad}/{n_cases} cases agree with the reference within {TOL}; {bad} failures")
-    sys.exit(1 if bad else 0)
+        out(f"case {case:3d} fs {fs:5d} n {n:6d} {kind:11s} {method:7s} fp {fp:4.1f}  {'  '.join(msg):60s} {status}  ({time.time() - t0:.1f}s)")
+    out(f"{n_cases - bad}/{n_cases} cases agree with the reference within {TOL}; {bad} failures")
+    return bad
 
 
 if __name__ == "__main__":

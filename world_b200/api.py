@@ -79,6 +79,12 @@ ABI = {
                                           _P, _P, C.c_int, _P, _P]),
     "world_b200_analyze_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, C.POINTER(AnalysisOption),
                                            _P, _P, C.c_int, _P, _P]),
+    "world_b200_analyze_batch_allgather": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, C.POINTER(AnalysisOption),
+                                                     _P, _P, C.c_int, _P, _P]),
+    "world_b200_comm_unique_id": (C.c_int, [_P, C.c_int]),
+    "world_b200_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
+    "world_b200_comm_destroy": (C.c_int, [_P]),
+    "world_b200_allgather_rows": (C.c_int, [_P, _P, C.c_ulonglong, C.c_ulonglong]),
     # legacy single-utterance API (host pointers)
     "Dio": (None, [_P, C.c_int, C.c_int, C.POINTER(DioOption), _P, _P]),
     "Harvest": (None, [_P, C.c_int, C.c_int, C.POINTER(HarvestOption), _P, _P]),
@@ -394,6 +400,41 @@ class World:
                                                       _ptr(time_axis), _ptr(f0), time_axis.shape[1],
                                                       _ptr(spectrogram), _ptr(aperiodicity)))
         return time_axis, f0, spectrogram, aperiodicity, fl
+
+    # -- multi-GPU: one World per GPU / process; the NCCL id travels by the caller's own means -------------------
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_ubyte * 128)()
+        rc = self.lib.world_b200_comm_unique_id(buf, 128)
+        if rc:
+            raise WorldError(f"world_b200_comm_unique_id failed ({rc}): NCCL not available")
+        return bytes(buf)
+
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id[:128])
+        self._check(self.lib.world_b200_comm_init(self._h, n_ranks, rank, buf, 128))
+
+    def comm_destroy(self):
+        self._check(self.lib.world_b200_comm_destroy(self._h))
+
+    def allgather_rows(self, full, rows_per_rank: int):
+        """In-place all-gather of [n_ranks * rows_per_rank, ...] (this rank's block already written)."""
+        row_elems = 1
+        for d in full.shape[1:]:
+            row_elems *= int(d)
+        self._use_current_stream()
+        self._check(self.lib.world_b200_allgather_rows(self._h, _ptr(full), row_elems, rows_per_rank))
+        return full
+
+    def analyze_batch_allgather(self, x, fs, option: AnalysisOption, time_axis_full, f0_full, spectrogram_full,
+                                aperiodicity_full, x_lengths=None):
+        """analyze_batch on this rank's shard with every finished slice broadcast into the FULL arrays of all ranks."""
+        n, stride = x.shape
+        xl, keep = _int_array(x_lengths, n)
+        self._use_current_stream()
+        self._check(self.lib.world_b200_analyze_batch_allgather(
+            self._h, _ptr(x), n, stride, xl, fs, C.byref(option), _ptr(time_axis_full), _ptr(f0_full),
+            time_axis_full.shape[1], _ptr(spectrogram_full) if spectrogram_full is not None else None,
+            _ptr(aperiodicity_full) if aperiodicity_full is not None else None))
 
     def analyze_host(self, x_host, fs, option: AnalysisOption, x_lengths=None, time_axis=None, f0=None,
                      spectrogram=None, aperiodicity=None, f0_stride=None):

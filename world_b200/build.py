@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 SOURCES = ["wb_api.cu", "wb_host.cu", "wb_rng.cu", "wb_cheaptrick.cu", "wb_d4c.cu", "wb_stonemask.cu", "wb_synthesis.cu", "wb_codec.cu", "wb_fileio.cu", "wb_matlab.cu",
-           "wb_f0common.cu", "wb_dio.cu", "wb_harvest.cu"]
+           "wb_f0common.cu", "wb_dio.cu", "wb_harvest.cu", "wb_multi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: values that feed int casts / comparisons must round like the reference's x86-64 -O1
 # build; hot loops use explicit fma() where contraction is harmless.
@@ -54,7 +54,7 @@ def build(verbose=False, force=False):
             print(l)
     objs = [os.path.join(OBJDIR, s.replace(".cu", ".o")) for s in SOURCES]
     if jobs or not os.path.exists(out):
-        r = subprocess.run([NVCC, "-shared", "-o", out] + objs + ["-lcudart"], capture_output=True, text=True)
+        r = subprocess.run([NVCC, "-shared", "-o", out] + objs + ["-lcudart", "-ldl"], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return out

@@ -7,6 +7,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <vector>
+#include <string>
 
 struct WorldB200 {
   wb::Ctx c;
@@ -17,6 +18,9 @@ struct WorldB200 {
   WorldB200 *lane[2] = {nullptr, nullptr};
   void *lane_stream[2] = {nullptr, nullptr};   // cudaStream_t
   void *ev_fork = nullptr, *ev_join[2] = {nullptr, nullptr};   // cudaEvent_t
+  // multi-GPU (wb_multi.cu): NCCL communicator + one event per utterance slice of analyze_batch_allgather
+  wb::Comm *comm = nullptr;
+  std::vector<void *> ev_slice;
 };
 
 namespace wb {
@@ -345,7 +349,9 @@ void world_b200_destroy(WorldB200 *h) {
   }
 #ifndef WB_EMU
   if (h->ev_fork) cudaEventDestroy((cudaEvent_t)h->ev_fork);
+  for (void *e : h->ev_slice) cudaEventDestroy((cudaEvent_t)e);
 #endif
+  if (h->comm) comm_destroy(h->comm);
   dev_free(h->c.twiddle);
   dev_free(h->c.rng_jump);
   dev_free(h->c.status_dev);
@@ -515,13 +521,24 @@ int world_b200_harvest_batch(WorldB200 *h, const double *x, int n, int x_stride,
 // concurrently, so the latency-bound per-utterance kernels of one slice (contour tracking, candidate clean-up, the
 // draw stream, decimation) execute under the FP64-bound kernels of the other.  Ordered after the work already on the
 // context's stream; that stream waits for both lanes before the function returns (no host synchronisation).
-int world_b200_analyze_batch(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths, int fs,
-                             const WorldB200AnalysisOption *opt, double *time_axis, double *f0, int f0_stride,
-                             double *spectrogram, double *aperiodicity) {
+// gather = false: time_axis / f0 / spectrogram / aperiodicity hold this call's n utterances.
+// gather = true (multi-GPU): they are the FULL arrays of n_ranks * n utterances; this rank computes into block `rank`
+// and every finished slice is broadcast to the other ranks on the communication stream while the next one is computed.
+static int analyze_batch_impl(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths, int fs,
+                              const WorldB200AnalysisOption *opt, double *time_axis, double *f0, int f0_stride,
+                              double *spectrogram, double *aperiodicity, bool gather) {
   if (!h || !x || !opt || !time_axis || !f0 || n < 0 || fs <= 0 || x_stride <= 0 || f0_stride <= 0) return WORLD_B200_EINVAL;
   if ((spectrogram || aperiodicity) && opt->cheaptrick.fft_size < 16) return WORLD_B200_EINVAL;
   DeviceGuard guard_(&h->c);
   if (n == 0) return 0;
+  size_t my_block = 0;
+  if (gather) {
+    if (!h->comm) { h->c.last_error = "analyze_batch_allgather: no communicator (world_b200_comm_init)"; return WORLD_B200_EINVAL; }
+    my_block = (size_t)comm_rank(h->comm) * (size_t)n;
+    time_axis += my_block * f0_stride; f0 += my_block * f0_stride;
+    if (spectrogram) spectrogram += my_block * f0_stride * (opt->cheaptrick.fft_size / 2 + 1);
+    if (aperiodicity) aperiodicity += my_block * f0_stride * (opt->cheaptrick.fft_size / 2 + 1);
+  }
   const int bins = opt->cheaptrick.fft_size / 2 + 1;
   const double frame_period = opt->f0_method == WORLD_B200_F0_HARVEST ? opt->harvest.frame_period : opt->dio.frame_period;
   int n_slices = 4;
@@ -582,8 +599,35 @@ int world_b200_analyze_batch(WorldB200 *h, const double *x, int n, int x_stride,
       rc = world_b200_d4c_batch(L, xs, m, x_stride, xl, fs, ts, fs_, fl.data() + u0, f0_stride, opt->cheaptrick.fft_size,
                                 &opt->d4c, aperiodicity + (size_t)u0 * f0_stride * bins);
     if (rc && L != h) h->c.last_error = L->c.last_error;
+#ifndef WB_EMU
+    if (!rc && gather && comm_ranks(h->comm) > 1) {
+      // rows u0..u1 of every rank's block, as soon as this rank's are final (event on the lane's stream)
+      while ((int)h->ev_slice.size() <= s) {
+        cudaEvent_t ev;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return WORLD_B200_ECUDA;
+        h->ev_slice.push_back(ev);
+      }
+      cudaEvent_t ev = (cudaEvent_t)h->ev_slice[s];
+      cudaEventRecord(ev, L->c.stream);
+      double *t_full = time_axis - my_block * f0_stride, *f_full = f0 - my_block * f0_stride;
+      std::string err;
+      int g = comm_gather_rows(h->comm, t_full, (size_t)f0_stride, (size_t)n, (size_t)u0, (size_t)m, ev, &err);
+      if (!g) g = comm_gather_rows(h->comm, f_full, (size_t)f0_stride, (size_t)n, (size_t)u0, (size_t)m, nullptr, &err);
+      if (!g && spectrogram)
+        g = comm_gather_rows(h->comm, spectrogram - my_block * f0_stride * bins, (size_t)f0_stride * bins, (size_t)n, (size_t)u0,
+                             (size_t)m, nullptr, &err);
+      if (!g && aperiodicity)
+        g = comm_gather_rows(h->comm, aperiodicity - my_block * f0_stride * bins, (size_t)f0_stride * bins, (size_t)n, (size_t)u0,
+                             (size_t)m, nullptr, &err);
+      if (g) { h->c.last_error = err; rc = WORLD_B200_ECUDA; }
+    }
+#endif
   }
 #ifndef WB_EMU
+  if (gather && comm_ranks(h->comm) > 1) {
+    std::string err;
+    if (comm_join(h->comm, h->c.stream, &err) && !rc) { h->c.last_error = err; rc = WORLD_B200_ECUDA; }
+  }
   if (lanes[0] != h)
     for (int l = 0; l < 2; ++l) {   // join even after an error: the caller's stream must not run ahead of the lanes
       cudaEventRecord((cudaEvent_t)h->ev_join[l], (cudaStream_t)h->lane_stream[l]);
@@ -591,6 +635,67 @@ int world_b200_analyze_batch(WorldB200 *h, const double *x, int n, int x_stride,
     }
 #endif
   return rc;
+}
+
+int world_b200_analyze_batch(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths, int fs,
+                             const WorldB200AnalysisOption *opt, double *time_axis, double *f0, int f0_stride,
+                             double *spectrogram, double *aperiodicity) {
+  return analyze_batch_impl(h, x, n, x_stride, x_lengths, fs, opt, time_axis, f0, f0_stride, spectrogram, aperiodicity, false);
+}
+
+// ---- multi-GPU: utterances sharded over ranks, outputs reassembled on every rank by NCCL
+int world_b200_comm_unique_id(unsigned char *id, int id_bytes) {
+  if (!id || id_bytes < 128) return WORLD_B200_EINVAL;
+  std::string err;
+  if (comm_unique_id(id, &err)) { fprintf(stderr, "world_b200: %s\n", err.c_str()); return WORLD_B200_ECUDA; }
+  return 0;
+}
+
+int world_b200_comm_init(WorldB200 *h, int n_ranks, int rank, const unsigned char *id, int id_bytes) {
+  if (!h || !id || id_bytes < 128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
+  if (h->comm) { comm_destroy(h->comm); h->comm = nullptr; }
+  std::string err;
+  if (comm_create(n_ranks, rank, id, &h->comm, &err)) { h->c.last_error = err; return WORLD_B200_ECUDA; }
+  return 0;
+}
+
+int world_b200_comm_destroy(WorldB200 *h) {
+  if (!h) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
+  if (h->comm) { comm_destroy(h->comm); h->comm = nullptr; }
+  return 0;
+}
+
+// In-place all-gather of an array of n_ranks blocks of rows_per_rank rows (row_elems doubles each): this rank's block
+// is already in place.  Ordered after the work on the context's stream; that stream waits for the result.
+int world_b200_allgather_rows(WorldB200 *h, double *full, unsigned long long row_elems, unsigned long long rows_per_rank) {
+  if (!h || !full) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
+  if (!h->comm) { h->c.last_error = "allgather_rows: no communicator (world_b200_comm_init)"; return WORLD_B200_EINVAL; }
+#ifndef WB_EMU
+  if (comm_ranks(h->comm) > 1) {
+    if (!h->ev_fork) {
+      cudaEvent_t ev;
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return WORLD_B200_ECUDA;
+      h->ev_fork = ev;
+    }
+    cudaEventRecord((cudaEvent_t)h->ev_fork, h->c.stream);
+    std::string err;
+    int g = comm_gather_rows(h->comm, full, (size_t)row_elems, (size_t)rows_per_rank, 0, (size_t)rows_per_rank,
+                             (cudaEvent_t)h->ev_fork, &err);
+    if (!g) g = comm_join(h->comm, h->c.stream, &err);
+    if (g) { h->c.last_error = err; return WORLD_B200_ECUDA; }
+  }
+#endif
+  return 0;
+}
+
+int world_b200_analyze_batch_allgather(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths, int fs,
+                                       const WorldB200AnalysisOption *opt, double *time_axis_full, double *f0_full,
+                                       int f0_stride, double *spectrogram_full, double *aperiodicity_full) {
+  return analyze_batch_impl(h, x, n, x_stride, x_lengths, fs, opt, time_axis_full, f0_full, f0_stride, spectrogram_full,
+                            aperiodicity_full, true);
 }
 
 // Per-kernel timing: enable, run, then fetch a JSON object {"kernel": {"launches": n, "ms": t}, ...}

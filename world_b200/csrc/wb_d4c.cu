@@ -31,6 +31,7 @@ struct D4cParams {
   const unsigned *off_a; unsigned *count_b; const unsigned *off_b;
   unsigned char *selected;  // [n][f_stride]
   int *slow_list; int *slow_count;   // frames whose window does not fit the fast body kernel (long windows, f0 near the floor)
+  int pw_doubles;                    // doubles of the fast body kernel's power row (d4c_body_pw_doubles)
   double *out;
   const double2 *tw;
   int *status;
@@ -268,18 +269,28 @@ WB_DEV bool select_kth_largest_fast(const double *a, int n, int kth, unsigned lo
 //     here as its two decimation-in-frequency halves -- even bins from z[n] + z[n + d_fft/2], odd bins from
 //     (z[n] - z[n + d_fft/2]) W^n -- one after the other in the same buffer (bins k and d_fft - k, which the
 //     split of the two real spectra pairs up, have the same parity).  The windowed signal waits in the power row.
-// The power row is sized for the longest window (f0 at the 47 Hz floor); slow_list / d4c_body_slow_kernel (the
-// round-1 body on the in-place DIT FFT) serve d_fft > 4096, where this kernel's thread count would not fit a CTA.
-// doubles of the power row: it also holds the windowed signal of the centroid transforms, whose longest window
-// (f0 at the 47 Hz floor, ratio 4) is a little longer than d_fft / 2 + 1
-WB_HD inline int d4c_body_pw_doubles(int d_fft, int fs) {
+// Frames whose window is longer than the power row (d4c_body_pw_doubles: f0 near the 47 Hz floor) go to slow_list
+// and are done by d4c_body_slow_kernel (the round-1 body on the in-place DIT FFT, any window length), as is every
+// frame when d_fft > 4096 (this kernel's thread count would not fit a CTA).
+// Doubles of the power row.  It also holds the windowed signal of the centroid transforms, whose longest window (f0
+// at the 47 Hz floor, ratio 4) is up to twice d_fft / 2 + 1; shared memory per CTA decides how many CTAs an SM holds
+// and the kernel is latency bound (profiles/r2e: sizing the row for the longest window cost a CTA per SM at 48 kHz
+// and 13 % of the kernel), so the row grows only as far as the CTA count of the minimal layout allows.  Frames with
+// a longer window (f0 below ~54 Hz at 16 kHz, ~75 Hz at 48 kHz) go to slow_list / d4c_body_slow_kernel.
+WB_HD inline size_t d4c_body_smem_bytes_for(int d_fft, int pw_doubles, int n_ap, int threads) {
+  return (size_t)WB_FPAD_SLOTS(d_fft / 2) * sizeof(double2) +
+         (size_t)((d_fft / 2 + 1) + pw_doubles + WB_RED_DOUBLES + (threads + 1) + (n_ap + 2) + 2) * sizeof(double);
+}
+WB_HD inline int d4c_body_pw_doubles(int d_fft, int fs, int n_ap, int threads) {
   const int nwin_max = 2 * round_half_away(4.0 * fs / 47.0 / 2.0) + 1;
   const int half1 = d_fft / 2 + 1;
-  return (nwin_max > half1 ? nwin_max : half1) + 1;
-}
-WB_HD inline size_t d4c_body_smem_bytes(int d_fft, int fs, int n_ap, int threads) {
-  return (size_t)WB_FPAD_SLOTS(d_fft / 2) * sizeof(double2) +
-         (size_t)((d_fft / 2 + 1) + d4c_body_pw_doubles(d_fft, fs) + WB_RED_DOUBLES + (threads + 1) + (n_ap + 2) + 2) * sizeof(double);
+  const size_t per_sm = (size_t)227 * 1024, reserved = 1024;
+  const size_t smem_min = d4c_body_smem_bytes_for(d_fft, half1, n_ap, threads);
+  const size_t ctas = per_sm / (smem_min + reserved);
+  if (ctas == 0) return half1;
+  const size_t slack = (per_sm / ctas - reserved - smem_min) / sizeof(double);
+  const int grown = half1 + (int)slack - 2;
+  return imax(half1, imin(nwin_max + 1, grown));
 }
 
 template <int kOcc>   // CTAs of 128 threads per SM the register budget is cut for (A/B: WB_D4C_OCC)
@@ -295,7 +306,7 @@ WB_DEV void d4c_body_frame(const D4cParams &p) {
   double2 *P = smem2;
   double *pd = reinterpret_cast<double *>(P);            // the same buffer as 2 * slots plain doubles
   double *cent = reinterpret_cast<double *>(P + slots);  // half + 1
-  const int pw_doubles = d4c_body_pw_doubles(N, fs);
+  const int pw_doubles = p.pw_doubles;
   double *pw = cent + (half + 1);          // power row (half + 1); the windowed signal during the centroid transforms
   double *red = pw + pw_doubles;           // WB_RED_DOUBLES
   double *red_big = red + WB_RED_DOUBLES;  // nth + 1
@@ -306,7 +317,7 @@ WB_DEV void d4c_body_frame(const D4cParams &p) {
   const double t = p.time_axis[fidx];
   {
     const int nwin4 = 2 * round_half_away(4.0 * fs / f / 2.0) + 1;   // both ratio-4 windows (d4c_windowed)
-    if (nwin4 > pw_doubles || nwin4 > 2 * slots) {   // cannot happen for f >= 47 Hz (the row is sized for it); kept as a guard
+    if (nwin4 > pw_doubles || nwin4 > 2 * slots) {   // long window: the any-length kernel takes the frame
       if (tid == 0) {
 #ifdef WB_EMU
         const int at = (*p.slow_count)++;
@@ -647,7 +658,8 @@ int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *ap
   int body_threads = imax(32, p.d_fft / 16), lt_threads = 128, slow_threads = 128;
   if (const char *e = getenv("WB_LT_THREADS")) lt_threads = atoi(e);
   const size_t smem_lt = (size_t)2 * WB_FPAD_SLOTS(p.lt_fft / 2) * sizeof(double2) + WB_RED_DOUBLES * sizeof(double);
-  const size_t smem_body = d4c_body_smem_bytes(p.d_fft, fs, p.n_ap, body_threads);
+  p.pw_doubles = d4c_body_pw_doubles(p.d_fft, fs, p.n_ap, body_threads);
+  const size_t smem_body = d4c_body_smem_bytes_for(p.d_fft, p.pw_doubles, p.n_ap, body_threads);
   const size_t smem_slow = (size_t)((2 * p.d_fft + 2) + 2 * (p.d_fft / 2 + 1) + WB_RED_DOUBLES +
                                     (slow_threads + 1) + (p.n_ap + 2) + 2) * sizeof(double);
 #ifndef WB_EMU

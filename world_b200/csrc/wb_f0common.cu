@@ -712,7 +712,7 @@ WB_KERNEL(256, 4) band_interp_kernel(SweepParams p) {
           mw[q][k] = first_frame_at_or_after(x, p.frame_period);
         }
       }
-      if (tid < 4) used[tid] = 0;
+      for (int q = tid; q < 4; q += nth) used[q] = 0;
       WB_SYNC();
       // interval j (first frame m_j < c1) owns the frames [m_j, m_{j+1}): their count of intervals <= t is j + 1
       for (int q = 0; q < 4; ++q) {

@@ -107,7 +107,9 @@ WB_HD inline int fe_seg_doubles(int max_taps) {   // one input segment: tile + f
   return (WB_FE_T + ((max_taps + WB_FE_R - 1) / WB_FE_R) * WB_FE_R + WB_FE_R + 8) & ~1;
 }
 WB_HD inline size_t fe_smem_bytes(int max_taps) {
-  return (size_t)(2 * fe_seg_doubles(max_taps) + (((max_taps + WB_FE_R - 1) / WB_FE_R) * WB_FE_R + WB_FE_R) + (WB_FE_T + 8) + 48) * 8;
+  // two segments, taps, filtered tile (+ carry), WB_SWEEP_THREADS packed counters + warp totals, two mbarriers
+  return (size_t)(2 * fe_seg_doubles(max_taps) + (((max_taps + WB_FE_R - 1) / WB_FE_R) * WB_FE_R + WB_FE_R) + (WB_FE_T + 8) +
+                  (WB_SWEEP_THREADS + 40) + 8) * 8;
 }
 
 WB_HD inline size_t sweep_smem_bytes(int max_taps) {

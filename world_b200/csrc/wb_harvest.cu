@@ -14,6 +14,7 @@
 #include "wb_internal.h"
 #include "wb_f0common.cuh"
 #include <stdlib.h>
+#include <stdio.h>
 #include <vector>
 
 namespace wb {
@@ -1045,6 +1046,12 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
       launch_band_sweep(ctx, sp, (unsigned)n);
     }
 
+#ifdef WB_EMU
+    if (const char *dump = getenv("WB_DUMP_RAW")) {   // host emulation only: the raw candidate map, for A/B of sweep variants
+      FILE *f = fopen(dump, "wb");
+      if (f) { fwrite(sp.cand, 8, (size_t)n * nb * l1_stride, f); fclose(f); }
+    }
+#endif
     const long long slots = (long long)n * l1_stride;
     HvDetectParams dp;
     dp.raw = sp.cand; dp.n_bands = nb; dp.l1_stride = l1_stride; dp.l1 = l1;

@@ -102,6 +102,19 @@ void rng_fill(const Ctx *ctx, const unsigned *totals_dev, unsigned *out, size_t 
 void scan_counts(const Ctx *ctx, const unsigned *counts, const int *lens_dev, int stride,
                  const unsigned *base, unsigned *offsets, unsigned *totals, int n_utts);
 
+// wb_multi.cu: NCCL communicator behind the C ABI (bound at run time)
+struct Comm;
+int comm_unique_id(unsigned char *id128, std::string *err);
+int comm_create(int n_ranks, int rank, const unsigned char *id128, Comm **out, std::string *err);
+void comm_destroy(Comm *c);
+int comm_ranks(const Comm *c);
+int comm_rank(const Comm *c);
+#ifndef WB_EMU
+int comm_gather_rows(Comm *c, double *full, size_t row_elems, size_t rows_per_rank, size_t row0, size_t rows,
+                     cudaEvent_t after, std::string *err);
+int comm_join(Comm *c, cudaStream_t s, std::string *err);
+#endif
+
 // Device-resident batch: N utterances, padded rows.
 struct Batch {
   const double *x;        // [n][x_stride]
