@@ -199,3 +199,40 @@ def test_gpu_zero_tail_f0(gpu_world, ref):
 
 def test_gpu_mirroring_ripple_cases(gpu_world, ref):
     pc.check_mirroring_ripple_cases(gpu_world, ref)
+
+
+def test_gpu_benchmark_scale_batch(gpu_world, ref):
+    """Parity at the scale the headline number is quoted on: 600 utterances x 10 s @16 kHz through the one-call
+    device path (world_b200_analyze_batch: two utterance slices on two streams, Harvest in its real passes with the
+    edge-list / candidate capacities of 10 s utterances), then the reference's own chain -- its Harvest f0 feeding
+    its CheapTrick and D4C -- on eight utterances including the first and last rows of every slice."""
+    import torch
+    from synth import synth_batch
+    from world_b200 import api
+    fs, n, U = 16000, 160000, 600
+    dev = f"cuda:{gpu_world.device}"
+    x = torch.empty((U, n), dtype=torch.float64, device=dev)
+    for u0 in range(0, U, 50):
+        x[u0:u0 + 50] = synth_batch(range(7001 + u0, 7051 + u0), fs, n, device=dev)
+    opt = gpu_world.analysis_option(fs, api.F0_HARVEST)
+    t, f0, sp, ap, fl = gpu_world.analyze_batch(x, fs, opt)
+    gpu_world.synchronize()
+    assert fl == [2001] * U
+    flips = frames = 0
+    worst = {"f0": 0.0, "sp": 0.0, "ap": 0.0}
+    for u in (0, 1, 150, 299, 300, 301, 450, 599):
+        xu = x[u].cpu().numpy()
+        tr, fr = ref.harvest(xu, fs)
+        o = ref.cheaptrick_option(fs)
+        spr = ref.cheaptrick(xu, fs, tr, fr, o)
+        apr = ref.d4c(xu, fs, tr, fr, o.fft_size)
+        g = f0[u].cpu().numpy()
+        assert np.array_equal(t[u].cpu().numpy(), tr)
+        flips += int(((g > 0) != (fr > 0)).sum())
+        frames += len(fr)
+        worst["f0"] = max(worst["f0"], pc.rel_err(g, fr).max())
+        worst["sp"] = max(worst["sp"], pc.rel_err(sp[u].cpu().numpy(), spr).max())
+        worst["ap"] = max(worst["ap"], pc.rel_err(ap[u].cpu().numpy(), apr).max())
+        assert (fr > 0).sum() > 1000
+    assert flips == 0, f"{flips} V/UV flips in {frames} frames"
+    assert max(worst.values()) <= pc.TOL, worst

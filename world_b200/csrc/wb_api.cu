@@ -541,7 +541,9 @@ static int analyze_batch_impl(WorldB200 *h, const double *x, int n, int x_stride
   }
   const int bins = opt->cheaptrick.fft_size / 2 + 1;
   const double frame_period = opt->f0_method == WORLD_B200_F0_HARVEST ? opt->harvest.frame_period : opt->dio.frame_period;
-  int n_slices = 4;
+  // two slices (one per lane) overlap best on one GPU (profiles/r2d: 861 / 869 / 872 ms for 2 / 4 / 8 slices); with the
+  // gather the exposed tail is the LAST slice's transfer, so more, smaller slices win there
+  int n_slices = gather ? 8 : 2;
   if (const char *e = getenv("WB_LANE_SLICES")) n_slices = atoi(e);
   n_slices = imax(1, imin(n_slices, n));
   WorldB200 *lanes[2] = {h, h};

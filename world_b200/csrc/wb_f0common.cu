@@ -513,152 +513,224 @@ WB_DEV unsigned fe_flags(double a, double bb, double cc, int i, int ylen) {
   return m;
 }
 
-WB_KERNEL(WB_SWEEP_THREADS, 3) band_fir_events_kernel(SweepParams p) {
+// Warp-specialised: warps 0-3 (128 threads) only filter -- tile t+1 while warps 4-7 pick the events of tile t out of
+// the other half of the double-buffered output tile.  The first version ran the two phases one after the other in
+// all eight warps: the FP64 pipe idled through every event phase (57 % busy, profiles/r2f_ncu_band_fir_events_kernel.txt).
+// Hand-over by named barriers (bar.arrive on one side, bar.sync on the other): full[2] filter -> events,
+// empty[2] events -> filter; the input segments arrive by TMA on two mbarriers.
+#define WB_FE_GROUP 128                      // threads per role
+#define WB_FE_TILE (WB_FE_R * WB_FE_GROUP)   // outputs per tile
+#ifndef WB_EMU
+WB_DEV void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+WB_DEV void bar_arrive_named(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+#endif
+
+// FIR of register group g (outputs 9 g .. 9 g + 8 of the tile): the same FMA order as band_sweep_kernel
+WB_DEV void fe_fir_group(const double *seg, const double *hrev, int ntaps, int g, double *st) {
+  const int R = WB_FE_R, base = R * g;
+  double acc[WB_FE_R], win[WB_FE_R];
+  const double *sp = seg + base + R;
+  const double *hp = hrev;
+#pragma unroll
+  for (int r = 0; r < R; ++r) { acc[r] = 0.0; win[r] = seg[base + r]; }
+  for (int j0 = 0; j0 < ntaps; j0 += R, sp += R, hp += R) {
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      const double hj = hp[jj];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fma(hj, win[(r + jj) % WB_FE_R], acc[r]);
+      win[jj] = sp[jj];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) st[base + r] = acc[r];
+}
+
+// the 11 filtered samples group g looks at: positions pos = 9 g + r (relative to n0 - 2) need s[pos .. pos + 2];
+// sample p of that axis is carry[p] for p < 2 (the last two outputs of the previous tile), st[p - 2] otherwise
+WB_DEV void fe_load_group(const double *st, double c0, double c1, int g, double (&v)[WB_FE_R + 2]) {
+  const int base = WB_FE_R * g;
+#pragma unroll
+  for (int k = 0; k < WB_FE_R + 2; ++k) {
+    const int pp = base + k;
+    v[k] = pp >= 2 ? st[pp - 2] : (pp == 0 ? c0 : c1);
+  }
+}
+
+WB_DEV unsigned long long fe_count_group(const double (&v)[WB_FE_R + 2], int i0, int ylen) {
+  unsigned long long c = 0ull;
+#pragma unroll
+  for (int r = 0; r < WB_FE_R; ++r) {
+    const unsigned m = fe_flags(v[r], v[r + 1], v[r + 2], i0 + r, ylen);
+    c += (unsigned long long)(m & 1u) + ((unsigned long long)((m >> 1) & 1u) << 16) +
+         ((unsigned long long)((m >> 2) & 1u) << 32) + ((unsigned long long)((m >> 3) & 1u) << 48);
+  }
+  return c;
+}
+
+// fine edges of group g's events (one division per event), appended in position order at tot[q] + (offsets in o)
+WB_DEV void fe_emit_group(const double (&v)[WB_FE_R + 2], int i0, int ylen, unsigned long long o, const int (&tot)[4],
+                          double *edges, int cap) {
+  int off[4] = {(int)(o & 0xffffull), (int)((o >> 16) & 0xffffull), (int)((o >> 32) & 0xffffull), (int)((o >> 48) & 0xffffull)};
+#pragma unroll
+  for (int r = 0; r < WB_FE_R; ++r) {
+    const double a = v[r], bb = v[r + 1], cc = v[r + 2];
+    unsigned m = fe_flags(a, bb, cc, i0 + r, ylen);
+    while (m) {
+#ifdef WB_EMU
+      const int q = __builtin_ctz(m);
+#else
+      const int q = __ffs((int)m) - 1;
+#endif
+      m &= m - 1u;
+      double e;
+      if (q < 2) {
+        e = (double)(i0 + r + 1) - a / (bb - a);
+      } else {
+        const double d0 = bb - a, d1 = cc - bb;
+        e = (double)(i0 + r + 1) - d0 / (d1 - d0);
+      }
+      const int at = tot[q] + off[q];
+      ++off[q];
+      if (at < cap) edges[(size_t)q * cap + at] = e;
+    }
+  }
+}
+
+WB_KERNEL(2 * WB_FE_GROUP, 3) band_fir_events_kernel(SweepParams p) {
   WB_DYN_SMEM(double, smem);
-  const int tid = WB_TID, nth = WB_NTH;
   const int b = blockIdx.x, u = blockIdx.y;
-  const int T = WB_FE_T, R = WB_FE_R, G = WB_FE_T / WB_FE_R;
+  const int T = WB_FE_TILE, R = WB_FE_R, G = WB_FE_GROUP;
   const int ntaps = p.ntaps[b], shift = p.shift[b];
   const int nt9 = ((ntaps + R - 1) / R) * R;     // taps in whole register rounds; hrev is zero beyond ntaps
   const int segd = fe_seg_doubles(p.max_taps);
   double *segbuf[2] = {smem, smem + segd};
   const int hcap = ((p.max_taps + R - 1) / R) * R + R;
   double *hrev = smem + 2 * segd;                // hcap
-  double *st = hrev + hcap;                      // [0..1] carry, [2..T+2) this tile
-  unsigned long long *cnt = reinterpret_cast<unsigned long long *>(st + (T + 8));   // G packed counters + 33 warp totals
-  unsigned long long *bars = cnt + G + 40;       // two mbarriers
+  double *stbuf[2] = {hrev + hcap, hrev + hcap + (T + 2)};
+  unsigned long long *wtot = reinterpret_cast<unsigned long long *>(stbuf[1] + (T + 2));   // [2][4] warp totals
+  unsigned long long *bars = wtot + 8;           // two mbarriers
   const int ylen = p.y_len[u];
   const size_t abs0 = (size_t)u * p.sig_stride + p.sig_origin;   // index of s(0) in p.sig
   double *edges = p.edges + (size_t)u * p.edge_stride + (size_t)p.edge_off[b];
   const int cap = p.edge_cap[b];
-  for (int j = tid; j < nt9 + R; j += nth) hrev[j] = j < ntaps ? __ldg(&p.taps_rev[p.tap_off[b] + j]) : 0.0;
-  if (tid == 0) { st[0] = 0.0; st[1] = 0.0; }
-  int tot[4] = {0, 0, 0, 0};   // events so far per train (identical in every thread)
   const int n_tiles = (ylen + 2 + T - 1) / T;
   // segment of tile t: seg[i] = s(n0 + shift - ntaps + 1 + i), i < T + nt9 (beyond the filter span the taps are zero;
   // the signal buffer is zero padded, so whatever lies there is finite)
   const int seg_count = (T + nt9 + 2) & ~1;
+  int tot[4] = {0, 0, 0, 0};   // events so far per train
 #ifndef WB_EMU
+  const int tid = threadIdx.x;
+  for (int j = tid; j < nt9 + R; j += blockDim.x) hrev[j] = j < ntaps ? __ldg(&p.taps_rev[p.tap_off[b] + j]) : 0.0;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0 && n_tiles > 0) {
-    const size_t a = abs0 + (size_t)(shift - ntaps + 1);
-    mbar_expect_tx(&bars[0], (unsigned)seg_count * 8u);
-    tma_load_1d(segbuf[0], p.sig + (a & ~(size_t)1), (unsigned)seg_count * 8u, &bars[0]);
+  if (tid < G) {
+    // ---------------------------------------------------------------- filter warps
+    if (tid == 0 && n_tiles > 0) {
+      const size_t a = abs0 + (size_t)(shift - ntaps + 1);
+      mbar_expect_tx(&bars[0], (unsigned)seg_count * 8u);
+      tma_load_1d(segbuf[0], p.sig + (a & ~(size_t)1), (unsigned)seg_count * 8u, &bars[0]);
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+      const size_t a0 = abs0 + (size_t)(t * T + shift - ntaps + 1);
+      // every filter thread has left tile t-1 (bar 5 at its end), whose FIR was the last reader of the other segment
+      if (tid == 0 && t + 1 < n_tiles) {
+        const size_t a1 = a0 + (size_t)T;
+        mbar_expect_tx(&bars[(t + 1) & 1], (unsigned)seg_count * 8u);
+        tma_load_1d(segbuf[(t + 1) & 1], p.sig + (a1 & ~(size_t)1), (unsigned)seg_count * 8u, &bars[(t + 1) & 1]);
+      }
+      mbar_wait(&bars[t & 1], (unsigned)((t >> 1) & 1));
+      if (t >= 2) bar_sync_named(3 + (t & 1), 2 * G);          // the event warps are done with this half (tile t-2)
+      fe_fir_group(segbuf[t & 1] + (a0 & 1), hrev, ntaps, tid, stbuf[t & 1]);
+      __threadfence_block();
+      bar_arrive_named(1 + (t & 1), 2 * G);                    // tile t is ready
+      bar_sync_named(5, G);
+    }
+  } else {
+    // ---------------------------------------------------------------- event warps
+    const int ct = tid - G, lane = ct & 31, w = ct >> 5;
+    double c0 = 0.0, c1 = 0.0;   // carry: only group 0 (positions 0 and 1) ever reads it, and group 0 is this role's thread 0
+    for (int t = 0; t < n_tiles; ++t) {
+      const int n0 = t * T;
+      bar_sync_named(1 + (t & 1), 2 * G);
+      const double *st = stbuf[t & 1];
+      double v[WB_FE_R + 2];
+      fe_load_group(st, c0, c1, ct, v);
+      const int i0 = n0 - 2 + R * ct;
+      const unsigned long long c = fe_count_group(v, i0, ylen);
+      unsigned long long inc = c;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += up;
+      }
+      unsigned long long *wt = wtot + 4 * (t & 1);
+      if (lane == 31) wt[w] = inc;
+      bar_sync_named(6, G);
+      unsigned long long basew = 0ull, all = 0ull;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const unsigned long long x = wt[k]; if (k < w) basew += x; all += x; }
+      fe_emit_group(v, i0, ylen, basew + inc - c, tot, edges, cap);
+      tot[0] += (int)(all & 0xffffull); tot[1] += (int)((all >> 16) & 0xffffull);
+      tot[2] += (int)((all >> 32) & 0xffffull); tot[3] += (int)((all >> 48) & 0xffffull);
+      if (ct == 0) { c0 = st[T - 2]; c1 = st[T - 1]; }
+      __threadfence_block();
+      bar_arrive_named(3 + (t & 1), 2 * G);                    // this half may be overwritten (tile t+2)
+    }
+    if (ct == 0) {
+      int *ec = p.ev_count + ((size_t)u * p.n_bands + b) * 4;
+      bool over = false;
+      for (int q = 0; q < 4; ++q) { ec[q] = tot[q]; over = over || tot[q] > cap; }
+      if (over) {
+        ec[0] = -1;
+        p.redo_list[atomicAdd(p.redo_count, 1)] = u * p.n_bands + b;
+      }
+    }
   }
 #else
-  WB_SYNC();
-#endif
+  // one emulated thread: both roles, tile after tile
+  for (int j = 0; j < nt9 + R; ++j) hrev[j] = j < ntaps ? p.taps_rev[p.tap_off[b] + j] : 0.0;
+  double c0 = 0.0, c1 = 0.0;
   for (int t = 0; t < n_tiles; ++t) {
     const int n0 = t * T;
     const size_t a0 = abs0 + (size_t)(n0 + shift - ntaps + 1);
-#ifndef WB_EMU
-    // every thread has left tile t-1 (barrier at its end), whose FIR was the last reader of the other buffer
-    if (tid == 0 && t + 1 < n_tiles) {
-      const size_t a1 = a0 + (size_t)T;
-      mbar_expect_tx(&bars[(t + 1) & 1], (unsigned)seg_count * 8u);
-      tma_load_1d(segbuf[(t + 1) & 1], p.sig + (a1 & ~(size_t)1), (unsigned)seg_count * 8u, &bars[(t + 1) & 1]);
+    for (int i = 0; i < seg_count; ++i) segbuf[0][i] = p.sig[a0 + i];
+    double *st = stbuf[0];
+    for (int g = 0; g < G; ++g) fe_fir_group(segbuf[0], hrev, ntaps, g, st);
+    unsigned long long run = 0ull;
+    for (int g = 0; g < G; ++g) {
+      double v[WB_FE_R + 2];
+      fe_load_group(st, c0, c1, g, v);
+      const int i0 = n0 - 2 + R * g;
+      fe_emit_group(v, i0, ylen, run, tot, edges, cap);
+      run += fe_count_group(v, i0, ylen);
     }
-    mbar_wait(&bars[t & 1], (unsigned)((t >> 1) & 1));
-    const double *seg = segbuf[t & 1] + (a0 & 1);
-#else
-    for (int i = tid; i < seg_count; i += nth) segbuf[0][i] = p.sig[a0 + i];
-    const double *seg = segbuf[0];
-#endif
-    for (int g = tid; g < G; g += nth) {
-      const int base = R * g;
-      double acc[WB_FE_R], win[WB_FE_R];
-      const double *sp = seg + base + R;
-      const double *hp = hrev;
-#pragma unroll
-      for (int r = 0; r < R; ++r) { acc[r] = 0.0; win[r] = seg[base + r]; }
-      for (int j0 = 0; j0 < ntaps; j0 += R, sp += R, hp += R) {
-#pragma unroll
-        for (int jj = 0; jj < R; ++jj) {
-          const double hj = hp[jj];
-#pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = fma(hj, win[(r + jj) % WB_FE_R], acc[r]);
-          win[jj] = sp[jj];
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r) st[2 + base + r] = acc[r];
-    }
-    WB_SYNC();
-    // ---- events at positions i = n0 - 2 + pos, pos = R g + r (they need s[i], s[i+1], s[i+2])
-    for (int g = tid; g < G; g += nth) {
-      unsigned long long c = 0ull;
-      const int base = R * g;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const unsigned m = fe_flags(st[base + r], st[base + r + 1], st[base + r + 2], n0 - 2 + base + r, ylen);
-        c += (unsigned long long)(m & 1u) + ((unsigned long long)((m >> 1) & 1u) << 16) +
-             ((unsigned long long)((m >> 2) & 1u) << 32) + ((unsigned long long)((m >> 3) & 1u) << 48);
-      }
-      cnt[g] = c;
-    }
-    WB_SYNC();
-    const unsigned long long tile_total = scan_packed(cnt, G, 0ull, cnt + G + 4);
-    // ---- fine edges straight from the detecting thread (one division per event), appended in position order
-    for (int g = tid; g < G; g += nth) {
-      const unsigned long long o = cnt[g];
-      int off[4] = {(int)(o & 0xffffull), (int)((o >> 16) & 0xffffull), (int)((o >> 32) & 0xffffull), (int)((o >> 48) & 0xffffull)};
-      const int base = R * g;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int pos = base + r;
-        const double a = st[pos], bb = st[pos + 1], cc = st[pos + 2];
-        unsigned m = fe_flags(a, bb, cc, n0 - 2 + pos, ylen);
-        while (m) {
-#ifdef WB_EMU
-          const int q = __builtin_ctz(m);
-#else
-          const int q = __ffs((int)m) - 1;
-#endif
-          m &= m - 1u;
-          double v;
-          if (q < 2) {
-            v = (double)(n0 - 2 + pos + 1) - a / (bb - a);
-          } else {
-            const double d0 = bb - a, d1 = cc - bb;
-            v = (double)(n0 - 2 + pos + 1) - d0 / (d1 - d0);
-          }
-          const int at = tot[q] + off[q];
-          ++off[q];
-          if (at < cap) edges[(size_t)q * cap + at] = v;
-        }
-      }
-    }
-    tot[0] += (int)(tile_total & 0xffffull); tot[1] += (int)((tile_total >> 16) & 0xffffull);
-    tot[2] += (int)((tile_total >> 32) & 0xffffull); tot[3] += (int)((tile_total >> 48) & 0xffffull);
-    // positions 0 and 1 of the next tile read st[0], st[1]: only thread 0 (group 0) reads them, so it can move the
-    // carry as soon as its own events are out
-    if (tid == 0) { st[0] = st[T]; st[1] = st[T + 1]; }
-    WB_SYNC();
+    tot[0] += (int)(run & 0xffffull); tot[1] += (int)((run >> 16) & 0xffffull);
+    tot[2] += (int)((run >> 32) & 0xffffull); tot[3] += (int)((run >> 48) & 0xffffull);
+    c0 = st[T - 2]; c1 = st[T - 1];
   }
-  if (tid == 0) {
-    int *ec = p.ev_count + ((size_t)u * p.n_bands + b) * 4;
-    bool over = false;
-    for (int q = 0; q < 4; ++q) { ec[q] = tot[q]; over = over || tot[q] > cap; }
-    if (over) {
-      ec[0] = -1;
-#ifdef WB_EMU
-      const int at = (*p.redo_count)++;
-#else
-      const int at = atomicAdd(p.redo_count, 1);
-#endif
-      p.redo_list[at] = u * p.n_bands + b;
-    }
+  int *ec = p.ev_count + ((size_t)u * p.n_bands + b) * 4;
+  bool over = false;
+  for (int q = 0; q < 4; ++q) { ec[q] = tot[q]; over = over || tot[q] > cap; }
+  if (over) {
+    ec[0] = -1;
+    p.redo_list[(*p.redo_count)++] = u * p.n_bands + b;
   }
+#endif
 }
 
 // ---- edge lists -> candidates
+// One CTA per (utterance, band); rounds of WB_IP_F frames, one frame per thread.  Per round and train a window of
+// intervals starting two before the cursor (the intervals already behind the round) is loaded into shared memory --
+// location x_j, value y_j and m_j = the first frame at or after x_j; its length follows the band (a 64 Hz band has
+// ~16 intervals per 256 ms, an 880 Hz band ~225).  interp1's segment index for frame i is cursor + #{j : m_j <= i}:
+// a binary search over the window's m.  A window that ends inside the round (far more crossings than the band
+// frequency suggests) leaves its last frames to the next iteration of the same round.
 #define WB_IP_F 256     // frames per round
-#define WB_IP_W 256     // intervals per train and window
+#define WB_IP_W 256     // intervals per train and window (capacity)
 struct IpTrain {        // one train of one band: complete edge list in global memory
   const double *e; int n_int; double afs;
 };
@@ -668,8 +740,8 @@ WB_DEV double ip_val(const IpTrain &T, int j) { return T.afs / (T.e[j + 1] - T.e
 WB_KERNEL(256, 4) band_interp_kernel(SweepParams p) {
   WB_SHARED double xw[4][WB_IP_W + 4], yw[4][WB_IP_W + 4];
   WB_SHARED int mw[4][WB_IP_W + 4];
-  WB_SHARED int cnt[4][WB_IP_F];
-  WB_SHARED int used[4];
+  WB_SHARED double vdone[4][WB_IP_F];        // per-train values of the frames already resolved in this round
+  WB_SHARED unsigned char resolved[4][WB_IP_F];
   const int tid = WB_TID, nth = WB_NTH;
   const int b = blockIdx.x, u = blockIdx.y;
   const int *ec = p.ev_count + ((size_t)u * p.n_bands + b) * 4;
@@ -694,70 +766,66 @@ WB_KERNEL(256, 4) band_interp_kernel(SweepParams p) {
     }
     return;
   }
+  // window length of this band: intervals expected per round (band frequency x round duration, both crossing
+  // directions give one train each) + 65 %, at least 24
+  int w_band = (int)(bf * 1.1 * (WB_IP_F * p.frame_period / 1000.0) * 1.65) + 24;
+  if (w_band > WB_IP_W) w_band = WB_IP_W;
   int cursor[4] = {0, 0, 0, 0};   // intervals whose first frame lies before the current round (identical in every thread)
   for (int c0 = 0; c0 < nf; c0 += WB_IP_F) {
     const int c1 = imin(nf, c0 + WB_IP_F);
-    int wbase[4] = {0, 0, 0, 0}, wlen[4] = {0, 0, 0, 0};
-    bool more = true;
     for (int q = 0; q < 4; ++q)
-      for (int i = tid; i < WB_IP_F; i += nth) cnt[q][i] = cursor[q];
-    for (int iter = 0; more; ++iter) {
-      // window of train q: intervals cursor-2 .. cursor+W (two before the cursor serve the frames no new interval reaches)
+      for (int i = tid; i < WB_IP_F; i += nth) resolved[q][i] = 0;
+    bool more = true;
+    while (more) {
+      int wbase[4], wlen[4], k0[4], nk[4];
       for (int q = 0; q < 4; ++q) {
         wbase[q] = imax(0, cursor[q] - 2);
-        wlen[q] = imin(tr[q].n_int - wbase[q], WB_IP_W + 3);
+        k0[q] = cursor[q] - wbase[q];
+        wlen[q] = imin(tr[q].n_int - wbase[q], k0[q] + w_band);
+        nk[q] = wlen[q] - k0[q];                    // intervals at / after the cursor in this window
         for (int k = tid; k < wlen[q]; k += nth) {
           const double x = ip_loc(tr[q], wbase[q] + k);
           xw[q][k] = x; yw[q][k] = ip_val(tr[q], wbase[q] + k);
           mw[q][k] = first_frame_at_or_after(x, p.frame_period);
         }
       }
-      for (int q = tid; q < 4; q += nth) used[q] = 0;
-      WB_SYNC();
-      // interval j (first frame m_j < c1) owns the frames [m_j, m_{j+1}): their count of intervals <= t is j + 1
-      for (int q = 0; q < 4; ++q) {
-        const int k0 = cursor[q] - wbase[q];
-        const int kend = imin(wlen[q], k0 + WB_IP_W);           // intervals examined in this window
-        for (int k = k0 + tid; k < kend; k += nth) {
-          const int m = mw[q][k];
-          if (m >= c1) continue;
-          const int m_next = (k + 1 < wlen[q]) ? mw[q][k + 1] : 0x7fffffff;   // beyond the window only when the list ends
-          for (int i = imax(m, c0); i < imin(m_next, c1); ++i) cnt[q][i - c0] = wbase[q] + k + 1;
-          if (k + 1 == kend || mw[q][k + 1] >= c1) used[q] = k + 1 - k0;      // the last interval consumed by this round
-        }
-      }
       WB_SYNC();
       more = false;
+      int consumed[4];
       for (int q = 0; q < 4; ++q) {
-        const int k0 = cursor[q] - wbase[q];
-        const int examined = imin(wlen[q], k0 + WB_IP_W) - k0;
-        const int un = used[q];
-        cursor[q] += un;
-        if (un == examined && examined == WB_IP_W && cursor[q] < tr[q].n_int) more = true;   // window exhausted inside the round
+        // intervals of the window that start before the end of the round (sorted: lower bound of c1)
+        int lo = 0, hi = nk[q];
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (mw[q][k0[q] + mid] < c1) lo = mid + 1; else hi = mid; }
+        consumed[q] = lo;
+        if (lo == nk[q] && wbase[q] + wlen[q] < tr[q].n_int) more = true;   // the window ended inside the round
       }
-      WB_SYNC();   // `used` and the windows are rewritten by the next iteration
-    }
-    // shared memory holds the windows of the LAST iteration (wbase / wlen); anything outside comes from the lists
-    for (int i = c0 + tid; i < c1; i += nth) {
-      const double t = i * p.frame_period / 1000.0;
-      double v[4];
+      for (int i = c0 + tid; i < c1; i += nth) {
+        const double t = i * p.frame_period / 1000.0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int k = imin(tr[q].n_int - 1, imax(1, cnt[q][i - c0]));   // interp1's segment (matlabfunctions.cpp:157-176)
-        double x0, x1, y0, y1;
-        const int w0 = k - 1 - wbase[q];
-        if (w0 >= 0 && w0 + 1 < wlen[q]) {
-          x0 = xw[q][w0]; x1 = xw[q][w0 + 1]; y0 = yw[q][w0]; y1 = yw[q][w0 + 1];
-        } else {
-          x0 = ip_loc(tr[q], k - 1); x1 = ip_loc(tr[q], k);
-          y0 = ip_val(tr[q], k - 1); y1 = ip_val(tr[q], k);
+        for (int q = 0; q < 4; ++q) {
+          if (resolved[q][i - c0]) continue;
+          int lo = 0, hi = nk[q];                   // #{k : m_k <= i} among the window's intervals at / after the cursor
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (mw[q][k0[q] + mid] <= i) lo = mid + 1; else hi = mid; }
+          if (lo == nk[q] && wbase[q] + wlen[q] < tr[q].n_int) continue;   // may continue in the next window
+          const int k = imin(tr[q].n_int - 1, imax(1, cursor[q] + lo));   // interp1's segment (matlabfunctions.cpp:157-176)
+          double x0, x1, y0, y1;
+          const int w0 = k - 1 - wbase[q];
+          if (w0 >= 0 && w0 + 1 < wlen[q]) {
+            x0 = xw[q][w0]; x1 = xw[q][w0 + 1]; y0 = yw[q][w0]; y1 = yw[q][w0 + 1];
+          } else {
+            x0 = ip_loc(tr[q], k - 1); x1 = ip_loc(tr[q], k);
+            y0 = ip_val(tr[q], k - 1); y1 = ip_val(tr[q], k);
+          }
+          const double s = (t - x0) / (x1 - x0);
+          vdone[q][i - c0] = y0 + s * (y1 - y0);
+          resolved[q][i - c0] = 1;
         }
-        const double s = (t - x0) / (x1 - x0);
-        v[q] = y0 + s * (y1 - y0);
       }
-      sweep_store_candidate(p, v[0], v[1], v[2], v[3], i, bf, cand, score);
+      for (int q = 0; q < 4; ++q) cursor[q] += consumed[q];
+      WB_SYNC();   // the windows are rewritten by the next iteration / round
     }
-    WB_SYNC();
+    for (int i = c0 + tid; i < c1; i += nth)
+      sweep_store_candidate(p, vdone[0][i - c0], vdone[1][i - c0], vdone[2][i - c0], vdone[3][i - c0], i, bf, cand, score);
   }
 }
 

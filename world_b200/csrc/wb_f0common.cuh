@@ -99,17 +99,17 @@ struct SweepParams {
   int *redo_list; int *redo_count;   // (utterance * n_bands + band) pairs for the streaming kernel (history rings)
 };
 
-// outputs per tile of band_fir_events_kernel: 9 per thread, so that consecutive threads walk shared memory with a
-// stride of 9 doubles -- conflict free WITHOUT padding, which lets the input segment arrive as one TMA bulk copy
+// band_fir_events_kernel: 9 outputs per thread, so that consecutive threads walk shared memory with a stride of 9
+// doubles -- conflict free WITHOUT padding, which lets the input segment arrive as one TMA bulk copy.  128 filter
+// threads -> tiles of 1152 outputs; two input segments (TMA double buffer) and two output tiles (filter / event warps).
 #define WB_FE_R 9
-#define WB_FE_T (WB_FE_R * WB_SWEEP_THREADS)
 WB_HD inline int fe_seg_doubles(int max_taps) {   // one input segment: tile + filter span + slack, even
-  return (WB_FE_T + ((max_taps + WB_FE_R - 1) / WB_FE_R) * WB_FE_R + WB_FE_R + 8) & ~1;
+  return (WB_FE_R * 128 + ((max_taps + WB_FE_R - 1) / WB_FE_R) * WB_FE_R + WB_FE_R + 8) & ~1;
 }
 WB_HD inline size_t fe_smem_bytes(int max_taps) {
-  // two segments, taps, filtered tile (+ carry), WB_SWEEP_THREADS packed counters + warp totals, two mbarriers
-  return (size_t)(2 * fe_seg_doubles(max_taps) + (((max_taps + WB_FE_R - 1) / WB_FE_R) * WB_FE_R + WB_FE_R) + (WB_FE_T + 8) +
-                  (WB_SWEEP_THREADS + 40) + 8) * 8;
+  // two segments, taps, two filtered tiles, 2 x 4 warp totals, two mbarriers
+  return (size_t)(2 * fe_seg_doubles(max_taps) + (((max_taps + WB_FE_R - 1) / WB_FE_R) * WB_FE_R + WB_FE_R) +
+                  2 * (WB_FE_R * 128 + 2) + 8 + 2 + 6) * 8;
 }
 
 WB_HD inline size_t sweep_smem_bytes(int max_taps) {
