@@ -87,7 +87,7 @@ WB_KERNEL(128, 8) ct_frame_kernel(CtParams p) {
   double sq = 0.0;
   for (int j = tid; j < nwin; j += nth) {
     const double pos = (j - h) / 1.5 / fs;
-    const double w = 0.5 * cos(kPi * pos * f) + 0.5;
+    const double w = 0.5 * cos_small(kPi * pos * f) + 0.5;
     wv[j] = w;
     sq += w * w;
   }
@@ -115,7 +115,7 @@ WB_KERNEL(128, 8) ct_frame_kernel(CtParams p) {
   double *pw = reinterpret_cast<double *>(o);
   rfft_unpack(z, p.lg_fft, p.tw, [&](int k, double2 c) { pw[k] = c.x * c.x + c.y * c.y; });
   WB_SYNC();
-  dc_correction(pw, f, fs, N, reinterpret_cast<double *>(z));
+  dc_correction<true>(pw, f, fs, N, reinterpret_cast<double *>(z));
   if (!linear_smoothing<true>(pw, f * 2.0 / 3.0, fs, N, pw, reinterpret_cast<double *>(z), red)) {
     if (tid == 0) atomicOr_status(p.status, 2);
     return;

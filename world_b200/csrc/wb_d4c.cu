@@ -65,10 +65,11 @@ WB_DEV int d4c_windowed(const double *__restrict__ x, int x_len, int fs, double 
   for (int j = tid; j < nwin; j += nth) {
     const double position = (2.0 * (j - h) / ratio) / fs;
     double w;
+    const double c1 = cos_small(kPi * position * f);
     if (window_type == 1)
-      w = 0.5 * cos(kPi * position * f) + 0.5;
+      w = 0.5 * c1 + 0.5;
     else
-      w = 0.42 + 0.5 * cos(kPi * position * f) + 0.08 * cos(kPi * position * f * 2);
+      w = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);   // cos(2a) = 2 cos(a)^2 - 1
     const int idx = imin(x_len - 1, imax(0, origin + j - h));
     const double v = x[idx] * w + randn_value(draw[j]) * 0.000001;  // kSafeGuardD4C
     *pv(j) = v;
@@ -447,7 +448,7 @@ WB_DEV void d4c_body_frame(const D4cParams &p) {
     const double x1 = (idx == nx - 1) ? fs / 2.0 : idx * 3000.0;
     const double s = (xi - x0) / (x1 - x0);
     const double y = coarse[idx - 1] + s * (coarse[idx] - coarse[idx - 1]);
-    row[k] = pow(10.0, y / 20.0);
+    row[k] = exp(y * 0.11512925464970228420);   // 10^(y/20) = e^(y ln10 / 20)
   }
 }
 

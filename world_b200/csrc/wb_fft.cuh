@@ -270,7 +270,7 @@ WB_DEV void sfft_pass2(const double2 *src, double2 *dst, int n, int lgp, const d
 // Forward complex FFT of the 2^lg values in padded buffer `a` (natural order); `b` is a second padded buffer of
 // the same size.  Both are clobbered; returns the one that holds the result (natural order, padded).  The caller
 // must have made `a` visible (barrier) before the call; ends with a barrier.
-WB_DEV double2 *sfft_forward(double2 *a, double2 *b, int lg, const double2 *__restrict__ tw) {
+WB_DEV_NOINLINE double2 *sfft_forward(double2 *a, double2 *b, int lg, const double2 *__restrict__ tw) {
   const int n = 1 << lg;
   double2 *src = a, *dst = b;
   int lgp = 0;
@@ -297,7 +297,7 @@ WB_DEV double2 *sfft_forward(double2 *a, double2 *b, int lg, const double2 *__re
 // registers -- load, barrier, butterflies + store, barrier.  Two barriers per pass instead of one, half the shared
 // memory (more CTAs per SM for the barrier-heavy frame kernels).  Needs 2^lg <= 8 * blockDim.x.  Natural order in,
 // natural order out, result in `a`; the caller must have made `a` visible; ends with a barrier.
-WB_DEV void sfft_forward_inplace(double2 *a, int lg, const double2 *__restrict__ tw) {
+WB_DEV_NOINLINE void sfft_forward_inplace(double2 *a, int lg, const double2 *__restrict__ tw) {
 #ifdef WB_EMU
   // one emulated thread: run the ping-pong passes against a scratch buffer (same arithmetic), copy back
   static double2 tmp[WB_FPAD_SLOTS(WB_TW_N)];

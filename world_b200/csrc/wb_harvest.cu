@@ -13,6 +13,7 @@
 // FixF0 reads (same linear functional).
 #include "wb_internal.h"
 #include "wb_f0common.cuh"
+#include "wb_spectral.cuh"
 #include <stdlib.h>
 #include <stdio.h>
 #include <vector>
@@ -137,27 +138,6 @@ WB_DEV double2 hv_tw(const double2 *__restrict__ tw, int idx) {
   return w;
 }
 
-// cos(theta) for |theta| <= ~3.3 (the Blackman window argument never leaves [-pi(1+1/(2h+1)), +...]):
-// cos = 1 - 2 sin^2(theta/2), sin by its Taylor series to x^25 (|x| <= 1.65: truncation < 1e-20).
-// ~16 FP64 operations instead of the ~45 of the general-purpose cos(); accuracy ~2 ulp.
-WB_DEV double hv_cos_small(double theta) {
-  const double x = 0.5 * theta, x2 = x * x;
-  double p = -1.0 / 15511210043330985984000000.0;             // -1/25!
-  p = fma(p, x2, 1.0 / 25852016738884976640000.0);            // +1/23!
-  p = fma(p, x2, -1.0 / 51090942171709440000.0);              // -1/21!
-  p = fma(p, x2, 1.0 / 121645100408832000.0);                 // +1/19!
-  p = fma(p, x2, -1.0 / 355687428096000.0);                   // -1/17!
-  p = fma(p, x2, 1.0 / 1307674368000.0);                      // +1/15!
-  p = fma(p, x2, -1.0 / 6227020800.0);                        // -1/13!
-  p = fma(p, x2, 1.0 / 39916800.0);                           // +1/11!
-  p = fma(p, x2, -1.0 / 362880.0);                            // -1/9!
-  p = fma(p, x2, 1.0 / 5040.0);                               // +1/7!
-  p = fma(p, x2, -1.0 / 120.0);                               // -1/5!
-  p = fma(p, x2, 1.0 / 6.0);                                  // +1/3!  (sign folded below)
-  const double sn = x - x * x2 * p;                           // sin(x) = x - x^3/3! + x^5/5! - ...
-  return 1.0 - 2.0 * sn * sn;
-}
-
 // GetRefinedF0 (harvest.cpp:589-617) for one candidate, executed by one warp.
 // wbuf / xbuf / dbuf: per-warp shared scratch of nwin doubles each (window, x*window, x*dwindow).
 // Loops are unrolled by four independent iterations per lane to keep several cosines / table
@@ -187,7 +167,7 @@ WB_DEV void hv_refine_one(const double *__restrict__ y, int y_len, double afs, d
       const int j = j0 + q * WB_LANES + lane;
       if (j < nwin) {
         const double tmp = ((basic + j) - 1.0) * inv_afs - t;
-        const double c1 = hv_cos_small(w_scale * tmp);
+        const double c1 = cos_small(w_scale * tmp);
         wbuf[j] = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
       }
     }
@@ -435,7 +415,7 @@ WB_KERNEL(32 * WB_HV_WARPS, 4) harvest_refine_chain_kernel(HvChainParams cp) {
       for (int i = l; i < nseg; i += 32) xs[i] = y[imax(0, imin(y_len - 1, basic0 + i - 1))];
       for (int i = l; i < nwin; i += 32) {
         const double tau = (i - h - 1.0) * inv_afs;
-        const double c1 = hv_cos_small(w_scale * tau);
+        const double c1 = cos_small(w_scale * tau);
         wbuf[i] = 0.42 + 0.5 * c1 + 0.08 * (2.0 * c1 * c1 - 1.0);
       }
     }
