@@ -19,7 +19,7 @@
 #include <cuda_runtime.h>
 #define WB_HD __host__ __device__
 #define WB_DEV __device__ __forceinline__
-#define WB_DEV_NOINLINE __device__ __noinline__   /* one copy per kernel: big helpers called from several places */
+#define WB_DEV_NOINLINE static __device__ __noinline__   /* one copy per kernel: big helpers called from several places */
 #define WB_DEV_MEMBER __device__ __forceinline__
 #define WB_KERNEL(bounds_threads, bounds_blocks) \
   __global__ void __launch_bounds__(bounds_threads, bounds_blocks)
