@@ -137,15 +137,17 @@ WB_KERNEL(128, 8) ct_frame_kernel(CtParams p) {
   {
     double *zin = reinterpret_cast<double *>(o2);
     const double q1 = p.q1;
+    // the lifters only scale floating-point values: quefrency through reciprocals, sin(pi a) by sinpi, 1/N exactly
+    const double f_over_fs = f / fs, inv_n = 1.0 / N;
     rfft_unpack(z2, p.lg_fft, p.tw, [&](int k, double2 c) {
       double sl = 1.0, cl = (1.0 - 2.0 * q1) + 2.0 * q1;
       if (k > 0) {
-        const double quef = static_cast<double>(k) / fs;
-        const double sn = sin(kPi * f * quef);
-        sl = sn / (kPi * f * quef);
+        const double a = f_over_fs * k;          // f * quefrency
+        const double sn = sinpi(a);
+        sl = sn / (kPi * a);
         cl = (1.0 - 2.0 * q1) + 2.0 * q1 * (1.0 - 2.0 * sn * sn);
       }
-      const double v = c.x * sl * cl / N;
+      const double v = c.x * sl * cl * inv_n;
       zin[rpad(k)] = v;
       if (k > 0 && k < half) zin[rpad(N - k)] = v;
     });

@@ -200,9 +200,9 @@ WB_DEV double select_kth_largest(const double *a, int n, int kth, double *red) {
 // The same order statistic through a short candidate list (GPU only; round 1's bisection -- 32 rounds over all n
 // values with a barrier each -- was a quarter of the body kernel's instructions, profiles/r2c_ncu_d4c_body_kernel.txt):
 //   1. every thread takes the maximum of the values it owns (a[tid], a[tid + nth], ...);
-//   2. L = the kth largest of those nth maxima is a lower bound of the answer (the kth largest maxima are kth
-//      distinct elements >= L), and for spectra -- no long runs of equal values -- only a few more than kth elements
-//      reach it;
+//   2. L = the kth largest of those maxima (of 32 maxima over four threads each when kth <= 32) is a lower bound of
+//      the answer (the kth largest maxima are kth distinct elements >= L), and for spectra -- no long runs of equal
+//      values -- only a few more than kth elements reach it;
 //   3. the elements >= L are collected (shared-memory counter) and ranked against each other exactly.
 // Comparisons run on the IEEE bit patterns (a total order on the non-negative values, ties broken by index), so the
 // value returned is the one the bisection returns.  Returns false to every thread -- nothing useful in *out -- when
@@ -226,7 +226,21 @@ WB_DEV bool select_kth_largest_fast(const double *a, int n, int kth, unsigned lo
   scratch[tid] = mx;
   if (tid == 0) *counter = 0u;
   __syncthreads();
-  {
+  if (kth <= 32) {
+    // 32 maxima (lane l of warp 0: the threads l, l + 32, ...) are enough for a lower bound when kth <= 32: the bound
+    // is a little lower, a few more elements pass it, and the ranking is 32 shuffles in one warp instead of nth
+    // shared-memory reads in every thread
+    if (tid < 32) {
+      unsigned long long m32 = 0ull;
+      for (int t = tid; t < nth; t += 32) { const unsigned long long kt = scratch[t]; m32 = kt > m32 ? kt : m32; }
+      int r = 0;
+      for (int t = 0; t < 32; ++t) {
+        const unsigned long long kt = __shfl_sync(0xffffffffu, m32, t);
+        r += (kt > m32 || (kt == m32 && t < tid)) ? 1 : 0;
+      }
+      if (r == kth - 1) scratch[nth] = m32;
+    }
+  } else {
     int r = 0;
     for (int t = 0; t < nth; ++t) {
       const unsigned long long kt = scratch[t];

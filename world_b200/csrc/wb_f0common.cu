@@ -597,7 +597,7 @@ WB_DEV void fe_emit_group(const double (&v)[WB_FE_R + 2], int i0, int ylen, unsi
   }
 }
 
-WB_KERNEL(2 * WB_FE_GROUP, 3) band_fir_events_kernel(SweepParams p) {
+WB_KERNEL(2 * WB_FE_GROUP, 4) band_fir_events_kernel(SweepParams p) {
   WB_DYN_SMEM(double, smem);
   const int b = blockIdx.x, u = blockIdx.y;
   const int T = WB_FE_TILE, R = WB_FE_R, G = WB_FE_GROUP;
@@ -739,9 +739,8 @@ WB_DEV double ip_val(const IpTrain &T, int j) { return T.afs / (T.e[j + 1] - T.e
 
 WB_KERNEL(256, 4) band_interp_kernel(SweepParams p) {
   WB_SHARED double xw[4][WB_IP_W + 4], yw[4][WB_IP_W + 4];
-  WB_SHARED int mw[4][WB_IP_W + 4];
-  WB_SHARED double vdone[4][WB_IP_F];        // per-train values of the frames already resolved in this round
-  WB_SHARED unsigned char resolved[4][WB_IP_F];
+  WB_SHARED unsigned long long marks[WB_IP_F + 40];   // per frame: intervals whose first frame it is, 4 x 16 bit; + scan scratch
+  WB_SHARED unsigned long long orig[WB_IP_F];
   const int tid = WB_TID, nth = WB_NTH;
   const int b = blockIdx.x, u = blockIdx.y;
   const int *ec = p.ev_count + ((size_t)u * p.n_bands + b) * 4;
@@ -766,66 +765,70 @@ WB_KERNEL(256, 4) band_interp_kernel(SweepParams p) {
     }
     return;
   }
-  // window length of this band: intervals expected per round (band frequency x round duration, both crossing
-  // directions give one train each) + 65 %, at least 24
+  // window length of this band: intervals expected per round (band frequency x round duration) + 65 %, at least 24
   int w_band = (int)(bf * 1.1 * (WB_IP_F * p.frame_period / 1000.0) * 1.65) + 24;
   if (w_band > WB_IP_W) w_band = WB_IP_W;
   int cursor[4] = {0, 0, 0, 0};   // intervals whose first frame lies before the current round (identical in every thread)
   for (int c0 = 0; c0 < nf; c0 += WB_IP_F) {
     const int c1 = imin(nf, c0 + WB_IP_F);
-    for (int q = 0; q < 4; ++q)
-      for (int i = tid; i < WB_IP_F; i += nth) resolved[q][i] = 0;
+    for (int i = tid; i < WB_IP_F; i += nth) marks[i] = 0ull;
+    int at[4] = {cursor[0], cursor[1], cursor[2], cursor[3]};   // first interval not yet examined in this round
+    int wbase[4] = {0, 0, 0, 0}, wlen[4] = {0, 0, 0, 0};
+    WB_SYNC();
     bool more = true;
     while (more) {
-      int wbase[4], wlen[4], k0[4], nk[4];
+      // windows: two intervals before the examined range serve the frames no new interval reaches
       for (int q = 0; q < 4; ++q) {
-        wbase[q] = imax(0, cursor[q] - 2);
-        k0[q] = cursor[q] - wbase[q];
-        wlen[q] = imin(tr[q].n_int - wbase[q], k0[q] + w_band);
-        nk[q] = wlen[q] - k0[q];                    // intervals at / after the cursor in this window
+        wbase[q] = imax(0, at[q] - 2);
+        const int k0 = at[q] - wbase[q];
+        wlen[q] = imin(tr[q].n_int - wbase[q], k0 + w_band);
         for (int k = tid; k < wlen[q]; k += nth) {
           const double x = ip_loc(tr[q], wbase[q] + k);
           xw[q][k] = x; yw[q][k] = ip_val(tr[q], wbase[q] + k);
-          mw[q][k] = first_frame_at_or_after(x, p.frame_period);
+          if (k >= k0) {   // interval (wbase + k) is counted by every frame from its first frame on
+            const int m = first_frame_at_or_after(x, p.frame_period);
+            if (m < c1) smem_add_u64(&marks[imax(m, c0) - c0], 1ull << (16 * q));
+          }
         }
       }
       WB_SYNC();
+      // a window whose LAST interval still starts inside the round may be followed by more of them: examine the next window
       more = false;
-      int consumed[4];
       for (int q = 0; q < 4; ++q) {
-        // intervals of the window that start before the end of the round (sorted: lower bound of c1)
-        int lo = 0, hi = nk[q];
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (mw[q][k0[q] + mid] < c1) lo = mid + 1; else hi = mid; }
-        consumed[q] = lo;
-        if (lo == nk[q] && wbase[q] + wlen[q] < tr[q].n_int) more = true;   // the window ended inside the round
+        const int last = wbase[q] + wlen[q] - 1;     // last interval loaded
+        at[q] = last + 1;
+        if (wlen[q] > 0 && last + 1 < tr[q].n_int && first_frame_at_or_after(xw[q][wlen[q] - 1], p.frame_period) < c1) more = true;
       }
-      for (int i = c0 + tid; i < c1; i += nth) {
-        const double t = i * p.frame_period / 1000.0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (resolved[q][i - c0]) continue;
-          int lo = 0, hi = nk[q];                   // #{k : m_k <= i} among the window's intervals at / after the cursor
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (mw[q][k0[q] + mid] <= i) lo = mid + 1; else hi = mid; }
-          if (lo == nk[q] && wbase[q] + wlen[q] < tr[q].n_int) continue;   // may continue in the next window
-          const int k = imin(tr[q].n_int - 1, imax(1, cursor[q] + lo));   // interp1's segment (matlabfunctions.cpp:157-176)
-          double x0, x1, y0, y1;
-          const int w0 = k - 1 - wbase[q];
-          if (w0 >= 0 && w0 + 1 < wlen[q]) {
-            x0 = xw[q][w0]; x1 = xw[q][w0 + 1]; y0 = yw[q][w0]; y1 = yw[q][w0 + 1];
-          } else {
-            x0 = ip_loc(tr[q], k - 1); x1 = ip_loc(tr[q], k);
-            y0 = ip_val(tr[q], k - 1); y1 = ip_val(tr[q], k);
-          }
-          const double s = (t - x0) / (x1 - x0);
-          vdone[q][i - c0] = y0 + s * (y1 - y0);
-          resolved[q][i - c0] = 1;
-        }
-      }
-      for (int q = 0; q < 4; ++q) cursor[q] += consumed[q];
-      WB_SYNC();   // the windows are rewritten by the next iteration / round
+      if (more) WB_SYNC();   // the windows are rewritten
     }
-    for (int i = c0 + tid; i < c1; i += nth)
-      sweep_store_candidate(p, vdone[0][i - c0], vdone[1][i - c0], vdone[2][i - c0], vdone[3][i - c0], i, bf, cand, score);
+    // inclusive counts per frame: exclusive scan + the frame's own marks
+    for (int i = tid; i < WB_IP_F; i += nth) orig[i] = marks[i];
+    WB_SYNC();
+    const unsigned long long all = scan_packed(marks, WB_IP_F, 0ull, marks + WB_IP_F + 4);
+    for (int i = c0 + tid; i < c1; i += nth) {
+      const unsigned long long inc = marks[i - c0] + orig[i - c0];
+      const double t = i * p.frame_period / 1000.0;
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int cnt = cursor[q] + (int)((inc >> (16 * q)) & 0xffffull);
+        const int k = imin(tr[q].n_int - 1, imax(1, cnt));   // interp1's segment (matlabfunctions.cpp:157-176)
+        double x0, x1, y0, y1;
+        const int w0 = k - 1 - wbase[q];
+        if (w0 >= 0 && w0 + 1 < wlen[q]) {
+          x0 = xw[q][w0]; x1 = xw[q][w0 + 1]; y0 = yw[q][w0]; y1 = yw[q][w0 + 1];
+        } else {
+          x0 = ip_loc(tr[q], k - 1); x1 = ip_loc(tr[q], k);
+          y0 = ip_val(tr[q], k - 1); y1 = ip_val(tr[q], k);
+        }
+        const double s = (t - x0) / (x1 - x0);
+        v[q] = y0 + s * (y1 - y0);
+      }
+      sweep_store_candidate(p, v[0], v[1], v[2], v[3], i, bf, cand, score);
+    }
+    cursor[0] += (int)(all & 0xffffull); cursor[1] += (int)((all >> 16) & 0xffffull);
+    cursor[2] += (int)((all >> 32) & 0xffffull); cursor[3] += (int)((all >> 48) & 0xffffull);
+    WB_SYNC();
   }
 }
 

@@ -270,7 +270,7 @@ WB_DEV void sfft_pass2(const double2 *src, double2 *dst, int n, int lgp, const d
 // Forward complex FFT of the 2^lg values in padded buffer `a` (natural order); `b` is a second padded buffer of
 // the same size.  Both are clobbered; returns the one that holds the result (natural order, padded).  The caller
 // must have made `a` visible (barrier) before the call; ends with a barrier.
-WB_DEV_NOINLINE double2 *sfft_forward(double2 *a, double2 *b, int lg, const double2 *__restrict__ tw) {
+WB_DEV double2 *sfft_forward(double2 *a, double2 *b, int lg, const double2 *__restrict__ tw) {
   const int n = 1 << lg;
   double2 *src = a, *dst = b;
   int lgp = 0;

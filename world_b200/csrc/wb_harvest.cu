@@ -1038,6 +1038,12 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
     dp.base = (double *)(blk + o_base); dp.base_count = (int *)(blk + o_bcnt); dp.nc = nc; dp.n_utts = n;
     WB_LAUNCH_FLAT(harvest_detect_kernel, dim3((unsigned)((slots + 127) / 128)), 128, 0, ctx->stream, dp);
 
+#ifdef WB_EMU
+    if (const char *dump = getenv("WB_DUMP_BASE")) {   // host emulation only: base candidates per 1 ms frame (experiments)
+      FILE *f = fopen(dump, "wb");
+      if (f) { fwrite(dp.base, 8, (size_t)n * l1_stride * WB_HV_BASE, f); fclose(f); }
+    }
+#endif
     HvRefineParams rp;
     rp.y = y; rp.y_stride = y_stride; rp.y_origin = padl; rp.y_len = ylen; rp.afs = afs;
     rp.base = dp.base; rp.nc = nc; rp.l1_stride = l1_stride; rp.l1 = l1; rp.max_cand = max_cand;
