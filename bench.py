@@ -215,6 +215,12 @@ def algorithmic_bytes_per_step(kernel, a, n_utts):
         # decimated waveform once + the candidate map it produces (152 channels x 1 ms frames)
         "band_sweep_kernel": n_utts * (ylen * 8 + (152 if a.f0 == "harvest" else 7) * (L1 if a.f0 == "harvest" else L) * 8),
         "band_sweep_ripple_kernel": n_utts * (ylen * 8 + (152 if a.f0 == "harvest" else 7) * (L1 if a.f0 == "harvest" else L) * 8),
+        # split sweep: decimated waveform once per band (L2 hits) + complete edge lists out; lists in, candidate map out
+        "band_fir_events_kernel": n_utts * (ylen * 8 + 152 * L1 * 8),
+        "band_interp_kernel": n_utts * 152 * L1 * 8,
+        "band_sweep_list_kernel": 0,
+        "harvest_refine_chain_o5_kernel": n_utts * (ylen * 8 + L1 * 21 * 16),
+        "d4c_body_slow_kernel": 0,
         "nyquist_bins_kernel": n_utts * ylen * 8,
         "harvest_refine_chain_kernel": n_utts * (ylen * 8 + L1 * 21 * 16),
         # candidate map in, refined candidates + scores out (upper bound 105 slots)

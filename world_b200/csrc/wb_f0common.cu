@@ -498,21 +498,6 @@ WB_DEV void mbar_wait(unsigned long long *bar, unsigned parity) {
 }
 #endif
 
-// event flags of position pos (relative to n0 - 2) from three consecutive filtered samples: bit q = train q
-WB_DEV unsigned fe_flags(double a, double bb, double cc, int i, int ylen) {
-  unsigned m = 0u;
-  const double d0 = bb - a, d1 = cc - bb;
-  if (i >= 0 && i + 1 <= ylen - 1) {
-    if (0.0 < a && bb <= 0.0) m |= 1u;
-    if (a < 0.0 && 0.0 <= bb) m |= 2u;
-  }
-  if (i >= 0 && i + 1 <= ylen - 2) {
-    if (0.0 < d0 && d1 <= 0.0) m |= 4u;
-    if (d0 < 0.0 && 0.0 <= d1) m |= 8u;
-  }
-  return m;
-}
-
 // Warp-specialised: warps 0-3 (128 threads) only filter -- tile t+1 while warps 4-7 pick the events of tile t out of
 // the other half of the double-buffered output tile.  The first version ran the two phases one after the other in
 // all eight warps: the FP64 pipe idled through every event phase (57 % busy, profiles/r2f_ncu_band_fir_events_kernel.txt).
@@ -557,43 +542,74 @@ WB_DEV void fe_load_group(const double *st, double c0, double c1, int g, double 
   }
 }
 
-WB_DEV unsigned long long fe_count_group(const double (&v)[WB_FE_R + 2], int i0, int ylen) {
-  unsigned long long c = 0ull;
+// sign tests on the bit pattern (integer pipe; DSETP would queue behind the filter's DFMAs on the FP64 pipe):
+// v > 0 <=> pattern > 0 as a signed integer; v < 0 <=> sign bit set and not -0.0.  (NaN never occurs here.)
+WB_DEV long long fe_bits(double v) {
+#ifdef WB_EMU
+  long long b; memcpy(&b, &v, 8); return b;
+#else
+  return __double_as_longlong(v);
+#endif
+}
+WB_DEV bool fe_pos(long long b) { return b > 0; }
+WB_DEV bool fe_neg(long long b) { return b < 0 && b != (long long)0x8000000000000000ull; }
+
+// Events of group g: 4 flag bits per position (bit q = train q, position r at bits 4 r .. 4 r + 3) and the packed
+// per-train counts.  `edge` = the tile touches the ends of the signal (positions before sample 0 / after the last
+// pair are not events); interior tiles skip those tests.
+WB_DEV unsigned long long fe_mask_group(const double (&v)[WB_FE_R + 2], int i0, int ylen, bool edge, unsigned long long *counts) {
+  long long sb[WB_FE_R + 2], db[WB_FE_R + 1];
+#pragma unroll
+  for (int k = 0; k < WB_FE_R + 2; ++k) sb[k] = fe_bits(v[k]);
+#pragma unroll
+  for (int k = 0; k < WB_FE_R + 1; ++k) db[k] = fe_bits(v[k + 1] - v[k]);
+  unsigned long long mask = 0ull, c = 0ull;
 #pragma unroll
   for (int r = 0; r < WB_FE_R; ++r) {
-    const unsigned m = fe_flags(v[r], v[r + 1], v[r + 2], i0 + r, ylen);
+    unsigned m = 0u;
+    if (fe_pos(sb[r]) && !fe_pos(sb[r + 1])) m |= 1u;   // s[i] > 0 >= s[i+1]
+    if (fe_neg(sb[r]) && !fe_neg(sb[r + 1])) m |= 2u;   // s[i] < 0 <= s[i+1]
+    if (fe_pos(db[r]) && !fe_pos(db[r + 1])) m |= 4u;   // d[i] > 0 >= d[i+1]
+    if (fe_neg(db[r]) && !fe_neg(db[r + 1])) m |= 8u;   // d[i] < 0 <= d[i+1]
+    if (edge) {
+      const int i = i0 + r;
+      if (!(i >= 0 && i + 1 <= ylen - 1)) m &= ~3u;
+      if (!(i >= 0 && i + 1 <= ylen - 2)) m &= ~12u;
+    }
+    mask |= (unsigned long long)m << (4 * r);
     c += (unsigned long long)(m & 1u) + ((unsigned long long)((m >> 1) & 1u) << 16) +
          ((unsigned long long)((m >> 2) & 1u) << 32) + ((unsigned long long)((m >> 3) & 1u) << 48);
   }
-  return c;
+  *counts = c;
+  return mask;
 }
 
 // fine edges of group g's events (one division per event), appended in position order at tot[q] + (offsets in o)
-WB_DEV void fe_emit_group(const double (&v)[WB_FE_R + 2], int i0, int ylen, unsigned long long o, const int (&tot)[4],
-                          double *edges, int cap) {
+WB_DEV void fe_emit_group(const double (&v)[WB_FE_R + 2], unsigned long long mask, int i0, unsigned long long o,
+                          const int (&tot)[4], double *edges, int cap) {
   int off[4] = {(int)(o & 0xffffull), (int)((o >> 16) & 0xffffull), (int)((o >> 32) & 0xffffull), (int)((o >> 48) & 0xffffull)};
-#pragma unroll
-  for (int r = 0; r < WB_FE_R; ++r) {
-    const double a = v[r], bb = v[r + 1], cc = v[r + 2];
-    unsigned m = fe_flags(a, bb, cc, i0 + r, ylen);
-    while (m) {
+  while (mask) {
 #ifdef WB_EMU
-      const int q = __builtin_ctz(m);
+    const int bit = __builtin_ctzll(mask);
 #else
-      const int q = __ffs((int)m) - 1;
+    const int bit = __ffsll((long long)mask) - 1;
 #endif
-      m &= m - 1u;
-      double e;
-      if (q < 2) {
-        e = (double)(i0 + r + 1) - a / (bb - a);
-      } else {
-        const double d0 = bb - a, d1 = cc - bb;
-        e = (double)(i0 + r + 1) - d0 / (d1 - d0);
-      }
-      const int at = tot[q] + off[q];
-      ++off[q];
-      if (at < cap) edges[(size_t)q * cap + at] = e;
+    mask &= mask - 1ull;
+    const int r = bit >> 2, q = bit & 3;
+    double a = v[0], bb = v[1], cc = v[2];
+#pragma unroll
+    for (int k = 1; k < WB_FE_R; ++k)            // register array: select by comparison, not by a runtime index
+      if (k == r) { a = v[k]; bb = v[k + 1]; cc = v[k + 2]; }
+    double e;
+    if (q < 2) {
+      e = (double)(i0 + r + 1) - a / (bb - a);
+    } else {
+      const double d0 = bb - a, d1 = cc - bb;
+      e = (double)(i0 + r + 1) - d0 / (d1 - d0);
     }
+    const int at = tot[q] + off[q];
+    ++off[q];
+    if (at < cap) edges[(size_t)q * cap + at] = e;
   }
 }
 
@@ -661,7 +677,9 @@ WB_KERNEL(2 * WB_FE_GROUP, 4) band_fir_events_kernel(SweepParams p) {
       double v[WB_FE_R + 2];
       fe_load_group(st, c0, c1, ct, v);
       const int i0 = n0 - 2 + R * ct;
-      const unsigned long long c = fe_count_group(v, i0, ylen);
+      const bool edge = n0 < 2 || n0 + T + 1 > ylen - 2;   // the tile reaches before sample 0 or past the last pair
+      unsigned long long c;
+      const unsigned long long mask = fe_mask_group(v, i0, ylen, edge, &c);
       unsigned long long inc = c;
       for (int o = 1; o < 32; o <<= 1) {
         const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o);
@@ -673,7 +691,7 @@ WB_KERNEL(2 * WB_FE_GROUP, 4) band_fir_events_kernel(SweepParams p) {
       unsigned long long basew = 0ull, all = 0ull;
 #pragma unroll
       for (int k = 0; k < 4; ++k) { const unsigned long long x = wt[k]; if (k < w) basew += x; all += x; }
-      fe_emit_group(v, i0, ylen, basew + inc - c, tot, edges, cap);
+      fe_emit_group(v, mask, i0, basew + inc - c, tot, edges, cap);
       tot[0] += (int)(all & 0xffffull); tot[1] += (int)((all >> 16) & 0xffffull);
       tot[2] += (int)((all >> 32) & 0xffffull); tot[3] += (int)((all >> 48) & 0xffffull);
       if (ct == 0) { c0 = st[T - 2]; c1 = st[T - 1]; }
@@ -705,8 +723,10 @@ WB_KERNEL(2 * WB_FE_GROUP, 4) band_fir_events_kernel(SweepParams p) {
       double v[WB_FE_R + 2];
       fe_load_group(st, c0, c1, g, v);
       const int i0 = n0 - 2 + R * g;
-      fe_emit_group(v, i0, ylen, run, tot, edges, cap);
-      run += fe_count_group(v, i0, ylen);
+      unsigned long long c;
+      const unsigned long long mask = fe_mask_group(v, i0, ylen, true, &c);
+      fe_emit_group(v, mask, i0, run, tot, edges, cap);
+      run += c;
     }
     tot[0] += (int)(run & 0xffffull); tot[1] += (int)((run >> 16) & 0xffffull);
     tot[2] += (int)((run >> 32) & 0xffffull); tot[3] += (int)((run >> 48) & 0xffffull);

@@ -377,7 +377,7 @@ struct HvChainParams {
   int frame_samples;   // S
 };
 
-WB_KERNEL(32 * WB_HV_WARPS, 4) harvest_refine_chain_kernel(HvChainParams cp) {
+WB_DEV void refine_chain_body(const HvChainParams &cp) {
   WB_DYN_SMEM(double, smem);
   const HvRefineParams &p = cp.r;
 #ifdef WB_EMU
@@ -510,6 +510,12 @@ WB_KERNEL(32 * WB_HV_WARPS, 4) harvest_refine_chain_kernel(HvChainParams cp) {
 #endif
   }
 }
+
+WB_KERNEL(32 * WB_HV_WARPS, 4) harvest_refine_chain_kernel(HvChainParams cp) { refine_chain_body(cp); }   // 128 registers
+#ifndef WB_EMU
+// the same body cut to 96 registers (76 bytes of spills): five CTAs per SM instead of four -- A/B with WB_REFINE_OCC=5
+__global__ void __launch_bounds__(32 * WB_HV_WARPS, 5) harvest_refine_chain_o5_kernel(HvChainParams cp) { refine_chain_body(cp); }
+#endif
 
 // ------------------------------------------------------------------ RemoveUnreliableCandidates
 struct HvRemoveParams {
@@ -1065,6 +1071,12 @@ int harvest_run(Ctx *ctx, const Batch &b, const HarvestParams &opt, double *time
       const size_t smem_chain = (size_t)WB_HV_WARPS * (3 * (size_t)nwin_max + 6 * frame_samples + 8) * 8;
 #ifndef WB_EMU
       cudaFuncSetAttribute(harvest_refine_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain);
+#endif
+#ifndef WB_EMU
+      if (getenv("WB_REFINE_OCC")) {
+        cudaFuncSetAttribute(harvest_refine_chain_o5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chain);
+        WB_LAUNCH_COOP(harvest_refine_chain_o5_kernel, dim3(refine_blocks, (unsigned)n), 32 * WB_HV_WARPS, smem_chain, ctx->stream, chp);
+      } else
 #endif
       WB_LAUNCH_COOP(harvest_refine_chain_kernel, dim3(refine_blocks, (unsigned)n), 32 * WB_HV_WARPS, smem_chain, ctx->stream, chp);
     } else {
