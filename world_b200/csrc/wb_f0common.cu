@@ -757,6 +757,18 @@ struct IpTrain {        // one train of one band: complete edge list in global m
 WB_DEV double ip_loc(const IpTrain &T, int j) { return (T.e[j] + T.e[j + 1]) / 2.0 / T.afs; }     // dio.cpp:357-393
 WB_DEV double ip_val(const IpTrain &T, int j) { return T.afs / (T.e[j + 1] - T.e[j]); }
 
+// first_frame_at_or_after() with the two exact verifications (a multiplication and a division each) only when
+// x * 1000 / frame_period lies within 1e-6 of an integer: otherwise t_g >= x > t_{g-1} hold with a margin ten
+// orders of magnitude above the rounding of t_i = i * frame_period / 1000.0, and the quotient itself may come from
+// a reciprocal.  Same result as the exact function in every case.
+WB_DEV int first_frame_fast(double x, double frame_period, double frames_per_second) {
+  const double r = x * frames_per_second;
+  const double c = ceil(r);
+  const double gap = c - r;
+  if (gap > 1e-6 && gap < 1.0 - 1e-6 && r > 1.0 && r < 1e7) return (int)c;   // margin 1e-6 frames >> 3e-16 r
+  return first_frame_at_or_after(x, frame_period);
+}
+
 WB_KERNEL(256, 4) band_interp_kernel(SweepParams p) {
   WB_SHARED double xw[4][WB_IP_W + 4], yw[4][WB_IP_W + 4];
   WB_SHARED unsigned long long marks[WB_IP_F + 40];   // per frame: intervals whose first frame it is, 4 x 16 bit; + scan scratch
@@ -788,6 +800,7 @@ WB_KERNEL(256, 4) band_interp_kernel(SweepParams p) {
   // window length of this band: intervals expected per round (band frequency x round duration) + 65 %, at least 24
   int w_band = (int)(bf * 1.1 * (WB_IP_F * p.frame_period / 1000.0) * 1.65) + 24;
   if (w_band > WB_IP_W) w_band = WB_IP_W;
+  const double fps = 1000.0 / p.frame_period;
   int cursor[4] = {0, 0, 0, 0};   // intervals whose first frame lies before the current round (identical in every thread)
   for (int c0 = 0; c0 < nf; c0 += WB_IP_F) {
     const int c1 = imin(nf, c0 + WB_IP_F);
@@ -806,7 +819,7 @@ WB_KERNEL(256, 4) band_interp_kernel(SweepParams p) {
           const double x = ip_loc(tr[q], wbase[q] + k);
           xw[q][k] = x; yw[q][k] = ip_val(tr[q], wbase[q] + k);
           if (k >= k0) {   // interval (wbase + k) is counted by every frame from its first frame on
-            const int m = first_frame_at_or_after(x, p.frame_period);
+            const int m = first_frame_fast(x, p.frame_period, fps);
             if (m < c1) smem_add_u64(&marks[imax(m, c0) - c0], 1ull << (16 * q));
           }
         }
@@ -817,7 +830,7 @@ WB_KERNEL(256, 4) band_interp_kernel(SweepParams p) {
       for (int q = 0; q < 4; ++q) {
         const int last = wbase[q] + wlen[q] - 1;     // last interval loaded
         at[q] = last + 1;
-        if (wlen[q] > 0 && last + 1 < tr[q].n_int && first_frame_at_or_after(xw[q][wlen[q] - 1], p.frame_period) < c1) more = true;
+        if (wlen[q] > 0 && last + 1 < tr[q].n_int && first_frame_fast(xw[q][wlen[q] - 1], p.frame_period, fps) < c1) more = true;
       }
       if (more) WB_SYNC();   // the windows are rewritten
     }
