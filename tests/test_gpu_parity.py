@@ -236,3 +236,37 @@ def test_gpu_benchmark_scale_batch(gpu_world, ref):
         assert (fr > 0).sum() > 1000
     assert flips == 0, f"{flips} V/UV flips in {frames} frames"
     assert max(worst.values()) <= pc.TOL, worst
+
+
+def test_gpu_unsupported_configurations_fail_cleanly(gpu_world):
+    """Where the on-chip tables / shared memory end the library returns
+    WORLD_B200_EINVAL with a message -- no kernel fault, no sticky CUDA error, and the context keeps working."""
+    import torch
+    from world_b200.api import WorldError
+    from synth import synth_batch
+    dev = f"cuda:{gpu_world.device}"
+    w = gpu_world
+    cases = []
+    # StoneMask / D4C above the twiddle table: fs = 192 kHz
+    x = torch.zeros((1, 19200), dtype=torch.float64, device=dev)
+    t = torch.arange(21, dtype=torch.float64, device=dev)[None] * 0.005
+    f = torch.full((1, 21), 150.0, dtype=torch.float64, device=dev)
+    cases.append(("StoneMask fs=192k", lambda: w.stonemask(x, 192000, t, f)))
+    cases.append(("D4C fs=192k", lambda: w.d4c(x, 192000, t, f, 8192)))
+    # Harvest with a floor whose refinement window / band filters do not fit on chip
+    o = w.harvest_option(); o.f0_floor = 8.0
+    cases.append(("Harvest floor 8 Hz", lambda: w.harvest(x[:, :16000], 16000, o)))
+    # DIO at 48 kHz, speed 1, very low floor: low-pass windows of thousands of taps
+    do = w.dio_option(); do.f0_floor = 5.0
+    cases.append(("Dio floor 5 Hz @48k", lambda: w.dio(x, 48000, do)))
+    # CheapTrick with a non power-of-two fft_size
+    co = w.cheaptrick_option(16000); co.fft_size = 1000
+    cases.append(("CheapTrick fft 1000", lambda: w.cheaptrick(x[:, :16000], 16000, t, f, co)))
+    for name, call in cases:
+        with pytest.raises(WorldError, match="error 3"):
+            call()
+    # ... and the context is still healthy
+    xs = synth_batch([3], 16000, 8000, device=dev)
+    tt, ff, fl = w.harvest(xs, 16000)
+    w.synchronize()
+    assert (ff > 0).any()

@@ -555,7 +555,12 @@ static int analyze_batch_impl(WorldB200 *h, const double *x, int n, int x_stride
         if (rc) { h->c.last_error = "analyze_batch: cannot create a lane context"; return rc; }
         cudaStream_t st;
         cudaEvent_t ev;
-        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess ||
+        // WB_LANE_PRIO=1 (experiment): lane 1 at the highest stream priority -- its blocks are placed first whenever a
+        // CTA retires, lane 0 fills what is left
+        int prio_least = 0, prio_greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+        const int prio = (l == 1 && getenv("WB_LANE_PRIO")) ? prio_greatest : prio_least;
+        if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio) != cudaSuccess ||
             cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
           h->c.last_error = "analyze_batch: cannot create a lane stream";
           return WORLD_B200_ECUDA;
@@ -611,16 +616,12 @@ static int analyze_batch_impl(WorldB200 *h, const double *x, int n, int x_stride
       }
       cudaEvent_t ev = (cudaEvent_t)h->ev_slice[s];
       cudaEventRecord(ev, L->c.stream);
-      double *t_full = time_axis - my_block * f0_stride, *f_full = f0 - my_block * f0_stride;
+      double *fulls[4] = {time_axis - my_block * f0_stride, f0 - my_block * f0_stride,
+                          spectrogram ? spectrogram - my_block * f0_stride * bins : nullptr,
+                          aperiodicity ? aperiodicity - my_block * f0_stride * bins : nullptr};
+      const size_t elems[4] = {(size_t)f0_stride, (size_t)f0_stride, (size_t)f0_stride * bins, (size_t)f0_stride * bins};
       std::string err;
-      int g = comm_gather_rows(h->comm, t_full, (size_t)f0_stride, (size_t)n, (size_t)u0, (size_t)m, ev, &err);
-      if (!g) g = comm_gather_rows(h->comm, f_full, (size_t)f0_stride, (size_t)n, (size_t)u0, (size_t)m, nullptr, &err);
-      if (!g && spectrogram)
-        g = comm_gather_rows(h->comm, spectrogram - my_block * f0_stride * bins, (size_t)f0_stride * bins, (size_t)n, (size_t)u0,
-                             (size_t)m, nullptr, &err);
-      if (!g && aperiodicity)
-        g = comm_gather_rows(h->comm, aperiodicity - my_block * f0_stride * bins, (size_t)f0_stride * bins, (size_t)n, (size_t)u0,
-                             (size_t)m, nullptr, &err);
+      const int g = comm_gather_rows_multi(h->comm, 4, fulls, elems, (size_t)n, (size_t)u0, (size_t)m, ev, &err);
       if (g) { h->c.last_error = err; rc = WORLD_B200_ECUDA; }
     }
 #endif

@@ -112,6 +112,8 @@ int comm_rank(const Comm *c);
 #ifndef WB_EMU
 int comm_gather_rows(Comm *c, double *full, size_t row_elems, size_t rows_per_rank, size_t row0, size_t rows,
                      cudaEvent_t after, std::string *err);
+int comm_gather_rows_multi(Comm *c, int n_arrays, double *const *full, const size_t *row_elems, size_t rows_per_rank,
+                           size_t row0, size_t rows, cudaEvent_t after, std::string *err);
 int comm_join(Comm *c, cudaStream_t s, std::string *err);
 #endif
 

@@ -84,7 +84,12 @@ int comm_create(int n_ranks, int rank, const unsigned char *id128, Comm **out, s
   memcpy(&id, id128, 128);
   ncclResult_t r = g_nccl.CommInitRank(&c->comm, n_ranks, id, rank);
   if (r != ncclSuccess) { *err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r); delete c; return 1; }
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+  // highest stream priority: when a compute kernel's CTA retires, the waiting blocks of the collective are placed
+  // first -- at equal priority the blocks of the (earlier launched, 10^5-block) compute kernels keep filling the SMs
+  // and the transfer only runs in their tails (profiles/r2j: 8 ranks at 0.84 with the transfer enqueued "under" the compute)
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming) != cudaSuccess) {
     *err = "cannot create the communication stream";
     g_nccl.CommDestroy(c->comm);
@@ -124,6 +129,24 @@ int comm_gather_rows(Comm *c, double *full, size_t row_elems, size_t rows_per_ra
     double *at = full + ((size_t)r * rows_per_rank + row0) * row_elems;
     ncclResult_t res = g_nccl.Broadcast(at, at, rows * row_elems, ncclDouble, r, c->comm, c->stream);
     if (res != ncclSuccess) { g_nccl.GroupEnd(); *err = std::string("ncclBroadcast: ") + g_nccl.GetErrorString(res); return 1; }
+  }
+  WB_NCCL(g_nccl.GroupEnd(), err);
+  return 0;
+}
+
+// The same for several arrays of one utterance slice in ONE NCCL group (one fused launch instead of one per array).
+int comm_gather_rows_multi(Comm *c, int n_arrays, double *const *full, const size_t *row_elems, size_t rows_per_rank,
+                           size_t row0, size_t rows, cudaEvent_t after, std::string *err) {
+  if (rows == 0) return 0;
+  if (after && cudaStreamWaitEvent(c->stream, after, 0) != cudaSuccess) { *err = "cudaStreamWaitEvent failed"; return 1; }
+  WB_NCCL(g_nccl.GroupStart(), err);
+  for (int a = 0; a < n_arrays; ++a) {
+    if (!full[a] || row_elems[a] == 0) continue;
+    for (int r = 0; r < c->n_ranks; ++r) {
+      double *at = full[a] + ((size_t)r * rows_per_rank + row0) * row_elems[a];
+      ncclResult_t res = g_nccl.Broadcast(at, at, rows * row_elems[a], ncclDouble, r, c->comm, c->stream);
+      if (res != ncclSuccess) { g_nccl.GroupEnd(); *err = std::string("ncclBroadcast: ") + g_nccl.GetErrorString(res); return 1; }
+    }
   }
   WB_NCCL(g_nccl.GroupEnd(), err);
   return 0;
