@@ -613,31 +613,52 @@ WB_DEV void fe_emit_group(const double (&v)[WB_FE_R + 2], unsigned long long mas
   }
 }
 
+// A CTA takes a PAIR of bands -- band pr (long filter) and band n_bands - 1 - pr (short filter) -- and alternates
+// between them tile by tile: filter work per tile varies 13x across bands while the event work is about constant,
+// so a CTA with one band is either waiting for its filter warps or for its event warps; the pair sums are within
+// 2x of each other and sit on the filter side.  Both bands read the same input segment (the long band's).
+struct FeBand {
+  int ntaps, seg_off, cap, band;   // seg_off: where this band's segment starts inside the pair's (long) segment
+  double *edges;
+};
+
 WB_KERNEL(2 * WB_FE_GROUP, 4) band_fir_events_kernel(SweepParams p) {
   WB_DYN_SMEM(double, smem);
-  const int b = blockIdx.x, u = blockIdx.y;
+  const int pr = blockIdx.x, u = blockIdx.y;
   const int T = WB_FE_TILE, R = WB_FE_R, G = WB_FE_GROUP;
-  const int ntaps = p.ntaps[b], shift = p.shift[b];
-  const int nt9 = ((ntaps + R - 1) / R) * R;     // taps in whole register rounds; hrev is zero beyond ntaps
   const int segd = fe_seg_doubles(p.max_taps);
   double *segbuf[2] = {smem, smem + segd};
   const int hcap = ((p.max_taps + R - 1) / R) * R + R;
-  double *hrev = smem + 2 * segd;                // hcap
-  double *stbuf[2] = {hrev + hcap, hrev + hcap + (T + 2)};
+  double *hrev[2] = {smem + 2 * segd, smem + 2 * segd + hcap};
+  double *stbuf[2] = {hrev[1] + hcap, hrev[1] + hcap + (T + 2)};
   unsigned long long *wtot = reinterpret_cast<unsigned long long *>(stbuf[1] + (T + 2));   // [2][4] warp totals
   unsigned long long *bars = wtot + 8;           // two mbarriers
   const int ylen = p.y_len[u];
   const size_t abs0 = (size_t)u * p.sig_stride + p.sig_origin;   // index of s(0) in p.sig
-  double *edges = p.edges + (size_t)u * p.edge_stride + (size_t)p.edge_off[b];
-  const int cap = p.edge_cap[b];
   const int n_tiles = (ylen + 2 + T - 1) / T;
-  // segment of tile t: seg[i] = s(n0 + shift - ntaps + 1 + i), i < T + nt9 (beyond the filter span the taps are zero;
-  // the signal buffer is zero padded, so whatever lies there is finite)
-  const int seg_count = (T + nt9 + 2) & ~1;
-  int tot[4] = {0, 0, 0, 0};   // events so far per train
+  const int b_long = pr, b_short = p.n_bands - 1 - pr;
+  const int nslot = b_short > b_long ? 2 : 1;    // the middle band of an odd count is alone
+  FeBand fb[2];
+  const int lead = p.shift[b_long] - p.ntaps[b_long] + 1;     // segment of tile t starts at s(t T + lead)
+  for (int s = 0; s < nslot; ++s) {
+    const int b = s == 0 ? b_long : b_short;
+    fb[s].band = b; fb[s].ntaps = p.ntaps[b];
+    fb[s].seg_off = (p.shift[b] - p.ntaps[b] + 1) - lead;     // >= 0: the short filter starts later and ends earlier
+    fb[s].cap = p.edge_cap[b];
+    fb[s].edges = p.edges + (size_t)u * p.edge_stride + (size_t)p.edge_off[b];
+  }
+  // seg[i] = s(n0 + lead + i), i < T + nt9 of the long band (beyond a filter's span its taps are zero; the signal
+  // buffer is zero padded, so whatever lies there is finite)
+  const int nt9_long = ((p.ntaps[b_long] + R - 1) / R) * R;
+  const int seg_count = (T + nt9_long + 2) & ~1;
+  int tot[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // events so far per band and train
 #ifndef WB_EMU
   const int tid = threadIdx.x;
-  for (int j = tid; j < nt9 + R; j += blockDim.x) hrev[j] = j < ntaps ? __ldg(&p.taps_rev[p.tap_off[b] + j]) : 0.0;
+  for (int s = 0; s < nslot; ++s) {
+    const int nt9 = ((fb[s].ntaps + R - 1) / R) * R;
+    for (int j = tid; j < nt9 + R; j += blockDim.x)
+      hrev[s][j] = j < fb[s].ntaps ? __ldg(&p.taps_rev[p.tap_off[fb[s].band] + j]) : 0.0;
+  }
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -647,97 +668,116 @@ WB_KERNEL(2 * WB_FE_GROUP, 4) band_fir_events_kernel(SweepParams p) {
   if (tid < G) {
     // ---------------------------------------------------------------- filter warps
     if (tid == 0 && n_tiles > 0) {
-      const size_t a = abs0 + (size_t)(shift - ntaps + 1);
+      const size_t a = abs0 + (size_t)lead;
       mbar_expect_tx(&bars[0], (unsigned)seg_count * 8u);
       tma_load_1d(segbuf[0], p.sig + (a & ~(size_t)1), (unsigned)seg_count * 8u, &bars[0]);
     }
+    int item = 0;                                 // work item = (tile, band slot); its output half is item & 1
     for (int t = 0; t < n_tiles; ++t) {
-      const size_t a0 = abs0 + (size_t)(t * T + shift - ntaps + 1);
-      // every filter thread has left tile t-1 (bar 5 at its end), whose FIR was the last reader of the other segment
+      const size_t a0 = abs0 + (size_t)(t * T + lead);
+      // every filter thread has left tile t-1 (bar 5 at its end), whose FIRs were the last readers of the other segment
       if (tid == 0 && t + 1 < n_tiles) {
         const size_t a1 = a0 + (size_t)T;
         mbar_expect_tx(&bars[(t + 1) & 1], (unsigned)seg_count * 8u);
         tma_load_1d(segbuf[(t + 1) & 1], p.sig + (a1 & ~(size_t)1), (unsigned)seg_count * 8u, &bars[(t + 1) & 1]);
       }
       mbar_wait(&bars[t & 1], (unsigned)((t >> 1) & 1));
-      if (t >= 2) bar_sync_named(3 + (t & 1), 2 * G);          // the event warps are done with this half (tile t-2)
-      fe_fir_group(segbuf[t & 1] + (a0 & 1), hrev, ntaps, tid, stbuf[t & 1]);
-      __threadfence_block();
-      bar_arrive_named(1 + (t & 1), 2 * G);                    // tile t is ready
+      for (int s = 0; s < nslot; ++s, ++item) {
+        if (item >= 2) bar_sync_named(3 + (item & 1), 2 * G);    // the event warps are done with this half (item - 2)
+        fe_fir_group(segbuf[t & 1] + (a0 & 1) + fb[s].seg_off, hrev[s], fb[s].ntaps, tid, stbuf[item & 1]);
+        __threadfence_block();
+        bar_arrive_named(1 + (item & 1), 2 * G);                 // the item is ready
+      }
       bar_sync_named(5, G);
     }
   } else {
     // ---------------------------------------------------------------- event warps
     const int ct = tid - G, lane = ct & 31, w = ct >> 5;
-    double c0 = 0.0, c1 = 0.0;   // carry: only group 0 (positions 0 and 1) ever reads it, and group 0 is this role's thread 0
+    // carry (the last two outputs of the band's previous tile): only group 0 reads it, and group 0 is this role's thread 0
+    double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+    int item = 0;
     for (int t = 0; t < n_tiles; ++t) {
       const int n0 = t * T;
-      bar_sync_named(1 + (t & 1), 2 * G);
-      const double *st = stbuf[t & 1];
-      double v[WB_FE_R + 2];
-      fe_load_group(st, c0, c1, ct, v);
-      const int i0 = n0 - 2 + R * ct;
       const bool edge = n0 < 2 || n0 + T + 1 > ylen - 2;   // the tile reaches before sample 0 or past the last pair
-      unsigned long long c;
-      const unsigned long long mask = fe_mask_group(v, i0, ylen, edge, &c);
-      unsigned long long inc = c;
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += up;
-      }
-      unsigned long long *wt = wtot + 4 * (t & 1);
-      if (lane == 31) wt[w] = inc;
-      bar_sync_named(6, G);
-      unsigned long long basew = 0ull, all = 0ull;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const unsigned long long x = wt[k]; if (k < w) basew += x; all += x; }
-      fe_emit_group(v, mask, i0, basew + inc - c, tot, edges, cap);
-      tot[0] += (int)(all & 0xffffull); tot[1] += (int)((all >> 16) & 0xffffull);
-      tot[2] += (int)((all >> 32) & 0xffffull); tot[3] += (int)((all >> 48) & 0xffffull);
-      if (ct == 0) { c0 = st[T - 2]; c1 = st[T - 1]; }
-      __threadfence_block();
-      bar_arrive_named(3 + (t & 1), 2 * G);                    // this half may be overwritten (tile t+2)
+      for (int s = 0; s < 2; ++s) {
+        if (s >= nslot) break;
+        bar_sync_named(1 + (item & 1), 2 * G);
+        const double *st = stbuf[item & 1];
+        double v[WB_FE_R + 2];
+        fe_load_group(st, c0[s], c1[s], ct, v);
+        const int i0 = n0 - 2 + R * ct;
+        unsigned long long c;
+        const unsigned long long mask = fe_mask_group(v, i0, ylen, edge, &c);
+        unsigned long long inc = c;
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += up;
+        }
+        unsigned long long *wt = wtot + 4 * (item & 1);
+        if (lane == 31) wt[w] = inc;
+        bar_sync_named(6, G);
+        unsigned long long basew = 0ull, all = 0ull;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const unsigned long long x = wt[k]; if (k < w) basew += x; all += x; }
+        fe_emit_group(v, mask, i0, basew + inc - c, tot[s], fb[s].edges, fb[s].cap);
+        tot[s][0] += (int)(all & 0xffffull); tot[s][1] += (int)((all >> 16) & 0xffffull);
+        tot[s][2] += (int)((all >> 32) & 0xffffull); tot[s][3] += (int)((all >> 48) & 0xffffull);
+        if (ct == 0) { c0[s] = st[T - 2]; c1[s] = st[T - 1]; }
+        __threadfence_block();
+        bar_arrive_named(3 + (item & 1), 2 * G);                 // this half may be overwritten (item + 2)
+        ++item;
+      }
     }
     if (ct == 0) {
-      int *ec = p.ev_count + ((size_t)u * p.n_bands + b) * 4;
-      bool over = false;
-      for (int q = 0; q < 4; ++q) { ec[q] = tot[q]; over = over || tot[q] > cap; }
-      if (over) {
-        ec[0] = -1;
-        p.redo_list[atomicAdd(p.redo_count, 1)] = u * p.n_bands + b;
+      for (int s = 0; s < nslot; ++s) {
+        int *ec = p.ev_count + ((size_t)u * p.n_bands + fb[s].band) * 4;
+        bool over = false;
+        for (int q = 0; q < 4; ++q) { ec[q] = tot[s][q]; over = over || tot[s][q] > fb[s].cap; }
+        if (over) {
+          ec[0] = -1;
+          p.redo_list[atomicAdd(p.redo_count, 1)] = u * p.n_bands + fb[s].band;
+        }
       }
     }
   }
 #else
-  // one emulated thread: both roles, tile after tile
-  for (int j = 0; j < nt9 + R; ++j) hrev[j] = j < ntaps ? p.taps_rev[p.tap_off[b] + j] : 0.0;
-  double c0 = 0.0, c1 = 0.0;
+  // one emulated thread: both roles, tile after tile, band after band
+  for (int s = 0; s < nslot; ++s) {
+    const int nt9 = ((fb[s].ntaps + R - 1) / R) * R;
+    for (int j = 0; j < nt9 + R; ++j) hrev[s][j] = j < fb[s].ntaps ? p.taps_rev[p.tap_off[fb[s].band] + j] : 0.0;
+  }
+  double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
   for (int t = 0; t < n_tiles; ++t) {
     const int n0 = t * T;
-    const size_t a0 = abs0 + (size_t)(n0 + shift - ntaps + 1);
+    const size_t a0 = abs0 + (size_t)(n0 + lead);
     for (int i = 0; i < seg_count; ++i) segbuf[0][i] = p.sig[a0 + i];
-    double *st = stbuf[0];
-    for (int g = 0; g < G; ++g) fe_fir_group(segbuf[0], hrev, ntaps, g, st);
-    unsigned long long run = 0ull;
-    for (int g = 0; g < G; ++g) {
-      double v[WB_FE_R + 2];
-      fe_load_group(st, c0, c1, g, v);
-      const int i0 = n0 - 2 + R * g;
-      unsigned long long c;
-      const unsigned long long mask = fe_mask_group(v, i0, ylen, true, &c);
-      fe_emit_group(v, mask, i0, run, tot, edges, cap);
-      run += c;
+    for (int s = 0; s < nslot; ++s) {
+      double *st = stbuf[s];
+      for (int g = 0; g < G; ++g) fe_fir_group(segbuf[0] + fb[s].seg_off, hrev[s], fb[s].ntaps, g, st);
+      unsigned long long run = 0ull;
+      for (int g = 0; g < G; ++g) {
+        double v[WB_FE_R + 2];
+        fe_load_group(st, c0[s], c1[s], g, v);
+        const int i0 = n0 - 2 + R * g;
+        unsigned long long c;
+        const unsigned long long mask = fe_mask_group(v, i0, ylen, true, &c);
+        fe_emit_group(v, mask, i0, run, tot[s], fb[s].edges, fb[s].cap);
+        run += c;
+      }
+      tot[s][0] += (int)(run & 0xffffull); tot[s][1] += (int)((run >> 16) & 0xffffull);
+      tot[s][2] += (int)((run >> 32) & 0xffffull); tot[s][3] += (int)((run >> 48) & 0xffffull);
+      c0[s] = st[T - 2]; c1[s] = st[T - 1];
     }
-    tot[0] += (int)(run & 0xffffull); tot[1] += (int)((run >> 16) & 0xffffull);
-    tot[2] += (int)((run >> 32) & 0xffffull); tot[3] += (int)((run >> 48) & 0xffffull);
-    c0 = st[T - 2]; c1 = st[T - 1];
   }
-  int *ec = p.ev_count + ((size_t)u * p.n_bands + b) * 4;
-  bool over = false;
-  for (int q = 0; q < 4; ++q) { ec[q] = tot[q]; over = over || tot[q] > cap; }
-  if (over) {
-    ec[0] = -1;
-    p.redo_list[(*p.redo_count)++] = u * p.n_bands + b;
+  for (int s = 0; s < nslot; ++s) {
+    int *ec = p.ev_count + ((size_t)u * p.n_bands + fb[s].band) * 4;
+    bool over = false;
+    for (int q = 0; q < 4; ++q) { ec[q] = tot[s][q]; over = over || tot[s][q] > fb[s].cap; }
+    if (over) {
+      ec[0] = -1;
+      p.redo_list[(*p.redo_count)++] = u * p.n_bands + fb[s].band;
+    }
   }
 #endif
 }
@@ -964,7 +1004,7 @@ void launch_band_sweep_split(Ctx *ctx, const SweepParams &p_in, unsigned n_utts)
   cudaFuncSetAttribute(band_fir_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fe);
   cudaFuncSetAttribute(band_sweep_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sw);
 #endif
-  WB_LAUNCH_COOP(band_fir_events_kernel, dim3((unsigned)p.n_bands, n_utts), WB_SWEEP_THREADS, smem_fe, ctx->stream, p);
+  WB_LAUNCH_COOP(band_fir_events_kernel, dim3((unsigned)((p.n_bands + 1) / 2), n_utts), WB_SWEEP_THREADS, smem_fe, ctx->stream, p);
   WB_LAUNCH_COOP(band_interp_kernel, dim3((unsigned)p.n_bands, n_utts), 256, 0, ctx->stream, p);
   // bands whose edge lists overflowed (usually none): the streaming kernel with its history rings, over the list
   WB_LAUNCH_COOP(band_sweep_list_kernel, dim3((unsigned)(3 * ctx->sm_count)), WB_SWEEP_THREADS, smem_sw, ctx->stream, p);

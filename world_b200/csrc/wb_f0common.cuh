@@ -107,8 +107,8 @@ WB_HD inline int fe_seg_doubles(int max_taps) {   // one input segment: tile + f
   return (WB_FE_R * 128 + ((max_taps + WB_FE_R - 1) / WB_FE_R) * WB_FE_R + WB_FE_R + 8) & ~1;
 }
 WB_HD inline size_t fe_smem_bytes(int max_taps) {
-  // two segments, taps, two filtered tiles, 2 x 4 warp totals, two mbarriers
-  return (size_t)(2 * fe_seg_doubles(max_taps) + (((max_taps + WB_FE_R - 1) / WB_FE_R) * WB_FE_R + WB_FE_R) +
+  // two segments, the taps of two bands, two filtered tiles, 2 x 4 warp totals, two mbarriers
+  return (size_t)(2 * fe_seg_doubles(max_taps) + 2 * (((max_taps + WB_FE_R - 1) / WB_FE_R) * WB_FE_R + WB_FE_R) +
                   2 * (WB_FE_R * 128 + 2) + 8 + 2 + 6) * 8;
 }
 
