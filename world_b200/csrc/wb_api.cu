@@ -555,12 +555,9 @@ static int analyze_batch_impl(WorldB200 *h, const double *x, int n, int x_stride
         if (rc) { h->c.last_error = "analyze_batch: cannot create a lane context"; return rc; }
         cudaStream_t st;
         cudaEvent_t ev;
-        // WB_LANE_PRIO=1 (experiment): lane 1 at the highest stream priority -- its blocks are placed first whenever a
-        // CTA retires, lane 0 fills what is left
-        int prio_least = 0, prio_greatest = 0;
-        cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-        const int prio = (l == 1 && getenv("WB_LANE_PRIO")) ? prio_greatest : prio_least;
-        if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio) != cudaSuccess ||
+        // equal (lowest) priority for both lanes: giving one lane the highest priority was measured slower
+        // (profiles/r2l: 804 vs 794 ms); only the communication stream outranks them (wb_multi.cu)
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
           h->c.last_error = "analyze_batch: cannot create a lane stream";
           return WORLD_B200_ECUDA;

@@ -510,6 +510,33 @@ WB_DEV void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" 
 WB_DEV void bar_arrive_named(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 #endif
 
+// acc[r] += h * w[r], r = 0..8, as ONE block of nine DFMAs in this order.  A DFMA reads three 64-bit operands; the
+// register file delivers two per issue slot of the half-rate FP64 pipe, the third has to come from the operand-reuse
+// cache, i.e. from the previous instruction's same slot.  Left to the scheduler, the nine FMAs of a tap were
+// interleaved with those of other taps (13 % of the kernel's DFMAs carried a reuse flag, FP64 pipe stuck at 58 %,
+// profiles/r2m); written as one block `h` stays in its slot for all nine.
+WB_DEV void fe_fma9(double (&acc)[9], double h, double w0, double w1, double w2, double w3, double w4, double w5,
+                    double w6, double w7, double w8) {
+#ifdef WB_EMU
+  acc[0] = fma(h, w0, acc[0]); acc[1] = fma(h, w1, acc[1]); acc[2] = fma(h, w2, acc[2]);
+  acc[3] = fma(h, w3, acc[3]); acc[4] = fma(h, w4, acc[4]); acc[5] = fma(h, w5, acc[5]);
+  acc[6] = fma(h, w6, acc[6]); acc[7] = fma(h, w7, acc[7]); acc[8] = fma(h, w8, acc[8]);
+#else
+  asm("fma.rn.f64 %0, %9, %10, %0;\n\t"
+      "fma.rn.f64 %1, %9, %11, %1;\n\t"
+      "fma.rn.f64 %2, %9, %12, %2;\n\t"
+      "fma.rn.f64 %3, %9, %13, %3;\n\t"
+      "fma.rn.f64 %4, %9, %14, %4;\n\t"
+      "fma.rn.f64 %5, %9, %15, %5;\n\t"
+      "fma.rn.f64 %6, %9, %16, %6;\n\t"
+      "fma.rn.f64 %7, %9, %17, %7;\n\t"
+      "fma.rn.f64 %8, %9, %18, %8;"
+      : "+d"(acc[0]), "+d"(acc[1]), "+d"(acc[2]), "+d"(acc[3]), "+d"(acc[4]), "+d"(acc[5]), "+d"(acc[6]), "+d"(acc[7]),
+        "+d"(acc[8])
+      : "d"(h), "d"(w0), "d"(w1), "d"(w2), "d"(w3), "d"(w4), "d"(w5), "d"(w6), "d"(w7), "d"(w8));
+#endif
+}
+
 // FIR of register group g (outputs 9 g .. 9 g + 8 of the tile): the same FMA order as band_sweep_kernel
 WB_DEV void fe_fir_group(const double *seg, const double *hrev, int ntaps, int g, double *st) {
   const int R = WB_FE_R, base = R * g;
@@ -522,8 +549,8 @@ WB_DEV void fe_fir_group(const double *seg, const double *hrev, int ntaps, int g
 #pragma unroll
     for (int jj = 0; jj < R; ++jj) {
       const double hj = hp[jj];
-#pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = fma(hj, win[(r + jj) % WB_FE_R], acc[r]);
+      fe_fma9(acc, hj, win[jj % 9], win[(jj + 1) % 9], win[(jj + 2) % 9], win[(jj + 3) % 9], win[(jj + 4) % 9],
+              win[(jj + 5) % 9], win[(jj + 6) % 9], win[(jj + 7) % 9], win[(jj + 8) % 9]);
       win[jj] = sp[jj];
     }
   }
@@ -622,7 +649,7 @@ struct FeBand {
   double *edges;
 };
 
-WB_KERNEL(2 * WB_FE_GROUP, 4) band_fir_events_kernel(SweepParams p) {
+WB_KERNEL(2 * WB_FE_GROUP, 3) band_fir_events_kernel(SweepParams p) {
   WB_DYN_SMEM(double, smem);
   const int pr = blockIdx.x, u = blockIdx.y;
   const int T = WB_FE_TILE, R = WB_FE_R, G = WB_FE_GROUP;
