@@ -451,21 +451,12 @@ WB_DEV void refine_chain_body(const HvChainParams &cp) {
 #pragma unroll
           for (int g = 0; g < 7; ++g) {
             const double xv = xs[i + S * g];
-#ifdef WB_EMU
+            // (pinning these four DFMAs in one asm block for operand reuse, as fe_fma9 does for the FIR, was measured
+            // slower here: 164 vs 152 ms, profiles/r2n -- the scheduler needs the freedom to hide the smem loads)
             a[4 * g + 0] = fma(xv, P, a[4 * g + 0]);
             a[4 * g + 1] = fma(xv, Q, a[4 * g + 1]);
             a[4 * g + 2] = fma(xv, R, a[4 * g + 2]);
             a[4 * g + 3] = fma(xv, Sd, a[4 * g + 3]);
-#else
-            // one block of four DFMAs in this order: xv stays in the operand-reuse cache (a DFMA reads three 64-bit
-            // operands, the register file delivers two per FP64 issue slot; see fe_fma9 in wb_f0common.cu)
-            asm("fma.rn.f64 %0, %4, %5, %0;\n\t"
-                "fma.rn.f64 %1, %4, %6, %1;\n\t"
-                "fma.rn.f64 %2, %4, %7, %2;\n\t"
-                "fma.rn.f64 %3, %4, %8, %3;"
-                : "+d"(a[4 * g + 0]), "+d"(a[4 * g + 1]), "+d"(a[4 * g + 2]), "+d"(a[4 * g + 3])
-                : "d"(xv), "d"(P), "d"(Q), "d"(R), "d"(Sd));
-#endif
           }
           const double nx = fma(w.x, rot.x, -(w.y * rot.y));
           const double ny = fma(w.x, rot.y, w.y * rot.x);
