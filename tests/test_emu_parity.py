@@ -172,6 +172,10 @@ def test_emu_harvest_per_frame_refinement(emu, ref):
             os.environ["WB_NO_REFINE_CHAIN"] = saved
 
 
+def test_emu_dio_silence_onset_is_bounded(emu, ref):
+    pc.check_dio_silence_onset_bound(emu, ref)
+
+
 def test_emu_mirroring_ripple_cases(emu, ref):
     pc.check_mirroring_ripple_cases(emu, ref)
 

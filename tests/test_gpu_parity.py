@@ -179,6 +179,10 @@ def test_gpu_legacy_codec(gpu_world, ref, golden):
     pc.assert_close(dap[::4], golden["decoded_ap_rows"], "legacy DecodeAperiodicity")
 
 
+def test_gpu_dio_silence_onset_is_bounded(gpu_world, ref):
+    pc.check_dio_silence_onset_bound(gpu_world, ref)
+
+
 def test_gpu_analyze_batch_lanes(gpu_world, golden):
     pc.check_analyze_batch(gpu_world, golden)
 

@@ -538,3 +538,36 @@ def check_mirroring_ripple_cases(world, ref):
         got = to_np(f0)[0]
         assert not ((got > 0) != (fr > 0)).any(), f"Harvest, digital silence at 8 kHz, case {case}: V/UV flips"
         assert_close(got, fr, f"Harvest, digital silence at 8 kHz, case {case}")
+
+
+def check_dio_silence_onset_bound(world, ref):
+    """The one deviation class the fuzz campaigns found: DIO on a signal that falls into embedded DIGITAL
+    silence.  On the one to four frames where the band-filtered signal decays into the silence the reference's
+    candidates are set by its whole-utterance FFT rounding (~1e-17 of the signal), which a tile-wise time-domain
+    filter cannot reproduce; everywhere else -- silence included, thanks to the mirroring-loop ripple -- the contour
+    matches to 1e-6.  This pins the class: no V/UV flip anywhere, 1e-6 outside the onset, 1e-3 on at most six frames
+    around it."""
+    from synth import synth_batch
+    worst_in = 0.0
+    for fs, seed, a, b, speed in ((48000, 77, 8533, 27619, 2), (16000, 78, 3000, 9000, 1), (44100, 79, 9000, 30000, 4)):
+        n = int(0.65 * fs)
+        x = synth_batch([seed], fs, n).numpy()[0]
+        x[a:b] = 0.0
+        x = np.ascontiguousarray(x)
+        o = world.dio_option(); ro = ref.dio_option()
+        for q in (o, ro):
+            q.speed = speed; q.f0_floor = 40.0; q.f0_ceil = 400.0
+        t, f0, fl = world.dio(make(world, x[None]), fs, o)
+        world.synchronize()
+        tr, fr = ref.dio(x, fs, ro)
+        got = to_np(f0)[0]
+        assert np.array_equal(to_np(t)[0], tr)
+        assert not ((got > 0) != (fr > 0)).any(), f"V/UV flip, fs {fs}"
+        e = rel_err(got, fr)
+        onset = int(a / fs / 0.005)
+        near = np.zeros(len(e), dtype=bool)
+        near[max(0, onset - 1):onset + 5] = True
+        assert e[~near].max() <= TOL, f"fs {fs}: {e[~near].max():.2e} away from the onset of the silence"
+        assert e[near].max() <= 1e-3, f"fs {fs}: {e[near].max():.2e} at the onset of the silence"
+        worst_in = max(worst_in, e[near].max())
+    return worst_in
