@@ -582,6 +582,22 @@ static int analyze_batch_impl(WorldB200 *h, const double *x, int n, int x_stride
   int rc = 0;
   std::vector<int> fl(n);
   for (int i = 0; i < n; ++i) fl[i] = frames_for(fs, x_lengths ? x_lengths[i] : x_stride, frame_period);
+#ifndef WB_EMU
+  // multi-GPU: the full arrays and how a finished slice reaches the other ranks -- pushed into their (IPC-mapped)
+  // arrays by the copy engines where that is possible, grouped NCCL broadcasts otherwise (wb_multi.cu)
+  double *fulls[4] = {time_axis - my_block * f0_stride, f0 - my_block * f0_stride,
+                      spectrogram ? spectrogram - my_block * f0_stride * bins : nullptr,
+                      aperiodicity ? aperiodicity - my_block * f0_stride * bins : nullptr};
+  const size_t full_elems[4] = {(size_t)f0_stride, (size_t)f0_stride, (size_t)f0_stride * bins, (size_t)f0_stride * bins};
+  const bool exchange = gather && comm_ranks(h->comm) > 1;
+  bool push = false;
+  if (exchange && !getenv("WB_NO_P2P")) {
+    std::string err;
+    const int pr = comm_p2p_prepare(h->comm, 4, fulls, &err);
+    if (pr == 2) { h->c.last_error = err; return WORLD_B200_ECUDA; }
+    push = pr == 0;
+  }
+#endif
   for (int s = 0; s < n_slices && !rc; ++s) {
     const int u0 = (int)((long long)n * s / n_slices), u1 = (int)((long long)n * (s + 1) / n_slices);
     const int m = u1 - u0;
@@ -604,7 +620,7 @@ static int analyze_batch_impl(WorldB200 *h, const double *x, int n, int x_stride
                                 &opt->d4c, aperiodicity + (size_t)u0 * f0_stride * bins);
     if (rc && L != h) h->c.last_error = L->c.last_error;
 #ifndef WB_EMU
-    if (!rc && gather && comm_ranks(h->comm) > 1) {
+    if (!rc && exchange) {
       // rows u0..u1 of every rank's block, as soon as this rank's are final (event on the lane's stream)
       while ((int)h->ev_slice.size() <= s) {
         cudaEvent_t ev;
@@ -613,20 +629,18 @@ static int analyze_batch_impl(WorldB200 *h, const double *x, int n, int x_stride
       }
       cudaEvent_t ev = (cudaEvent_t)h->ev_slice[s];
       cudaEventRecord(ev, L->c.stream);
-      double *fulls[4] = {time_axis - my_block * f0_stride, f0 - my_block * f0_stride,
-                          spectrogram ? spectrogram - my_block * f0_stride * bins : nullptr,
-                          aperiodicity ? aperiodicity - my_block * f0_stride * bins : nullptr};
-      const size_t elems[4] = {(size_t)f0_stride, (size_t)f0_stride, (size_t)f0_stride * bins, (size_t)f0_stride * bins};
       std::string err;
-      const int g = comm_gather_rows_multi(h->comm, 4, fulls, elems, (size_t)n, (size_t)u0, (size_t)m, ev, &err);
+      const int g = push ? comm_p2p_push(h->comm, 4, full_elems, (size_t)n, (size_t)u0, (size_t)m, ev, &err)
+                         : comm_gather_rows_multi(h->comm, 4, fulls, full_elems, (size_t)n, (size_t)u0, (size_t)m, ev, &err);
       if (g) { h->c.last_error = err; rc = WORLD_B200_ECUDA; }
     }
 #endif
   }
 #ifndef WB_EMU
-  if (gather && comm_ranks(h->comm) > 1) {
+  if (exchange) {
     std::string err;
-    if (comm_join(h->comm, h->c.stream, &err) && !rc) { h->c.last_error = err; rc = WORLD_B200_ECUDA; }
+    const int g = push ? comm_p2p_finish(h->comm, h->c.stream, &err) : comm_join(h->comm, h->c.stream, &err);
+    if (g && !rc) { h->c.last_error = err; rc = WORLD_B200_ECUDA; }
   }
   if (lanes[0] != h)
     for (int l = 0; l < 2; ++l) {   // join even after an error: the caller's stream must not run ahead of the lanes

@@ -115,6 +115,11 @@ int comm_gather_rows(Comm *c, double *full, size_t row_elems, size_t rows_per_ra
 int comm_gather_rows_multi(Comm *c, int n_arrays, double *const *full, const size_t *row_elems, size_t rows_per_rank,
                            size_t row0, size_t rows, cudaEvent_t after, std::string *err);
 int comm_join(Comm *c, cudaStream_t s, std::string *err);
+// peer-to-peer push of finished rows over CUDA IPC mappings (copy engines); prepare: 0 usable, 1 not usable, 2 error
+int comm_p2p_prepare(Comm *c, int n_arrays, double *const *full, std::string *err);
+int comm_p2p_push(Comm *c, int n_arrays, const size_t *row_elems, size_t rows_per_rank, size_t row0, size_t rows,
+                  cudaEvent_t after, std::string *err);
+int comm_p2p_finish(Comm *c, cudaStream_t s, std::string *err);
 #endif
 
 // Device-resident batch: N utterances, padded rows.
