@@ -746,7 +746,7 @@ def main():
            "config": {"workload": workload_name(a), "baseline_config": a.config or None, "fs": fs, "frame_period_ms": 5.0, "frames_per_step": frames_step,
                       "l2_policy": "inputs+outputs per step (>= 18 GB) exceed the 126 MB L2; no flush needed",
                       "multi_gpu": ("utterances sharded over ranks; the library's own NCCL communicator (C ABI) reassembles f0/time_axis" +
-                                    ("/spectrogram/aperiodicity, slice by slice under the compute" if gather_full else "")) if world > 1 else "single GPU",
+                                    ("/spectrogram/aperiodicity, slice by slice under the compute (peer-to-peer copies over CUDA IPC mappings; NCCL broadcasts with WB_NO_P2P=1)" if gather_full else "")) if world > 1 else "single GPU",
                       "gathered_equals_local_recompute": gather_check},
            "clocks": clocks, "e2e": e2e, "slices": n_slices,
            "device_resident_api": ("world_b200_analyze_batch (utterance slices on two internal streams; per-kernel times below overlap, "

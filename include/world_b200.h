@@ -185,10 +185,13 @@ int world_b200_allgather_rows(WorldB200 *ctx, double *full, unsigned long long r
                               unsigned long long rows_per_rank);
 /* world_b200_analyze_batch on this rank's n_utts utterances (every rank passes the same n_utts, strides and options),
  * with the four outputs given as the FULL arrays of n_ranks * n_utts utterances: the rank computes into its own
- * block and each finished utterance slice is sent to all other ranks (grouped ncclBroadcast on a communication
- * stream) while the next slice is computed -- the transfer hides under the compute.  On return the work is
- * enqueued; after the context's stream (world_b200_synchronize) every rank holds the complete arrays, bit-identical
- * to a single-GPU run. */
+ * block and each finished utterance slice is sent to all other ranks while the next slice is computed -- the
+ * transfer hides under the compute.  Transport: the rank copies its rows into the peers' arrays, mapped through CUDA
+ * IPC (copy engines over NVLink, no SM involved; the handles are exchanged once per set of arrays through the
+ * communicator, which briefly synchronises the communication stream with the host), or, where the arrays cannot be
+ * exported, grouped ncclBroadcasts on a high-priority stream (WB_NO_P2P=1 forces this).  Collective: every rank
+ * must make the call.  On return the work is enqueued; after the context's stream (world_b200_synchronize) every
+ * rank holds the complete arrays, bit-identical to a single-GPU run. */
 int world_b200_analyze_batch_allgather(WorldB200 *ctx, const double *x, int n_utts, int x_stride,
                                        const int *x_lengths, int fs, const WorldB200AnalysisOption *option,
                                        double *time_axis_full, double *f0_full, int f0_stride,

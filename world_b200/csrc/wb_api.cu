@@ -543,9 +543,21 @@ static int analyze_batch_impl(WorldB200 *h, const double *x, int n, int x_stride
   const double frame_period = opt->f0_method == WORLD_B200_F0_HARVEST ? opt->harvest.frame_period : opt->dio.frame_period;
   // two slices (one per lane) overlap best on one GPU (profiles/r2d: 861 / 869 / 872 ms for 2 / 4 / 8 slices); with the
   // gather the exposed tail is the LAST slice's transfer, so more, smaller slices win there
-  int n_slices = gather ? 8 : 2;
+  int n_slices = gather ? 10 : 2;
   if (const char *e = getenv("WB_LANE_SLICES")) n_slices = atoi(e);
   n_slices = imax(1, imin(n_slices, n));
+  // Slice boundaries.  From six slices on the slices taper (weights 3 .. 3 2 2 1 1): the two lanes finish together, so
+  // the transfers of the LAST slice of each lane are the exposed tail of the gather -- they should be small, while
+  // small slices everywhere would only multiply the launches of the latency-bound kernels.
+  std::vector<int> bounds(n_slices + 1, 0);
+  {
+    std::vector<int> wgt(n_slices, 1);
+    if (n_slices >= 6)
+      for (int s = 0; s < n_slices; ++s) wgt[s] = s >= n_slices - 2 ? 1 : (s >= n_slices - 4 ? 2 : 3);
+    long long total = 0, run = 0;
+    for (int s = 0; s < n_slices; ++s) total += wgt[s];
+    for (int s = 0; s < n_slices; ++s) { run += wgt[s]; bounds[s + 1] = (int)((long long)n * run / total); }
+  }
   WorldB200 *lanes[2] = {h, h};
 #ifndef WB_EMU
   if (n_slices > 1) {
@@ -576,8 +588,6 @@ static int analyze_batch_impl(WorldB200 *h, const double *x, int n, int x_stride
     cudaEventRecord((cudaEvent_t)h->ev_fork, h->c.stream);
     for (int l = 0; l < 2; ++l) cudaStreamWaitEvent((cudaStream_t)h->lane_stream[l], (cudaEvent_t)h->ev_fork, 0);
   }
-#else
-  n_slices = imin(n_slices, 2);   // one emulated stream: the slicing itself is still exercised
 #endif
   int rc = 0;
   std::vector<int> fl(n);
@@ -599,7 +609,7 @@ static int analyze_batch_impl(WorldB200 *h, const double *x, int n, int x_stride
   }
 #endif
   for (int s = 0; s < n_slices && !rc; ++s) {
-    const int u0 = (int)((long long)n * s / n_slices), u1 = (int)((long long)n * (s + 1) / n_slices);
+    const int u0 = bounds[s], u1 = bounds[s + 1];
     const int m = u1 - u0;
     if (m <= 0) continue;
     WorldB200 *L = lanes[s & 1];
