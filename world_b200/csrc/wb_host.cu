@@ -84,22 +84,36 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
 
 #ifndef WB_EMU
   cudaStream_t s_compute = ctx->stream, s_in = nullptr, s_out = nullptr;
-  if (cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) != cudaSuccess) {
     ctx->last_error = "cudaStreamCreate failed";
+    cudaGetLastError();
+    return WORLD_B200_ECUDA;
+  }
+  if (cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess) {
+    ctx->last_error = "cudaStreamCreate failed";
+    cudaGetLastError();
+    cudaStreamDestroy(s_in);
     return WORLD_B200_ECUDA;
   }
   cudaEvent_t ev_in[2], ev_cdone[2], ev_f0[2], ev_tf[2];
+  bool ev_ok = true;
   for (int i = 0; i < 2; ++i) {
-    cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_cdone[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_f0[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_tf[i], cudaEventDisableTiming);
+    ev_ok = ev_ok && cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming) == cudaSuccess;
+    ev_ok = ev_ok && cudaEventCreateWithFlags(&ev_cdone[i], cudaEventDisableTiming) == cudaSuccess;
+    ev_ok = ev_ok && cudaEventCreateWithFlags(&ev_f0[i], cudaEventDisableTiming) == cudaSuccess;
+    ev_ok = ev_ok && cudaEventCreateWithFlags(&ev_tf[i], cudaEventDisableTiming) == cudaSuccess;
   }
   std::vector<cudaEvent_t> ev_sub_done(ring), ev_sub_out(ring);
   for (int i = 0; i < ring; ++i) {
-    cudaEventCreateWithFlags(&ev_sub_done[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_sub_out[i], cudaEventDisableTiming);
+    ev_ok = ev_ok && cudaEventCreateWithFlags(&ev_sub_done[i], cudaEventDisableTiming) == cudaSuccess;
+    ev_ok = ev_ok && cudaEventCreateWithFlags(&ev_sub_out[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ev_ok) {   // (events created so far are released with the process; this only happens when the driver is out of resources)
+    ctx->last_error = "cudaEventCreate failed";
+    cudaGetLastError();
+    cudaStreamDestroy(s_in);
+    cudaStreamDestroy(s_out);
+    return WORLD_B200_ECUDA;
   }
 #endif
   // WB_HOST_TRACE=1: timeline of this call on stderr (timing events on the three streams + host clock)
@@ -243,9 +257,11 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
   }
 #ifndef WB_EMU
   const double issued_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
-  cudaStreamSynchronize(s_in);
-  cudaStreamSynchronize(s_compute);
-  cudaStreamSynchronize(s_out);
+  // copies and memsets above are not checked one by one: a failure is sticky and surfaces here
+  cudaError_t e_sync = cudaStreamSynchronize(s_in);
+  if (e_sync == cudaSuccess) e_sync = cudaStreamSynchronize(s_compute);
+  if (e_sync == cudaSuccess) e_sync = cudaStreamSynchronize(s_out);
+  if (e_sync != cudaSuccess && !rc) { ctx->last_error = std::string("analyze pipeline: ") + cudaGetErrorString(e_sync); rc = WORLD_B200_ECUDA; }
   if (trace && !marks.empty()) {
     const double done_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     fprintf(stderr, "[wb trace] outer %d sub %d ring %d n %d: all work issued at %.1f ms, finished at %.1f ms (host clock)\n",
