@@ -135,6 +135,21 @@ int world_b200_code_spectral_envelope_batch(WorldB200 *ctx, const double *spectr
 int world_b200_decode_spectral_envelope_batch(WorldB200 *ctx, const double *coded_spectral_envelope,
                                               int n_utts, const int *f0_lengths, int f0_stride, int fs,
                                               int fft_size, int number_of_dimensions, double *spectrogram);
+/* CheapTrick() + CodeSpectralEnvelope() (cheaptrick.h:38, codec.h:62-64) and D4C() + CodeAperiodicity()
+ * (d4c.h:35, codec.h:33-34) in ONE kernel per frame: the coded row is computed in the frame kernel's shared memory
+ * and the fft_size/2+1 bin rows are never written.  Arguments as in world_b200_cheaptrick_batch /
+ * world_b200_d4c_batch; coded_spectral_envelope [n][f0_stride][number_of_dimensions], coded_aperiodicity
+ * [n][f0_stride][GetNumberOfAperiodicities(fs)] (DEVICE).  Same values as the two-step path up to the rounding of
+ * the exp/log (10^x/log10) pair that cancels. */
+int world_b200_cheaptrick_coded_batch(WorldB200 *ctx, const double *x, int n_utts, int x_stride,
+                                      const int *x_lengths, int fs, const double *time_axis,
+                                      const double *f0, const int *f0_lengths, int f0_stride,
+                                      const CheapTrickOption *option, int number_of_dimensions,
+                                      double *coded_spectral_envelope);
+int world_b200_d4c_coded_batch(WorldB200 *ctx, const double *x, int n_utts, int x_stride,
+                               const int *x_lengths, int fs, const double *time_axis,
+                               const double *f0, const int *f0_lengths, int f0_stride, int fft_size,
+                               const D4COption *option, double *coded_aperiodicity);
 
 /* ---- ingest (tools/audioio.cpp:217-252) -- SURVEY.md 8 row f3 --------------------------- */
 /* Host-only: locates the sample data of a mono PCM RIFF/WAVE image held in memory, with the

@@ -98,6 +98,10 @@ def test_emu_codec(emu, ref, golden):
     pc.check_codec(emu, ref, golden)
 
 
+def test_emu_coded_frame_kernels(emu, ref, golden):
+    pc.check_coded_frame_kernels(emu, ref, golden)
+
+
 def test_emu_ingest(emu, ref, golden, tmp_path):
     pc.check_ingest(emu, golden, ref, tmp_path)
 

@@ -149,6 +149,10 @@ def test_gpu_codec(gpu_world, ref, golden):
     pc.check_codec(gpu_world, ref, golden)
 
 
+def test_gpu_coded_frame_kernels(gpu_world, ref, golden):
+    pc.check_coded_frame_kernels(gpu_world, ref, golden)
+
+
 def test_gpu_ingest(gpu_world, ref, golden, tmp_path):
     pc.check_ingest(gpu_world, golden, ref, tmp_path)
 

@@ -294,6 +294,64 @@ def check_codec(world, ref, golden):
             assert_close(to_np(b)[u, :lens[u]], want_ap, f"DecodeAperiodicity fs={fs2} utt {u}")
 
 
+def check_coded_frame_kernels(world, ref, golden):
+    """CheapTrick + CodeSpectralEnvelope / D4C + CodeAperiodicity fused into the frame kernels: against the golden
+    coded rows, against the two-step path of the same library (full rows, then the codec kernels), and -- other
+    rates, dimensions, ragged rows, unvoiced and noise frames -- against the compiled reference's two calls."""
+    x, fs = wav_from_golden(golden)
+    fft, dims = int(golden["fft_size"]), int(golden["coded_dims"])
+    xb = make(world, x[None, :])
+    t = make(world, golden["time_axis"][None, :])
+    f0 = make(world, golden["f0_stonemask"][None, :])
+    opt = world.cheaptrick_option(fs)
+    csp = world.cheaptrick_coded(xb, fs, t, f0, dims, opt)
+    cap = world.d4c_coded(xb, fs, t, f0, fft)
+    two_sp = world.code_spectral_envelope(world.cheaptrick(xb, fs, t, f0, opt), fs, fft, dims)
+    two_ap = world.code_aperiodicity(world.d4c(xb, fs, t, f0, fft), fs, fft)
+    world.synchronize()
+    assert_close_signed(csp[0], golden["coded_sp"], "fused coded spectral envelope (golden)")
+    assert_close_signed(cap[0], golden["coded_ap"], "fused coded aperiodicity (golden)")
+    assert_close_signed(csp[0], to_np(two_sp)[0], "fused vs two-step coded spectral envelope", tol=1e-9)
+    assert_close_signed(cap[0], to_np(two_ap)[0], "fused vs two-step coded aperiodicity", tol=1e-9)
+    for fs2, n2, d2, seed in [(16000, 9000, 24, 5), (48000, 20000, 60, 6), (8000, 5000, 1, 7), (44100, 15000, 513, 8),
+                              (22050, 9000, 40, 9)]:
+        rng = np.random.default_rng(seed)
+        tt = np.arange(n2) / fs2
+        sig = 0.4 * np.sin(2 * np.pi * 180.0 * tt * (1 + 0.2 * tt)) + 0.2 * np.sin(2 * np.pi * 360.0 * tt)
+        sig[n2 // 2:] = 0.0
+        xs = np.stack([sig + 1e-3 * rng.normal(size=n2), 0.1 * rng.normal(size=n2)])
+        lens = [n2, n2 - 1234]
+        opt2 = world.cheaptrick_option(fs2)
+        fft2 = opt2.fft_size
+        d2 = min(d2, fft2 // 4 + 1)
+        frames = [int(1000.0 * l / fs2 / 5.0) + 1 for l in lens]
+        L = max(frames)
+        tb, fb = np.zeros((2, L)), np.zeros((2, L))
+        for u in range(2):
+            tb[u, :frames[u]] = np.arange(frames[u]) * 0.005
+            fb[u, :frames[u]] = np.where(rng.uniform(size=frames[u]) < 0.75, rng.uniform(60, 500, size=frames[u]), 0.0)
+        a = world.cheaptrick_coded(make(world, xs), fs2, make(world, tb), make(world, fb), d2, opt2, x_lengths=lens,
+                                   f0_lengths=frames)
+        b = world.d4c_coded(make(world, xs), fs2, make(world, tb), make(world, fb), fft2, x_lengths=lens,
+                            f0_lengths=frames)
+        world.synchronize()
+        a, b = to_np(a), to_np(b)
+        n_ap = ref.number_of_aperiodicities(fs2)
+        for u in range(2):
+            xu, tu, fu = xs[u, :lens[u]], tb[u, :frames[u]], fb[u, :frames[u]]
+            sp = ref.cheaptrick(xu, fs2, tu, fu)
+            want = ref.code_spectral_envelope(sp, fs2, fft2, d2)
+            assert_close_signed(a[u, :frames[u]], want, f"fused coded sp fs={fs2} d={d2} utt {u}")
+            assert not a[u, frames[u]:].any()
+            if n_ap > 0:
+                ap = ref.d4c(xu, fs2, tu, fu, fft2)
+                assert_close_signed(b[u, :frames[u]], ref.code_aperiodicity(ap, fs2, fft2),
+                                    f"fused coded ap fs={fs2} utt {u}")
+                assert not b[u, frames[u]:].any()
+        if n_ap == 0:
+            assert not b.any()                                  # nothing is written below 12 kHz
+
+
 def wav_image(pcm_bytes, fs, nbit, extra_chunk=b""):
     """RIFF/WAVE image like the reference's wavwrite (tools/audioio.cpp:121-171), optionally with
     another chunk between fmt and data (the case wavread's scan for "data" exists for)."""

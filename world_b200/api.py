@@ -72,6 +72,10 @@ ABI = {
                                               C.POINTER(CheapTrickOption), _P]),
     "world_b200_d4c_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, _P, _P, _IP, C.c_int, C.c_int,
                                        C.POINTER(D4COption), _P]),
+    "world_b200_cheaptrick_coded_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, _P, _P, _IP, C.c_int,
+                                                    C.POINTER(CheapTrickOption), C.c_int, _P]),
+    "world_b200_d4c_coded_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, _IP, C.c_int, _P, _P, _IP, C.c_int, C.c_int,
+                                             C.POINTER(D4COption), _P]),
     "world_b200_synthesis_batch": (C.c_int, [_P, _P, _IP, C.c_int, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int, _IP,
                                              C.c_int, _P]),
     "world_b200_default_analysis_option": (None, [C.c_int, C.c_int, C.POINTER(AnalysisOption)]),
@@ -359,6 +363,33 @@ class World:
         self._use_current_stream()
         self._check(self.lib.world_b200_d4c_batch(self._h, _ptr(x), n, stride, xl, fs, _ptr(time_axis), _ptr(f0),
                                                   fl, f0.shape[1], fft_size, C.byref(option), _ptr(out)))
+        return out
+
+    def cheaptrick_coded(self, x, fs, time_axis, f0, number_of_dimensions, option: CheapTrickOption | None = None,
+                         x_lengths=None, f0_lengths=None):
+        """CheapTrick + CodeSpectralEnvelope in one kernel per frame -> [n, L, number_of_dimensions]."""
+        option = option or self.cheaptrick_option(fs)
+        n, stride = x.shape
+        out = self._zeros(x, (n, f0.shape[1], number_of_dimensions))
+        xl, k1 = _int_array(x_lengths, n)
+        fl, k2 = _int_array(f0_lengths, n)
+        self._use_current_stream()
+        self._check(self.lib.world_b200_cheaptrick_coded_batch(self._h, _ptr(x), n, stride, xl, fs, _ptr(time_axis),
+                                                               _ptr(f0), fl, f0.shape[1], C.byref(option),
+                                                               number_of_dimensions, _ptr(out)))
+        return out
+
+    def d4c_coded(self, x, fs, time_axis, f0, fft_size, option: D4COption | None = None, x_lengths=None,
+                  f0_lengths=None):
+        """D4C + CodeAperiodicity in one kernel per frame -> [n, L, GetNumberOfAperiodicities(fs)]."""
+        option = option or self.d4c_option()
+        n, stride = x.shape
+        out = self._zeros(x, (n, f0.shape[1], max(1, self.number_of_aperiodicities(fs))))
+        xl, k1 = _int_array(x_lengths, n)
+        fl, k2 = _int_array(f0_lengths, n)
+        self._use_current_stream()
+        self._check(self.lib.world_b200_d4c_coded_batch(self._h, _ptr(x), n, stride, xl, fs, _ptr(time_axis), _ptr(f0),
+                                                        fl, f0.shape[1], fft_size, C.byref(option), _ptr(out)))
         return out
 
     def synthesis(self, f0, spectrogram, aperiodicity, fft_size, frame_period, fs, y_length, f0_lengths=None,

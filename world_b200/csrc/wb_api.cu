@@ -454,6 +454,39 @@ int world_b200_d4c_batch(WorldB200 *h, const double *x, int n, int x_stride, con
   return d4c_run(&h->c, b, fft_size, opt->threshold, aperiodicity);
 }
 
+int world_b200_cheaptrick_coded_batch(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths,
+                                      int fs, const double *time_axis, const double *f0, const int *f0_lengths,
+                                      int f0_stride, const CheapTrickOption *opt, int number_of_dimensions,
+                                      double *coded_spectral_envelope) {
+  if (!h || !x || !time_axis || !f0 || !opt || !coded_spectral_envelope || n < 0 || fs <= 0) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
+  CodecTables t;
+  int rc = codec_sp_tables(&h->c, fs, opt->fft_size, number_of_dimensions, &t);
+  if (rc) return rc;
+  Batch b;
+  b.x = x; b.n = n; b.x_stride = x_stride; b.fs = fs; b.time_axis = time_axis; b.f0 = f0; b.f_stride = f0_stride;
+  rc = upload_lengths(h, n, x_stride, x_lengths, f0_stride, f0_lengths, &b);
+  if (rc) return rc;
+  return cheaptrick_run(&h->c, b, opt->q1, opt->fft_size, nullptr, &t, coded_spectral_envelope);
+}
+
+int world_b200_d4c_coded_batch(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths, int fs,
+                               const double *time_axis, const double *f0, const int *f0_lengths, int f0_stride,
+                               int fft_size, const D4COption *opt, double *coded_aperiodicity) {
+  if (!h || !x || !time_axis || !f0 || !opt || n < 0 || fs <= 0 || fft_size < 2) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(&h->c);
+  CodecTables t;
+  int rc = codec_ap_tables(&h->c, fs, fft_size, &t);
+  if (rc) return rc;
+  if (t.dims == 0) return 0;        // nothing to write below 12 kHz, like the reference's empty loops
+  if (!coded_aperiodicity) return WORLD_B200_EINVAL;
+  Batch b;
+  b.x = x; b.n = n; b.x_stride = x_stride; b.fs = fs; b.time_axis = time_axis; b.f0 = f0; b.f_stride = f0_stride;
+  rc = upload_lengths(h, n, x_stride, x_lengths, f0_stride, f0_lengths, &b);
+  if (rc) return rc;
+  return d4c_run(&h->c, b, fft_size, opt->threshold, nullptr, &t, coded_aperiodicity);
+}
+
 int world_b200_stonemask_batch(WorldB200 *h, const double *x, int n, int x_stride, const int *x_lengths,
                                int fs, const double *time_axis, const double *f0, const int *f0_lengths,
                                int f0_stride, double *refined_f0) {

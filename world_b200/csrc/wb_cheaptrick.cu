@@ -25,6 +25,9 @@ struct CtParams {
   double *out;            // [n][f_stride][fft/2+1]
   const double2 *tw;
   int *status;
+  // coded tail (ct_coded_kernel): mel interpolation + DCT of the log envelope, CodeSpectralEnvelope (codec.cpp:279-295)
+  int c_dims; const int *c_idx; const double *c_frac; const double2 *c_weight; double c_norm;
+  double *c_out;          // [n][f_stride][c_dims]
 };
 
 WB_DEV double ct_effective_f0(double f0, double f0_floor) {
@@ -54,7 +57,8 @@ WB_HD inline size_t ct_smem_bytes(int fft_size) {
   return (size_t)2 * WB_FPAD_SLOTS(fft_size / 2) * sizeof(double2) + WB_RED_DOUBLES * sizeof(double);
 }
 
-WB_KERNEL(128, 8) ct_frame_kernel(CtParams p) {
+template <bool kCoded>
+WB_DEV void ct_frame_body(const CtParams &p) {
   WB_DYN_SMEM(double2, smem2);
   const int tid = WB_TID, nth = WB_NTH;
   const int u = blockIdx.y, i = blockIdx.x;
@@ -74,7 +78,6 @@ WB_KERNEL(128, 8) ct_frame_kernel(CtParams p) {
 
   const int h = round_half_away(1.5 * fs / f);
   const int nwin = 2 * h + 1;
-  double *row = p.out + fidx * (size_t)(half + 1);
   if (nwin > N) {  // f0 below the floor implied by fft_size: undefined in the reference
     if (tid == 0) atomicOr_status(p.status, 1);
     return;
@@ -153,11 +156,52 @@ WB_KERNEL(128, 8) ct_frame_kernel(CtParams p) {
     });
   }
   WB_SYNC();
-  const double2 *z3 = sfft_forward(o2, z2, lgc, p.tw);
-  rfft_unpack(z3, p.lg_fft, p.tw, [&](int k, double2 c) { row[k] = exp(c.x); });
+  double2 *z3 = sfft_forward(o2, z2, lgc, p.tw);
+  if (!kCoded) {
+    double *row = p.out + fidx * (size_t)(half + 1);
+    rfft_unpack(z3, p.lg_fft, p.tw, [&](int k, double2 c) { row[k] = exp(c.x); });
+    return;
+  }
+  // ---- coded row: CodeSpectralEnvelope takes the log of the envelope (codec.cpp:288-289) -- the transform's real
+  // part as it stands, the exp / log pair of the unfused path cancels -- interpolates it onto the mel grid (:121-122)
+  // and runs DCTForCodec (:73-89) as one real FFT of fft_size / 2 points
+  double2 *o3 = (z3 == A) ? B : A;
+  double *lgs = reinterpret_cast<double *>(o3);   // half + 1 plain doubles
+  rfft_unpack(z3, p.lg_fft, p.tw, [&](int k, double2 c) { lgs[k] = c.x; });
+  WB_SYNC();
+  {
+    double *zin = reinterpret_cast<double *>(z3);
+    const int bias = half / 2;
+    for (int j = tid; j < bias; j += nth) {        // even samples ascending, odd samples descending (:77-81)
+      const int a = 2 * j, b = half - 2 * j - 1;
+      const int ka = __ldg(p.c_idx + a), kb = __ldg(p.c_idx + b);
+      zin[rpad(j)] = lgs[ka] + __ldg(p.c_frac + a) * (lgs[ka + 1] - lgs[ka]);
+      zin[rpad(j + bias)] = lgs[kb] + __ldg(p.c_frac + b) * (lgs[kb + 1] - lgs[kb]);
+    }
+  }
+  WB_SYNC();
+  const double2 *zc = sfft_forward(z3, o3, lgc - 1, p.tw);
+  double *crow = p.c_out + fidx * (size_t)p.c_dims;
+  const int dims = p.c_dims;
+  const double cn = p.c_norm;
+  rfft_unpack(zc, lgc, p.tw, [&](int d, double2 X) {     // :85-88
+    if (d < dims) {
+      const double2 w = __ldg(p.c_weight + d);
+      crow[d] = (X.x * w.x - X.y * w.y) / cn;
+    }
+  });
 }
 
-int cheaptrick_run(Ctx *ctx, const Batch &b, double q1, int fft_size, double *spectrogram) {
+#ifndef WB_EMU
+__global__ void __launch_bounds__(128, 8) ct_frame_kernel(CtParams p) { ct_frame_body<false>(p); }
+__global__ void __launch_bounds__(128, 8) ct_coded_kernel(CtParams p) { ct_frame_body<true>(p); }
+#else
+void ct_frame_kernel(CtParams p) { ct_frame_body<false>(p); }
+void ct_coded_kernel(CtParams p) { ct_frame_body<true>(p); }
+#endif
+
+int cheaptrick_run(Ctx *ctx, const Batch &b, double q1, int fft_size, double *spectrogram,
+                   const CodecTables *coded, double *coded_out) {
   if (b.n <= 0 || b.max_f_len <= 0) return 0;
   int lg = 0;
   while ((1 << lg) < fft_size) ++lg;
@@ -176,7 +220,9 @@ int cheaptrick_run(Ctx *ctx, const Batch &b, double q1, int fft_size, double *sp
   const size_t smem = ct_smem_bytes(fft_size);
 #ifndef WB_EMU
   cudaFuncSetAttribute(ct_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(ct_coded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
+  const size_t n_tab = coded ? coded->idx.size() : 0, n_w = coded ? coded->weight.size() : 0;
   for (int u0 = 0; u0 < b.n; u0 += chunk) {
     const int n = imin(chunk, b.n - u0);
     ArenaPlan plan;
@@ -184,6 +230,7 @@ int cheaptrick_run(Ctx *ctx, const Batch &b, double q1, int fft_size, double *sp
     const size_t o_offs = plan.add((size_t)n * b.f_stride * 4);
     const size_t o_totals = plan.add((size_t)n * 4);
     const size_t o_draws = plan.add((size_t)n * draw_stride_full * 4);
+    const size_t o_cidx = plan.add(n_tab * 4 + 4), o_cfrac = plan.add(n_tab * 8 + 8), o_cw = plan.add(n_w * 16 + 16);
     unsigned char *blk = arena_block(ctx, plan.total);
     if (!blk) return 2;
     unsigned *counts = (unsigned *)(blk + o_counts), *offs = (unsigned *)(blk + o_offs);
@@ -201,10 +248,21 @@ int cheaptrick_run(Ctx *ctx, const Batch &b, double q1, int fft_size, double *sp
     p.f_stride = b.f_stride; p.fs = b.fs; p.fft_size = fft_size; p.lg_fft = lg;
     p.q1 = q1; p.f0_floor = f0_floor;
     p.draws = draws; p.draw_stride = draw_stride_full; p.draw_off = offs;
-    p.out = spectrogram + (size_t)u0 * b.f_stride * bins;
+    p.out = spectrogram ? spectrogram + (size_t)u0 * b.f_stride * bins : nullptr;
     p.tw = ctx->twiddle; p.status = ctx->status_dev;
+    p.c_dims = 0; p.c_idx = nullptr; p.c_frac = nullptr; p.c_weight = nullptr; p.c_norm = 1.0; p.c_out = nullptr;
     int ct_threads = 128;
     if (const char *e = getenv("WB_CT_THREADS")) ct_threads = atoi(e);
+    if (coded) {
+      int rc = dev_memcpy_h2d(ctx, blk + o_cidx, coded->idx.data(), n_tab * 4);
+      if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_cfrac, coded->frac.data(), n_tab * 8);
+      if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_cw, coded->weight.data(), n_w * 16);
+      if (rc) return rc;
+      p.c_dims = coded->dims; p.c_idx = (const int *)(blk + o_cidx); p.c_frac = (const double *)(blk + o_cfrac);
+      p.c_weight = (const double2 *)(blk + o_cw); p.c_norm = coded->norm;
+      p.c_out = coded_out + (size_t)u0 * b.f_stride * coded->dims;
+      WB_LAUNCH_COOP(ct_coded_kernel, dim3((unsigned)b.max_f_len, (unsigned)n), ct_threads, smem, ctx->stream, p);
+    } else
     WB_LAUNCH_COOP(ct_frame_kernel, dim3((unsigned)b.max_f_len, (unsigned)n), ct_threads, smem, ctx->stream, p);
     int rc = dev_check(ctx, "cheaptrick");
     if (rc) return rc;

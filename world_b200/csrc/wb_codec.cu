@@ -185,9 +185,7 @@ int check_fft(Ctx *ctx, int fft_size, int *lg_half) {
 }
 
 // lengths + tables into one arena block, then one launch per <= 65535 utterances
-struct Tables {
-  std::vector<int> idx; std::vector<double> frac; std::vector<double2> weight;
-};
+typedef CodecTables Tables;
 
 int run_frames(Ctx *ctx, int which, CodecParams p, const Tables &t, const int *f0_lengths, int n_utts,
                size_t in_row, size_t out_row, size_t smem) {
@@ -232,22 +230,9 @@ int run_frames(Ctx *ctx, int which, CodecParams p, const Tables &t, const int *f
 }
 
 }  // namespace
-}  // namespace wb
 
-using namespace wb;
-
-extern "C" {
-
-int GetNumberOfAperiodicities(int fs) {
-  return static_cast<int>(dmin(kCodecUpperLimit, fs / 2.0 - kCodecFrequencyInterval) / kCodecFrequencyInterval);
-}
-
-int world_b200_code_spectral_envelope_batch(WorldB200 *h, const double *spectrogram, int n_utts,
-                                            const int *f0_lengths, int f0_stride, int fs, int fft_size,
-                                            int number_of_dimensions, double *coded) {
-  if (!h || !spectrogram || !coded || n_utts < 0 || fs <= 0 || f0_stride <= 0) return WORLD_B200_EINVAL;
-  DeviceGuard guard_(reinterpret_cast<const Ctx *>(h));  // Ctx is the first member of WorldB200
-  Ctx *ctx = reinterpret_cast<Ctx *>(h);
+// GetParametersForCoding (codec.cpp:161-181) + the DCT weights of DCTForCodec (:73-89)
+int codec_sp_tables(Ctx *ctx, int fs, int fft_size, int number_of_dimensions, CodecTables *t) {
   int lg = 0;
   int rc = check_fft(ctx, fft_size, &lg);
   if (rc) return rc;
@@ -256,19 +241,59 @@ int world_b200_code_spectral_envelope_batch(WorldB200 *h, const double *spectrog
     ctx->last_error = "CodeSpectralEnvelope: number_of_dimensions must be in [1, fft_size/4 + 1]";
     return WORLD_B200_EINVAL;
   }
-  // GetParametersForCoding (codec.cpp:161-181)
   const double floor_mel = frequency_to_mel(kCodecFloorFrequency);
   const double ceil_mel = frequency_to_mel(dmin(fs / 2.0, kCodecCeilFrequency));
   std::vector<double> mel_axis(M), frequency_axis(M + 1);
-  Tables t;
-  t.weight.resize(number_of_dimensions);
+  t->weight.resize(number_of_dimensions);
   for (int i = 0; i < M; ++i) mel_axis[i] = (ceil_mel - floor_mel) * i / M + floor_mel;
   for (int i = 0; i < number_of_dimensions; ++i)
-    t.weight[i] = make_double2(2.0 * cos(i * kPi / fft_size) / sqrt((double)fft_size),
-                               2.0 * sin(i * kPi / fft_size) / sqrt((double)fft_size));
-  t.weight[0].x /= sqrt(2.0);
+    t->weight[i] = make_double2(2.0 * cos(i * kPi / fft_size) / sqrt((double)fft_size),
+                                2.0 * sin(i * kPi / fft_size) / sqrt((double)fft_size));
+  t->weight[0].x /= sqrt(2.0);
   for (int i = 0; i <= M; ++i) frequency_axis[i] = frequency_to_mel(static_cast<double>(i) * fs / fft_size);
-  interp1_tables(frequency_axis, mel_axis, &t.idx, &t.frac);
+  interp1_tables(frequency_axis, mel_axis, &t->idx, &t->frac);
+  t->dims = number_of_dimensions; t->lg_half = lg; t->norm = sqrt((double)M);
+  return 0;
+}
+
+static int number_of_aperiodicities(int fs) {   // codec.cpp:216-219
+  return static_cast<int>(dmin(kCodecUpperLimit, fs / 2.0 - kCodecFrequencyInterval) / kCodecFrequencyInterval);
+}
+
+// interp1Q(0, fs / fft_size, ..., 3000 (i + 1)) of CodeAperiodicity (codec.cpp:228-238, matlabfunctions.cpp:214-235)
+int codec_ap_tables(Ctx *ctx, int fs, int fft_size, CodecTables *t) {
+  const int n_ap = number_of_aperiodicities(fs);
+  t->dims = n_ap > 0 ? n_ap : 0;
+  t->idx.resize(t->dims); t->frac.resize(t->dims);
+  const double dx = static_cast<double>(fs) / fft_size;
+  for (int i = 0; i < t->dims; ++i) {
+    const double xi = kCodecFrequencyInterval * (i + 1.0);
+    const int base = static_cast<int>((xi - 0) / dx);
+    t->idx[i] = base;
+    t->frac[i] = (xi - 0) / dx - base;
+    if (base < 0 || base > fft_size / 2) { ctx->last_error = "CodeAperiodicity: band centre beyond fs/2"; return WORLD_B200_EINVAL; }
+  }
+  return 0;
+}
+
+}  // namespace wb
+
+using namespace wb;
+
+extern "C" {
+
+int GetNumberOfAperiodicities(int fs) { return number_of_aperiodicities(fs); }
+
+int world_b200_code_spectral_envelope_batch(WorldB200 *h, const double *spectrogram, int n_utts,
+                                            const int *f0_lengths, int f0_stride, int fs, int fft_size,
+                                            int number_of_dimensions, double *coded) {
+  if (!h || !spectrogram || !coded || n_utts < 0 || fs <= 0 || f0_stride <= 0) return WORLD_B200_EINVAL;
+  DeviceGuard guard_(reinterpret_cast<const Ctx *>(h));  // Ctx is the first member of WorldB200
+  Ctx *ctx = reinterpret_cast<Ctx *>(h);
+  Tables t;
+  int rc = codec_sp_tables(ctx, fs, fft_size, number_of_dimensions, &t);
+  if (rc) return rc;
+  const int M = fft_size / 2, lg = t.lg_half;
   CodecParams p;
   memset(&p, 0, sizeof(p));
   p.f_stride = f0_stride; p.in = spectrogram; p.out = coded; p.bins = M + 1; p.dims = number_of_dimensions;
@@ -323,15 +348,8 @@ int world_b200_code_aperiodicity_batch(WorldB200 *h, const double *aperiodicity,
   if (n_ap <= 0) return 0;          // nothing to write below 12 kHz, like the reference's empty loops
   if (!coded) return WORLD_B200_EINVAL;
   Tables t;
-  t.idx.resize(n_ap); t.frac.resize(n_ap);
-  const double dx = static_cast<double>(fs) / fft_size;
-  for (int i = 0; i < n_ap; ++i) {   // interp1Q(0, fs / fft_size, ..., 3000 (i + 1)) -- matlabfunctions.cpp:214-235
-    const double xi = kCodecFrequencyInterval * (i + 1.0);
-    const int base = static_cast<int>((xi - 0) / dx);
-    t.idx[i] = base;
-    t.frac[i] = (xi - 0) / dx - base;
-    if (base < 0 || base > fft_size / 2) { ctx->last_error = "CodeAperiodicity: band centre beyond fs/2"; return WORLD_B200_EINVAL; }
-  }
+  int rc = codec_ap_tables(ctx, fs, fft_size, &t);
+  if (rc) return rc;
   CodecParams p;
   memset(&p, 0, sizeof(p));
   p.f_stride = f0_stride; p.in = aperiodicity; p.out = coded; p.bins = fft_size / 2 + 1; p.dims = n_ap;

@@ -35,6 +35,9 @@ struct D4cParams {
   double *out;
   const double2 *tw;
   int *status;
+  // coded output (CodeAperiodicity, codec.cpp:228-238): with c_out set the kernels write the dB value at the c_n
+  // band centres instead of the ct_fft_size/2+1 bins
+  int c_n; const int *c_idx; const double *c_frac; double *c_out;
 };
 
 WB_KERNEL_PLAIN d4c_count_a_kernel(const double *__restrict__ f0, const int *__restrict__ f_len,
@@ -84,8 +87,56 @@ WB_DEV int d4c_windowed(const double *__restrict__ x, int x_len, int fs, double 
   return nwin;
 }
 
-WB_DEV void d4c_fill_row(double *row, int bins) {
+// a frame D4C does not analyse (unvoiced, or LoveTrain says noise): 1 - 1e-12 in every bin (d4c.cpp:372-383);
+// coded: 20 log10 of that at every band centre (interp1Q between equal nodes)
+WB_DEV void d4c_fill_frame(const D4cParams &p, size_t fidx) {
+  if (p.c_out) {
+    const double v = 20 * log10(1.0 - kTiny);
+    for (int b = WB_TID; b < p.c_n; b += WB_NTH) p.c_out[fidx * (size_t)p.c_n + b] = v;
+    return;
+  }
+  const int bins = p.ct_fft_size / 2 + 1;
+  double *row = p.out + fidx * (size_t)bins;
   for (int k = WB_TID; k < bins; k += WB_NTH) row[k] = 1.0 - kTiny;
+}
+
+// interp1 of the coarse aperiodicity (dB at 0, 3k, ..., fs/2) at bin k of the CheapTrick grid (d4c.cpp:330-338)
+WB_DEV double d4c_bin_db(const double *coarse, int n_ap, int fs, int ct_fft_size, int k) {
+  const int nx = n_ap + 2;
+  const double xi = static_cast<double>(k) * fs / ct_fft_size;
+  int idx = 0;  // number of axis points <= xi
+  for (int j = 0; j < nx; ++j) {
+    const double xj = (j == nx - 1) ? fs / 2.0 : j * 3000.0;
+    idx += (xj <= xi) ? 1 : 0;
+  }
+  idx = imin(nx - 1, imax(1, idx));
+  const double x0 = (idx - 1) * 3000.0;
+  const double x1 = (idx == nx - 1) ? fs / 2.0 : idx * 3000.0;
+  const double s = (xi - x0) / (x1 - x0);
+  return coarse[idx - 1] + s * (coarse[idx] - coarse[idx - 1]);
+}
+
+// dB -> amplitude row (d4c.cpp:372-383), or the coded row: the dB values themselves, interp1Q'd onto the band centres
+// (the 10^(y/20) / 20 log10 pair of the unfused path cancels)
+template <bool kFastExp>
+WB_DEV void d4c_write_frame(const D4cParams &p, size_t fidx, const double *coarse) {
+  const int tid = WB_TID, nth = WB_NTH;
+  const int bins = p.ct_fft_size / 2 + 1;
+  if (p.c_out) {
+    for (int b = tid; b < p.c_n; b += nth) {
+      const int k = __ldg(p.c_idx + b);
+      const double y0 = d4c_bin_db(coarse, p.n_ap, p.fs, p.ct_fft_size, k);
+      const double dy = (k + 1 < bins) ? d4c_bin_db(coarse, p.n_ap, p.fs, p.ct_fft_size, k + 1) - y0 : 0.0;
+      p.c_out[fidx * (size_t)p.c_n + b] = y0 + dy * __ldg(p.c_frac + b);
+    }
+    return;
+  }
+  double *row = p.out + fidx * (size_t)bins;
+  for (int k = tid; k < bins; k += nth) {
+    const double y = d4c_bin_db(coarse, p.n_ap, p.fs, p.ct_fft_size, k);
+    row[k] = kFastExp ? exp(y * 0.11512925464970228420)   // 10^(y/20) = e^(y ln10 / 20)
+                      : pow(10.0, y / 20.0);
+  }
 }
 
 // ------------------------------------------------------------------ pass A: LoveTrain
@@ -95,11 +146,9 @@ WB_KERNEL(128, 4) d4c_lovetrain_kernel(D4cParams p) {
   const int u = blockIdx.y, i = blockIdx.x;
   if (i >= p.f_len[u]) return;
   const size_t fidx = (size_t)u * p.f_stride + i;
-  const int bins = p.ct_fft_size / 2 + 1;
-  double *row = p.out + fidx * (size_t)bins;
   const double f0 = p.f0[fidx];
   if (f0 == 0.0) {
-    d4c_fill_row(row, bins);
+    d4c_fill_frame(p, fidx);
     if (tid == 0) { p.selected[fidx] = 0; p.count_b[fidx] = 0; }
     return;
   }
@@ -129,7 +178,7 @@ WB_KERNEL(128, 4) d4c_lovetrain_kernel(D4cParams p) {
   block_sum2(s_lo, s_hi, red);
   const double ap0 = s_lo / s_hi;
   const bool sel = ap0 > p.threshold;  // d4c.cpp:386
-  if (!sel) d4c_fill_row(row, bins);
+  if (!sel) d4c_fill_frame(p, fidx);
   if (tid == 0) {
     p.selected[fidx] = sel ? 1 : 0;
     unsigned c = 0;
@@ -447,23 +496,7 @@ WB_DEV void d4c_body_frame(const D4cParams &p) {
   WB_SYNC();
 
   // ---- interp1 onto the CheapTrick frequency grid, dB -> amplitude (d4c.cpp:330-338, 372-383)
-  const int bins = p.ct_fft_size / 2 + 1;
-  double *row = p.out + fidx * (size_t)bins;
-  const int nx = p.n_ap + 2;
-  for (int k = tid; k < bins; k += nth) {
-    const double xi = static_cast<double>(k) * fs / p.ct_fft_size;
-    int idx = 0;  // number of axis points <= xi
-    for (int j = 0; j < nx; ++j) {
-      const double xj = (j == nx - 1) ? fs / 2.0 : j * 3000.0;
-      idx += (xj <= xi) ? 1 : 0;
-    }
-    idx = imin(nx - 1, imax(1, idx));
-    const double x0 = (idx - 1) * 3000.0;
-    const double x1 = (idx == nx - 1) ? fs / 2.0 : idx * 3000.0;
-    const double s = (xi - x0) / (x1 - x0);
-    const double y = coarse[idx - 1] + s * (coarse[idx] - coarse[idx - 1]);
-    row[k] = exp(y * 0.11512925464970228420);   // 10^(y/20) = e^(y ln10 / 20)
-  }
+  d4c_write_frame<true>(p, fidx, coarse);
 }
 
 #ifndef WB_EMU
@@ -586,23 +619,7 @@ WB_DEV void d4c_body_slow_frame(const D4cParams &p, int u, int i, double *smem) 
   WB_SYNC();
 
   // ---- interp1 onto the CheapTrick frequency grid, dB -> amplitude (d4c.cpp:330-338, 372-383)
-  const int bins = p.ct_fft_size / 2 + 1;
-  double *row = p.out + fidx * (size_t)bins;
-  const int nx = p.n_ap + 2;
-    for (int k = tid; k < bins; k += nth) {
-    const double xi = static_cast<double>(k) * fs / p.ct_fft_size;
-    int idx = 0;  // number of axis points <= xi
-    for (int j = 0; j < nx; ++j) {
-      const double xj = (j == nx - 1) ? fs / 2.0 : j * 3000.0;
-      idx += (xj <= xi) ? 1 : 0;
-    }
-    idx = imin(nx - 1, imax(1, idx));
-    const double x0 = (idx - 1) * 3000.0;
-    const double x1 = (idx == nx - 1) ? fs / 2.0 : idx * 3000.0;
-    const double s = (xi - x0) / (x1 - x0);
-    const double y = coarse[idx - 1] + s * (coarse[idx] - coarse[idx - 1]);
-    row[k] = pow(10.0, y / 20.0);
-  }
+  d4c_write_frame<false>(p, fidx, coarse);
 }
 
 WB_KERNEL(256, 2) d4c_body_slow_kernel(D4cParams p) {
@@ -629,8 +646,10 @@ WB_KERNEL_PLAIN d4c_list_all_kernel(D4cParams p, int n_utts) {
   p.slow_list[at] = (int)g;
 }
 
-int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *aperiodicity) {
+int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *aperiodicity,
+            const CodecTables *coded, double *coded_out) {
   if (b.n <= 0 || b.max_f_len <= 0) return 0;
+  if (coded && coded->dims == 0) return 0;   // below 12 kHz the coded row is empty (codec.cpp:216-219)
   const int fs = b.fs;
   D4cParams p;
   memset(&p, 0, sizeof(p));
@@ -695,6 +714,8 @@ int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *ap
     const size_t o_sel = plan.add(slots), o_nut = plan.add((size_t)p.win_len * 8);
     const size_t o_slow = plan.add(slots * 4), o_nslow = plan.add(4);
     const size_t o_draws = plan.add((size_t)n * draw_stride_full * 4);
+    const size_t n_tab = coded ? coded->idx.size() : 0;
+    const size_t o_cidx = plan.add(n_tab * 4 + 4), o_cfrac = plan.add(n_tab * 8 + 8);
     unsigned char *blk = arena_block(ctx, plan.total);
     if (!blk) { rc = 2; break; }
     unsigned *count_a = (unsigned *)(blk + o_ca), *off_a = (unsigned *)(blk + o_oa);
@@ -711,8 +732,15 @@ int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *ap
     p.f_stride = b.f_stride;
     p.nuttall = nuttall; p.draws = draws; p.draw_stride = draw_stride_full;
     p.off_a = off_a; p.count_b = count_b; p.off_b = off_b; p.selected = selected;
-    p.out = aperiodicity + (size_t)u0 * b.f_stride * bins;
+    p.out = aperiodicity ? aperiodicity + (size_t)u0 * b.f_stride * bins : nullptr;
     p.tw = ctx->twiddle; p.status = ctx->status_dev;
+    if (coded) {
+      rc = dev_memcpy_h2d(ctx, blk + o_cidx, coded->idx.data(), n_tab * 4);
+      if (!rc) rc = dev_memcpy_h2d(ctx, blk + o_cfrac, coded->frac.data(), n_tab * 8);
+      if (rc) break;
+      p.c_n = coded->dims; p.c_idx = (const int *)(blk + o_cidx); p.c_frac = (const double *)(blk + o_cfrac);
+      p.c_out = coded_out + (size_t)u0 * b.f_stride * coded->dims;
+    }
     p.slow_list = (int *)(blk + o_slow); p.slow_count = (int *)(blk + o_nslow);
     dev_memset(ctx, p.slow_count, 0, 4);
 

@@ -60,6 +60,9 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
       opt->f0_method == WORLD_B200_F0_HARVEST ? opt->harvest.frame_period : opt->dio.frame_period;
   const bool want_sp = out_sp != nullptr, want_ap = out_ap != nullptr && (!dims || n_ap > 0);
   if (n_utts == 0) return 0;
+  // coded mode: the frame kernels write the coded rows themselves (world_b200_cheaptrick_coded_batch /
+  // world_b200_d4c_coded_batch); WB_CODEC_UNFUSED=1 keeps round 1's full rows + codec kernels for A/B runs
+  const bool unfused = dims && getenv("WB_CODEC_UNFUSED") != nullptr;
 
   int sub = 128, outer = 512;
   if (const char *e = getenv("WB_HOST_SUB")) sub = atoi(e) > 0 ? atoi(e) : sub;
@@ -75,7 +78,7 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
   outer = imin(outer, (n_utts + sub - 1) / sub * sub);
   const int subs_per_outer = outer / sub;
   const double ring_budget = (double)third - (double)imin(n_utts, outer) * 2.0 * (double)per_outer -
-                             (dims ? (double)sub * (double)per_sub_raw : 0.0);
+                             (unfused ? (double)sub * (double)per_sub_raw : 0.0);
   int ring = 2 * subs_per_outer;
   if (per_sub_out > 0)
     ring = imax(2, imin(ring, (int)dmax(0.0, ring_budget / ((double)sub * (double)per_sub_out))));
@@ -138,7 +141,7 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
   mark("start", 0, s_compute);
 #endif
   DevBuf din[2], dx[2], dt[2], df[2];
-  const int raw_slots = dims ? 1 : ring;   // coded mode: the full rows are consumed on the same stream
+  const int raw_slots = dims ? (unfused ? 1 : 0) : ring;   // unfused coded mode: the full rows are consumed on the same stream
   std::vector<DevBuf> dsp(raw_slots), dap(raw_slots), dcs(dims ? ring : 0), dca(dims ? ring : 0);
   int rc = 0;
   const int n_outer_bufs = n_utts > outer ? 2 : 1;
@@ -223,18 +226,27 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
         if (dims && want_sp) dev_memset(ctx, dcs[slot].p, 0, ssz * sp_row * 8);
         if (dims && want_ap) dev_memset(ctx, dca[slot].p, 0, ssz * ap_row * 8);
       }
-      if (want_sp)
-        rc = world_b200_cheaptrick_batch(h, sx, m, x_stride, sxl, fs, st, sf, sfl, f0_stride, &opt->cheaptrick,
-                                         (double *)dsp[rslot].p);
-      if (!rc && want_ap)
-        rc = world_b200_d4c_batch(h, sx, m, x_stride, sxl, fs, st, sf, sfl, f0_stride, opt->cheaptrick.fft_size,
-                                  &opt->d4c, (double *)dap[rslot].p);
-      if (!rc && dims && want_sp)
-        rc = world_b200_code_spectral_envelope_batch(h, (const double *)dsp[0].p, m, sfl, f0_stride, fs,
-                                                     opt->cheaptrick.fft_size, dims, (double *)dcs[slot].p);
-      if (!rc && dims && want_ap)
-        rc = world_b200_code_aperiodicity_batch(h, (const double *)dap[0].p, m, sfl, f0_stride, fs,
-                                                opt->cheaptrick.fft_size, (double *)dca[slot].p);
+      if (dims && !unfused) {
+        if (want_sp)
+          rc = world_b200_cheaptrick_coded_batch(h, sx, m, x_stride, sxl, fs, st, sf, sfl, f0_stride, &opt->cheaptrick,
+                                                 dims, (double *)dcs[slot].p);
+        if (!rc && want_ap)
+          rc = world_b200_d4c_coded_batch(h, sx, m, x_stride, sxl, fs, st, sf, sfl, f0_stride,
+                                          opt->cheaptrick.fft_size, &opt->d4c, (double *)dca[slot].p);
+      } else {
+        if (want_sp)
+          rc = world_b200_cheaptrick_batch(h, sx, m, x_stride, sxl, fs, st, sf, sfl, f0_stride, &opt->cheaptrick,
+                                           (double *)dsp[rslot].p);
+        if (!rc && want_ap)
+          rc = world_b200_d4c_batch(h, sx, m, x_stride, sxl, fs, st, sf, sfl, f0_stride, opt->cheaptrick.fft_size,
+                                    &opt->d4c, (double *)dap[rslot].p);
+        if (!rc && dims && want_sp)
+          rc = world_b200_code_spectral_envelope_batch(h, (const double *)dsp[0].p, m, sfl, f0_stride, fs,
+                                                       opt->cheaptrick.fft_size, dims, (double *)dcs[slot].p);
+        if (!rc && dims && want_ap)
+          rc = world_b200_code_aperiodicity_batch(h, (const double *)dap[0].p, m, sfl, f0_stride, fs,
+                                                  opt->cheaptrick.fft_size, (double *)dca[slot].p);
+      }
       if (rc) break;
       const void *sp_src = dims ? dcs[slot].p : dsp[rslot].p, *ap_src = dims ? dca[slot].p : dap[rslot].p;
       const size_t row0 = (size_t)(u0 + v0) * f0_stride;

@@ -137,8 +137,20 @@ struct Batch {
 };
 
 // stage drivers (each: enqueue on ctx->stream, return 0 / error code)
-int cheaptrick_run(Ctx *ctx, const Batch &b, double q1, int fft_size, double *spectrogram);
-int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *aperiodicity);
+// Coded output straight from the frame kernels: the tables of CodeSpectralEnvelope /
+// CodeAperiodicity (codec.cpp:161-181, :228-238), host made by wb_codec.cu, ride along to the stage drivers; with
+// them the frame kernels write the coded row instead of the fft_size/2+1 bins and the full row never reaches HBM.
+struct CodecTables {
+  std::vector<int> idx; std::vector<double> frac; std::vector<double2> weight;
+  int dims = 0, lg_half = 0;   // coded values per frame; log2(fft_size / 2) (spectral envelope only)
+  double norm = 1.0;           // sqrt(fft_size / 2)
+};
+int codec_sp_tables(Ctx *ctx, int fs, int fft_size, int number_of_dimensions, CodecTables *t);
+int codec_ap_tables(Ctx *ctx, int fs, int fft_size, CodecTables *t);   // t->dims = 0 below 12 kHz
+int cheaptrick_run(Ctx *ctx, const Batch &b, double q1, int fft_size, double *spectrogram,
+                   const CodecTables *coded = nullptr, double *coded_out = nullptr);
+int d4c_run(Ctx *ctx, const Batch &b, int fft_size, double threshold, double *aperiodicity,
+            const CodecTables *coded = nullptr, double *coded_out = nullptr);
 int stonemask_run(Ctx *ctx, const Batch &b, double *refined_f0);
 struct DioParams { double f0_floor, f0_ceil, channels_in_octave, frame_period, allowed_range; int speed; };
 int dio_run(Ctx *ctx, const Batch &b, const DioParams &p, double *time_axis_out, double *f0_out);
