@@ -444,13 +444,16 @@ def check_host_pipeline_chunking(world, golden, f0_method=0):
         rows[u, :lens[u]] = pcm16[2000 + 97 * u: 2000 + 97 * u + lens[u]]
     xd = rows.astype(np.float64) / 32768.0
     opt = world.analysis_option(fs, f0_method)
-    saved = {k: os.environ.get(k) for k in ("WB_HOST_SUB", "WB_HOST_CHUNK")}
+    saved = {k: os.environ.get(k) for k in ("WB_HOST_SUB", "WB_HOST_CHUNK", "WB_HOST_TAPER_MIN", "WB_HOST_TAPER")}
     try:
-        os.environ.pop("WB_HOST_SUB", None); os.environ.pop("WB_HOST_CHUNK", None)
+        for k in saved:
+            os.environ.pop(k, None)
         want_raw = world.analyze_host(xd, fs, opt, x_lengths=lens)
         want_cod = world.analyze_coded_host(rows, 16, fs, opt, dims, x_lengths=lens)
-        for sub, outer in ((1, 2), (2, 4), (3, 3)):
+        # (4, 4, 1): the last outer chunk (3 utterances) runs in quarter-size sub-chunks, the first in one
+        for sub, outer, taper_min in ((1, 2, 16), (2, 4, 16), (3, 3, 16), (4, 4, 1), (4, 8, 1)):
             os.environ["WB_HOST_SUB"], os.environ["WB_HOST_CHUNK"] = str(sub), str(outer)
+            os.environ["WB_HOST_TAPER_MIN"] = str(taper_min)
             got_raw = world.analyze_host(xd, fs, opt, x_lengths=lens)
             got_cod = world.analyze_coded_host(rows, 16, fs, opt, dims, x_lengths=lens)
             for a, b in zip(got_raw[:4] + got_cod[:4], want_raw[:4] + want_cod[:4]):

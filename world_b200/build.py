@@ -26,20 +26,24 @@ def _newer(src, obj):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(verbose=False, force=False):
+def build(verbose=False, force=False, defines=(), tag=""):
+    """tag / defines: an A/B variant (lib/libworld_b200_<tag>.so built with -D<define>...), loaded through
+    WORLD_B200_LIB; the product library is the untagged one."""
+    objdir = OBJDIR + ("_" + tag if tag else "")
     os.makedirs(LIBDIR, exist_ok=True)
-    os.makedirs(OBJDIR, exist_ok=True)
-    out = os.path.join(LIBDIR, "libworld_b200.so")
+    os.makedirs(objdir, exist_ok=True)
+    out = os.path.join(LIBDIR, "libworld_b200%s.so" % ("_" + tag if tag else ""))
+    flags = FLAGS + ["-D" + d for d in defines]
     jobs = []
     for s in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(OBJDIR, s.replace(".cu", ".o"))
+        obj = os.path.join(objdir, s.replace(".cu", ".o"))
         if force or _newer(src, obj):
             jobs.append((src, obj))
 
     def compile_one(job):
         src, obj = job
-        r = subprocess.run([NVCC] + FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
+        r = subprocess.run([NVCC] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(obj + ".ptxas.log", "w") as f:
             f.write(log)
@@ -52,7 +56,7 @@ def build(verbose=False, force=False):
     if verbose:
         for l in logs:
             print(l)
-    objs = [os.path.join(OBJDIR, s.replace(".cu", ".o")) for s in SOURCES]
+    objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
     if jobs or not os.path.exists(out):
         r = subprocess.run([NVCC, "-shared", "-o", out] + objs + ["-lcudart", "-ldl"], capture_output=True, text=True)
         if r.returncode != 0:

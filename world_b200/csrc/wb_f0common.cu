@@ -840,6 +840,7 @@ WB_KERNEL(256, 4) band_interp_kernel(SweepParams p) {
   WB_SHARED double xw[4][WB_IP_W + 4], yw[4][WB_IP_W + 4];
   WB_SHARED unsigned long long marks[WB_IP_F + 40];   // per frame: intervals whose first frame it is, 4 x 16 bit; + scan scratch
   WB_SHARED unsigned long long orig[WB_IP_F];
+  WB_SHARED int more_flag[2];   // "the last interval of a window still starts inside the round", per iteration parity
   const int tid = WB_TID, nth = WB_NTH;
   const int b = blockIdx.x, u = blockIdx.y;
   const int *ec = p.ev_count + ((size_t)u * p.n_bands + b) * 4;
@@ -872,33 +873,45 @@ WB_KERNEL(256, 4) band_interp_kernel(SweepParams p) {
   for (int c0 = 0; c0 < nf; c0 += WB_IP_F) {
     const int c1 = imin(nf, c0 + WB_IP_F);
     for (int i = tid; i < WB_IP_F; i += nth) marks[i] = 0ull;
+    for (int i = tid; i < 2; i += nth) more_flag[i] = 0;
     int at[4] = {cursor[0], cursor[1], cursor[2], cursor[3]};   // first interval not yet examined in this round
     int wbase[4] = {0, 0, 0, 0}, wlen[4] = {0, 0, 0, 0};
     WB_SYNC();
     bool more = true;
-    while (more) {
-      // windows: two intervals before the examined range serve the frames no new interval reaches
+    // One pass over the (train, interval) pairs of all four windows: the four trains' loads and divisions run side by
+    // side instead of one latency chain after the other (profiles/r2p: a quarter of the kernel's samples waited at the
+    // barrier behind the 20-60 loading threads of a low band).  The thread that loads a window's last interval tells
+    // the CTA through more_flag[] whether that interval still starts inside the round; the flag of the next iteration
+    // is cleared while this one's is read.
+    for (int itn = 0; more; ++itn) {
       for (int q = 0; q < 4; ++q) {
         wbase[q] = imax(0, at[q] - 2);
-        const int k0 = at[q] - wbase[q];
-        wlen[q] = imin(tr[q].n_int - wbase[q], k0 + w_band);
-        for (int k = tid; k < wlen[q]; k += nth) {
-          const double x = ip_loc(tr[q], wbase[q] + k);
-          xw[q][k] = x; yw[q][k] = ip_val(tr[q], wbase[q] + k);
-          if (k >= k0) {   // interval (wbase + k) is counted by every frame from its first frame on
-            const int m = first_frame_fast(x, p.frame_period, fps);
-            if (m < c1) smem_add_u64(&marks[imax(m, c0) - c0], 1ull << (16 * q));
+        wlen[q] = imin(tr[q].n_int - wbase[q], at[q] - wbase[q] + w_band);
+      }
+      const int off1 = wlen[0], off2 = off1 + wlen[1], off3 = off2 + wlen[2], total = off3 + wlen[3];
+      for (int j = tid; j < total; j += nth) {
+        const int q = (j >= off1 ? 1 : 0) + (j >= off2 ? 1 : 0) + (j >= off3 ? 1 : 0);
+        const int k = j - (q == 0 ? 0 : q == 1 ? off1 : q == 2 ? off2 : off3);
+        const int wb = q == 0 ? wbase[0] : q == 1 ? wbase[1] : q == 2 ? wbase[2] : wbase[3];
+        const int aq = q == 0 ? at[0] : q == 1 ? at[1] : q == 2 ? at[2] : at[3];
+        const int wl = q == 0 ? wlen[0] : q == 1 ? wlen[1] : q == 2 ? wlen[2] : wlen[3];
+        const int ni = q == 0 ? tr[0].n_int : q == 1 ? tr[1].n_int : q == 2 ? tr[2].n_int : tr[3].n_int;
+        IpTrain T;
+        T.e = edges + (size_t)q * cap; T.n_int = ni; T.afs = p.afs;
+        const double x = ip_loc(T, wb + k);
+        xw[q][k] = x; yw[q][k] = ip_val(T, wb + k);
+        if (k >= aq - wb) {   // interval (wbase + k) is counted by every frame from its first frame on
+          const int m = first_frame_fast(x, p.frame_period, fps);
+          if (m < c1) {
+            smem_add_u64(&marks[imax(m, c0) - c0], 1ull << (16 * q));
+            if (k == wl - 1 && wb + wl < ni) more_flag[itn & 1] = 1;   // may be followed by more of them
           }
         }
       }
       WB_SYNC();
-      // a window whose LAST interval still starts inside the round may be followed by more of them: examine the next window
-      more = false;
-      for (int q = 0; q < 4; ++q) {
-        const int last = wbase[q] + wlen[q] - 1;     // last interval loaded
-        at[q] = last + 1;
-        if (wlen[q] > 0 && last + 1 < tr[q].n_int && first_frame_fast(xw[q][wlen[q] - 1], p.frame_period, fps) < c1) more = true;
-      }
+      more = more_flag[itn & 1] != 0;
+      if (tid == 0) more_flag[(itn & 1) ^ 1] = 0;
+      for (int q = 0; q < 4; ++q) at[q] = wbase[q] + wlen[q];
       if (more) WB_SYNC();   // the windows are rewritten
     }
     // inclusive counts per frame: exclusive scan + the frame's own marks

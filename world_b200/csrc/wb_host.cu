@@ -207,8 +207,17 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
     if (time_axis) memcpy(time_axis + (size_t)u0 * f0_stride, td, fsz * 8);
     if (f0) memcpy(f0 + (size_t)u0 * f0_stride, fd, fsz * 8);
 #endif
-    for (int v0 = 0; v0 < n && !rc && (want_sp || want_ap); v0 += sub, ++g) {
-      const int m = imin(sub, n - v0);
+    // Sub-chunk size.  A sub-chunk's rows go to the host while the next one is computed, and in the full-row mode a
+    // sub-chunk takes ~12 % longer to download than to compute: after the LAST outer chunk the copy engine is the
+    // critical path, finishing (first sub-chunk's compute + every download) after the chunk's Harvest -- ~50 ms behind
+    // the kernels of a 850 ms step at 1024 x 10 s with sub-chunks of 128.  Quarter-size sub-chunks there start the
+    // downloads earlier and leave a shorter last one (~25 ms behind).  WB_HOST_TAPER=0 disables it.
+    const bool taper = !dims && u0 + outer >= n_utts && !(getenv("WB_HOST_TAPER") && atoi(getenv("WB_HOST_TAPER")) == 0);
+    int taper_min = 16;   // (WB_HOST_TAPER_MIN: tests exercise the path with a handful of utterances)
+    if (const char *e = getenv("WB_HOST_TAPER_MIN")) taper_min = imax(1, atoi(e));
+    const int sub_here = taper ? imax(imin(sub, taper_min), sub / 4) : sub;
+    for (int v0 = 0; v0 < n && !rc && (want_sp || want_ap); v0 += sub_here, ++g) {
+      const int m = imin(sub_here, n - v0);
       const int slot = g % ring, rslot = dims ? 0 : slot;
       const int *sxl = xl ? xl + v0 : nullptr;
       const int *sfl = fl + v0;
