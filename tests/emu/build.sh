@@ -9,7 +9,7 @@ OBJS=""
 for f in $FILES; do
   o="_$(basename $f .cu).o"
   if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find $SRC -name '*.cuh' -newer $o -o -name '*.h' -newer $o)" ]; then
-    g++ -x c++ -std=c++17 -O2 -fPIC -DWB_EMU -ffp-contract=off -mfma -I../../include -c "$f" -o "$o" &
+    g++ -x c++ -std=c++17 -O2 -fPIC -DWB_EMU $WB_EMU_DEFS -ffp-contract=off -mfma -I../../include -c "$f" -o "$o" &
   fi
   OBJS="$OBJS $o"
 done

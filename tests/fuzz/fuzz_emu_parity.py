@@ -118,10 +118,26 @@ def run(emu, ref, n_cases, seed, out=print):
                 ap = emu.d4c(xd, fs, make(emu, tr[None]), make(emu, frc[None]), co.fft_size, do)
                 emu.synchronize()
                 sp, ap = to_np(sp), to_np(ap)
-                e_sp = rel_err(sp[0], ref.cheaptrick(x, fs, tr, frc, rco)).max()
-                e_ap = rel_err(ap[0], ref.d4c(x, fs, tr, frc, rco.fft_size, rdo)).max()
+                spr, apr = ref.cheaptrick(x, fs, tr, frc, rco), ref.d4c(x, fs, tr, frc, rco.fft_size, rdo)
+                e_sp = rel_err(sp[0], spr).max()
+                e_ap = rel_err(ap[0], apr).max()
                 msg.append(f"sp {e_sp:.1e} ap {e_ap:.1e}")
                 assert e_sp <= TOL and e_ap <= TOL
+                # the same frames through the fused kernels: coded rows against the reference's two-call chain.
+                # Coded values live in the log domain -- a relative error e of a bin is an ABSOLUTE error of
+                # 20 / ln(10) * e dB in a coded aperiodicity and of at most sqrt(fft_size / 2) * e in a cepstral
+                # coefficient (orthonormal DCT of the log envelope) -- so the 1e-6 relative bound of the rows becomes
+                # these absolute bounds (near-periodic tones reach ap errors of 5e-7, i.e. 4e-6 dB around -2 dB).
+                dims = [24, 60, 1, co.fft_size // 4 + 1][case % 4]
+                csp = emu.cheaptrick_coded(xd, fs, make(emu, tr[None]), make(emu, frc[None]), dims, co)
+                cap = emu.d4c_coded(xd, fs, make(emu, tr[None]), make(emu, frc[None]), co.fft_size, do)
+                emu.synchronize()
+                want = ref.code_spectral_envelope(spr, fs, rco.fft_size, dims)
+                e_csp = np.abs(to_np(csp)[0] - want).max()
+                want = ref.code_aperiodicity(apr, fs, rco.fft_size)
+                e_cap = np.abs(to_np(cap)[0] - want).max()
+                msg.append(f"coded abs {e_csp:.1e} {e_cap:.1e}")
+                assert e_csp <= np.sqrt(rco.fft_size / 2.0) * TOL and e_cap <= 20.0 / np.log(10.0) * TOL
             status = "ok"
         except AssertionError as e:
             status = f"MISMATCH {e}"
@@ -129,7 +145,7 @@ def run(emu, ref, n_cases, seed, out=print):
         except Exception as e:   # library errors (EDOMAIN etc.) are reported, not hidden
             status = f"ERROR {type(e).__name__}: {e}"
             bad += 1
-        out(f"case {case:3d} fs {fs:5d} n {n:6d} {kind:11s} {method:7s} fp {fp:4.1f}  {'  '.join(msg):60s} {status}  ({time.time() - t0:.1f}s)")
+        out(f"case {case:3d} fs {fs:5d} n {n:6d} {kind:11s} {method:7s} fp {fp:4.1f}  {'  '.join(msg):84s} {status}  ({time.time() - t0:.1f}s)")
     out(f"{n_cases - bad}/{n_cases} cases agree with the reference within {TOL}; {bad} failures")
     return bad
 

@@ -94,14 +94,20 @@ WB_DEV void ct_frame_body(const CtParams &p) {
     wv[j] = w;
     sq += w * w;
   }
+  // first round's sample and draw requested before the reduction's barriers, every later round's one round ahead
+  double x_next = 0.0;
+  unsigned d_next = 0u;
+  if (tid < nwin) { x_next = x[imin(x_len - 1, imax(0, origin + tid - h))]; d_next = draw[tid]; }
   const double norm = sqrt(block_sum(sq, red));
   // ---- windowed waveform + 1e-12 * randn, weighted-mean removal (:126-137)
   double s1 = 0.0, s2 = 0.0;
   for (int j = tid; j < nwin; j += nth) {
+    const double x_now = x_next;
+    const unsigned d_now = d_next;
+    if (j + nth < nwin) { x_next = x[imin(x_len - 1, imax(0, origin + j + nth - h))]; d_next = draw[j + nth]; }
     const double w = wv[j] / norm;
     wv[j] = w;
-    const int idx = imin(x_len - 1, imax(0, origin + j - h));
-    const double v = x[idx] * w + randn_value(draw[j]) * kTiny;
+    const double v = x_now * w + randn_value(d_now) * kTiny;
     za[rpad(j)] = v;
     s1 += v;
     s2 += w;
@@ -118,6 +124,12 @@ WB_DEV void ct_frame_body(const CtParams &p) {
   double *pw = reinterpret_cast<double *>(o);
   rfft_unpack(z, p.lg_fft, p.tw, [&](int k, double2 c) { pw[k] = c.x * c.x + c.y * c.y; });
   WB_SYNC();
+  // the draws of the +eps noise below are requested now: they arrive while the smoothing (barriers, one thread's
+  // index-order running sum) keeps the CTA waiting anyway.  (half + 1 <= 5 * 128 up to fft_size 1024; beyond that
+  // the tail of the loop below loads as before.)
+  unsigned dpre[5];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) { const int k = tid + q * nth; dpre[q] = (k <= half) ? draw[nwin + k] : 0u; }
   dc_correction<true>(pw, f, fs, N, reinterpret_cast<double *>(z));
   if (!linear_smoothing<true>(pw, f * 2.0 / 3.0, fs, N, pw, reinterpret_cast<double *>(z), red)) {
     if (tid == 0) atomicOr_status(p.status, 2);
@@ -126,7 +138,17 @@ WB_DEV void ct_frame_body(const CtParams &p) {
   // ---- + |randn| * eps (:147-151), log, mirrored to an even sequence of N (:39-42) = input of the next FFT
   {
     double *zin = reinterpret_cast<double *>(z);
-    for (int k = tid; k <= half; k += nth) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const int k = tid + q * nth;
+      if (k <= half) {
+        const double v = pw[k] + fabs(randn_value(dpre[q])) * kEps;
+        const double l = log(v);
+        zin[rpad(k)] = l;
+        if (k > 0 && k < half) zin[rpad(N - k)] = l;
+      }
+    }
+    for (int k = tid + 5 * nth; k <= half; k += nth) {
       const double v = pw[k] + fabs(randn_value(draw[nwin + k])) * kEps;
       const double l = log(v);
       zin[rpad(k)] = l;

@@ -215,7 +215,9 @@ int analyze_pipeline(WorldB200 *h, const void *x, int nbit, int n_utts, int x_st
     const bool taper = !dims && u0 + outer >= n_utts && !(getenv("WB_HOST_TAPER") && atoi(getenv("WB_HOST_TAPER")) == 0);
     int taper_min = 16;   // (WB_HOST_TAPER_MIN: tests exercise the path with a handful of utterances)
     if (const char *e = getenv("WB_HOST_TAPER_MIN")) taper_min = imax(1, atoi(e));
-    const int sub_here = taper ? imax(imin(sub, taper_min), sub / 4) : sub;
+    int taper_div = 4;
+    if (const char *e = getenv("WB_HOST_TAPER_DIV")) taper_div = imax(1, atoi(e));
+    const int sub_here = taper ? imax(imin(sub, taper_min), sub / taper_div) : sub;
     for (int v0 = 0; v0 < n && !rc && (want_sp || want_ap); v0 += sub_here, ++g) {
       const int m = imin(sub_here, n - v0);
       const int slot = g % ring, rslot = dims ? 0 : slot;
