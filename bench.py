@@ -610,7 +610,7 @@ def main():
                "utts_per_gpu": Ue, "steps": ke, "ms_per_step_rank0": e2e_steps_ms,
                "note": ("world_b200_cheaptrick_batch + world_b200_d4c_batch on 32-utterance rounds: pinned host waveform / f0 up, pinned host rows down"
                         if spectral else
-                        "world_b200_analyze_host: pinned host buffers in/out; F0 stage on 512-utterance chunks, CheapTrick+D4C on 128-utterance sub-chunks whose rows are downloaded while the next ones are computed")}
+                        "world_b200_analyze_host: pinned host buffers in/out; F0 stage on 512-utterance chunks, CheapTrick+D4C on 128-utterance sub-chunks (32 in the last chunk) whose rows are downloaded while the next ones are computed")}
         if spectral:
             e2e["h2d_bytes_per_step"] = int(Ue * n * 8 + 2 * Ue * L * 8)
             e2e["d2h_bytes_per_step"] = int(2 * Ue * L * bins * 8)
@@ -651,7 +651,8 @@ def main():
                                 "h2d_bytes_per_step": int(Ue * n * 2),
                                 "d2h_bytes_per_step": int(Ue * L * (dims + n_ap) * 8 + 2 * Ue * L * 8),
                                 "note": "world_b200_analyze_coded_host: int16 PCM in, CodeSpectralEnvelope(60) + "
-                                        "CodeAperiodicity rows out; input is the 16-bit quantisation of the same waveforms"}
+                                        "CodeAperiodicity rows out, computed in the frame kernels (no full rows in HBM); "
+                                        "input is the 16-bit quantisation of the same waveforms"}
             except Exception as exc:   # the secondary leg must never take the bench line down
                 e2e["coded"] = {"error": f"{type(exc).__name__}: {exc}"}
 
