@@ -10,7 +10,7 @@ OUT=${1:-/tmp/asan}
 cd "$(dirname "$0")"
 SRC=../../world_b200/csrc
 mkdir -p "$OUT"
-for f in wb_api wb_rng wb_cheaptrick wb_d4c wb_stonemask wb_synthesis wb_codec wb_fileio wb_matlab wb_f0common wb_dio wb_harvest wb_host; do
+for f in wb_api wb_rng wb_cheaptrick wb_d4c wb_stonemask wb_synthesis wb_codec wb_fileio wb_matlab wb_f0common wb_dio wb_harvest wb_host wb_multi; do
   g++ -x c++ -std=c++17 -O1 -g -fPIC -DWB_EMU -ffp-contract=off -mfma -fsanitize=address -fno-omit-frame-pointer \
       -I../../include -c $SRC/$f.cu -o "$OUT/$f.o" &
 done
